@@ -1,0 +1,210 @@
+/*
+ * licos_b200 -- C ABI of the B200-native learned-codec hot path.
+ *
+ * The reference (gomezzz/LICOS) has no FFI of its own: it drives the path through the CompressAI
+ * nn.Module API.  Every entry point below therefore names the upstream
+ * CompressAI call it replaces and the reference line that reaches it.  The Python host layer
+ * (the licos_b200 Python package) mirrors the CompressAI module API on top of these calls.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; device pointers unless the parameter says "host";
+ *   - returns LICOS_OK (0) or a negative LICOS_ERR_* code; never throws, never allocates device
+ *     memory, never synchronises; work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - all buffers are caller-owned and must stay alive until the stream has drained.
+ */
+#ifndef LICOS_B200_H
+#define LICOS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LICOS_ABI_VERSION 1
+
+enum {
+    LICOS_OK = 0,
+    LICOS_ERR_INVALID = -1,     /* bad argument (shape, null pointer, unsupported combination) */
+    LICOS_ERR_CUDA = -2,        /* a CUDA runtime/driver call failed: see licos_last_cuda_error() */
+    LICOS_ERR_UNSUPPORTED = -3, /* valid request this build has no kernel for */
+    LICOS_ERR_NO_DEVICE = -4,   /* no sm_100 device */
+    LICOS_ERR_DOMAIN = -5,      /* pmf_to_quantized_cdf: negative / non-finite / all-zero pmf */
+    LICOS_ERR_NOMEM = -6,       /* host allocation failed */
+    LICOS_ERR_BUFFER = -7       /* caller's output buffer too small */
+};
+
+int licos_abi_version(void);
+const char* licos_strerror(int code);
+int licos_last_cuda_error(void); /* cudaError_t of the last LICOS_ERR_CUDA on this thread */
+/* LICOS_OK when `device` is a compute-capability 10.x GPU (B200), else LICOS_ERR_NO_DEVICE. */
+int licos_device_ok(int device);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Tensor layouts                                                                             */
+/* ------------------------------------------------------------------------------------------ */
+#define LICOS_LAYOUT_NCHW_F32 0  /* the CompressAI-facing layout (x, y, x_hat, likelihoods)     */
+#define LICOS_LAYOUT_NHWC_BF16 1 /* inter-layer activations; C must be a multiple of 64         */
+
+/* fp32 NCHW -> bf16 NHWC (optionally |x|: ScaleHyperprior.forward's `h_a(torch.abs(y))`). */
+int licos_nchw_f32_to_nhwc_bf16(const float* in, void* out, int batch, int channels, int64_t hw,
+                                int take_abs, void* stream);
+int licos_nhwc_bf16_to_nchw_f32(const void* in, float* out, int batch, int channels, int64_t hw,
+                                void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Convolutions (replaces torch.nn.Conv2d / ConvTranspose2d / compressai.layers.GDN forward    */
+/* inside g_a / g_s / h_a / h_s; reached from licos/train.py:190 and eval_utils.py:200-201)    */
+/* ------------------------------------------------------------------------------------------ */
+#define LICOS_CONV_5X5_S2 0   /* compressai.models.utils.conv:   Conv2d(k=5, s=2, p=2)          */
+#define LICOS_DECONV_5X5_S2 1 /* compressai.models.utils.deconv: ConvTranspose2d(k=5,s=2,p=2,op=1) */
+#define LICOS_CONV_3X3_S1 2   /* conv(.., stride=1, kernel_size=3): Conv2d(k=3, s=1, p=1)       */
+
+#define LICOS_EPI_NONE 0 /* + bias                                                             */
+#define LICOS_EPI_GDN 1  /* + bias, then GDN:  v * rsqrt(beta + gamma . v^2)                    */
+#define LICOS_EPI_IGDN 2 /* + bias, then IGDN: v *  sqrt(beta + gamma . v^2)                    */
+#define LICOS_EPI_RELU 3 /* + bias, then max(v, 0)                                             */
+
+/* Bytes needed for the packed bf16 weight of one layer (see licos_pack_conv_weight). */
+int64_t licos_packed_weight_bytes(int kind, int out_c, int in_c, int in_layout);
+
+/* Re-packs a torch-layout fp32 weight for the kernels.
+ *   kind = CONV_*  : w is (out_c, in_c, KH, KW)   [torch.nn.Conv2d.weight]
+ *   kind = DECONV_*: w is (in_c, out_c, KH, KW)   [torch.nn.ConvTranspose2d.weight]
+ * in_layout selects the kernel family the weight is for: NHWC_BF16 -> [tap][out_c_pad][in_c_pad64],
+ * NCHW_F32 (first layer, in_c <= 16) -> [out_c][K_pad64] with K = (c, kh, kw). */
+int licos_pack_conv_weight(const float* w, int kind, int out_c, int in_c, int in_layout, void* packed,
+                           void* stream);
+
+/* GDN parameters after NonNegativeParametrizer: beta_hat = max(beta, beta_bound)^2 - pedestal (fp32),
+ * gamma_hat = max(gamma, gamma_bound)^2 - pedestal (bf16, [C][C] row = output channel). */
+int licos_gdn_pack(const float* beta, const float* gamma, int channels, float beta_bound, float gamma_bound,
+                   float pedestal, float* beta_hat, void* gamma_hat_bf16, void* stream);
+
+typedef struct licos_conv_args {
+    int kind;       /* LICOS_CONV_* / LICOS_DECONV_*                                           */
+    int epilogue;   /* LICOS_EPI_*                                                             */
+    int batch;
+    int in_h, in_w; /* spatial size of `in`                                                    */
+    int in_c;       /* logical input channels                                                  */
+    int out_c;      /* logical output channels                                                 */
+    int in_layout;  /* LICOS_LAYOUT_*                                                          */
+    int out_layout; /* LICOS_LAYOUT_*                                                          */
+    const void* in;
+    void* out;
+    const void* weight; /* from licos_pack_conv_weight                                         */
+    const float* bias;  /* [out_c] fp32, may be NULL                                           */
+    const float* beta;  /* [out_c] fp32 from licos_gdn_pack  (EPI_GDN / EPI_IGDN)              */
+    const void* gamma;  /* [out_c][out_c] bf16 from licos_gdn_pack                             */
+    void* workspace;    /* scratch for in_layout == NCHW_F32 (licos_conv_workspace_bytes)        */
+    int64_t workspace_bytes;
+    int sm_count;       /* 0 = query the device                                                */
+    int reserved;
+} licos_conv_args;
+
+/* Scratch bytes licos_conv_forward needs for these args (0 unless in_layout == NCHW_F32). */
+int64_t licos_conv_workspace_bytes(const licos_conv_args* args);
+
+/* One conv / deconv layer with its fused epilogue.  Output spatial size:
+ * CONV_5X5_S2 -> ceil(in/2), DECONV_5X5_S2 -> 2*in, CONV_3X3_S1 -> in. */
+int licos_conv_forward(const licos_conv_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* EntropyBottleneck (compressai.entropy_models.EntropyBottleneck)   */
+/* ------------------------------------------------------------------------------------------ */
+#define LICOS_EB_MAX_LAYERS 8
+#define LICOS_EB_FORM_PLAIN 0  /* sigmoid(upper) - sigmoid(lower)            (CompressAI >= 1.2) */
+#define LICOS_EB_FORM_STABLE 1 /* |sigmoid(s*upper) - sigmoid(s*lower)|, s = -sign(lower+upper)   */
+#define LICOS_EB_LUT_RADIUS 128 /* eval-mode table covers symbols in [-128, 128]                 */
+
+typedef struct licos_eb_params {
+    int channels;
+    int n_layers;                        /* len(filters) + 1                                    */
+    int widths[LICOS_EB_MAX_LAYERS + 1]; /* (1,) + filters + (1,)                               */
+    int params_per_channel;              /* floats per channel in `packed`                      */
+    /* [channels][params_per_channel]; per layer i: softplus(_matrix_i) row-major (out, in),
+     * _bias_i, then tanh(_factor_i) for i < n_layers - 1 */
+    const float* packed;
+    const float* medians; /* [channels] = quantiles[:, 0, 1]                                    */
+    int form;             /* LICOS_EB_FORM_*                                                    */
+    float likelihood_bound; /* <= 0 disables the LowerBound                                     */
+} licos_eb_params;
+
+int64_t licos_eb_lut_floats(int channels); /* size of the eval-mode workspace, in floats */
+
+/* EntropyBottleneck.forward(x, training=False): y_hat = round(x - med) + med, likelihood(y_hat).
+ * x, y_hat, lik: fp32 [batch][channels][hw].  lut_ws: licos_eb_lut_floats(channels) floats. */
+int licos_eb_forward_eval(const licos_eb_params* p, const float* x, int batch, int64_t hw, float* lut_ws,
+                          float* y_hat, float* lik, void* stream);
+/* EntropyBottleneck.forward(x, training=True): y_hat = x + noise.  noise == NULL draws U(-0.5, 0.5)
+ * from an in-kernel Philox stream keyed by (seed, element index). */
+int licos_eb_forward_noise(const licos_eb_params* p, const float* x, const float* noise, uint64_t seed,
+                           int batch, int64_t hw, float* y_hat, float* lik, void* stream);
+/* EntropyModel.quantize(x, "symbols", medians) and EntropyBottleneck._build_indexes.
+ * symbols / indexes: int32 [batch][channels][hw]; indexes may be NULL. */
+int licos_eb_symbols(const float* x, const float* medians, int batch, int channels, int64_t hw,
+                     int32_t* symbols, int32_t* indexes, void* stream);
+/* EntropyModel.dequantize(symbols, medians) */
+int licos_eb_dequantize(const int32_t* symbols, const float* medians, int batch, int channels, int64_t hw,
+                        float* y_hat, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* GaussianConditional (compressai.entropy_models.GaussianConditional)   */
+/* ------------------------------------------------------------------------------------------ */
+/* forward(y, scales, means, training): mode 0 = dequantize, 1 = noise (noise may be NULL -> Philox). */
+int licos_gc_forward(const float* y, const float* scales, const float* means, const float* noise,
+                     uint64_t seed, int64_t n, int training, float scale_bound, float likelihood_bound,
+                     float* y_hat, float* lik, void* stream);
+/* build_indexes(scales): idx = n_table-1 - #{k < n_table-1 : max(scale, bound) <= table[k]} */
+int licos_gc_build_indexes(const float* scales, int64_t n, const float* table, int n_table,
+                           float scale_bound, int32_t* indexes, void* stream);
+/* quantize(y, "symbols", means): int32 round-half-even of (y - means); means may be NULL. */
+int licos_gc_symbols(const float* y, const float* means, int64_t n, int32_t* symbols, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Rate-distortion reductions (compressai.losses.RateDistortionLoss, eval_utils.py:172-186)    */
+/* ------------------------------------------------------------------------------------------ */
+/* acc[0] += sum(ln(lik[i])) ; caller zeroes acc (double, device).  bpp = acc / (-ln2 * N*H*W). */
+int licos_sum_log(const float* lik, int64_t n, double* acc, void* stream);
+/* acc[0] += sum((a[i]-b[i])^2) */
+int licos_sum_sq_err(const float* a, const float* b, int64_t n, double* acc, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Host-side integer path (compressai._CXX.pmf_to_quantized_cdf, compressai.ans)               */
+/* ------------------------------------------------------------------------------------------ */
+/* pmf (host, n floats) -> cdf (host, n + 1 uint32), strictly increasing, cdf[n] = 1 << precision. */
+int licos_pmf_to_quantized_cdf(const float* pmf, int n, int precision, uint32_t* cdf);
+
+/* rANS (64-bit state, 32-bit renormalisation, 16-bit precision, 4-bit bypass), bitstream-compatible
+ * with compressai.ans.RansEncoder.encode_with_indexes.  All pointers are host pointers.
+ * cdfs is [n_cdfs][cdf_stride] int32.  Returns the number of bytes written or a negative error. */
+int64_t licos_rans_encode(const int32_t* symbols, const int32_t* indexes, int64_t n, const int32_t* cdfs,
+                          int n_cdfs, int cdf_stride, const int32_t* cdf_sizes, const int32_t* offsets,
+                          uint8_t* out, int64_t out_capacity);
+int licos_rans_decode(const uint8_t* encoded, int64_t n_bytes, const int32_t* indexes, int64_t n,
+                      const int32_t* cdfs, int n_cdfs, int cdf_stride, const int32_t* cdf_sizes,
+                      const int32_t* offsets, int32_t* symbols);
+/* The per-image loop of EntropyModel.compress, run on `threads` host threads.  symbols/indexes are
+ * [batch][n]; image i is written at out + i*out_stride, its length to out_sizes[i]. */
+int licos_rans_encode_batch(const int32_t* symbols, const int32_t* indexes, int batch, int64_t n,
+                            int64_t index_batch_stride, const int32_t* cdfs, int n_cdfs, int cdf_stride,
+                            const int32_t* cdf_sizes, const int32_t* offsets, uint8_t* out,
+                            int64_t out_stride, int64_t* out_sizes, int threads);
+int licos_rans_decode_batch(const uint8_t* const* encoded, const int64_t* n_bytes, const int32_t* indexes,
+                            int batch, int64_t n, int64_t index_batch_stride, const int32_t* cdfs,
+                            int n_cdfs, int cdf_stride, const int32_t* cdf_sizes, const int32_t* offsets,
+                            int32_t* symbols, int threads);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Federated merge (licos/federation_utils.py:47-53)                                           */
+/* ------------------------------------------------------------------------------------------ */
+/* dst[i] = w_a * a[i] + w_b * b[i] over a flat fp32 parameter buffer. */
+int licos_weighted_sum2(const float* a, const float* b, float w_a, float w_b, int64_t n, float* dst,
+                        void* stream);
+/* buf[i] *= w   (the per-rank pre-multiply in front of the NCCL all-reduce) */
+int licos_scale_inplace(float* buf, float w, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LICOS_B200_H */

@@ -1,0 +1,119 @@
+"""ctypes binding of liblicos_b200.so (the C ABI declared in include/licos_b200.h).
+
+There is no fallback: if the shared library cannot be loaded (or built with nvcc), importing this
+module raises, and every op of the package raises with it.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "liblicos_b200.so")
+
+LICOS_OK = 0
+ERR_NAMES = {
+    -1: "LICOS_ERR_INVALID", -2: "LICOS_ERR_CUDA", -3: "LICOS_ERR_UNSUPPORTED", -4: "LICOS_ERR_NO_DEVICE",
+    -5: "LICOS_ERR_DOMAIN", -6: "LICOS_ERR_NOMEM", -7: "LICOS_ERR_BUFFER",
+}
+
+LAYOUT_NCHW_F32 = 0
+LAYOUT_NHWC_BF16 = 1
+CONV_5X5_S2 = 0
+DECONV_5X5_S2 = 1
+CONV_3X3_S1 = 2
+EPI_NONE, EPI_GDN, EPI_IGDN, EPI_RELU = 0, 1, 2, 3
+EB_MAX_LAYERS = 8
+EB_FORM_PLAIN, EB_FORM_STABLE = 0, 1
+EB_LUT_RADIUS = 128
+
+c_int, c_i64, c_u64, c_f32, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_float, ctypes.c_void_p
+
+
+class ConvArgs(ctypes.Structure):
+    _fields_ = [
+        ("kind", c_int), ("epilogue", c_int), ("batch", c_int), ("in_h", c_int), ("in_w", c_int),
+        ("in_c", c_int), ("out_c", c_int), ("in_layout", c_int), ("out_layout", c_int),
+        ("in_", c_vp), ("out", c_vp), ("weight", c_vp), ("bias", c_vp), ("beta", c_vp), ("gamma", c_vp),
+        ("workspace", c_vp), ("workspace_bytes", c_i64), ("sm_count", c_int), ("reserved", c_int),
+    ]
+
+
+class EbParams(ctypes.Structure):
+    _fields_ = [
+        ("channels", c_int), ("n_layers", c_int), ("widths", c_int * (EB_MAX_LAYERS + 1)),
+        ("params_per_channel", c_int), ("packed", c_vp), ("medians", c_vp), ("form", c_int),
+        ("likelihood_bound", c_f32),
+    ]
+
+
+# name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
+SIGNATURES = {
+    "licos_abi_version": (c_int, []),
+    "licos_strerror": (ctypes.c_char_p, [c_int]),
+    "licos_last_cuda_error": (c_int, []),
+    "licos_device_ok": (c_int, [c_int]),
+    "licos_nchw_f32_to_nhwc_bf16": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_int, c_vp]),
+    "licos_nhwc_bf16_to_nchw_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
+    "licos_packed_weight_bytes": (c_i64, [c_int, c_int, c_int, c_int]),
+    "licos_pack_conv_weight": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "licos_gdn_pack": (c_int, [c_vp, c_vp, c_int, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp]),
+    "licos_conv_workspace_bytes": (c_i64, [ctypes.POINTER(ConvArgs)]),
+    "licos_conv_forward": (c_int, [ctypes.POINTER(ConvArgs), c_vp]),
+    "licos_eb_lut_floats": (c_i64, [c_int]),
+    "licos_eb_forward_eval": (c_int, [ctypes.POINTER(EbParams), c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "licos_eb_forward_noise": (c_int, [ctypes.POINTER(EbParams), c_vp, c_vp, c_u64, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "licos_eb_symbols": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "licos_eb_dequantize": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_vp]),
+    "licos_gc_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_u64, c_i64, c_int, c_f32, c_f32, c_vp, c_vp, c_vp]),
+    "licos_gc_build_indexes": (c_int, [c_vp, c_i64, c_vp, c_int, c_f32, c_vp, c_vp]),
+    "licos_gc_symbols": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "licos_sum_log": (c_int, [c_vp, c_i64, c_vp, c_vp]),
+    "licos_sum_sq_err": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "licos_pmf_to_quantized_cdf": (c_int, [c_vp, c_int, c_int, c_vp]),
+    "licos_rans_encode": (c_i64, [c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_i64]),
+    "licos_rans_decode": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
+    "licos_rans_encode_batch": (c_int, [c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_vp,
+                                        c_i64, c_vp, c_int]),
+    "licos_rans_decode_batch": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_int, c_int, c_vp, c_vp,
+                                        c_vp, c_int]),
+    "licos_weighted_sum2": (c_int, [c_vp, c_vp, c_f32, c_f32, c_i64, c_vp, c_vp]),
+    "licos_scale_inplace": (c_int, [c_vp, c_f32, c_i64, c_vp]),
+}
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        # in-tree build (nvcc cross-compiles without a GPU); raises if nvcc is missing or fails
+        from .csrc.build import build
+        build()
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == header / library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.licos_abi_version() != 1:
+        raise ImportError(f"liblicos_b200.so ABI version {lib.licos_abi_version()} != 1")
+    return lib
+
+
+lib = _load()
+
+
+class LicosError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = "") -> int:
+    """Translate a negative status into the Python exception the CompressAI call would raise."""
+    if rc >= 0:
+        return rc
+    msg = lib.licos_strerror(int(rc)).decode()
+    name = ERR_NAMES.get(int(rc), str(rc))
+    if rc == -2:
+        msg += f" [cudaError {lib.licos_last_cuda_error()}]"
+    if rc in (-1, -5, -7):
+        raise ValueError(f"{what}: {name}: {msg}")
+    if rc == -3:
+        raise NotImplementedError(f"{what}: {name}: {msg}")
+    raise LicosError(f"{what}: {name}: {msg}")

@@ -1,0 +1,856 @@
+// Implicit-GEMM convolution engine for sm_100a: strided 5x5 conv, 5x5 stride-2 transposed conv (as four
+// output-parity sub-convolutions), 3x3 stride-1 conv, each with its epilogue (bias, GDN / IGDN, ReLU)
+// fused.  One persistent, warp-specialised kernel:
+//
+//   warp 0  A producer   TMA loads "slabs" of the NHWC bf16 activation: for one column tap kw and one
+//                        64-channel chunk, a box of (TH+2) rows x 16 columns x 64 channels.  Every row
+//                        tap kh that shares this kw reads the SAME slab at a row offset (a multiple of
+//                        2 KB, so the 128-byte swizzle phase is unchanged) -> each activation byte is
+//                        fetched 5x (not 25x) per 5x5 layer.
+//   warp 1  B producer   TMA loads one [N x 64] weight tile per (tap, chunk); for GDN layers also the
+//                        gamma tiles, through the same ring.
+//   warp 2  MMA issuer   tcgen05.mma (M=128, N<=256, K=16) into TMEM accumulators; also issues the
+//                        second, chained GEMM of the GDN epilogue (gamma x v^2).
+//   warps 4-7 epilogue   TMEM -> registers -> (+bias, square) -> smem -> [gamma MMA] -> rsqrt/sqrt ->
+//                        bf16 NHWC via TMA store, or fp32 NCHW direct stores.
+//
+// Stride-2 addressing is done with four parity views of the input (conv) or output (deconv) tensor,
+// each an ordinary tiled TMA descriptor; padding and ragged edges are TMA out-of-bounds zero fill /
+// store clipping.  Replaces SURVEY.md section 8a rows A3, A4, A5.
+#include "common.cuh"
+
+#include <math.h>
+#include <mutex>
+#include <string.h>
+
+namespace licos {
+
+constexpr int kMaxSlabs = 10;
+constexpr int kMaxTaps = 10;
+constexpr int kMaxPasses = 4;
+constexpr int kTileW = 16;    // tile columns
+constexpr int kAccRows = 8;   // tile rows per accumulator: 8 x 16 = 128 = MMA M
+constexpr int kKChunk = 64;   // channels per K chunk = one 128-byte swizzle atom of bf16
+constexpr uint32_t kRowBytes = kTileW * kKChunk * 2;  // one slab row: 2 KB
+constexpr int kThreads = 256;
+constexpr int kMaxSA = 4, kMaxSB = 8;
+constexpr uint32_t kTmemCols = 512;
+
+struct Tap {
+    int8_t row_off;  // slab row of the tile's first row for this tap
+    int8_t group;    // accumulator group (output parity for the merged narrow deconv)
+    int16_t w_tap;   // tap index into the packed weight
+};
+struct Slab {
+    int8_t in_map;
+    int8_t dw;  // column shift of the slab relative to the tile
+    int8_t n_taps;
+    int8_t pad_;
+    Tap taps[kMaxTaps];
+};
+struct Pass {
+    int8_t n_slabs;
+    int8_t n_groups;
+    int8_t pad_[2];
+    int8_t out_map[4];  // per group: TMA store map (NHWC output)
+    int8_t dy[4];       // per group: output position = grid position * out_s + (dy, dx)
+    int8_t dx[4];
+    Slab slabs[kMaxSlabs];
+};
+
+struct ConvParams {
+    CUtensorMap in_maps[4];
+    CUtensorMap out_maps[4];
+    CUtensorMap w_map;
+    CUtensorMap g_map;
+    Pass passes[kMaxPasses];
+    int n_passes;
+    int batch;
+    int grid_h, grid_w;  // extent of the position grid the M tile walks over
+    int tiles_h, tiles_w;
+    int n_acc;       // 128-row sub-tiles per CTA tile (tile rows = 8 * n_acc)
+    int N;           // MMA N
+    int n_split;     // output-channel splits (out_c > 256)
+    int cin_chunks;  // padded input channels / 64
+    int w_rows_per_tap;
+    int epilogue;
+    int out_layout;
+    int out_c, out_h, out_w, out_s;
+    float* out_f32;
+    const float* bias;
+    const float* beta;
+    int sa, sb;
+    uint32_t a_slot_bytes, b_slot_bytes, staging_bytes;
+    int total_tiles;
+};
+
+struct TileCoord {
+    int b, gh0, gw0, ns;
+};
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
+    TileCoord t;
+    t.ns = tile % p.n_split;
+    int r = tile / p.n_split;
+    t.gw0 = (r % p.tiles_w) * kTileW;
+    r /= p.tiles_w;
+    t.gh0 = (r % p.tiles_h) * (kAccRows * p.n_acc);
+    t.b = r / p.tiles_h;
+    return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], b_full[kMaxSB], b_empty[kMaxSB];
+    __shared__ uint64_t acc_full, acc_empty, x2_full, norm_full;
+    __shared__ uint32_t tmem_base_smem;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = a_ring + (size_t)p.sa * p.a_slot_bytes;
+    uint8_t* staging = b_ring + (size_t)p.sb * p.b_slot_bytes;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const bool has_gdn = (p.epilogue == LICOS_EPI_GDN || p.epilogue == LICOS_EPI_IGDN);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.sa; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < p.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        mbar_init(&acc_full, 1);
+        mbar_init(&acc_empty, 128);
+        mbar_init(&x2_full, 128);
+        mbar_init(&norm_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(&tmem_base_smem, kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0 && lane == 0) {
+        // ===================== A producer =====================
+        for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.in_maps[i]);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const TileCoord t = decode_tile(p, tile);
+            for (int pi = 0; pi < p.n_passes; ++pi) {
+                const Pass& ps = p.passes[pi];
+                for (int c = 0; c < p.cin_chunks; ++c) {
+                    for (int s = 0; s < ps.n_slabs; ++s) {
+                        const Slab& sl = ps.slabs[s];
+                        const uint32_t slot = it % p.sa, ph = (it / p.sa) & 1u;
+                        mbar_wait(&a_empty[slot], ph ^ 1u);
+                        mbar_arrive_expect_tx(&a_full[slot], p.a_slot_bytes);
+                        tma_load_4d(a_ring + (size_t)slot * p.a_slot_bytes, &p.in_maps[sl.in_map], &a_full[slot],
+                                    c * kKChunk, t.gw0 + sl.dw, t.gh0 - 1, t.b);
+                        ++it;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================== B producer =====================
+        tma_prefetch_desc(&p.w_map);
+        if (has_gdn) tma_prefetch_desc(&p.g_map);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const TileCoord t = decode_tile(p, tile);
+            for (int pi = 0; pi < p.n_passes; ++pi) {
+                const Pass& ps = p.passes[pi];
+                for (int c = 0; c < p.cin_chunks; ++c) {
+                    for (int s = 0; s < ps.n_slabs; ++s) {
+                        const Slab& sl = ps.slabs[s];
+                        for (int k = 0; k < sl.n_taps; ++k) {
+                            const uint32_t slot = it % p.sb, ph = (it / p.sb) & 1u;
+                            mbar_wait(&b_empty[slot], ph ^ 1u);
+                            mbar_arrive_expect_tx(&b_full[slot], p.b_slot_bytes);
+                            tma_load_2d(b_ring + (size_t)slot * p.b_slot_bytes, &p.w_map, &b_full[slot], c * kKChunk,
+                                        sl.taps[k].w_tap * p.w_rows_per_tap + t.ns * p.N);
+                            ++it;
+                        }
+                    }
+                }
+                if (has_gdn) {
+                    for (int g = 0; g < ps.n_groups * p.n_acc; ++g) {
+                        for (int gc = 0; gc < p.N / kKChunk; ++gc) {
+                            const uint32_t slot = it % p.sb, ph = (it / p.sb) & 1u;
+                            mbar_wait(&b_empty[slot], ph ^ 1u);
+                            mbar_arrive_expect_tx(&b_full[slot], p.b_slot_bytes);
+                            tma_load_2d(b_ring + (size_t)slot * p.b_slot_bytes, &p.g_map, &b_full[slot], gc * kKChunk, 0);
+                            ++it;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 2 && lane == 0) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = umma_idesc_bf16(128, p.N);
+        const uint32_t a_ring_addr = smem_u32(a_ring), b_ring_addr = smem_u32(b_ring);
+        const uint32_t staging_addr = smem_u32(staging);
+        uint32_t ita = 0, itb = 0, pit = 0, git = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int pi = 0; pi < p.n_passes; ++pi) {
+                const Pass& ps = p.passes[pi];
+                mbar_wait(&acc_empty, (pit & 1u) ^ 1u);
+                tc_fence_after();
+                uint32_t touched = 0;
+                for (int c = 0; c < p.cin_chunks; ++c) {
+                    for (int s = 0; s < ps.n_slabs; ++s) {
+                        const Slab& sl = ps.slabs[s];
+                        const uint32_t sa_slot = ita % p.sa;
+                        mbar_wait(&a_full[sa_slot], (ita / p.sa) & 1u);
+                        const uint32_t a_slab = a_ring_addr + sa_slot * p.a_slot_bytes;
+                        for (int k = 0; k < sl.n_taps; ++k) {
+                            const Tap tp = sl.taps[k];
+                            const uint32_t sb_slot = itb % p.sb;
+                            mbar_wait(&b_full[sb_slot], (itb / p.sb) & 1u);
+                            tc_fence_after();
+                            const uint32_t b_tile = b_ring_addr + sb_slot * p.b_slot_bytes;
+                            for (int a = 0; a < p.n_acc; ++a) {
+                                const uint32_t acc = (uint32_t)tp.group * p.n_acc + a;
+                                const uint32_t d = tmem_base + acc * p.N;
+                                const uint32_t a_tile = a_slab + (uint32_t)(tp.row_off + a * kAccRows) * kRowBytes;
+#pragma unroll
+                                for (int kk = 0; kk < kKChunk / 16; ++kk) {
+                                    umma_bf16(d, umma_desc_sw128(a_tile + kk * 32), umma_desc_sw128(b_tile + kk * 32),
+                                              idesc, ((touched >> acc) & 1u) | (uint32_t)(kk > 0));
+                                }
+                                touched |= 1u << acc;
+                            }
+                            umma_commit(&b_empty[sb_slot]);
+                            ++itb;
+                        }
+                        umma_commit(&a_empty[sa_slot]);
+                        ++ita;
+                    }
+                }
+                umma_commit(&acc_full);
+                if (has_gdn) {
+                    const uint32_t d = tmem_base + (uint32_t)(ps.n_groups * p.n_acc) * p.N;
+                    for (int g = 0; g < ps.n_groups * p.n_acc; ++g) {
+                        mbar_wait(&x2_full, git & 1u);
+                        tc_fence_after();
+                        for (int gc = 0; gc < p.N / kKChunk; ++gc) {
+                            const uint32_t sb_slot = itb % p.sb;
+                            mbar_wait(&b_full[sb_slot], (itb / p.sb) & 1u);
+                            tc_fence_after();
+                            const uint32_t b_tile = b_ring_addr + sb_slot * p.b_slot_bytes;
+                            const uint32_t a_tile = staging_addr + gc * (128 * 128);
+#pragma unroll
+                            for (int kk = 0; kk < kKChunk / 16; ++kk) {
+                                umma_bf16(d, umma_desc_sw128(a_tile + kk * 32), umma_desc_sw128(b_tile + kk * 32), idesc,
+                                          (uint32_t)((gc | kk) > 0));
+                            }
+                            umma_commit(&b_empty[sb_slot]);
+                            ++itb;
+                        }
+                        umma_commit(&norm_full);
+                        ++git;
+                    }
+                }
+                ++pit;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int et = threadIdx.x - 128;  // == TMEM lane == row of the 128-row sub-tile
+        const uint32_t lane_sel = ((uint32_t)(warp & 3) * 32u) << 16;
+        const int th = et / kTileW, tw = et % kTileW;
+        uint32_t pit = 0, git = 0;
+        const int n32 = p.N / 32, n16rem = (p.N % 32) / 16;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const TileCoord t = decode_tile(p, tile);
+            for (int pi = 0; pi < p.n_passes; ++pi) {
+                const Pass& ps = p.passes[pi];
+                mbar_wait(&acc_full, pit & 1u);
+                tc_fence_after();
+                for (int g = 0; g < ps.n_groups; ++g) {
+                    for (int a = 0; a < p.n_acc; ++a) {
+                        const uint32_t acc = (uint32_t)g * p.n_acc + a;
+                        const uint32_t t_acc = tmem_base + lane_sel + acc * p.N;
+                        const uint32_t t_norm = tmem_base + lane_sel + (uint32_t)(ps.n_groups * p.n_acc) * p.N;
+                        const int gh = t.gh0 + a * kAccRows + th, gw = t.gw0 + tw;
+                        const int c_base = t.ns * p.N;
+
+                        if (has_gdn) {
+                            // stage 1: v = acc + bias; v^2 (bf16) -> staging as the A operand of the gamma GEMM
+                            for (int cc = 0; cc < n32; ++cc) {
+                                float v[32];
+                                tmem_ld32(t_acc + cc * 32, v);
+                                tmem_ld_wait();
+                                uint32_t pk[16];
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    const float x0 = v[2 * j] + __ldg(p.bias + c_base + cc * 32 + 2 * j);
+                                    const float x1 = v[2 * j + 1] + __ldg(p.bias + c_base + cc * 32 + 2 * j + 1);
+                                    pk[j] = pack_bf16x2(x0 * x0, x1 * x1);
+                                }
+                                uint8_t* atom = staging + (size_t)((cc * 32) / kKChunk) * (128 * 128);
+                                const uint32_t chunk0 = ((cc * 32) % kKChunk) / 8;
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    *reinterpret_cast<uint4*>(atom + sw128_offset(et, chunk0 + q)) =
+                                        make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                                }
+                            }
+                            fence_proxy_async();
+                            tc_fence_before();
+                            mbar_arrive(&x2_full);
+                            mbar_wait(&norm_full, git & 1u);
+                            tc_fence_after();
+                            ++git;
+                        }
+
+                        // stage 2: activation, then write out
+                        for (int cc = 0; cc < n32 + n16rem; ++cc) {
+                            float v[32];
+                            const bool half = (cc == n32);  // trailing 16 columns (N % 32 == 16)
+                            if (!half) {
+                                tmem_ld32(t_acc + cc * 32, v);
+                            } else {
+                                float h16[16];
+                                tmem_ld16(t_acc + cc * 32, h16);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) { v[j] = h16[j]; v[16 + j] = 0.f; }
+                            }
+                            float nrm[32];
+                            if (has_gdn) tmem_ld32(t_norm + cc * 32, nrm);
+                            tmem_ld_wait();
+                            const int ncols = half ? 16 : 32;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int c = c_base + cc * 32 + j;
+                                float x = v[j];
+                                if (j < ncols && c < p.out_c && p.bias) x += __ldg(p.bias + c);
+                                if (has_gdn) {
+                                    const float d = nrm[j] + __ldg(p.beta + c);
+                                    x = (p.epilogue == LICOS_EPI_GDN) ? x * rsqrtf(d) : x * sqrtf(d);
+                                } else if (p.epilogue == LICOS_EPI_RELU) {
+                                    x = fmaxf(x, 0.f);
+                                }
+                                v[j] = x;
+                            }
+                            if (p.out_layout == LICOS_LAYOUT_NHWC_BF16) {
+                                uint8_t* atom = staging + (size_t)((cc * 32) / kKChunk) * (128 * 128);
+                                const uint32_t chunk0 = ((cc * 32) % kKChunk) / 8;
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    *reinterpret_cast<uint4*>(atom + sw128_offset(et, chunk0 + q)) =
+                                        make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                                   pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+                                }
+                            } else {
+                                const int oh = gh * p.out_s + ps.dy[g], ow = gw * p.out_s + ps.dx[g];
+                                if (gh < p.grid_h && gw < p.grid_w && oh < p.out_h && ow < p.out_w) {
+                                    float* o = p.out_f32 + ((size_t)t.b * p.out_c * p.out_h + oh) * p.out_w + ow;
+                                    const size_t cs = (size_t)p.out_h * p.out_w;
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) {
+                                        const int c = c_base + cc * 32 + j;
+                                        if (j < ncols && c < p.out_c) o[(size_t)c * cs] = v[j];
+                                    }
+                                }
+                            }
+                        }
+                        if (p.out_layout == LICOS_LAYOUT_NHWC_BF16) {
+                            fence_proxy_async();
+                            named_bar_sync(1, 128);
+                            if (et == 0) {
+                                for (int at = 0; at < p.N / kKChunk; ++at) {
+                                    tma_store_4d(&p.out_maps[ps.out_map[g]], staging + (size_t)at * (128 * 128),
+                                                 at * kKChunk, t.gw0, t.gh0 + a * kAccRows, t.b);
+                                }
+                                tma_store_commit();
+                                tma_store_wait_read();
+                            }
+                            named_bar_sync(1, 128);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&acc_empty);
+                ++pit;
+            }
+        }
+        if (et == 0) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// small helper kernels: weight / GDN packing, first-layer im2col
+// ----------------------------------------------------------------------------------------------
+
+// packed[t][o][i], t = kh*KW + kw
+__global__ void pack_weight_kernel(const float* __restrict__ w, int transposed, int out_c, int in_c, int KH, int KW,
+                                   int rows, int cin_pad, __nv_bfloat16* __restrict__ packed) {
+    const int64_t total = (int64_t)KH * KW * rows * cin_pad;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int i = (int)(e % cin_pad);
+        const int o = (int)((e / cin_pad) % rows);
+        const int t = (int)(e / ((int64_t)cin_pad * rows));
+        float v = 0.f;
+        if (o < out_c && i < in_c) {
+            const int kh = t / KW, kw = t % KW;
+            v = transposed ? w[(((size_t)i * out_c + o) * KH + kh) * KW + kw]
+                           : w[(((size_t)o * in_c + i) * KH + kh) * KW + kw];
+        }
+        packed[e] = __float2bfloat16_rn(v);
+    }
+}
+
+// first layer: packed[o][k], k = (c*KH + kh)*KW + kw == the flattened torch weight row, zero padded
+__global__ void pack_weight_first_kernel(const float* __restrict__ w, int out_c, int K, int rows, int k_pad,
+                                         __nv_bfloat16* __restrict__ packed) {
+    const int64_t total = (int64_t)rows * k_pad;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int k = (int)(e % k_pad);
+        const int o = (int)(e / k_pad);
+        packed[e] = __float2bfloat16_rn((o < out_c && k < K) ? w[(size_t)o * K + k] : 0.f);
+    }
+}
+
+__global__ void gdn_pack_kernel(const float* __restrict__ beta, const float* __restrict__ gamma, int C, float bb,
+                                float gb, float ped, float* __restrict__ beta_hat, __nv_bfloat16* __restrict__ gamma_hat) {
+    const int64_t total = (int64_t)C * C;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const float g = fmaxf(gamma[e], gb);
+        gamma_hat[e] = __float2bfloat16_rn(g * g - ped);
+        if (e < C) {
+            const float b = fmaxf(beta[e], bb);
+            beta_hat[e] = b * b - ped;
+        }
+    }
+}
+
+// rows[(b, oh, ow)][k] = x[b][c][2*oh + kh - 2][2*ow + kw - 2], k = (c*5 + kh)*5 + kw; one 16-byte
+// group of 8 k's per thread.
+__global__ void im2col_first_kernel(const float* __restrict__ x, int B, int C, int H, int W, int OH, int OW, int k_pad,
+                                    __nv_bfloat16* __restrict__ rows) {
+    const int groups = k_pad / 8;
+    const int64_t total = (int64_t)B * OH * OW * groups;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int K = C * 25;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int gk = (int)(e % groups);
+        int64_t pix = e / groups;
+        const int ow = (int)(pix % OW);
+        pix /= OW;
+        const int oh = (int)(pix % OH);
+        const int b = (int)(pix / OH);
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = gk * 8 + j;
+            float val = 0.f;
+            if (k < K) {
+                const int c = k / 25, r = k % 25;
+                const int ih = 2 * oh + r / 5 - 2, iw = 2 * ow + r % 5 - 2;
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = __ldg(x + (((size_t)b * C + c) * H + ih) * W + iw);
+            }
+            v[j] = val;
+        }
+        *reinterpret_cast<uint4*>(rows + (size_t)e * 8) =
+            make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    });
+    return fn;
+}
+
+// bf16 tensor, up to 4 dims, innermost dim contiguous; strides in elements for dims 1..rank-1
+static bool make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                     const uint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdims[4], gstrides[3];
+    cuuint32_t gbox[4], estr[4];
+    for (int i = 0; i < rank; ++i) {
+        gdims[i] = dims[i];
+        gbox[i] = box[i];
+        estr[i] = 1;
+        if (dims[i] == 0) return false;
+    }
+    for (int i = 0; i + 1 < rank; ++i) gstrides[i] = strides_elems[i] * 2;
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstrides,
+                          gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+struct NPlan {
+    int N, n_split, rows;
+};
+static NPlan plan_n(int out_c) {
+    NPlan pl;
+    const int pad = (out_c + 15) / 16 * 16;
+    pl.n_split = (pad + 255) / 256;
+    pl.N = ((pad + pl.n_split - 1) / pl.n_split + 15) / 16 * 16;
+    pl.rows = pl.N * pl.n_split;
+    return pl;
+}
+static int taps_of(int kind) { return kind == LICOS_CONV_3X3_S1 ? 9 : 25; }
+static int first_kpad(int in_c) { return (in_c * 25 + 63) / 64 * 64; }
+
+static int ew_grid(int64_t n) {
+    int64_t g = (n + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    return (int)(g < 1 ? 1 : g);
+}
+
+static void set_tap(Slab& s, int i, int row_off, int group, int w_tap) {
+    s.taps[i].row_off = (int8_t)row_off;
+    s.taps[i].group = (int8_t)group;
+    s.taps[i].w_tap = (int16_t)w_tap;
+}
+
+}  // namespace licos
+
+using namespace licos;
+
+extern "C" {
+
+int licos_device_ok(int device) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return LICOS_ERR_NO_DEVICE;
+    return prop.major == 10 ? LICOS_OK : LICOS_ERR_NO_DEVICE;
+}
+
+int64_t licos_packed_weight_bytes(int kind, int out_c, int in_c, int in_layout) {
+    if (out_c < 1 || in_c < 1) return LICOS_ERR_INVALID;
+    const NPlan pl = plan_n(out_c);
+    if (in_layout == LICOS_LAYOUT_NCHW_F32) {
+        if (kind != LICOS_CONV_5X5_S2 || in_c > 16) return LICOS_ERR_UNSUPPORTED;
+        return (int64_t)pl.rows * first_kpad(in_c) * 2;
+    }
+    const int cin_pad = (in_c + 63) / 64 * 64;
+    return (int64_t)taps_of(kind) * pl.rows * cin_pad * 2;
+}
+
+int licos_pack_conv_weight(const float* w, int kind, int out_c, int in_c, int in_layout, void* packed, void* stream) {
+    if (!w || !packed || out_c < 1 || in_c < 1) return LICOS_ERR_INVALID;
+    if (kind != LICOS_CONV_5X5_S2 && kind != LICOS_DECONV_5X5_S2 && kind != LICOS_CONV_3X3_S1) return LICOS_ERR_INVALID;
+    const NPlan pl = plan_n(out_c);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (in_layout == LICOS_LAYOUT_NCHW_F32) {
+        if (kind != LICOS_CONV_5X5_S2 || in_c > 16) return LICOS_ERR_UNSUPPORTED;
+        const int kp = first_kpad(in_c);
+        pack_weight_first_kernel<<<ew_grid((int64_t)pl.rows * kp), 256, 0, s>>>(w, out_c, in_c * 25, pl.rows, kp,
+                                                                               (__nv_bfloat16*)packed);
+    } else {
+        const int cin_pad = (in_c + 63) / 64 * 64;
+        const int K = kind == LICOS_CONV_3X3_S1 ? 3 : 5;
+        pack_weight_kernel<<<ew_grid((int64_t)K * K * pl.rows * cin_pad), 256, 0, s>>>(
+            w, kind == LICOS_DECONV_5X5_S2, out_c, in_c, K, K, pl.rows, cin_pad, (__nv_bfloat16*)packed);
+    }
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_gdn_pack(const float* beta, const float* gamma, int channels, float beta_bound, float gamma_bound,
+                   float pedestal, float* beta_hat, void* gamma_hat_bf16, void* stream) {
+    if (!beta || !gamma || !beta_hat || !gamma_hat_bf16 || channels < 1) return LICOS_ERR_INVALID;
+    gdn_pack_kernel<<<ew_grid((int64_t)channels * channels), 256, 0, (cudaStream_t)stream>>>(
+        beta, gamma, channels, beta_bound, gamma_bound, pedestal, beta_hat, (__nv_bfloat16*)gamma_hat_bf16);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int64_t licos_conv_workspace_bytes(const licos_conv_args* a) {
+    if (!a) return LICOS_ERR_INVALID;
+    if (a->in_layout != LICOS_LAYOUT_NCHW_F32) return 0;
+    const int oh = (a->in_h + 1) / 2, ow = (a->in_w + 1) / 2;
+    return (int64_t)a->batch * oh * ow * first_kpad(a->in_c) * 2;
+}
+
+int licos_conv_forward(const licos_conv_args* a, void* stream) {
+    if (!a || !a->in || !a->out || !a->weight) return LICOS_ERR_INVALID;
+    if (a->batch < 0 || a->in_h < 1 || a->in_w < 1 || a->in_c < 1 || a->out_c < 1) return LICOS_ERR_INVALID;
+    if (a->batch == 0) return LICOS_OK;
+    const bool gdn = (a->epilogue == LICOS_EPI_GDN || a->epilogue == LICOS_EPI_IGDN);
+    if (a->epilogue < LICOS_EPI_NONE || a->epilogue > LICOS_EPI_RELU) return LICOS_ERR_INVALID;
+    if (gdn && (!a->beta || !a->gamma || !a->bias)) return LICOS_ERR_INVALID;
+    if (a->out_layout != LICOS_LAYOUT_NCHW_F32 && a->out_layout != LICOS_LAYOUT_NHWC_BF16) return LICOS_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+
+    ConvParams p;  // ~3.3 KB of plain data, passed by value as a __grid_constant__ kernel parameter
+    memset(&p, 0, sizeof(p));
+
+    const NPlan pl = plan_n(a->out_c);
+    p.N = pl.N;
+    p.n_split = pl.n_split;
+    p.w_rows_per_tap = pl.rows;
+    p.epilogue = a->epilogue;
+    p.out_layout = a->out_layout;
+    p.out_c = a->out_c;
+    p.batch = a->batch;
+    p.bias = a->bias;
+    p.beta = a->beta;
+    p.out_f32 = (a->out_layout == LICOS_LAYOUT_NCHW_F32) ? (float*)a->out : nullptr;
+
+    if (a->out_layout == LICOS_LAYOUT_NHWC_BF16 && (a->out_c % 64 != 0 || a->out_c > 256)) return LICOS_ERR_UNSUPPORTED;
+    if (gdn && (a->out_c % 64 != 0 || a->out_c > 256)) return LICOS_ERR_UNSUPPORTED;
+
+    // ---- geometry of the position grid, the input view(s) and the pass table -------------------
+    const void* in_base = a->in;
+    int in_h = a->in_h, in_w = a->in_w, cin_pad;
+    int kind = a->kind;
+    bool pointwise = false;
+    if (a->in_layout == LICOS_LAYOUT_NCHW_F32) {
+        // first layer: explicit im2col of the tiny-Cin input, then a 1x1 "conv" over K_pad channels
+        if (kind != LICOS_CONV_5X5_S2 || a->in_c > 16) return LICOS_ERR_UNSUPPORTED;
+        if (!a->workspace || a->workspace_bytes < licos_conv_workspace_bytes(a)) return LICOS_ERR_BUFFER;
+        const int oh = (a->in_h + 1) / 2, ow = (a->in_w + 1) / 2;
+        const int kp = first_kpad(a->in_c);
+        const int64_t groups = (int64_t)a->batch * oh * ow * (kp / 8);
+        im2col_first_kernel<<<ew_grid(groups), 256, 0, s>>>((const float*)a->in, a->batch, a->in_c, a->in_h, a->in_w, oh,
+                                                            ow, kp, (__nv_bfloat16*)a->workspace);
+        LICOS_CUDA_OK(cudaGetLastError());
+        in_base = a->workspace;
+        in_h = oh;
+        in_w = ow;
+        cin_pad = kp;
+        pointwise = true;
+    } else if (a->in_layout == LICOS_LAYOUT_NHWC_BF16) {
+        if (a->in_c % 64 != 0) return LICOS_ERR_UNSUPPORTED;
+        cin_pad = a->in_c;
+    } else {
+        return LICOS_ERR_INVALID;
+    }
+    p.cin_chunks = cin_pad / kKChunk;
+
+    int out_h, out_w;
+    if (pointwise) { out_h = in_h; out_w = in_w; p.grid_h = in_h; p.grid_w = in_w; p.out_s = 1; }
+    else if (kind == LICOS_CONV_5X5_S2) {
+        if (in_h < 2 || in_w < 2) return LICOS_ERR_UNSUPPORTED;
+        out_h = (in_h + 1) / 2; out_w = (in_w + 1) / 2; p.grid_h = out_h; p.grid_w = out_w; p.out_s = 1;
+    } else if (kind == LICOS_DECONV_5X5_S2) {
+        out_h = 2 * in_h; out_w = 2 * in_w; p.grid_h = in_h; p.grid_w = in_w; p.out_s = 2;
+    } else if (kind == LICOS_CONV_3X3_S1) {
+        out_h = in_h; out_w = in_w; p.grid_h = in_h; p.grid_w = in_w; p.out_s = 1;
+    } else {
+        return LICOS_ERR_INVALID;
+    }
+    p.out_h = out_h;
+    p.out_w = out_w;
+
+    const bool merged = (kind == LICOS_DECONV_5X5_S2 && a->out_layout == LICOS_LAYOUT_NCHW_F32 && pl.N <= 32 &&
+                         pl.n_split == 1 && !gdn);
+    const int groups = merged ? 4 : 1;
+
+    // accumulators per tile
+    int n_acc = 2;
+    if ((groups * 2 + (gdn ? 1 : 0)) * pl.N > (int)kTmemCols) n_acc = 1;
+    if (p.grid_h <= kAccRows) n_acc = 1;
+    if ((groups * n_acc + (gdn ? 1 : 0)) * pl.N > (int)kTmemCols) return LICOS_ERR_UNSUPPORTED;
+    p.n_acc = n_acc;
+    const int TH = kAccRows * n_acc;
+    const int R = TH + 2;
+
+    // ---- passes ------------------------------------------------------------------------------
+    if (pointwise) {
+        p.n_passes = 1;
+        Pass& ps = p.passes[0];
+        ps.n_slabs = 1; ps.n_groups = 1;
+        ps.slabs[0].in_map = 0; ps.slabs[0].dw = 0; ps.slabs[0].n_taps = 1;
+        set_tap(ps.slabs[0], 0, 1, 0, 0);
+    } else if (kind == LICOS_CONV_5X5_S2) {
+        p.n_passes = 1;
+        Pass& ps = p.passes[0];
+        ps.n_groups = 1;
+        int ns = 0;
+        for (int kw = 0; kw < 5; ++kw) {
+            const int pw = kw & 1, dw = (kw - 2 - pw) / 2;
+            for (int ph = 0; ph < 2; ++ph) {
+                Slab& sl = ps.slabs[ns++];
+                sl.in_map = (int8_t)(ph * 2 + pw);
+                sl.dw = (int8_t)dw;
+                int nt = 0;
+                for (int kh = ph; kh < 5; kh += 2) {
+                    const int dh = (kh - 2 - ph) / 2;
+                    set_tap(sl, nt++, dh + 1, 0, kh * 5 + kw);
+                }
+                sl.n_taps = (int8_t)nt;
+            }
+        }
+        ps.n_slabs = (int8_t)ns;
+    } else if (kind == LICOS_CONV_3X3_S1) {
+        p.n_passes = 1;
+        Pass& ps = p.passes[0];
+        ps.n_groups = 1;
+        ps.n_slabs = 3;
+        for (int kw = 0; kw < 3; ++kw) {
+            Slab& sl = ps.slabs[kw];
+            sl.in_map = 0; sl.dw = (int8_t)(kw - 1); sl.n_taps = 3;
+            for (int kh = 0; kh < 3; ++kh) set_tap(sl, kh, kh, 0, kh * 3 + kw);
+        }
+    } else if (merged) {
+        // all four output parities at once: slab per column shift, every tap that uses it
+        p.n_passes = 1;
+        Pass& ps = p.passes[0];
+        ps.n_groups = 4;
+        for (int g = 0; g < 4; ++g) { ps.dy[g] = (int8_t)(g >> 1); ps.dx[g] = (int8_t)(g & 1); ps.out_map[g] = (int8_t)g; }
+        int ns = 0;
+        for (int dw = 1; dw >= -1; --dw) {
+            Slab& sl = ps.slabs[ns++];
+            sl.in_map = 0; sl.dw = (int8_t)dw;
+            int nt = 0;
+            for (int kw = 0; kw < 5; ++kw) {
+                const int b = kw & 1;
+                if ((b + 2 - kw) / 2 != dw) continue;
+                for (int kh = 0; kh < 5; ++kh) {
+                    const int aa = kh & 1, dh = (aa + 2 - kh) / 2;
+                    set_tap(sl, nt++, dh + 1, aa * 2 + b, kh * 5 + kw);
+                }
+            }
+            sl.n_taps = (int8_t)nt;
+        }
+        ps.n_slabs = (int8_t)ns;
+    } else {  // deconv, one pass per output parity
+        p.n_passes = 4;
+        for (int pi = 0; pi < 4; ++pi) {
+            const int aa = pi >> 1, b = pi & 1;
+            Pass& ps = p.passes[pi];
+            ps.n_groups = 1;
+            ps.dy[0] = (int8_t)aa; ps.dx[0] = (int8_t)b; ps.out_map[0] = (int8_t)pi;
+            int ns = 0;
+            for (int kw = b; kw < 5; kw += 2) {
+                Slab& sl = ps.slabs[ns++];
+                sl.in_map = 0; sl.dw = (int8_t)((b + 2 - kw) / 2);
+                int nt = 0;
+                for (int kh = aa; kh < 5; kh += 2) set_tap(sl, nt++, (aa + 2 - kh) / 2 + 1, 0, kh * 5 + kw);
+                sl.n_taps = (int8_t)nt;
+            }
+            ps.n_slabs = (int8_t)ns;
+        }
+    }
+
+    // ---- tensor maps ---------------------------------------------------------------------------
+    const uint64_t C = (uint64_t)cin_pad, H = (uint64_t)in_h, W = (uint64_t)in_w, B = (uint64_t)a->batch;
+    const uint32_t in_box[4] = {(uint32_t)kKChunk, (uint32_t)kTileW, (uint32_t)R, 1};
+    if (!pointwise && kind == LICOS_CONV_5X5_S2) {
+        for (int ph = 0; ph < 2; ++ph)
+            for (int pw = 0; pw < 2; ++pw) {
+                const uint64_t dims[4] = {C, (W - pw + 1) / 2, (H - ph + 1) / 2, B};
+                const uint64_t strides[3] = {2 * C, 2 * W * C, H * W * C};
+                const __nv_bfloat16* base = (const __nv_bfloat16*)in_base + ((size_t)ph * W + pw) * C;
+                if (!make_map(&p.in_maps[ph * 2 + pw], base, 4, dims, strides, in_box)) return LICOS_ERR_CUDA;
+            }
+    } else {
+        const uint64_t dims[4] = {C, W, H, B};
+        const uint64_t strides[3] = {C, W * C, H * W * C};
+        if (!make_map(&p.in_maps[0], in_base, 4, dims, strides, in_box)) return LICOS_ERR_CUDA;
+        for (int i = 1; i < 4; ++i) p.in_maps[i] = p.in_maps[0];
+    }
+    {
+        const uint64_t w_taps = pointwise ? 1 : (uint64_t)taps_of(kind);
+        const uint64_t dims[2] = {C, w_taps * (uint64_t)pl.rows};
+        const uint64_t strides[1] = {C};
+        const uint32_t box[2] = {(uint32_t)kKChunk, (uint32_t)pl.N};
+        if (!make_map(&p.w_map, a->weight, 2, dims, strides, box)) return LICOS_ERR_CUDA;
+    }
+    if (gdn) {
+        const uint64_t dims[2] = {(uint64_t)a->out_c, (uint64_t)a->out_c};
+        const uint64_t strides[1] = {(uint64_t)a->out_c};
+        const uint32_t box[2] = {(uint32_t)kKChunk, (uint32_t)pl.N};
+        if (!make_map(&p.g_map, a->gamma, 2, dims, strides, box)) return LICOS_ERR_CUDA;
+    } else {
+        p.g_map = p.w_map;
+    }
+    if (a->out_layout == LICOS_LAYOUT_NHWC_BF16) {
+        const uint64_t OC = (uint64_t)a->out_c, OH = (uint64_t)out_h, OW = (uint64_t)out_w;
+        const uint32_t box[4] = {(uint32_t)kKChunk, (uint32_t)kTileW, (uint32_t)kAccRows, 1};
+        if (kind == LICOS_DECONV_5X5_S2 && !pointwise) {
+            for (int pi = 0; pi < 4; ++pi) {
+                const int aa = pi >> 1, b = pi & 1;
+                const uint64_t dims[4] = {OC, W, H, B};
+                const uint64_t strides[3] = {2 * OC, 2 * OW * OC, OH * OW * OC};
+                __nv_bfloat16* base = (__nv_bfloat16*)a->out + ((size_t)aa * OW + b) * OC;
+                if (!make_map(&p.out_maps[pi], base, 4, dims, strides, box)) return LICOS_ERR_CUDA;
+            }
+        } else {
+            const uint64_t dims[4] = {OC, OW, OH, B};
+            const uint64_t strides[3] = {OC, OW * OC, OH * OW * OC};
+            if (!make_map(&p.out_maps[0], a->out, 4, dims, strides, box)) return LICOS_ERR_CUDA;
+            for (int i = 1; i < 4; ++i) p.out_maps[i] = p.out_maps[0];
+        }
+    } else {
+        for (int i = 0; i < 4; ++i) p.out_maps[i] = p.in_maps[0];
+    }
+
+    // ---- shared memory plan --------------------------------------------------------------------
+    p.a_slot_bytes = (uint32_t)R * kRowBytes;
+    p.b_slot_bytes = (uint32_t)pl.N * 128u;
+    p.staging_bytes = (gdn || a->out_layout == LICOS_LAYOUT_NHWC_BF16) ? (uint32_t)(pl.N / kKChunk) * 128u * 128u : 0u;
+    const int64_t b_slot_al = p.b_slot_bytes;  // N is a multiple of 16, so N*128 is a multiple of 2 KB
+    const int64_t budget = 230000 - 1024 - (int64_t)p.staging_bytes;
+    int sb = 4;
+    int sa = (int)((budget - (int64_t)sb * b_slot_al) / p.a_slot_bytes);
+    if (sa > kMaxSA) sa = kMaxSA;
+    if (sa < 2) { sb = 3; sa = (int)((budget - (int64_t)sb * b_slot_al) / p.a_slot_bytes); }
+    if (sa < 2) return LICOS_ERR_UNSUPPORTED;
+    if (sa > kMaxSA) sa = kMaxSA;
+    int64_t left = budget - (int64_t)sa * p.a_slot_bytes - (int64_t)sb * b_slot_al;
+    while (sb < kMaxSB && left >= b_slot_al) { ++sb; left -= b_slot_al; }
+    p.sa = sa;
+    p.sb = sb;
+    const size_t smem_bytes = 1024 + (size_t)sa * p.a_slot_bytes + (size_t)sb * b_slot_al + p.staging_bytes;
+
+    p.tiles_h = (p.grid_h + TH - 1) / TH;
+    p.tiles_w = (p.grid_w + kTileW - 1) / kTileW;
+    const int64_t tiles = (int64_t)a->batch * p.tiles_h * p.tiles_w * p.n_split;
+    if (tiles > 0x7fffffff) return LICOS_ERR_UNSUPPORTED;
+    p.total_tiles = (int)tiles;
+
+    int sms = a->sm_count;
+    if (sms <= 0) {
+        int dev = 0;
+        LICOS_CUDA_OK(cudaGetDevice(&dev));
+        LICOS_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, []() {
+        attr_err = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 231000);
+    });
+    LICOS_CUDA_OK(attr_err);
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    conv_igemm_kernel<<<grid, kThreads, smem_bytes, s>>>(p);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+}  // extern "C"

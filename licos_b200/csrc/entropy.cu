@@ -1,0 +1,545 @@
+// Quantisation, factorized / Gaussian likelihoods, symbol + CDF-index integer path, reductions, layout
+// conversion.  All of these are HBM-bound elementwise passes: vectorised, coalesced, no tensor cores.
+//
+// Replaces: A8/A9 EntropyBottleneck._logits_cumulative / forward, A10
+// EntropyModel.quantize / dequantize / _build_indexes, A12 GaussianConditional.forward / build_indexes,
+// A13 the two reductions of RateDistortionLoss.
+#include "common.cuh"
+
+namespace licos {
+
+// ----------------------------------------------------------------------------------------------
+// EntropyBottleneck density network
+// ----------------------------------------------------------------------------------------------
+struct EbMeta {
+    int n_layers;
+    int widths[LICOS_EB_MAX_LAYERS + 1];
+    int ppc;
+    int form;
+    float bound;
+};
+
+// logits = L_{n-1}(...L_0(x)), L_i(v) = M_i v + b_i (+ t_i * tanh(.) except for the last layer);
+// M_i = softplus(_matrix_i), t_i = tanh(_factor_i) are pre-applied in `p`.
+template <int W>
+__device__ __forceinline__ float eb_logits(const float* __restrict__ p, const EbMeta& m, float x) {
+    float cur[W], nxt[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) cur[k] = 0.f;
+    cur[0] = x;
+    int off = 0;
+    for (int i = 0; i < m.n_layers; ++i) {
+        const int fi = m.widths[i], fo = m.widths[i + 1];
+        const float* M = p + off;
+        const float* b = M + fo * fi;
+        const float* t = b + fo;
+        const bool last = (i == m.n_layers - 1);
+#pragma unroll
+        for (int o = 0; o < W; ++o) {
+            float acc = 0.f;
+            if (o < fo) {
+#pragma unroll
+                for (int k = 0; k < W; ++k)
+                    if (k < fi) acc += M[o * fi + k] * cur[k];
+                acc += b[o];
+                if (!last) acc += t[o] * tanhf(acc);
+            }
+            nxt[o] = acc;
+        }
+#pragma unroll
+        for (int k = 0; k < W; ++k) cur[k] = nxt[k];
+        off += fo * fi + fo + (last ? 0 : fo);
+    }
+    return cur[0];
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int W>
+__device__ __forceinline__ float eb_likelihood(const float* __restrict__ p, const EbMeta& m, float v) {
+    const float lower = eb_logits<W>(p, m, v - 0.5f);
+    const float upper = eb_logits<W>(p, m, v + 0.5f);
+    float lik;
+    if (m.form == LICOS_EB_FORM_PLAIN) {
+        lik = sigmoidf_(upper) - sigmoidf_(lower);
+    } else {
+        const float su = lower + upper;
+        const float s = (su > 0.f) ? -1.f : ((su < 0.f) ? 1.f : 0.f);
+        lik = fabsf(sigmoidf_(s * upper) - sigmoidf_(s * lower));
+    }
+    if (m.bound > 0.f) lik = fmaxf(lik, m.bound);
+    return lik;
+}
+
+constexpr int kLutR = LICOS_EB_LUT_RADIUS;
+constexpr int kLutN = 2 * kLutR + 1;
+
+// One block per channel: likelihood of every value med + s, s in [-R, R].
+template <int W>
+__global__ void eb_lut_kernel(EbMeta m, const float* __restrict__ packed, const float* __restrict__ med,
+                              float* __restrict__ lut) {
+    extern __shared__ float sp[];
+    const int c = blockIdx.x;
+    for (int i = threadIdx.x; i < m.ppc; i += blockDim.x) sp[i] = packed[(size_t)c * m.ppc + i];
+    __syncthreads();
+    const float md = med[c];
+    for (int k = threadIdx.x; k < kLutN; k += blockDim.x) {
+        const float v = (float)(k - kLutR) + md;
+        lut[(size_t)c * kLutN + k] = eb_likelihood<W>(sp, m, v);
+    }
+}
+
+// rare path: symbol outside the table
+__device__ __noinline__ float eb_likelihood_slow(const float* __restrict__ packed, EbMeta m, int c, float v) {
+    return eb_likelihood<16>(packed + (size_t)c * m.ppc, m, v);
+}
+
+template <int VEC>
+__global__ void eb_eval_kernel(EbMeta m, const float* __restrict__ x, const float* __restrict__ packed,
+                               const float* __restrict__ med, const float* __restrict__ lut, int C, int64_t hw,
+                               int64_t n_vec, float* __restrict__ y_hat, float* __restrict__ lik) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+        const int64_t e0 = i * VEC;
+        const int c = (int)((e0 / hw) % C);
+        const float md = __ldg(med + c);
+        float xv[VEC], yv[VEC], lv[VEC];
+        if (VEC == 4) {
+            const float4 t = __ldcs(reinterpret_cast<const float4*>(x) + i);
+            xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+        } else {
+            xv[0] = __ldcs(x + i);
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const float r = rintf(xv[j] - md);
+            yv[j] = r + md;
+            if (fabsf(r) <= (float)kLutR) {
+                lv[j] = __ldg(lut + (size_t)c * kLutN + ((int)r + kLutR));
+            } else {
+                lv[j] = eb_likelihood_slow(packed, m, c, yv[j]);
+            }
+        }
+        if (VEC == 4) {
+            __stcs(reinterpret_cast<float4*>(y_hat) + i, make_float4(yv[0], yv[1], yv[2], yv[3]));
+            __stcs(reinterpret_cast<float4*>(lik) + i, make_float4(lv[0], lv[1], lv[2], lv[3]));
+        } else {
+            __stcs(y_hat + i, yv[0]);
+            __stcs(lik + i, lv[0]);
+        }
+    }
+}
+
+// Philox4x32-10, one draw per element: counter = element index, key = seed.
+__device__ __forceinline__ uint32_t philox_u32(uint64_t seed, uint64_t idx) {
+    uint32_t c0 = (uint32_t)idx, c1 = (uint32_t)(idx >> 32), c2 = 0x6c69636fu, c3 = 0x73623230u;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c0;
+}
+__device__ __forceinline__ float uniform_pm_half(uint64_t seed, uint64_t idx) {
+    return (float)(philox_u32(seed, idx) >> 8) * (1.0f / 16777216.0f) - 0.5f;  // [-0.5, 0.5)
+}
+
+// blockIdx.y = channel (parameters staged in shared memory); x-blocks stride over (batch, hw).
+template <int W>
+__global__ void eb_noise_kernel(EbMeta m, const float* __restrict__ x, const float* __restrict__ noise,
+                                uint64_t seed, const float* __restrict__ packed, int B, int C, int64_t hw,
+                                float* __restrict__ y_hat, float* __restrict__ lik) {
+    extern __shared__ float sp[];
+    const int c = blockIdx.y;
+    for (int i = threadIdx.x; i < m.ppc; i += blockDim.x) sp[i] = packed[(size_t)c * m.ppc + i];
+    __syncthreads();
+    const int64_t n = (int64_t)B * hw;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const int64_t b = j / hw, i = j - b * hw;
+        const int64_t e = (b * C + c) * hw + i;
+        const float nz = noise ? __ldcs(noise + e) : uniform_pm_half(seed, (uint64_t)e);
+        const float v = __ldcs(x + e) + nz;
+        __stcs(y_hat + e, v);
+        __stcs(lik + e, eb_likelihood<W>(sp, m, v));
+    }
+}
+
+__global__ void eb_symbols_kernel(const float* __restrict__ x, const float* __restrict__ med, int C, int64_t hw,
+                                  int64_t n, int32_t* __restrict__ sym, int32_t* __restrict__ idx) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int c = (int)((i / hw) % C);
+        sym[i] = (int32_t)rintf(__ldcs(x + i) - __ldg(med + c));
+        if (idx) idx[i] = c;
+    }
+}
+
+__global__ void eb_dequant_kernel(const int32_t* __restrict__ sym, const float* __restrict__ med, int C,
+                                  int64_t hw, int64_t n, float* __restrict__ y_hat) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int c = (int)((i / hw) % C);
+        y_hat[i] = (float)sym[i] + __ldg(med + c);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// GaussianConditional
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float std_cumulative(float v) { return 0.5f * erfcf(-0.70710678118654752440f * v); }
+
+__global__ void gc_forward_kernel(const float* __restrict__ y, const float* __restrict__ scales,
+                                  const float* __restrict__ means, const float* __restrict__ noise, uint64_t seed,
+                                  int64_t n, int training, float scale_bound, float lik_bound,
+                                  float* __restrict__ y_hat, float* __restrict__ lik) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float mu = means ? __ldcs(means + i) : 0.f;
+        const float yi = __ldcs(y + i);
+        float out;
+        if (training) {
+            const float nz = noise ? __ldcs(noise + i) : uniform_pm_half(seed, (uint64_t)i);
+            out = yi + nz;
+        } else if (means) {
+            out = rintf(yi - mu) + mu;
+        } else {
+            out = rintf(yi);
+        }
+        const float val = fabsf(means ? out - mu : out);
+        const float s = fmaxf(__ldcs(scales + i), scale_bound);
+        const float upper = std_cumulative((0.5f - val) / s);
+        const float lower = std_cumulative((-0.5f - val) / s);
+        float l = upper - lower;
+        if (lik_bound > 0.f) l = fmaxf(l, lik_bound);
+        __stcs(y_hat + i, out);
+        __stcs(lik + i, l);
+    }
+}
+
+__global__ void gc_indexes_kernel(const float* __restrict__ scales, int64_t n, const float* __restrict__ table,
+                                  int n_table, float scale_bound, int32_t* __restrict__ idx) {
+    extern __shared__ float st[];
+    for (int k = threadIdx.x; k < n_table; k += blockDim.x) st[k] = table[k];
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float s = fmaxf(__ldcs(scales + i), scale_bound);
+        int v = n_table - 1;
+        for (int k = 0; k < n_table - 1; ++k) v -= (s <= st[k]) ? 1 : 0;
+        idx[i] = v;
+    }
+}
+
+__global__ void gc_symbols_kernel(const float* __restrict__ y, const float* __restrict__ means, int64_t n,
+                                  int32_t* __restrict__ sym) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float v = means ? __ldcs(y + i) - __ldcs(means + i) : __ldcs(y + i);
+        sym[i] = (int32_t)rintf(v);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Reductions
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_accumulate(double v, double* acc) {
+    __shared__ double warp_sums[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) warp_sums[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) atomicAdd(acc, v);
+    }
+}
+
+__global__ void sum_log_kernel(const float* __restrict__ lik, int64_t n, double* acc) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double s = 0.0;
+    float part = 0.f;
+    int cnt = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        part += logf(__ldcs(lik + i));
+        if (++cnt == 32) { s += (double)part; part = 0.f; cnt = 0; }
+    }
+    s += (double)part;
+    block_accumulate(s, acc);
+}
+
+__global__ void sum_sq_err_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, double* acc) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double s = 0.0;
+    float part = 0.f;
+    int cnt = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float d = __ldcs(a + i) - __ldcs(b + i);
+        part += d * d;
+        if (++cnt == 32) { s += (double)part; part = 0.f; cnt = 0; }
+    }
+    s += (double)part;
+    block_accumulate(s, acc);
+}
+
+__global__ void weighted_sum2_kernel(const float* __restrict__ a, const float* __restrict__ b, float wa, float wb,
+                                     int64_t n, float* __restrict__ dst) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        // two roundings, like `wa * a` followed by `+= wb * b` in the reference
+        const float t = __fmul_rn(wa, a[i]);
+        dst[i] = __fadd_rn(t, __fmul_rn(wb, b[i]));
+    }
+}
+__global__ void scale_kernel(float* __restrict__ buf, float w, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) buf[i] *= w;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Layout conversion: per image a [C][HW] <-> [HW][C] transpose through a 32x33 shared tile
+// ----------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C,
+                                         int64_t hw, int take_abs) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int64_t p0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const float* src = in + (size_t)b * C * hw;
+    __nv_bfloat16* dst = out + (size_t)b * C * hw;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int c = c0 + r;
+        const int64_t p = p0 + threadIdx.x;
+        float v = 0.f;
+        if (c < C && p < hw) v = src[(size_t)c * hw + p];
+        tile[r][threadIdx.x] = take_abs ? fabsf(v) : v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t p = p0 + r;
+        const int c = c0 + threadIdx.x;
+        if (c < C && p < hw) dst[(size_t)p * C + c] = __float2bfloat16_rn(tile[threadIdx.x][r]);
+    }
+}
+
+__global__ void nhwc_bf16_to_nchw_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, int C,
+                                         int64_t hw) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int64_t p0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const __nv_bfloat16* src = in + (size_t)b * C * hw;
+    float* dst = out + (size_t)b * C * hw;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int64_t p = p0 + r;
+        const int c = c0 + threadIdx.x;
+        float v = 0.f;
+        if (c < C && p < hw) v = __bfloat162float(src[(size_t)p * C + c]);
+        tile[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int c = c0 + r;
+        const int64_t p = p0 + threadIdx.x;
+        if (c < C && p < hw) dst[(size_t)c * hw + p] = tile[threadIdx.x][r];
+    }
+}
+
+static int grid_for(int64_t n, int threads, int per_sm = 8) {
+    int64_t g = (n + threads - 1) / threads;
+    const int64_t cap = 148LL * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+static bool make_meta(const licos_eb_params* p, EbMeta& m, int& max_w) {
+    if (!p || p->n_layers < 1 || p->n_layers > LICOS_EB_MAX_LAYERS || p->channels < 1 || !p->packed || !p->medians)
+        return false;
+    m.n_layers = p->n_layers;
+    max_w = 1;
+    int ppc = 0;
+    for (int i = 0; i <= p->n_layers; ++i) {
+        m.widths[i] = p->widths[i];
+        if (p->widths[i] < 1 || p->widths[i] > 16) return false;
+        if (p->widths[i] > max_w) max_w = p->widths[i];
+    }
+    for (int i = p->n_layers + 1; i <= LICOS_EB_MAX_LAYERS; ++i) m.widths[i] = 0;
+    if (p->widths[0] != 1 || p->widths[p->n_layers] != 1) return false;
+    for (int i = 0; i < p->n_layers; ++i) {
+        ppc += p->widths[i + 1] * p->widths[i] + p->widths[i + 1];
+        if (i < p->n_layers - 1) ppc += p->widths[i + 1];
+    }
+    if (ppc != p->params_per_channel) return false;
+    m.ppc = ppc;
+    m.form = p->form;
+    m.bound = p->likelihood_bound;
+    return true;
+}
+
+}  // namespace licos
+
+using namespace licos;
+
+extern "C" {
+
+int64_t licos_eb_lut_floats(int channels) { return (int64_t)channels * kLutN; }
+
+int licos_eb_forward_eval(const licos_eb_params* p, const float* x, int batch, int64_t hw, float* lut_ws,
+                          float* y_hat, float* lik, void* stream) {
+    EbMeta m;
+    int max_w;
+    if (!make_meta(p, m, max_w) || !x || !lut_ws || !y_hat || !lik || batch < 0 || hw < 0) return LICOS_ERR_INVALID;
+    const int64_t n = (int64_t)batch * p->channels * hw;
+    if (n == 0) return LICOS_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t sm = (size_t)m.ppc * sizeof(float);
+    if (max_w <= 3) eb_lut_kernel<3><<<p->channels, 288, sm, s>>>(m, p->packed, p->medians, lut_ws);
+    else eb_lut_kernel<16><<<p->channels, 288, sm, s>>>(m, p->packed, p->medians, lut_ws);
+    LICOS_CUDA_OK(cudaGetLastError());
+    const bool vec = (hw % 4 == 0) && (((uintptr_t)x | (uintptr_t)y_hat | (uintptr_t)lik) % 16 == 0);
+    if (vec) {
+        const int64_t nv = n / 4;
+        eb_eval_kernel<4><<<grid_for(nv, 256), 256, 0, s>>>(m, x, p->packed, p->medians, lut_ws, p->channels, hw, nv,
+                                                           y_hat, lik);
+    } else {
+        eb_eval_kernel<1><<<grid_for(n, 256), 256, 0, s>>>(m, x, p->packed, p->medians, lut_ws, p->channels, hw, n,
+                                                          y_hat, lik);
+    }
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_eb_forward_noise(const licos_eb_params* p, const float* x, const float* noise, uint64_t seed, int batch,
+                           int64_t hw, float* y_hat, float* lik, void* stream) {
+    EbMeta m;
+    int max_w;
+    if (!make_meta(p, m, max_w) || !x || !y_hat || !lik || batch < 0 || hw < 0) return LICOS_ERR_INVALID;
+    const int64_t n = (int64_t)batch * hw;
+    if (n == 0) return LICOS_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t sm = (size_t)m.ppc * sizeof(float);
+    int gx = (int)((n + 255) / 256);
+    const int cap = (148 * 8 + p->channels - 1) / p->channels;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, p->channels);
+    if (max_w <= 3) eb_noise_kernel<3><<<grid, 256, sm, s>>>(m, x, noise, seed, p->packed, batch, p->channels, hw, y_hat, lik);
+    else eb_noise_kernel<16><<<grid, 256, sm, s>>>(m, x, noise, seed, p->packed, batch, p->channels, hw, y_hat, lik);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_eb_symbols(const float* x, const float* medians, int batch, int channels, int64_t hw, int32_t* symbols,
+                     int32_t* indexes, void* stream) {
+    if (!x || !medians || !symbols || batch < 0 || channels < 1 || hw < 0) return LICOS_ERR_INVALID;
+    const int64_t n = (int64_t)batch * channels * hw;
+    if (n == 0) return LICOS_OK;
+    eb_symbols_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, medians, channels, hw, n, symbols, indexes);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_eb_dequantize(const int32_t* symbols, const float* medians, int batch, int channels, int64_t hw,
+                        float* y_hat, void* stream) {
+    if (!symbols || !medians || !y_hat || batch < 0 || channels < 1 || hw < 0) return LICOS_ERR_INVALID;
+    const int64_t n = (int64_t)batch * channels * hw;
+    if (n == 0) return LICOS_OK;
+    eb_dequant_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(symbols, medians, channels, hw, n, y_hat);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_gc_forward(const float* y, const float* scales, const float* means, const float* noise, uint64_t seed,
+                     int64_t n, int training, float scale_bound, float likelihood_bound, float* y_hat, float* lik,
+                     void* stream) {
+    if (!y || !scales || !y_hat || !lik || n < 0) return LICOS_ERR_INVALID;
+    if (n == 0) return LICOS_OK;
+    gc_forward_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(y, scales, means, noise, seed, n, training,
+                                                                        scale_bound, likelihood_bound, y_hat, lik);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_gc_build_indexes(const float* scales, int64_t n, const float* table, int n_table, float scale_bound,
+                           int32_t* indexes, void* stream) {
+    if (!scales || !table || !indexes || n < 0 || n_table < 1 || n_table > 4096) return LICOS_ERR_INVALID;
+    if (n == 0) return LICOS_OK;
+    gc_indexes_kernel<<<grid_for(n, 256), 256, n_table * sizeof(float), (cudaStream_t)stream>>>(
+        scales, n, table, n_table, scale_bound, indexes);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_gc_symbols(const float* y, const float* means, int64_t n, int32_t* symbols, void* stream) {
+    if (!y || !symbols || n < 0) return LICOS_ERR_INVALID;
+    if (n == 0) return LICOS_OK;
+    gc_symbols_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(y, means, n, symbols);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_sum_log(const float* lik, int64_t n, double* acc, void* stream) {
+    if (!lik || !acc || n < 0) return LICOS_ERR_INVALID;
+    if (n == 0) return LICOS_OK;
+    sum_log_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(lik, n, acc);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_sum_sq_err(const float* a, const float* b, int64_t n, double* acc, void* stream) {
+    if (!a || !b || !acc || n < 0) return LICOS_ERR_INVALID;
+    if (n == 0) return LICOS_OK;
+    sum_sq_err_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(a, b, n, acc);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_weighted_sum2(const float* a, const float* b, float w_a, float w_b, int64_t n, float* dst, void* stream) {
+    if (!a || !b || !dst || n < 0) return LICOS_ERR_INVALID;
+    if (n == 0) return LICOS_OK;
+    weighted_sum2_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, w_a, w_b, n, dst);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_scale_inplace(float* buf, float w, int64_t n, void* stream) {
+    if (!buf || n < 0) return LICOS_ERR_INVALID;
+    if (n == 0) return LICOS_OK;
+    scale_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(buf, w, n);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_nchw_f32_to_nhwc_bf16(const float* in, void* out, int batch, int channels, int64_t hw, int take_abs,
+                                void* stream) {
+    if (!in || !out || batch < 0 || channels < 1 || hw < 0) return LICOS_ERR_INVALID;
+    if (batch == 0 || hw == 0) return LICOS_OK;
+    if (batch > 65535) return LICOS_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((channels + 31) / 32), (unsigned)batch);
+    nchw_to_nhwc_bf16_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, channels, hw,
+                                                                           take_abs);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_nhwc_bf16_to_nchw_f32(const void* in, float* out, int batch, int channels, int64_t hw, void* stream) {
+    if (!in || !out || batch < 0 || channels < 1 || hw < 0) return LICOS_ERR_INVALID;
+    if (batch == 0 || hw == 0) return LICOS_OK;
+    if (batch > 65535) return LICOS_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((channels + 31) / 32), (unsigned)batch);
+    nhwc_bf16_to_nchw_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, out, channels,
+                                                                           hw);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,460 @@
+"""Host-side mirrors of compressai.entropy_models.{EntropyModel, EntropyBottleneck, GaussianConditional}
+ on top of the C ABI.
+
+Division of labour:
+  * forward() with autograd off -> one fused CUDA pass (licos_eb_forward_* / licos_gc_forward);
+  * quantize("symbols") / build_indexes / dequantize -> bit-exact integer kernels;
+  * update() -> host logic exactly as upstream (torch CPU ops for the tiny PMF tables) + the C++
+    licos_pmf_to_quantized_cdf; run once per model (eval_script.py:72,88);
+  * compress()/decompress() -> symbols on the GPU, one D2H per batch, C++ rANS on host threads;
+  * forward() with autograd on -> the differentiable torch expression (training step, train.py:190-193).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import numpy as np
+import scipy.stats
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch import Tensor
+
+from . import _lib, ops
+from .layers import LowerBound
+
+
+def _require_cuda(t: Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"licos_b200: {what} needs CUDA tensors on a B200 (this package has no CPU path)")
+
+
+def _wants_grad(module: nn.Module, *tensors: Optional[Tensor]) -> bool:
+    if not torch.is_grad_enabled():
+        return False
+    if any(t is not None and t.requires_grad for t in tensors):
+        return True
+    return any(p.requires_grad for p in module.parameters())
+
+
+class EntropyModel(nn.Module):
+    def __init__(self, likelihood_bound: float = 1e-9, entropy_coder: Optional[str] = None,
+                 entropy_coder_precision: int = 16):
+        super().__init__()
+        if entropy_coder not in (None, "ans"):
+            raise ValueError(f'Unknown entropy coder "{entropy_coder}" (only "ans" is built in)')
+        self.entropy_coder_precision = int(entropy_coder_precision)
+        self.likelihood_bound = float(likelihood_bound)
+        self.use_likelihood_bound = likelihood_bound > 0
+        if self.use_likelihood_bound:
+            self.likelihood_lower_bound = LowerBound(likelihood_bound)
+        self.register_buffer("_offset", torch.IntTensor())
+        self.register_buffer("_quantized_cdf", torch.IntTensor())
+        self.register_buffer("_cdf_length", torch.IntTensor())
+        self.coder_threads = 0  # 0 = all host cores
+
+    offset = property(lambda self: self._offset)
+    quantized_cdf = property(lambda self: self._quantized_cdf)
+    cdf_length = property(lambda self: self._cdf_length)
+
+    # ------------------------------------------------------------------ quantisation
+    def quantize(self, inputs: Tensor, mode: str, means: Optional[Tensor] = None) -> Tensor:
+        if mode not in ("noise", "dequantize", "symbols"):
+            raise ValueError(f'Invalid quantization mode: "{mode}"')
+        if mode == "noise":
+            return inputs + torch.empty_like(inputs).uniform_(-0.5, 0.5)
+        if mode == "symbols":
+            _require_cuda(inputs, "quantize('symbols')")
+            m = None if means is None else means.expand_as(inputs).contiguous()
+            return ops.gc_symbols(inputs.detach().contiguous(), m)
+        outputs = inputs.clone()
+        if means is not None:
+            outputs -= means
+        outputs = torch.round(outputs)
+        if means is not None:
+            outputs += means
+        return outputs
+
+    @staticmethod
+    def dequantize(inputs: Tensor, means: Optional[Tensor] = None, dtype: torch.dtype = torch.float) -> Tensor:
+        if means is not None:
+            outputs = inputs.type_as(means)
+            outputs += means
+        else:
+            outputs = inputs.type(dtype)
+        return outputs
+
+    # ------------------------------------------------------------------ tables
+    def _pmf_to_cdf(self, pmf: Tensor, tail_mass: Tensor, pmf_length: Tensor, max_length: int) -> Tensor:
+        pmf_np = pmf.detach().cpu().float().numpy()
+        tail_np = tail_mass.detach().cpu().float().numpy().reshape(len(pmf_np), -1)
+        lengths = pmf_length.cpu().numpy()
+        cdf = np.zeros((len(lengths), max_length + 2), dtype=np.int32)
+        for i in range(len(lengths)):
+            prob = np.concatenate((pmf_np[i, : lengths[i]], tail_np[i, :1]))
+            row = ops.pmf_to_quantized_cdf(prob, self.entropy_coder_precision)
+            cdf[i, : row.size] = row.astype(np.int32)
+        return torch.from_numpy(cdf)
+
+    def _check_tables(self) -> None:
+        if self._quantized_cdf.numel() == 0:
+            raise ValueError("Uninitialized CDFs. Run update() first")
+        if self._quantized_cdf.dim() != 2:
+            raise ValueError(f"Invalid CDF size {self._quantized_cdf.size()}")
+        if self._offset.numel() == 0:
+            raise ValueError("Uninitialized offsets. Run update() first")
+        if self._offset.dim() != 1:
+            raise ValueError(f"Invalid offsets size {self._offset.size()}")
+        if self._cdf_length.numel() == 0:
+            raise ValueError("Uninitialized CDF lengths. Run update() first")
+        if self._cdf_length.dim() != 1:
+            raise ValueError(f"Invalid offsets size {self._cdf_length.size()}")
+
+    def _host_tables(self):
+        return (self._quantized_cdf.cpu().numpy(), self._cdf_length.cpu().numpy(), self._offset.cpu().numpy())
+
+    # ------------------------------------------------------------------ range coding
+    def compress(self, inputs: Tensor, indexes: Tensor, means: Optional[Tensor] = None):
+        if inputs.dim() < 2:
+            raise ValueError("Invalid `inputs` size. Expected a tensor with at least 2 dimensions.")
+        if inputs.size() != indexes.size():
+            raise ValueError("`inputs` and `indexes` should have the same size.")
+        self._check_tables()
+        symbols = self.quantize(inputs, "symbols", means)
+        B = symbols.size(0)
+        sym = symbols.reshape(B, -1).cpu().numpy()
+        idx = indexes.reshape(B, -1).int().cpu().numpy()
+        cdf, lengths, offsets = self._host_tables()
+        return ops.rans_encode_batch(sym, idx, cdf, lengths, offsets, threads=self.coder_threads)
+
+    def decompress(self, strings, indexes: Tensor, dtype: torch.dtype = torch.float, means: Optional[Tensor] = None):
+        if not isinstance(strings, (tuple, list)):
+            raise ValueError("Invalid `strings` parameter type.")
+        if not len(strings) == indexes.size(0):
+            raise ValueError("Invalid strings or indexes parameters")
+        if indexes.dim() < 2:
+            raise ValueError("Invalid `indexes` size. Expected a tensor with at least 2 dimensions.")
+        self._check_tables()
+        if means is not None:
+            if means.size()[:2] != indexes.size()[:2]:
+                raise ValueError("Invalid means or indexes parameters")
+            if means.size() != indexes.size():
+                for i in range(2, indexes.dim()):
+                    if means.size(i) != 1:
+                        raise ValueError("Invalid means parameters")
+        B = indexes.size(0)
+        n = indexes[0].numel() if B else 0
+        cdf, lengths, offsets = self._host_tables()
+        idx = indexes.reshape(B, -1).int().cpu().numpy()
+        sym = ops.rans_decode_batch(list(strings), idx, n, cdf, lengths, offsets, threads=self.coder_threads)
+        outputs = torch.from_numpy(sym).reshape(indexes.size()).to(self._quantized_cdf.device)
+        return self.dequantize(outputs, means, dtype)
+
+
+class EntropyBottleneck(EntropyModel):
+    """Fully-factorized density (Balle et al. 2018).  ``filters`` may be any widths <= 16: LICOS uses
+    ``(in_channels, in_channels, 3, 3)`` (/root/reference/licos/model_utils.py:25-29)."""
+
+    # "plain" = CompressAI >= 1.2 forward; "stable" = the sign-stabilised form (<= 1.1, still used in update()).
+    likelihood_form = "plain"
+
+    def __init__(self, channels: int, *args, tail_mass: float = 1e-9, init_scale: float = 10,
+                 filters: Tuple[int, ...] = (3, 3, 3, 3), **kwargs):
+        super().__init__(*args, **kwargs)
+        self.channels = int(channels)
+        self.filters = tuple(int(f) for f in filters)
+        self.init_scale = float(init_scale)
+        self.tail_mass = float(tail_mass)
+        if len(self.filters) + 1 > _lib.EB_MAX_LAYERS or max(self.filters) > 16:
+            raise ValueError("EntropyBottleneck: at most 7 hidden layers of width <= 16 are supported")
+
+        widths = (1,) + self.filters + (1,)
+        scale = self.init_scale ** (1 / (len(self.filters) + 1))
+        for i in range(len(self.filters) + 1):
+            init = np.log(np.expm1(1 / scale / widths[i + 1]))
+            self.register_parameter(f"_matrix{i:d}", nn.Parameter(torch.full((channels, widths[i + 1], widths[i]), float(init))))
+            self.register_parameter(f"_bias{i:d}", nn.Parameter(torch.empty(channels, widths[i + 1], 1).uniform_(-0.5, 0.5)))
+            if i < len(self.filters):
+                self.register_parameter(f"_factor{i:d}", nn.Parameter(torch.zeros(channels, widths[i + 1], 1)))
+        self.quantiles = nn.Parameter(torch.Tensor([-self.init_scale, 0, self.init_scale]).repeat(channels, 1, 1))
+        target = np.log(2 / self.tail_mass - 1)
+        self.register_buffer("target", torch.Tensor([-target, 0, target]))
+        self._packed_key = None
+        self._packed = None
+
+    # accept the ParameterList naming of newer CompressAI releases
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        for old, new in (("matrices.", "_matrix"), ("biases.", "_bias"), ("factors.", "_factor"),
+                         ("_matrices.", "_matrix"), ("_biases.", "_bias"), ("_factors.", "_factor")):
+            for key in [k for k in state_dict if k.startswith(prefix + old)]:
+                state_dict[prefix + new + key[len(prefix + old):]] = state_dict.pop(key)
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    def _get_medians(self) -> Tensor:
+        return self.quantiles[:, :, 1:2]
+
+    # ------------------------------------------------------------------ differentiable / host expressions
+    def _logits_cumulative(self, inputs: Tensor, stop_gradient: bool) -> Tensor:
+        logits = inputs
+        for i in range(len(self.filters) + 1):
+            matrix = getattr(self, f"_matrix{i:d}")
+            bias = getattr(self, f"_bias{i:d}")
+            if stop_gradient:
+                matrix, bias = matrix.detach(), bias.detach()
+            logits = torch.matmul(F.softplus(matrix), logits) + bias
+            if i < len(self.filters):
+                factor = getattr(self, f"_factor{i:d}")
+                if stop_gradient:
+                    factor = factor.detach()
+                logits = logits + torch.tanh(factor) * torch.tanh(logits)
+        return logits
+
+    def _likelihood(self, inputs: Tensor, stop_gradient: bool = False, form: Optional[str] = None):
+        lower = self._logits_cumulative(inputs - 0.5, stop_gradient=stop_gradient)
+        upper = self._logits_cumulative(inputs + 0.5, stop_gradient=stop_gradient)
+        if (form or self.likelihood_form) == "plain":
+            likelihood = torch.sigmoid(upper) - torch.sigmoid(lower)
+        else:
+            sign = -torch.sign(lower + upper).detach()
+            likelihood = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))
+        return likelihood, lower, upper
+
+    def loss(self) -> Tensor:
+        logits = self._logits_cumulative(self.quantiles, stop_gradient=True)
+        return torch.abs(logits - self.target).sum()
+
+    def update(self, force: bool = False) -> bool:
+        if self._offset.numel() > 0 and not force:
+            return False
+        device = self.quantiles.device
+        host = self if device.type == "cpu" else _cpu_twin(self)
+        with torch.no_grad():
+            q = host.quantiles
+            medians = q[:, 0, 1]
+            minima = torch.clamp(torch.ceil(medians - q[:, 0, 0]).int(), min=0)
+            maxima = torch.clamp(torch.ceil(q[:, 0, 2] - medians).int(), min=0)
+            pmf_start = medians - minima
+            pmf_length = maxima + minima + 1
+            max_length = int(pmf_length.max().item())
+            samples = torch.arange(max_length)[None, :] + pmf_start[:, None, None]
+            pmf, lower, upper = host._likelihood(samples, stop_gradient=True, form="stable")
+            pmf = pmf[:, 0, :]
+            tail_mass = torch.sigmoid(lower[:, 0, :1]) + torch.sigmoid(-upper[:, 0, -1:])
+            quantized_cdf = self._pmf_to_cdf(pmf, tail_mass, pmf_length, max_length)
+        self._offset = (-minima).to(device)
+        self._quantized_cdf = quantized_cdf.to(device)
+        self._cdf_length = (pmf_length + 2).to(device)
+        return True
+
+    # ------------------------------------------------------------------ kernel parameter block
+    def _params(self):
+        names = []
+        for i in range(len(self.filters) + 1):
+            names += [f"_matrix{i:d}", f"_bias{i:d}"] + ([f"_factor{i:d}"] if i < len(self.filters) else [])
+        return [getattr(self, n) for n in names] + [self.quantiles]
+
+    def packed_params(self) -> ops.EbPacked:
+        key = tuple((p.data_ptr(), p._version) for p in self._params()) + (self.likelihood_form,)
+        if key != self._packed_key:
+            with torch.no_grad():
+                C = self.channels
+                parts = []
+                for i in range(len(self.filters) + 1):
+                    parts.append(F.softplus(getattr(self, f"_matrix{i:d}")).reshape(C, -1))
+                    parts.append(getattr(self, f"_bias{i:d}").reshape(C, -1))
+                    if i < len(self.filters):
+                        parts.append(torch.tanh(getattr(self, f"_factor{i:d}")).reshape(C, -1))
+                packed = torch.cat(parts, dim=1).contiguous().float()
+                medians = self.quantiles[:, 0, 1].contiguous().float()
+            form = _lib.EB_FORM_PLAIN if self.likelihood_form == "plain" else _lib.EB_FORM_STABLE
+            self._packed = ops.EbPacked(packed, medians, (1,) + self.filters + (1,), form,
+                                        self.likelihood_bound if self.use_likelihood_bound else 0.0)
+            self._packed_key = key
+        return self._packed
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: Tensor, training: Optional[bool] = None, noise: Optional[Tensor] = None,
+                seed: Optional[int] = None) -> Tuple[Tensor, Tensor]:
+        if training is None:
+            training = self.training
+        _require_cuda(x, "EntropyBottleneck.forward")
+        if _wants_grad(self, x):
+            return self._forward_autograd(x, training, noise)
+        x = x.contiguous()
+        ebp = self.packed_params()
+        if not training:
+            return ops.eb_forward_eval(ebp, x)
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if noise is None else 0
+        return ops.eb_forward_noise(ebp, x, None if noise is None else noise.contiguous(), seed)
+
+    def _forward_autograd(self, x: Tensor, training: bool, noise: Optional[Tensor]):
+        perm = [1, 0] + list(range(2, x.dim()))
+        xp = x.permute(*perm).contiguous()
+        shape = xp.size()
+        values = xp.reshape(xp.size(0), 1, -1)
+        if training:
+            nz = (torch.empty_like(values).uniform_(-0.5, 0.5) if noise is None
+                  else noise.permute(*perm).contiguous().reshape(values.shape))
+            outputs = values + nz
+        else:
+            med = self._get_medians().detach()
+            outputs = torch.round(values - med) + med
+        likelihood, _, _ = self._likelihood(outputs)
+        if self.use_likelihood_bound:
+            likelihood = self.likelihood_lower_bound(likelihood)
+        outputs = outputs.reshape(shape).permute(*perm).contiguous()
+        likelihood = likelihood.reshape(shape).permute(*perm).contiguous()
+        return outputs, likelihood
+
+    # ------------------------------------------------------------------ integer path
+    @staticmethod
+    def _build_indexes(size) -> Tensor:
+        dims = len(size)
+        view = [1] * dims
+        view[1] = -1
+        return torch.arange(size[1]).view(*view).int().repeat(size[0], 1, *size[2:])
+
+    @staticmethod
+    def _extend_ndims(tensor: Tensor, n: int) -> Tensor:
+        return tensor.reshape(-1, *([1] * n)) if n > 0 else tensor.reshape(-1)
+
+    def symbols(self, x: Tensor) -> Tensor:
+        """round(x - medians) as int32, on the device (the quantiser the range coder consumes)."""
+        return ops.eb_symbols(x.contiguous(), self.packed_params().medians)
+
+    def compress(self, x: Tensor):
+        if x.dim() < 2:
+            raise ValueError("Invalid `inputs` size. Expected a tensor with at least 2 dimensions.")
+        self._check_tables()
+        B, C = x.size(0), x.size(1)
+        n_spatial = int(np.prod(x.shape[2:])) if x.dim() > 2 else 1
+        sym = self.symbols(x).reshape(B, -1).cpu().numpy()
+        idx = np.repeat(np.arange(C, dtype=np.int32), n_spatial)  # same index plane for every image
+        cdf, lengths, offsets = self._host_tables()
+        return ops.rans_encode_batch(sym, idx, cdf, lengths, offsets, threads=self.coder_threads)
+
+    def decompress(self, strings, size):
+        if not isinstance(strings, (tuple, list)):
+            raise ValueError("Invalid `strings` parameter type.")
+        self._check_tables()
+        C = self._quantized_cdf.size(0)
+        n_spatial = int(np.prod(size)) if len(size) else 1
+        idx = np.repeat(np.arange(C, dtype=np.int32), n_spatial)
+        cdf, lengths, offsets = self._host_tables()
+        sym = ops.rans_decode_batch(list(strings), idx, C * n_spatial, cdf, lengths, offsets,
+                                    threads=self.coder_threads)
+        _require_cuda(self.quantiles, "EntropyBottleneck.decompress")
+        symbols = torch.from_numpy(sym).reshape(len(strings), C, *size).to(self.quantiles.device)
+        return ops.eb_dequantize(symbols.contiguous(), self.packed_params().medians)
+
+
+def _cpu_twin(eb: EntropyBottleneck) -> EntropyBottleneck:
+    """CPU copy of the parameters: update() evaluates the (tiny) PMF grid with the same torch CPU ops
+    upstream uses, so the integer tables do not depend on where the model lives."""
+    twin = EntropyBottleneck(eb.channels, filters=eb.filters, tail_mass=eb.tail_mass, init_scale=eb.init_scale)
+    with torch.no_grad():
+        for name, p in eb.named_parameters():
+            getattr(twin, name).copy_(p.detach().cpu())
+    return twin
+
+
+SCALES_MIN, SCALES_MAX, SCALES_LEVELS = 0.11, 256, 64
+
+
+def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS):
+    return torch.exp(torch.linspace(math.log(min), math.log(max), levels))
+
+
+class GaussianConditional(EntropyModel):
+    def __init__(self, scale_table, *args, scale_bound: float = 0.11, tail_mass: float = 1e-9, **kwargs):
+        super().__init__(*args, **kwargs)
+        if not isinstance(scale_table, (type(None), list, tuple)):
+            raise ValueError(f'Invalid type for scale_table "{type(scale_table)}"')
+        if isinstance(scale_table, (list, tuple)) and len(scale_table) < 1:
+            raise ValueError(f'Invalid scale_table length "{len(scale_table)}"')
+        if scale_table and (scale_table != sorted(scale_table) or any(s <= 0 for s in scale_table)):
+            raise ValueError(f'Invalid scale_table "({scale_table})"')
+        self.tail_mass = float(tail_mass)
+        if scale_bound is None and scale_table:
+            scale_bound = scale_table[0]
+        if scale_bound is None or scale_bound <= 0:
+            raise ValueError("Invalid parameters")
+        self.lower_bound_scale = LowerBound(scale_bound)
+        self.register_buffer("scale_table", self._prepare_scale_table(scale_table) if scale_table else torch.Tensor())
+        self.register_buffer("scale_bound", torch.Tensor([float(scale_bound)]))
+        self._scale_bound_f = float(torch.tensor(float(scale_bound), dtype=torch.float32))
+
+    @staticmethod
+    def _prepare_scale_table(scale_table):
+        return torch.Tensor(tuple(float(s) for s in scale_table))
+
+    @staticmethod
+    def _standardized_cumulative(inputs: Tensor) -> Tensor:
+        return 0.5 * torch.erfc(float(-(2 ** -0.5)) * inputs)
+
+    @staticmethod
+    def _standardized_quantile(quantile):
+        return scipy.stats.norm.ppf(quantile)
+
+    def update_scale_table(self, scale_table, force: bool = False) -> bool:
+        if self._offset.numel() > 0 and not force:
+            return False
+        device = self.scale_table.device
+        self.scale_table = self._prepare_scale_table(scale_table).to(device)
+        self.update()
+        return True
+
+    def update(self) -> None:
+        device = self.scale_table.device
+        table = self.scale_table.detach().cpu()
+        multiplier = -self._standardized_quantile(self.tail_mass / 2)
+        pmf_center = torch.ceil(table * multiplier).int()
+        pmf_length = 2 * pmf_center + 1
+        max_length = int(torch.max(pmf_length).item())
+        samples = torch.abs(torch.arange(max_length).int() - pmf_center[:, None]).float()
+        samples_scale = table.unsqueeze(1).float()
+        upper = self._standardized_cumulative((0.5 - samples) / samples_scale)
+        lower = self._standardized_cumulative((-0.5 - samples) / samples_scale)
+        pmf = upper - lower
+        tail_mass = 2 * lower[:, :1]
+        self._quantized_cdf = self._pmf_to_cdf(pmf, tail_mass, pmf_length, max_length).to(device)
+        self._offset = (-pmf_center).to(device)
+        self._cdf_length = (pmf_length + 2).to(device)
+
+    def _likelihood(self, inputs: Tensor, scales: Tensor, means: Optional[Tensor] = None) -> Tensor:
+        values = inputs - means if means is not None else inputs
+        scales = self.lower_bound_scale(scales)
+        values = torch.abs(values)
+        upper = self._standardized_cumulative((0.5 - values) / scales)
+        lower = self._standardized_cumulative((-0.5 - values) / scales)
+        return upper - lower
+
+    def forward(self, inputs: Tensor, scales: Tensor, means: Optional[Tensor] = None,
+                training: Optional[bool] = None, noise: Optional[Tensor] = None, seed: Optional[int] = None):
+        if training is None:
+            training = self.training
+        _require_cuda(inputs, "GaussianConditional.forward")
+        if _wants_grad(self, inputs, scales, means):
+            if training:
+                nz = torch.empty_like(inputs).uniform_(-0.5, 0.5) if noise is None else noise
+                outputs = inputs + nz
+            else:
+                outputs = self.quantize(inputs, "dequantize", means)
+            likelihood = self._likelihood(outputs, scales, means)
+            if self.use_likelihood_bound:
+                likelihood = self.likelihood_lower_bound(likelihood)
+            return outputs, likelihood
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (training and noise is None) else 0
+        m = None if means is None else means.expand_as(inputs).contiguous()
+        return ops.gc_forward(inputs.contiguous(), scales.contiguous(), m,
+                              None if noise is None else noise.contiguous(), training=bool(training),
+                              scale_bound=self._scale_bound_f,
+                              likelihood_bound=self.likelihood_bound if self.use_likelihood_bound else 0.0,
+                              seed=seed)
+
+    def build_indexes(self, scales: Tensor) -> Tensor:
+        _require_cuda(scales, "GaussianConditional.build_indexes")
+        return ops.gc_build_indexes(scales.detach().contiguous(), self.scale_table.contiguous(), self._scale_bound_f)

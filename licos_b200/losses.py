@@ -1,0 +1,59 @@
+"""compressai.losses.RateDistortionLoss (/root/reference/licos/train.py:123,192) and the
+bpp / PSNR metrics of /root/reference/eval_utils.py:145-186, with the reductions done by the C-ABI kernels
+when autograd is off."""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class RateDistortionLoss(nn.Module):
+    def __init__(self, lmbda: float = 0.01, metric: str = "mse", return_type: str = "all"):
+        super().__init__()
+        if metric != "mse":
+            raise NotImplementedError(f"{metric} is not implemented (LICOS trains with mse, train.py:123)")
+        self.lmbda = lmbda
+        self.return_type = return_type
+
+    def forward(self, output, target):
+        N, _, H, W = target.size()
+        num_pixels = N * H * W
+        needs_grad = torch.is_grad_enabled() and (
+            output["x_hat"].requires_grad or any(v.requires_grad for v in output["likelihoods"].values()))
+        out = {}
+        if needs_grad:
+            out["bpp_loss"] = sum(torch.log(lk).sum() / (-math.log(2) * num_pixels)
+                                  for lk in output["likelihoods"].values())
+            out["mse_loss"] = torch.mean((output["x_hat"] - target) ** 2)
+        else:
+            acc = torch.zeros(2, dtype=torch.float64, device=target.device)
+            for lk in output["likelihoods"].values():
+                ops.sum_log(lk.contiguous(), acc[0:1])
+            ops.sum_sq_err(output["x_hat"].contiguous(), target.contiguous(), acc[1:2])
+            out["bpp_loss"] = (acc[0] / (-math.log(2) * num_pixels)).float()
+            out["mse_loss"] = (acc[1] / target.numel()).float()
+        distortion = 255 ** 2 * out["mse_loss"]
+        out["loss"] = self.lmbda * distortion + out["bpp_loss"]
+        return out if self.return_type == "all" else out[self.return_type]
+
+
+@torch.no_grad()
+def compute_bpp(out_net) -> float:
+    """eval_utils.py:172-186"""
+    size = out_net["x_hat"].size()
+    num_pixels = size[0] * size[2] * size[3]
+    acc = torch.zeros(1, dtype=torch.float64, device=out_net["x_hat"].device)
+    for lk in out_net["likelihoods"].values():
+        ops.sum_log(lk.contiguous(), acc)
+    return float(acc.item() / (-math.log(2) * num_pixels))
+
+
+@torch.no_grad()
+def compute_psnr(a, b) -> float:
+    """eval_utils.py:145-156"""
+    acc = ops.sum_sq_err(a.contiguous(), b.contiguous())
+    return -10 * math.log10(acc.item() / a.numel())

@@ -1,0 +1,193 @@
+"""Host-side mirrors of compressai.models.{CompressionModel, FactorizedPrior, FactorizedPriorReLU,
+ScaleHyperprior} and of compressai.zoo.image_models (section 8b).
+
+The model object keeps CompressAI's surface -- ``net(x) -> {"x_hat", "likelihoods"}``, ``compress`` /
+``decompress``, ``aux_loss``, ``update``, ``state_dict`` key names, indexable ``g_a`` / ``g_s`` -- so it drops
+into /root/reference/licos/model_utils.py:19-45, train.py:190-200 and eval_utils.py:199-201 unchanged.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from .entropy_models import EntropyBottleneck, GaussianConditional, get_scale_table
+from .layers import GDN, FusedSequential, conv, deconv
+
+__all__ = ["CompressionModel", "FactorizedPrior", "FactorizedPriorReLU", "ScaleHyperprior", "image_models",
+           "model_architectures"]
+
+
+def _resize_buffers(module: nn.Module, prefix: str, names, state_dict) -> None:
+    """Checkpoints written after update() carry non-empty integer tables; give them room before loading."""
+    for name in names:
+        key = f"{prefix}.{name}"
+        if key not in state_dict:
+            continue
+        new = state_dict[key]
+        cur = getattr(module, name, None)
+        if cur is None or cur.size() != new.size():
+            device = cur.device if cur is not None else new.device
+            module.register_buffer(name, torch.zeros(new.size(), dtype=new.dtype, device=device))
+
+
+class CompressionModel(nn.Module):
+    def aux_loss(self) -> Tensor:
+        return sum(m.loss() for m in self.modules() if isinstance(m, EntropyBottleneck))
+
+    def update(self, scale_table=None, force: bool = False) -> bool:
+        if scale_table is None:
+            scale_table = get_scale_table()
+        updated = False
+        for module in self.modules():
+            if isinstance(module, EntropyBottleneck):
+                updated |= module.update(force=force)
+            if isinstance(module, GaussianConditional):
+                updated |= module.update_scale_table(scale_table, force=force)
+        return updated
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kwargs):
+        for name, module in self.named_modules():
+            if not any(k.startswith(name) for k in state_dict.keys()):
+                continue
+            if isinstance(module, EntropyBottleneck):
+                _resize_buffers(module, name, ["_quantized_cdf", "_offset", "_cdf_length"], state_dict)
+            if isinstance(module, GaussianConditional):
+                _resize_buffers(module, name, ["_quantized_cdf", "_offset", "_cdf_length", "scale_table"], state_dict)
+        return super().load_state_dict(state_dict, strict=strict, **kwargs)
+
+
+def _analysis(cin: int, N: int, M: int, relu: bool = False) -> FusedSequential:
+    act = (lambda: nn.ReLU(inplace=True)) if relu else (lambda: GDN(N))
+    return FusedSequential(conv(cin, N), act(), conv(N, N), act(), conv(N, N), act(), conv(N, M))
+
+
+def _synthesis(cout: int, N: int, M: int, relu: bool = False) -> FusedSequential:
+    act = (lambda: nn.ReLU(inplace=True)) if relu else (lambda: GDN(N, inverse=True))
+    return FusedSequential(deconv(M, N), act(), deconv(N, N), act(), deconv(N, N), act(), deconv(N, cout))
+
+
+class FactorizedPrior(CompressionModel):
+    def __init__(self, N: int, M: int, **kwargs):
+        super().__init__(**kwargs)
+        self.entropy_bottleneck = EntropyBottleneck(M)
+        self.g_a = _analysis(3, N, M)
+        self.g_s = _synthesis(3, N, M)
+        self.N, self.M = N, M
+
+    @property
+    def downsampling_factor(self) -> int:
+        return 2 ** 4
+
+    def forward(self, x: Tensor) -> Dict:
+        y = self.g_a(x)
+        y_hat, y_likelihoods = self.entropy_bottleneck(y)
+        x_hat = self.g_s(y_hat)
+        return {"x_hat": x_hat, "likelihoods": {"y": y_likelihoods}}
+
+    @classmethod
+    def from_state_dict(cls, state_dict):
+        net = cls(state_dict["g_a.0.weight"].size(0), state_dict["g_a.6.weight"].size(0))
+        net.load_state_dict(state_dict)
+        return net
+
+    @torch.no_grad()
+    def compress(self, x: Tensor) -> Dict:
+        y = self.g_a(x)
+        return {"strings": [self.entropy_bottleneck.compress(y)], "shape": y.size()[-2:]}
+
+    @torch.no_grad()
+    def decompress(self, strings, shape) -> Dict:
+        assert isinstance(strings, list) and len(strings) == 1
+        y_hat = self.entropy_bottleneck.decompress(strings[0], shape)
+        return {"x_hat": self.g_s(y_hat).clamp_(0, 1)}
+
+
+class FactorizedPriorReLU(FactorizedPrior):
+    def __init__(self, N: int, M: int, **kwargs):
+        super().__init__(N=N, M=M, **kwargs)
+        self.g_a = _analysis(3, N, M, relu=True)
+        self.g_s = _synthesis(3, N, M, relu=True)
+
+
+class ScaleHyperprior(CompressionModel):
+    def __init__(self, N: int, M: int, **kwargs):
+        super().__init__(**kwargs)
+        self.entropy_bottleneck = EntropyBottleneck(N)
+        self.g_a = _analysis(3, N, M)
+        self.g_s = _synthesis(3, N, M)
+        self.h_a = FusedSequential(conv(M, N, stride=1, kernel_size=3), nn.ReLU(inplace=True),
+                                   conv(N, N), nn.ReLU(inplace=True), conv(N, N))
+        self.h_s = FusedSequential(deconv(N, N), nn.ReLU(inplace=True), deconv(N, N), nn.ReLU(inplace=True),
+                                   conv(N, M, stride=1, kernel_size=3), nn.ReLU(inplace=True))
+        self.gaussian_conditional = GaussianConditional(None)
+        self.N, self.M = int(N), int(M)
+
+    @property
+    def downsampling_factor(self) -> int:
+        return 2 ** (4 + 2)
+
+    def forward(self, x: Tensor) -> Dict:
+        y = self.g_a(x)
+        z = self.h_a(y, take_abs=True)
+        z_hat, z_likelihoods = self.entropy_bottleneck(z)
+        scales_hat = self.h_s(z_hat)
+        y_hat, y_likelihoods = self.gaussian_conditional(y, scales_hat)
+        x_hat = self.g_s(y_hat)
+        return {"x_hat": x_hat, "likelihoods": {"y": y_likelihoods, "z": z_likelihoods}}
+
+    @classmethod
+    def from_state_dict(cls, state_dict):
+        net = cls(state_dict["g_a.0.weight"].size(0), state_dict["g_a.6.weight"].size(0))
+        net.load_state_dict(state_dict)
+        return net
+
+    @torch.no_grad()
+    def compress(self, x: Tensor) -> Dict:
+        y = self.g_a(x)
+        z = self.h_a(y, take_abs=True)
+        z_strings = self.entropy_bottleneck.compress(z)
+        z_hat = self.entropy_bottleneck.decompress(z_strings, z.size()[-2:])
+        scales_hat = self.h_s(z_hat)
+        indexes = self.gaussian_conditional.build_indexes(scales_hat)
+        y_strings = self.gaussian_conditional.compress(y, indexes)
+        return {"strings": [y_strings, z_strings], "shape": z.size()[-2:]}
+
+    @torch.no_grad()
+    def decompress(self, strings, shape) -> Dict:
+        assert isinstance(strings, list) and len(strings) == 2
+        z_hat = self.entropy_bottleneck.decompress(strings[1], shape)
+        scales_hat = self.h_s(z_hat)
+        indexes = self.gaussian_conditional.build_indexes(scales_hat)
+        y_hat = self.gaussian_conditional.decompress(strings[0], indexes, z_hat.dtype)
+        return {"x_hat": self.g_s(y_hat).clamp_(0, 1)}
+
+
+# ---------------------------------------------------------------------------------------------
+# zoo: quality -> (N, M), as compressai/zoo/image.py `cfgs`
+# ---------------------------------------------------------------------------------------------
+_NM = {q: ((128, 192) if q <= 5 else (192, 320)) for q in range(1, 9)}
+model_architectures = {
+    "bmshj2018-factorized": FactorizedPrior,
+    "bmshj2018-factorized-relu": FactorizedPriorReLU,
+    "bmshj2018-hyperprior": ScaleHyperprior,
+}
+
+
+def _zoo_entry(name: str):
+    def build(quality, metric="mse", pretrained=False, progress=True, **kwargs):
+        if metric not in ("mse", "ms-ssim"):
+            raise ValueError(f'Invalid metric "{metric}"')
+        if quality < 1 or quality > 8:
+            raise ValueError(f'Invalid quality "{quality}", should be between (1, 8)')
+        if pretrained:
+            raise RuntimeError("pretrained CompressAI weights need a download; load a state_dict instead")
+        return model_architectures[name](*_NM[quality], **kwargs)
+
+    build.__name__ = name.replace("-", "_")
+    return build
+
+
+image_models = {name: _zoo_entry(name) for name in model_architectures}

@@ -1,0 +1,342 @@
+"""Tensor-level wrappers over the C ABI: translate torch tensors <-> raw pointers and status codes <->
+exceptions.  torch is used for device memory and streams only; no torch op computes anything here.
+
+Every device op requires CUDA tensors; there is no CPU path (the CPU restatement lives in oracle/ and is
+test infrastructure).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ConvArgs, EbParams, check, lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*tensors: Optional[torch.Tensor]) -> None:
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("licos_b200 kernels need CUDA tensors: there is no CPU path in this package")
+        if not t.is_contiguous():
+            raise ValueError("licos_b200 kernels need contiguous tensors")
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"expected float32, got {t.dtype}")
+    return t
+
+
+# ---------------------------------------------------------------------------------------------
+# layout
+# ---------------------------------------------------------------------------------------------
+
+def nchw_to_nhwc_bf16(x: torch.Tensor, take_abs: bool = False) -> torch.Tensor:
+    """fp32 (B, C, H, W) -> bf16 tensor of logical shape (B, H, W, C)."""
+    _need_cuda(_f32(x))
+    B, C, H, W = x.shape
+    out = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=x.device)
+    check(lib.licos_nchw_f32_to_nhwc_bf16(x.data_ptr(), out.data_ptr(), B, C, H * W, int(take_abs), _stream()),
+          "nchw_to_nhwc_bf16")
+    return out
+
+
+def nhwc_bf16_to_nchw(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    if x.dtype != torch.bfloat16:
+        raise TypeError("expected bfloat16")
+    B, H, W, C = x.shape
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+    check(lib.licos_nhwc_bf16_to_nchw_f32(x.data_ptr(), out.data_ptr(), B, C, H * W, _stream()), "nhwc_bf16_to_nchw")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# convolutions
+# ---------------------------------------------------------------------------------------------
+
+def pack_conv_weight(w: torch.Tensor, kind: int, out_c: int, in_c: int, in_layout: int) -> torch.Tensor:
+    _need_cuda(_f32(w))
+    nbytes = lib.licos_packed_weight_bytes(kind, out_c, in_c, in_layout)
+    check(int(nbytes), "packed_weight_bytes")
+    packed = torch.empty(int(nbytes) // 2, dtype=torch.bfloat16, device=w.device)
+    check(lib.licos_pack_conv_weight(w.data_ptr(), kind, out_c, in_c, in_layout, packed.data_ptr(), _stream()),
+          "pack_conv_weight")
+    return packed
+
+
+def gdn_pack(beta: torch.Tensor, gamma: torch.Tensor, beta_bound: float, gamma_bound: float, pedestal: float):
+    _need_cuda(_f32(beta), _f32(gamma))
+    C = beta.numel()
+    beta_hat = torch.empty(C, dtype=torch.float32, device=beta.device)
+    gamma_hat = torch.empty((C, C), dtype=torch.bfloat16, device=beta.device)
+    check(lib.licos_gdn_pack(beta.data_ptr(), gamma.data_ptr(), C, beta_bound, gamma_bound, pedestal,
+                             beta_hat.data_ptr(), gamma_hat.data_ptr(), _stream()), "gdn_pack")
+    return beta_hat, gamma_hat
+
+
+def conv_forward(x: torch.Tensor, *, kind: int, epilogue: int, in_layout: int, out_layout: int, in_c: int,
+                 out_c: int, weight: torch.Tensor, bias: Optional[torch.Tensor], beta: Optional[torch.Tensor] = None,
+                 gamma: Optional[torch.Tensor] = None, sm_count: int = 0) -> torch.Tensor:
+    """One conv / deconv layer with its fused epilogue.  x is fp32 NCHW or bf16 NHWC (see in_layout)."""
+    _need_cuda(x, weight, bias, beta, gamma)
+    if in_layout == _lib.LAYOUT_NCHW_F32:
+        B, C, H, W = x.shape
+        _f32(x)
+    else:
+        B, H, W, C = x.shape
+        if x.dtype != torch.bfloat16:
+            raise TypeError("NHWC input must be bfloat16")
+    if C != in_c:
+        raise ValueError(f"input has {C} channels, layer expects {in_c}")
+    if kind == _lib.CONV_5X5_S2:
+        OH, OW = (H + 1) // 2, (W + 1) // 2
+    elif kind == _lib.DECONV_5X5_S2:
+        OH, OW = 2 * H, 2 * W
+    else:
+        OH, OW = H, W
+    if out_layout == _lib.LAYOUT_NCHW_F32:
+        out = torch.empty((B, out_c, OH, OW), dtype=torch.float32, device=x.device)
+    else:
+        out = torch.empty((B, OH, OW, out_c), dtype=torch.bfloat16, device=x.device)
+    a = ConvArgs()
+    a.kind, a.epilogue, a.batch, a.in_h, a.in_w, a.in_c, a.out_c = kind, epilogue, B, H, W, in_c, out_c
+    a.in_layout, a.out_layout = in_layout, out_layout
+    a.in_, a.out, a.weight = x.data_ptr(), out.data_ptr(), weight.data_ptr()
+    a.bias, a.beta, a.gamma = _ptr(bias), _ptr(beta), _ptr(gamma)
+    a.sm_count = sm_count
+    ws = None
+    nws = int(lib.licos_conv_workspace_bytes(ctypes.byref(a)))
+    check(nws, "conv_workspace_bytes")
+    if nws > 0:
+        ws = torch.empty(nws, dtype=torch.uint8, device=x.device)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), nws
+    check(lib.licos_conv_forward(ctypes.byref(a), _stream()), "conv_forward")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# entropy bottleneck
+# ---------------------------------------------------------------------------------------------
+
+class EbPacked:
+    """Device-side parameter block of one EntropyBottleneck (see licos_eb_params)."""
+
+    def __init__(self, packed: torch.Tensor, medians: torch.Tensor, widths: Sequence[int], form: int,
+                 likelihood_bound: float):
+        _need_cuda(_f32(packed), _f32(medians))
+        self.packed, self.medians = packed, medians
+        self.p = EbParams()
+        self.p.channels = packed.shape[0]
+        self.p.n_layers = len(widths) - 1
+        for i, w in enumerate(widths):
+            self.p.widths[i] = int(w)
+        self.p.params_per_channel = packed.shape[1]
+        self.p.packed, self.p.medians = packed.data_ptr(), medians.data_ptr()
+        self.p.form = form
+        self.p.likelihood_bound = float(likelihood_bound)
+
+
+def eb_forward_eval(ebp: EbPacked, x: torch.Tensor):
+    _need_cuda(_f32(x))
+    B, C = x.shape[0], x.shape[1]
+    if C != ebp.p.channels:
+        raise ValueError("channel mismatch")
+    hw = x.numel() // max(B * C, 1)
+    y_hat, lik = torch.empty_like(x), torch.empty_like(x)
+    lut = torch.empty(int(lib.licos_eb_lut_floats(C)), dtype=torch.float32, device=x.device)
+    check(lib.licos_eb_forward_eval(ctypes.byref(ebp.p), x.data_ptr(), B, hw, lut.data_ptr(), y_hat.data_ptr(),
+                                    lik.data_ptr(), _stream()), "eb_forward_eval")
+    return y_hat, lik
+
+
+def eb_forward_noise(ebp: EbPacked, x: torch.Tensor, noise: Optional[torch.Tensor], seed: int = 0):
+    _need_cuda(_f32(x), noise)
+    B, C = x.shape[0], x.shape[1]
+    if C != ebp.p.channels:
+        raise ValueError("channel mismatch")
+    hw = x.numel() // max(B * C, 1)
+    y_hat, lik = torch.empty_like(x), torch.empty_like(x)
+    check(lib.licos_eb_forward_noise(ctypes.byref(ebp.p), x.data_ptr(), _ptr(noise), seed & (2 ** 64 - 1), B, hw,
+                                     y_hat.data_ptr(), lik.data_ptr(), _stream()), "eb_forward_noise")
+    return y_hat, lik
+
+
+def eb_symbols(x: torch.Tensor, medians: torch.Tensor, want_indexes: bool = False):
+    _need_cuda(_f32(x), _f32(medians))
+    B, C = x.shape[0], x.shape[1]
+    hw = x.numel() // max(B * C, 1)
+    sym = torch.empty(x.shape, dtype=torch.int32, device=x.device)
+    idx = torch.empty(x.shape, dtype=torch.int32, device=x.device) if want_indexes else None
+    check(lib.licos_eb_symbols(x.data_ptr(), medians.data_ptr(), B, C, hw, sym.data_ptr(), _ptr(idx), _stream()),
+          "eb_symbols")
+    return (sym, idx) if want_indexes else sym
+
+
+def eb_dequantize(sym: torch.Tensor, medians: torch.Tensor) -> torch.Tensor:
+    _need_cuda(sym, _f32(medians))
+    if sym.dtype != torch.int32:
+        raise TypeError("symbols must be int32")
+    B, C = sym.shape[0], sym.shape[1]
+    hw = sym.numel() // max(B * C, 1)
+    out = torch.empty(sym.shape, dtype=torch.float32, device=sym.device)
+    check(lib.licos_eb_dequantize(sym.data_ptr(), medians.data_ptr(), B, C, hw, out.data_ptr(), _stream()),
+          "eb_dequantize")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# gaussian conditional
+# ---------------------------------------------------------------------------------------------
+
+def gc_forward(y, scales, means=None, noise=None, *, training=False, scale_bound=0.11, likelihood_bound=1e-9,
+               seed: int = 0):
+    _need_cuda(_f32(y), _f32(scales), means, noise)
+    if scales.shape != y.shape or (means is not None and means.shape != y.shape):
+        raise ValueError("scales / means must have the shape of the input")
+    y_hat, lik = torch.empty_like(y), torch.empty_like(y)
+    check(lib.licos_gc_forward(y.data_ptr(), scales.data_ptr(), _ptr(means), _ptr(noise), seed & (2 ** 64 - 1),
+                               y.numel(), int(training), scale_bound, likelihood_bound, y_hat.data_ptr(),
+                               lik.data_ptr(), _stream()), "gc_forward")
+    return y_hat, lik
+
+
+def gc_build_indexes(scales: torch.Tensor, table: torch.Tensor, scale_bound: float) -> torch.Tensor:
+    _need_cuda(_f32(scales), _f32(table))
+    idx = torch.empty(scales.shape, dtype=torch.int32, device=scales.device)
+    check(lib.licos_gc_build_indexes(scales.data_ptr(), scales.numel(), table.data_ptr(), table.numel(), scale_bound,
+                                     idx.data_ptr(), _stream()), "gc_build_indexes")
+    return idx
+
+
+def gc_symbols(y: torch.Tensor, means: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(_f32(y), means)
+    sym = torch.empty(y.shape, dtype=torch.int32, device=y.device)
+    check(lib.licos_gc_symbols(y.data_ptr(), _ptr(means), y.numel(), sym.data_ptr(), _stream()), "gc_symbols")
+    return sym
+
+
+# ---------------------------------------------------------------------------------------------
+# reductions
+# ---------------------------------------------------------------------------------------------
+
+def sum_log(lik: torch.Tensor, acc: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """acc (1-element float64 device tensor) += sum(ln(lik))."""
+    _need_cuda(_f32(lik))
+    if acc is None:
+        acc = torch.zeros(1, dtype=torch.float64, device=lik.device)
+    check(lib.licos_sum_log(lik.data_ptr(), lik.numel(), acc.data_ptr(), _stream()), "sum_log")
+    return acc
+
+
+def sum_sq_err(a: torch.Tensor, b: torch.Tensor, acc: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(_f32(a), _f32(b))
+    if a.shape != b.shape:
+        raise ValueError("shape mismatch")
+    if acc is None:
+        acc = torch.zeros(1, dtype=torch.float64, device=a.device)
+    check(lib.licos_sum_sq_err(a.data_ptr(), b.data_ptr(), a.numel(), acc.data_ptr(), _stream()), "sum_sq_err")
+    return acc
+
+
+def weighted_sum2(a: torch.Tensor, b: torch.Tensor, wa: float, wb: float, out: Optional[torch.Tensor] = None):
+    _need_cuda(_f32(a), _f32(b), out)
+    if out is None:
+        out = torch.empty_like(a)
+    check(lib.licos_weighted_sum2(a.data_ptr(), b.data_ptr(), wa, wb, a.numel(), out.data_ptr(), _stream()),
+          "weighted_sum2")
+    return out
+
+
+def scale_inplace(buf: torch.Tensor, w: float) -> torch.Tensor:
+    _need_cuda(_f32(buf))
+    check(lib.licos_scale_inplace(buf.data_ptr(), w, buf.numel(), _stream()), "scale_inplace")
+    return buf
+
+
+# ---------------------------------------------------------------------------------------------
+# host integer path
+# ---------------------------------------------------------------------------------------------
+
+def pmf_to_quantized_cdf(pmf, precision: int = 16) -> np.ndarray:
+    p = np.ascontiguousarray(np.asarray(pmf, dtype=np.float32))
+    cdf = np.zeros(p.size + 1, dtype=np.uint32)
+    rc = lib.licos_pmf_to_quantized_cdf(p.ctypes.data, p.size, precision, cdf.ctypes.data)
+    if rc == -5:
+        raise ValueError("Invalid `pmf`: negative, non-finite or all-zero")
+    check(rc, "pmf_to_quantized_cdf")
+    return cdf
+
+
+def _i32(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+
+
+def rans_encode(symbols, indexes, cdfs, cdf_sizes, offsets) -> bytes:
+    symbols, indexes = _i32(symbols).reshape(-1), _i32(indexes).reshape(-1)
+    cdfs, cdf_sizes, offsets = _i32(cdfs), _i32(cdf_sizes), _i32(offsets)
+    if symbols.size != indexes.size or cdfs.ndim != 2:
+        raise ValueError("bad symbols / indexes / cdfs")
+    cap = 4 * (symbols.size * 12 + 16)
+    out = np.empty(cap, dtype=np.uint8)
+    n = lib.licos_rans_encode(symbols.ctypes.data, indexes.ctypes.data, symbols.size, cdfs.ctypes.data,
+                              cdfs.shape[0], cdfs.shape[1], cdf_sizes.ctypes.data, offsets.ctypes.data,
+                              out.ctypes.data, cap)
+    check(int(n), "rans_encode")
+    return out[:n].tobytes()
+
+
+def rans_decode(encoded: bytes, indexes, cdfs, cdf_sizes, offsets) -> np.ndarray:
+    indexes = _i32(indexes).reshape(-1)
+    cdfs, cdf_sizes, offsets = _i32(cdfs), _i32(cdf_sizes), _i32(offsets)
+    enc = np.frombuffer(encoded, dtype=np.uint8)
+    out = np.empty(indexes.size, dtype=np.int32)
+    check(lib.licos_rans_decode(enc.ctypes.data, enc.size, indexes.ctypes.data, indexes.size, cdfs.ctypes.data,
+                                cdfs.shape[0], cdfs.shape[1], cdf_sizes.ctypes.data, offsets.ctypes.data,
+                                out.ctypes.data), "rans_decode")
+    return out
+
+
+def rans_encode_batch(symbols: np.ndarray, indexes: np.ndarray, cdfs, cdf_sizes, offsets, threads: int = 0):
+    """symbols: (B, n) int32.  indexes: (B, n) or (n,) int32 (shared by every image).  -> list[bytes]."""
+    symbols = _i32(symbols)
+    B, n = symbols.shape
+    indexes = _i32(indexes)
+    stride = 0 if indexes.ndim == 1 else n
+    cdfs, cdf_sizes, offsets = _i32(cdfs), _i32(cdf_sizes), _i32(offsets)
+    out_stride = 4 * (n * 12 + 16)
+    # worst case is generous; shrink for big batches by encoding in slices
+    out = np.empty((B, out_stride), dtype=np.uint8)
+    sizes = np.zeros(B, dtype=np.int64)
+    check(lib.licos_rans_encode_batch(symbols.ctypes.data, indexes.ctypes.data, B, n, stride, cdfs.ctypes.data,
+                                      cdfs.shape[0], cdfs.shape[1], cdf_sizes.ctypes.data, offsets.ctypes.data,
+                                      out.ctypes.data, out_stride, sizes.ctypes.data, threads), "rans_encode_batch")
+    return [out[i, : sizes[i]].tobytes() for i in range(B)]
+
+
+def rans_decode_batch(strings, indexes: np.ndarray, n: int, cdfs, cdf_sizes, offsets, threads: int = 0) -> np.ndarray:
+    B = len(strings)
+    indexes = _i32(indexes)
+    stride = 0 if indexes.ndim == 1 else n
+    cdfs, cdf_sizes, offsets = _i32(cdfs), _i32(cdf_sizes), _i32(offsets)
+    bufs = [np.frombuffer(s, dtype=np.uint8) for s in strings]
+    ptrs = (ctypes.c_void_p * B)(*[b.ctypes.data for b in bufs])
+    sizes = np.asarray([b.size for b in bufs], dtype=np.int64)
+    out = np.empty((B, n), dtype=np.int32)
+    check(lib.licos_rans_decode_batch(ctypes.cast(ptrs, ctypes.c_void_p), sizes.ctypes.data, indexes.ctypes.data, B, n,
+                                      stride, cdfs.ctypes.data, cdfs.shape[0], cdfs.shape[1], cdf_sizes.ctypes.data,
+                                      offsets.ctypes.data, out.ctypes.data, threads), "rans_decode_batch")
+    return out

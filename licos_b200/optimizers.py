@@ -1,0 +1,21 @@
+"""compressai.optimizers.net_aux_optimizer (reached from /root/reference/licos/utils.py:65-73): every parameter
+whose name ends in ``.quantiles`` goes to the auxiliary optimizer, everything else to the main one."""
+from __future__ import annotations
+
+from typing import Any, Dict
+
+import torch
+import torch.nn as nn
+
+
+def net_aux_optimizer(net: nn.Module, conf: Dict[str, Dict[str, Any]]) -> Dict[str, torch.optim.Optimizer]:
+    named = dict(net.named_parameters())
+    groups = {"net": [], "aux": []}
+    for name in sorted(named):
+        if named[name].requires_grad:
+            groups["aux" if name.endswith(".quantiles") else "net"].append(named[name])
+    out = {}
+    for key in ("net", "aux"):
+        kwargs = dict(conf[key])
+        out[key] = getattr(torch.optim, kwargs.pop("type"))(groups[key], **kwargs)
+    return out
