@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""Benchmark of the learned-codec hot path (BASELINE.json: encode/decode MPix/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic tiles that is already resident in HBM:
+    encode: y = g_a(x); y_hat, likelihoods = entropy_bottleneck(y); symbols = round(y - median)
+    decode: x_hat = g_s(y_hat)
+Workload at N = 1: BASELINE.json configs[1] (bmshj2018-factorized q1, N=128 / M=192, 256 tiles of 3x256x256).
+N > 1 (torchrun, one rank per GPU): every rank codes its own 256 tiles -- tiles are independent, so there is
+no data-path collective (weak scaling).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL = "bmshj2018-factorized"
+QUALITY = 1
+TILE = (3, 256, 256)
+# 2 x MACs of conv + deconv + GDN for one 3x256x256 tile (5.528 GFLOP each way)
+FLOP_PER_TILE_ENCODE = 2 * 2764.05e6
+FLOP_PER_TILE_DECODE = 2 * 2764.05e6
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="tiles per GPU per step")
+    ap.add_argument("--ref-batch", type=int, default=16, help="tiles per step of the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunk", type=int, default=32)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "source": "MEASURED_PEAKS.json (bf16_tflops_sustained: kernel timed inside a long step)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference arm / baseline: the oracle restatement on the host cores
+# ---------------------------------------------------------------------------------------------
+
+def cpu_reference(batch: int, steps: int, warmup: int, state_dict=None):
+    """Times the oracle (pure PyTorch CPU restatement of the CompressAI path) on `batch` tiles per step."""
+    import torch
+    from licos_b200 import synth
+    from oracle import compressai_ref as R  # allowed here only: cpu_baseline / --impl reference legs
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(42)
+    ref = R.image_models[MODEL](quality=QUALITY)
+    if state_dict is None:
+        synth.condition_weights(ref)
+    else:
+        ref.load_state_dict(state_dict)
+    ref.eval()
+    x = synth.make_input("rgb256", batch)
+    med = ref.entropy_bottleneck.quantiles[:, 0, 1].detach().reshape(1, -1, 1, 1)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            y = ref.g_a(x)
+            y_hat, lik = ref.entropy_bottleneck(y)
+            sym = ref.entropy_bottleneck.quantize(y, "symbols", med)
+            x_hat = ref.g_s(y_hat)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    pix = batch * TILE[1] * TILE[2]
+    med_t = statistics.median(times)
+    del sym, lik, x_hat
+    return {"value": pix / med_t / 1e6, "unit": "MPix/s", "cores": threads, "kind": "port",
+            "sample": f"{batch} tiles of 3x256x256 per step, median of {steps} steps after {warmup} warm-ups, "
+                      f"torch {torch.__version__} CPU fp32, {threads} threads",
+            "ms_per_step": med_t * 1e3, "best_mpix_s": pix / min(times) / 1e6}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 10))
+    warmup = max(1, min(args.warmup, 2))
+    r = cpu_reference(args.ref_batch, steps, warmup)
+    line = {
+        "impl": "reference", "metric": "encode+decode throughput", "value": r["value"], "unit": "MPix/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{MODEL} q{QUALITY} encode+decode, {args.ref_batch}-tile sample of the "
+                               f"256 x 3x256x256 batch (CPU reference arm: oracle port of the CompressAI path)"},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# clock sampling
+# ---------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+        if not self.samples:
+            try:
+                out = subprocess.check_output(
+                    ["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                     "--format=csv,noheader,nounits"], text=True).strip().split(",")
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": ["unsampled"]}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    import licos_b200 as L
+    from licos_b200 import _lib, ops, synth
+
+    if _lib.lib.licos_device_ok(local) != 0:
+        raise SystemExit("bench.py: no sm_100 device -- the licos_b200 path has no fallback")
+
+    # ---- model, weights, input (identical on every rank; each rank codes its own tiles) ----
+    torch.manual_seed(42)
+    net = L.image_models[MODEL](quality=QUALITY, pretrained=False)
+    synth.condition_weights(net)
+    net = net.to(device).eval()
+    B = args.batch
+    x = synth.make_input("rgb256", B, seed=42 + rank, device=device)
+    eb = net.entropy_bottleneck
+
+    launches = {"n": 0}
+    conv_ms = {"events": None}
+    orig_conv = ops.conv_forward
+
+    def counted_conv(*a, **k):
+        # one igemm launch (+ the first-layer im2col launch) per call
+        launches["n"] += 2 if k.get("in_layout") == _lib.LAYOUT_NCHW_F32 else 1
+        if conv_ms["events"] is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = orig_conv(*a, **k)
+            e1.record()
+            conv_ms["events"].append((e0, e1, k["kind"], k["in_c"], k["out_c"], tuple(out.shape)))
+            return out
+        return orig_conv(*a, **k)
+
+    ops.conv_forward = counted_conv
+
+    def encode(xb):
+        y = net.g_a(xb)
+        y_hat, lik = eb(y)
+        sym = eb.symbols(y)
+        return y, y_hat, lik, sym
+
+    def step(xb):
+        y, y_hat, lik, sym = encode(xb)
+        x_hat = net.g_s(y_hat)
+        # kernels besides the convs: EB table + gather, symbols, NCHW->NHWC of y_hat
+        launches["n"] += 4
+        return y_hat, lik, sym, x_hat
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            step(x)
+        sync_all()
+
+        sampler = ClockSampler(local)
+        sampler.start()
+        launches["n"] = 0
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        enc_ms = dec_ms = 0.0
+        sync_all()
+        t_start = torch.cuda.Event(enable_timing=True)
+        t_end = torch.cuda.Event(enable_timing=True)
+        marks = []
+        t_start.record()
+        for _ in range(args.steps):
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            y, y_hat, lik, sym = encode(x)
+            e1.record()
+            x_hat = net.g_s(y_hat)
+            e2.record()
+            launches["n"] += 4
+            marks.append((e0, e1, e2))
+        t_end.record()
+        sync_all()
+        clocks = sampler.stop()
+        total_ms = t_start.elapsed_time(t_end)
+        for e0, e1, e2 in marks:
+            enc_ms += e0.elapsed_time(e1)
+            dec_ms += e1.elapsed_time(e2)
+        n_launch = launches["n"]
+
+        # ---- per-launch durations of the dominant kernel (conv igemm), live, CUDA events on this stream ----
+        conv_ms["events"] = []
+        inst_steps = 3
+        for _ in range(inst_steps):
+            step(x)
+        torch.cuda.synchronize()
+        per_layer = {}
+        conv_total_ms = 0.0
+        for e0, e1, kind, cin, cout, shape in conv_ms["events"]:
+            ms = e0.elapsed_time(e1)
+            conv_total_ms += ms
+            key = f"{['conv5s2', 'deconv5s2', 'conv3s1'][kind]}_{cin}->{cout}_{shape[-2] if len(shape) == 4 else ''}"
+            per_layer.setdefault(key, []).append(ms)
+        conv_ms["events"] = None
+        conv_ms_per_step = conv_total_ms / inst_steps
+
+        # ---- end to end through the public model API with HOST buffers ----
+        e2e = run_e2e(net, eb, x, args, torch, device, world)
+
+    # max over ranks
+    t = torch.tensor([total_ms, enc_ms, dec_ms, conv_ms_per_step, e2e["ms_per_step"]], dtype=torch.float64,
+                     device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, enc_ms, dec_ms, conv_ms_per_step, e2e_ms = t.tolist()
+
+    pix_per_step = B * TILE[1] * TILE[2] * world
+    ms_per_step = total_ms / args.steps
+    value = pix_per_step / (ms_per_step * 1e-3) / 1e6
+    pk = peaks()
+    flop_per_step_gpu = B * (FLOP_PER_TILE_ENCODE + FLOP_PER_TILE_DECODE)
+    achieved_tflops = flop_per_step_gpu / (conv_ms_per_step * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("conv_igemm_dram_bytes_per_launch")
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            sd = {k: v.cpu() for k, v in net.state_dict().items()}
+            cpu = cpu_reference(args.ref_batch, steps=6, warmup=2, state_dict=sd)
+        line = {
+            "metric": "encode+decode throughput", "value": value, "unit": "MPix/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"{MODEL} q{QUALITY} (N=128, M=192) encode+decode of {B} synthetic 3x256x256 tiles "
+                                   f"per GPU (BASELINE.json configs[1])",
+                       "tiles_per_gpu": B, "l2": "inputs larger than L2 (201 MB input, >1 GB of activations per step)",
+                       "weights": "random init seed 42 + synth.condition_weights"},
+            "encode_mpix_s": pix_per_step / (enc_ms / args.steps * 1e-3) / 1e6,
+            "decode_mpix_s": pix_per_step / (dec_ms / args.steps * 1e-3) / 1e6,
+            "clocks": clocks,
+            "e2e": {"value": pix_per_step / (e2e_ms * 1e-3) / 1e6, "unit": "MPix/s",
+                    "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                    "path": "pinned host x -> model.g_a / entropy_bottleneck / g_s -> x_hat, symbols, bpp on host"},
+            "gpu_launches": n_launch,
+            "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (8 launches per step: 4 conv + 4 deconv layers, GDN/IGDN fused)",
+                         "achieved": achieved_tflops, "peak": pk["tflops"], "unit": "TFLOP/s",
+                         "frac": achieved_tflops / pk["tflops"], "traffic": traffic,
+                         "peak_source": pk["source"],
+                         "per_launch_ms": {k: round(statistics.mean(v), 4) for k, v in per_layer.items()},
+                         "conv_share_of_step": conv_ms_per_step / ms_per_step},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(net, eb, x_dev, args, torch, device, world):
+    """Same step through the public API with host buffers: H2D of the tiles, D2H of x_hat, symbols, bpp."""
+    import torch.distributed as dist
+    from licos_b200 import ops
+
+    B = x_dev.shape[0]
+    x_host = x_dev.cpu().pin_memory()
+    ysz = (B, eb.channels, TILE[1] // 16, TILE[2] // 16)
+    xhat_host = torch.empty(x_host.shape, dtype=torch.float32).pin_memory()
+    sym_host = torch.empty(ysz, dtype=torch.int32).pin_memory()
+    bpp_host = torch.empty(1, dtype=torch.float64).pin_memory()
+    chunk = max(1, min(args.e2e_chunk, B))
+    streams = [torch.cuda.Stream(device=device) for _ in range(3)]
+    steps = max(3, min(args.steps, 10))
+
+    def one():
+        accs = [torch.zeros(1, dtype=torch.float64, device=device) for _ in streams]
+        main = torch.cuda.current_stream()
+        for s in streams:
+            s.wait_stream(main)
+        for i, lo in enumerate(range(0, B, chunk)):
+            hi = min(B, lo + chunk)
+            s = streams[i % len(streams)]
+            with torch.cuda.stream(s):
+                xb = x_host[lo:hi].to(device, non_blocking=True)
+                y = net.g_a(xb)
+                y_hat, lik = eb(y)
+                sym = eb.symbols(y)
+                x_hat = net.g_s(y_hat)
+                ops.sum_log(lik, accs[i % len(streams)])  # per-stream accumulator, summed after the join
+                xhat_host[lo:hi].copy_(x_hat, non_blocking=True)
+                sym_host[lo:hi].copy_(sym, non_blocking=True)
+        for s in streams:
+            main.wait_stream(s)
+        total = accs[0] + accs[1] + accs[2]
+        bpp_host.copy_(total / (-math.log(2) * B * TILE[1] * TILE[2]), non_blocking=True)
+
+    for _ in range(2):
+        one()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    return {"ms_per_step": dt * 1e3, "h2d": x_host.numel() * 4,
+            "d2h": xhat_host.numel() * 4 + sym_host.numel() * 4 + 8, "bpp": float(bpp_host.item())}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

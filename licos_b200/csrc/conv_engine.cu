@@ -827,7 +827,8 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     while (sb < kMaxSB && left >= b_slot_al) { ++sb; left -= b_slot_al; }
     p.sa = sa;
     p.sb = sb;
-    const size_t smem_bytes = 1024 + (size_t)sa * p.a_slot_bytes + (size_t)sb * b_slot_al + p.staging_bytes;
+    size_t smem_bytes = 1024 + (size_t)sa * p.a_slot_bytes + (size_t)sb * b_slot_al + p.staging_bytes;
+    if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;  // one CTA per SM: each CTA owns all 512 TMEM columns
 
     p.tiles_h = (p.grid_h + TH - 1) / TH;
     p.tiles_w = (p.grid_w + kTileW - 1) / kTileW;

@@ -142,7 +142,7 @@ def py_encode_with_indexes(symbols, indexes, cdfs, cdfs_sizes, offsets) -> bytes
     syms = []
     for s, ci in zip(symbols, indexes):
         cdf = cdfs[ci]
-        max_value = cdfs_sizes[ci] - 2
+        max_value = int(cdfs_sizes[ci]) - 2
         value = int(s) - int(offsets[ci])
         raw = 0
         if value < 0:
@@ -202,7 +202,7 @@ def py_decode_with_indexes(encoded: bytes, indexes, cdfs, cdfs_sizes, offsets):
 
     for ci in indexes:
         cdf = cdfs[ci]
-        max_value = cdfs_sizes[ci] - 2
+        max_value = int(cdfs_sizes[ci]) - 2
         cum = x & 0xFFFF
         k = 0
         while k < cdfs_sizes[ci] and not (int(cdf[k]) > cum):
