@@ -60,6 +60,7 @@ SIGNATURES = {
     "licos_gdn_pack": (c_int, [c_vp, c_vp, c_int, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp]),
     "licos_conv_workspace_bytes": (c_i64, [ctypes.POINTER(ConvArgs)]),
     "licos_conv_forward": (c_int, [ctypes.POINTER(ConvArgs), c_vp]),
+    "licos_debug_set_conv_probe": (None, [c_vp]),
     "licos_eb_lut_floats": (c_i64, [c_int]),
     "licos_eb_forward_eval": (c_int, [ctypes.POINTER(EbParams), c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "licos_eb_forward_noise": (c_int, [ctypes.POINTER(EbParams), c_vp, c_vp, c_u64, c_int, c_i64, c_vp, c_vp, c_vp]),

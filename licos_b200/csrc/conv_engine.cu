@@ -82,7 +82,14 @@ struct ConvParams {
     int sa, sb;
     uint32_t a_slot_bytes, b_slot_bytes, staging_bytes;
     int total_tiles;
+    unsigned long long* dbg;  // optional per-CTA cycle probes (licos_debug_set_conv_probe)
 };
+
+// probe slots (per CTA, 16 x u64)
+enum { DBG_PA_WAIT = 0, DBG_PB_WAIT, DBG_MMA_A, DBG_MMA_B, DBG_MMA_ACC, DBG_MMA_X2, DBG_MMA_TOTAL, DBG_EPI_ACC,
+       DBG_EPI_S1, DBG_EPI_NORM, DBG_EPI_S2, DBG_EPI_STORE, DBG_EPI_TOTAL, DBG_TILES, DBG_PA_TOTAL, DBG_PB_TOTAL };
+#define PROBE_T0() const long long _t0 = p.dbg ? clock64() : 0
+#define PROBE_ADD(var) do { if (p.dbg) (var) += clock64() - _t0; } while (0)
 
 struct TileCoord {
     int b, gh0, gw0, ns;
@@ -136,6 +143,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         // ===================== A producer =====================
         for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.in_maps[i]);
         uint32_t it = 0;
+        long long w_wait = 0;
+        const long long t_begin = p.dbg ? clock64() : 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const TileCoord t = decode_tile(p, tile);
             for (int pi = 0; pi < p.n_passes; ++pi) {
@@ -144,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                     for (int s = 0; s < ps.n_slabs; ++s) {
                         const Slab& sl = ps.slabs[s];
                         const uint32_t slot = it % p.sa, ph = (it / p.sa) & 1u;
-                        mbar_wait(&a_empty[slot], ph ^ 1u);
+                        { PROBE_T0(); mbar_wait(&a_empty[slot], ph ^ 1u); PROBE_ADD(w_wait); }
                         mbar_arrive_expect_tx(&a_full[slot], p.a_slot_bytes);
                         tma_load_4d(a_ring + (size_t)slot * p.a_slot_bytes, &p.in_maps[sl.in_map], &a_full[slot],
                                     c * kKChunk, t.gw0 + sl.dw, t.gh0 - 1, t.b);
@@ -153,11 +162,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                 }
             }
         }
+        if (p.dbg) {
+            p.dbg[blockIdx.x * 16 + DBG_PA_WAIT] = w_wait;
+            p.dbg[blockIdx.x * 16 + DBG_PA_TOTAL] = clock64() - t_begin;
+        }
     } else if (warp == 1 && lane == 0) {
         // ===================== B producer =====================
         tma_prefetch_desc(&p.w_map);
         if (has_gdn) tma_prefetch_desc(&p.g_map);
         uint32_t it = 0;
+        long long w_wait = 0;
+        const long long t_begin = p.dbg ? clock64() : 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const TileCoord t = decode_tile(p, tile);
             for (int pi = 0; pi < p.n_passes; ++pi) {
@@ -167,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                         const Slab& sl = ps.slabs[s];
                         for (int k = 0; k < sl.n_taps; ++k) {
                             const uint32_t slot = it % p.sb, ph = (it / p.sb) & 1u;
-                            mbar_wait(&b_empty[slot], ph ^ 1u);
+                            { PROBE_T0(); mbar_wait(&b_empty[slot], ph ^ 1u); PROBE_ADD(w_wait); }
                             mbar_arrive_expect_tx(&b_full[slot], p.b_slot_bytes);
                             tma_load_2d(b_ring + (size_t)slot * p.b_slot_bytes, &p.w_map, &b_full[slot], c * kKChunk,
                                         sl.taps[k].w_tap * p.w_rows_per_tap + t.ns * p.N);
@@ -188,28 +203,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                 }
             }
         }
+        if (p.dbg) {
+            p.dbg[blockIdx.x * 16 + DBG_PB_WAIT] = w_wait;
+            p.dbg[blockIdx.x * 16 + DBG_PB_TOTAL] = clock64() - t_begin;
+        }
     } else if (warp == 2 && lane == 0) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = umma_idesc_bf16(128, p.N);
         const uint32_t a_ring_addr = smem_u32(a_ring), b_ring_addr = smem_u32(b_ring);
         const uint32_t staging_addr = smem_u32(staging);
         uint32_t ita = 0, itb = 0, pit = 0, git = 0;
+        long long w_a = 0, w_b = 0, w_acc = 0, w_x2 = 0, n_tiles = 0;
+        const long long t_begin = p.dbg ? clock64() : 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            ++n_tiles;
             for (int pi = 0; pi < p.n_passes; ++pi) {
                 const Pass& ps = p.passes[pi];
-                mbar_wait(&acc_empty, (pit & 1u) ^ 1u);
+                { PROBE_T0(); mbar_wait(&acc_empty, (pit & 1u) ^ 1u); PROBE_ADD(w_acc); }
                 tc_fence_after();
                 uint32_t touched = 0;
                 for (int c = 0; c < p.cin_chunks; ++c) {
                     for (int s = 0; s < ps.n_slabs; ++s) {
                         const Slab& sl = ps.slabs[s];
                         const uint32_t sa_slot = ita % p.sa;
-                        mbar_wait(&a_full[sa_slot], (ita / p.sa) & 1u);
+                        { PROBE_T0(); mbar_wait(&a_full[sa_slot], (ita / p.sa) & 1u); PROBE_ADD(w_a); }
                         const uint32_t a_slab = a_ring_addr + sa_slot * p.a_slot_bytes;
                         for (int k = 0; k < sl.n_taps; ++k) {
                             const Tap tp = sl.taps[k];
                             const uint32_t sb_slot = itb % p.sb;
-                            mbar_wait(&b_full[sb_slot], (itb / p.sb) & 1u);
+                            { PROBE_T0(); mbar_wait(&b_full[sb_slot], (itb / p.sb) & 1u); PROBE_ADD(w_b); }
                             tc_fence_after();
                             const uint32_t b_tile = b_ring_addr + sb_slot * p.b_slot_bytes;
                             for (int a = 0; a < p.n_acc; ++a) {
@@ -234,11 +256,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                 if (has_gdn) {
                     const uint32_t d = tmem_base + (uint32_t)(ps.n_groups * p.n_acc) * p.N;
                     for (int g = 0; g < ps.n_groups * p.n_acc; ++g) {
-                        mbar_wait(&x2_full, git & 1u);
+                        { PROBE_T0(); mbar_wait(&x2_full, git & 1u); PROBE_ADD(w_x2); }
                         tc_fence_after();
                         for (int gc = 0; gc < p.N / kKChunk; ++gc) {
                             const uint32_t sb_slot = itb % p.sb;
-                            mbar_wait(&b_full[sb_slot], (itb / p.sb) & 1u);
+                            { PROBE_T0(); mbar_wait(&b_full[sb_slot], (itb / p.sb) & 1u); PROBE_ADD(w_b); }
                             tc_fence_after();
                             const uint32_t b_tile = b_ring_addr + sb_slot * p.b_slot_bytes;
                             const uint32_t a_tile = staging_addr + gc * (128 * 128);
@@ -257,6 +279,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                 ++pit;
             }
         }
+        if (p.dbg) {
+            unsigned long long* d = p.dbg + blockIdx.x * 16;
+            d[DBG_MMA_A] = w_a; d[DBG_MMA_B] = w_b; d[DBG_MMA_ACC] = w_acc; d[DBG_MMA_X2] = w_x2;
+            d[DBG_MMA_TOTAL] = clock64() - t_begin; d[DBG_TILES] = n_tiles;
+        }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int et = threadIdx.x - 128;  // == TMEM lane == row of the 128-row sub-tile
@@ -264,11 +291,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         const int th = et / kTileW, tw = et % kTileW;
         uint32_t pit = 0, git = 0;
         const int n32 = p.N / 32, n16rem = (p.N % 32) / 16;
+        long long e_acc = 0, e_s1 = 0, e_norm = 0, e_s2 = 0, e_store = 0;
+        const long long t_begin = p.dbg ? clock64() : 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const TileCoord t = decode_tile(p, tile);
             for (int pi = 0; pi < p.n_passes; ++pi) {
                 const Pass& ps = p.passes[pi];
-                mbar_wait(&acc_full, pit & 1u);
+                { PROBE_T0(); mbar_wait(&acc_full, pit & 1u); PROBE_ADD(e_acc); }
                 tc_fence_after();
                 for (int g = 0; g < ps.n_groups; ++g) {
                     for (int a = 0; a < p.n_acc; ++a) {
@@ -280,6 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
 
                         if (has_gdn) {
                             // stage 1: v = acc + bias; v^2 (bf16) -> staging as the A operand of the gamma GEMM
+                            const long long _s1 = p.dbg ? clock64() : 0;
                             for (int cc = 0; cc < n32; ++cc) {
                                 float v[32];
                                 tmem_ld32(t_acc + cc * 32, v);
@@ -302,10 +332,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                             fence_proxy_async();
                             tc_fence_before();
                             mbar_arrive(&x2_full);
-                            mbar_wait(&norm_full, git & 1u);
+                            if (p.dbg) e_s1 += clock64() - _s1;
+                            { PROBE_T0(); mbar_wait(&norm_full, git & 1u); PROBE_ADD(e_norm); }
                             tc_fence_after();
                             ++git;
                         }
+                        const long long _s2 = p.dbg ? clock64() : 0;
 
                         // stage 2: activation, then write out
                         for (int cc = 0; cc < n32 + n16rem; ++cc) {
@@ -359,6 +391,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                                 }
                             }
                         }
+                        if (p.dbg) e_s2 += clock64() - _s2;
+                        const long long _st = p.dbg ? clock64() : 0;
                         if (p.out_layout == LICOS_LAYOUT_NHWC_BF16) {
                             fence_proxy_async();
                             named_bar_sync(1, 128);
@@ -372,6 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                             }
                             named_bar_sync(1, 128);
                         }
+                        if (p.dbg) e_store += clock64() - _st;
                     }
                 }
                 tc_fence_before();
@@ -380,6 +415,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             }
         }
         if (et == 0) tma_store_wait_all();
+        if (p.dbg && et == 0) {
+            unsigned long long* d = p.dbg + blockIdx.x * 16;
+            d[DBG_EPI_ACC] = e_acc; d[DBG_EPI_S1] = e_s1; d[DBG_EPI_NORM] = e_norm; d[DBG_EPI_S2] = e_s2;
+            d[DBG_EPI_STORE] = e_store; d[DBG_EPI_TOTAL] = clock64() - t_begin;
+        }
     }
 
     tc_fence_before();
@@ -531,6 +571,8 @@ static int ew_grid(int64_t n) {
     return (int)(g < 1 ? 1 : g);
 }
 
+static unsigned long long* g_conv_probe = nullptr;
+
 static void set_tap(Slab& s, int i, int row_off, int group, int w_tap) {
     s.taps[i].row_off = (int8_t)row_off;
     s.taps[i].group = (int8_t)group;
@@ -588,6 +630,8 @@ int licos_gdn_pack(const float* beta, const float* gamma, int channels, float be
     LICOS_CUDA_OK(cudaGetLastError());
     return LICOS_OK;
 }
+
+void licos_debug_set_conv_probe(unsigned long long* device_buf) { g_conv_probe = device_buf; }
 
 int64_t licos_conv_workspace_bytes(const licos_conv_args* a) {
     if (!a) return LICOS_ERR_INVALID;
@@ -835,6 +879,7 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     const int64_t tiles = (int64_t)a->batch * p.tiles_h * p.tiles_w * p.n_split;
     if (tiles > 0x7fffffff) return LICOS_ERR_UNSUPPORTED;
     p.total_tiles = (int)tiles;
+    p.dbg = g_conv_probe;
 
     int sms = a->sm_count;
     if (sms <= 0) {

@@ -157,6 +157,8 @@ def eb_forward_eval(ebp: EbPacked, x: torch.Tensor):
         raise ValueError("channel mismatch")
     hw = x.numel() // max(B * C, 1)
     y_hat, lik = torch.empty_like(x), torch.empty_like(x)
+    if x.numel() == 0:
+        return y_hat, lik
     lut = torch.empty(int(lib.licos_eb_lut_floats(C)), dtype=torch.float32, device=x.device)
     check(lib.licos_eb_forward_eval(ctypes.byref(ebp.p), x.data_ptr(), B, hw, lut.data_ptr(), y_hat.data_ptr(),
                                     lik.data_ptr(), _stream()), "eb_forward_eval")
@@ -170,6 +172,8 @@ def eb_forward_noise(ebp: EbPacked, x: torch.Tensor, noise: Optional[torch.Tenso
         raise ValueError("channel mismatch")
     hw = x.numel() // max(B * C, 1)
     y_hat, lik = torch.empty_like(x), torch.empty_like(x)
+    if x.numel() == 0:
+        return y_hat, lik
     check(lib.licos_eb_forward_noise(ctypes.byref(ebp.p), x.data_ptr(), _ptr(noise), seed & (2 ** 64 - 1), B, hw,
                                      y_hat.data_ptr(), lik.data_ptr(), _stream()), "eb_forward_noise")
     return y_hat, lik
@@ -181,6 +185,8 @@ def eb_symbols(x: torch.Tensor, medians: torch.Tensor, want_indexes: bool = Fals
     hw = x.numel() // max(B * C, 1)
     sym = torch.empty(x.shape, dtype=torch.int32, device=x.device)
     idx = torch.empty(x.shape, dtype=torch.int32, device=x.device) if want_indexes else None
+    if x.numel() == 0:
+        return (sym, idx) if want_indexes else sym
     check(lib.licos_eb_symbols(x.data_ptr(), medians.data_ptr(), B, C, hw, sym.data_ptr(), _ptr(idx), _stream()),
           "eb_symbols")
     return (sym, idx) if want_indexes else sym
@@ -193,6 +199,8 @@ def eb_dequantize(sym: torch.Tensor, medians: torch.Tensor) -> torch.Tensor:
     B, C = sym.shape[0], sym.shape[1]
     hw = sym.numel() // max(B * C, 1)
     out = torch.empty(sym.shape, dtype=torch.float32, device=sym.device)
+    if sym.numel() == 0:
+        return out
     check(lib.licos_eb_dequantize(sym.data_ptr(), medians.data_ptr(), B, C, hw, out.data_ptr(), _stream()),
           "eb_dequantize")
     return out
@@ -208,6 +216,8 @@ def gc_forward(y, scales, means=None, noise=None, *, training=False, scale_bound
     if scales.shape != y.shape or (means is not None and means.shape != y.shape):
         raise ValueError("scales / means must have the shape of the input")
     y_hat, lik = torch.empty_like(y), torch.empty_like(y)
+    if y.numel() == 0:
+        return y_hat, lik
     check(lib.licos_gc_forward(y.data_ptr(), scales.data_ptr(), _ptr(means), _ptr(noise), seed & (2 ** 64 - 1),
                                y.numel(), int(training), scale_bound, likelihood_bound, y_hat.data_ptr(),
                                lik.data_ptr(), _stream()), "gc_forward")

@@ -18,10 +18,14 @@ LIK_TOL = 1e-6
 
 
 def _pair(in_ch, device):
-    torch.manual_seed(42)
-    net = L.get_model("bmshj2018-factorized", False, in_ch, 1)
+    torch.manual_seed(42)  # same construction order as tests/golden/make_golden.py (no surgery for RGB)
+    if in_ch == 3:
+        net = L.image_models["bmshj2018-factorized"](quality=1, pretrained=False)
+        ref = R.image_models["bmshj2018-factorized"](quality=1)
+    else:
+        net = L.get_model("bmshj2018-factorized", False, in_ch, 1)
+        ref = R.get_model("bmshj2018-factorized", False, in_ch, 1)
     synth.condition_weights(net)
-    ref = R.get_model("bmshj2018-factorized", False, in_ch, 1)
     ref.load_state_dict(net.state_dict())
     return net.to(device).eval(), ref.eval()
 
@@ -92,7 +96,7 @@ def test_gaussian_conditional_matches_golden_and_oracle(cuda):
     z = np.load(os.path.join(GOLD, "hyperprior_rgb.npz"))
     gc = L.GaussianConditional(None)
     gc.update_scale_table(L.get_scale_table())
-    gc = gc.to(cuda)
+    gc = gc.to(cuda).eval()
     assert np.array_equal(gc._quantized_cdf[0, :5].cpu().numpy(), z["gc_cdf_row0"])
     y, s = torch.from_numpy(z["y"]).to(cuda), torch.from_numpy(z["scales"]).to(cuda)
     with torch.no_grad():
@@ -102,7 +106,7 @@ def test_gaussian_conditional_matches_golden_and_oracle(cuda):
     assert np.array_equal(y_hat.cpu().numpy(), z["y_hat"])
     assert np.abs(lik.cpu().numpy() - z["y_lik"]).max() <= LIK_TOL
     # sigma exactly on table entries, both clamps, means, given noise
-    rgc = R.GaussianConditional(None)
+    rgc = R.GaussianConditional(None).eval()
     rgc.update_scale_table(R.get_scale_table())
     t = rgc.scale_table
     s2 = torch.cat([t, t * (1 + 1e-6), t * (1 - 1e-6), torch.tensor([0.0, 0.05, 0.11, 1e3, 1e6])]).reshape(1, 1, -1, 1)

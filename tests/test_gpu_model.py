@@ -101,7 +101,7 @@ def test_factorized_integer_path_bit_exact_and_strings(cuda):
 
 
 def test_hyperprior_forward_compress_vs_oracle(cuda):
-    for q, hw in ((1, (128, 128)), (6, (64, 192))):
+    for q, hw in ((1, (256, 256)), (6, (128, 192))):
         net, ref = _models("bmshj2018-hyperprior", 3, q, cuda)
         g = torch.Generator().manual_seed(12)
         x = torch.rand(2, 3, *hw, generator=g)
