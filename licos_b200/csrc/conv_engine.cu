@@ -35,6 +35,7 @@ constexpr uint32_t kRowBytes = kTileW * kKChunk * 2;  // one slab row: 2 KB
 constexpr int kThreads = 256;
 constexpr int kMaxSA = 4, kMaxSB = 8;
 constexpr uint32_t kTmemCols = 512;
+constexpr int kMaxDynSmem = 228000;  // 227 KB opt-in limit minus ~3.4 KB of static shared memory
 
 struct Tap {
     int8_t row_off;  // slab row of the tile's first row for this tap
@@ -105,11 +106,23 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) 
     return t;
 }
 
+// ring cursor: slot index + phase bit, advanced without integer division
+struct Ring {
+    uint32_t slot = 0, phase = 0;
+    __device__ __forceinline__ void advance(uint32_t n) {
+        if (++slot == n) { slot = 0; phase ^= 1u; }
+    }
+};
+
+template <int EPI, bool OUT_NHWC>
 __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+    constexpr bool kGdn = (EPI == LICOS_EPI_GDN || EPI == LICOS_EPI_IGDN);
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], b_full[kMaxSB], b_empty[kMaxSB];
     __shared__ uint64_t acc_full, acc_empty, x2_full, norm_full;
     __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float bias_s[512];
+    __shared__ __align__(16) float beta_s[256];
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -119,7 +132,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const bool has_gdn = (p.epilogue == LICOS_EPI_GDN || p.epilogue == LICOS_EPI_IGDN);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.sa; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
@@ -130,6 +142,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         mbar_init(&norm_full, 1);
         mbar_fence_init();
     }
+    for (int i = threadIdx.x; i < p.N * p.n_split; i += kThreads) bias_s[i] = (p.bias && i < p.out_c) ? p.bias[i] : 0.f;
+    if (kGdn)
+        for (int i = threadIdx.x; i < p.N; i += kThreads) beta_s[i] = p.beta[i];
     if (warp == 2) {
         tmem_alloc(&tmem_base_smem, kTmemCols);
         tmem_relinquish();
@@ -142,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     if (warp == 0 && lane == 0) {
         // ===================== A producer =====================
         for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.in_maps[i]);
-        uint32_t it = 0;
+        Ring ra;
         long long w_wait = 0;
         const long long t_begin = p.dbg ? clock64() : 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -152,12 +167,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                 for (int c = 0; c < p.cin_chunks; ++c) {
                     for (int s = 0; s < ps.n_slabs; ++s) {
                         const Slab& sl = ps.slabs[s];
-                        const uint32_t slot = it % p.sa, ph = (it / p.sa) & 1u;
-                        { PROBE_T0(); mbar_wait(&a_empty[slot], ph ^ 1u); PROBE_ADD(w_wait); }
-                        mbar_arrive_expect_tx(&a_full[slot], p.a_slot_bytes);
-                        tma_load_4d(a_ring + (size_t)slot * p.a_slot_bytes, &p.in_maps[sl.in_map], &a_full[slot],
+                        { PROBE_T0(); mbar_wait(&a_empty[ra.slot], ra.phase ^ 1u); PROBE_ADD(w_wait); }
+                        mbar_arrive_expect_tx(&a_full[ra.slot], p.a_slot_bytes);
+                        tma_load_4d(a_ring + (size_t)ra.slot * p.a_slot_bytes, &p.in_maps[sl.in_map], &a_full[ra.slot],
                                     c * kKChunk, t.gw0 + sl.dw, t.gh0 - 1, t.b);
-                        ++it;
+                        ra.advance(p.sa);
                     }
                 }
             }
@@ -169,8 +183,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     } else if (warp == 1 && lane == 0) {
         // ===================== B producer =====================
         tma_prefetch_desc(&p.w_map);
-        if (has_gdn) tma_prefetch_desc(&p.g_map);
-        uint32_t it = 0;
+        if (kGdn) tma_prefetch_desc(&p.g_map);
+        Ring rb;
         long long w_wait = 0;
         const long long t_begin = p.dbg ? clock64() : 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -181,23 +195,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                     for (int s = 0; s < ps.n_slabs; ++s) {
                         const Slab& sl = ps.slabs[s];
                         for (int k = 0; k < sl.n_taps; ++k) {
-                            const uint32_t slot = it % p.sb, ph = (it / p.sb) & 1u;
-                            { PROBE_T0(); mbar_wait(&b_empty[slot], ph ^ 1u); PROBE_ADD(w_wait); }
-                            mbar_arrive_expect_tx(&b_full[slot], p.b_slot_bytes);
-                            tma_load_2d(b_ring + (size_t)slot * p.b_slot_bytes, &p.w_map, &b_full[slot], c * kKChunk,
+                            { PROBE_T0(); mbar_wait(&b_empty[rb.slot], rb.phase ^ 1u); PROBE_ADD(w_wait); }
+                            mbar_arrive_expect_tx(&b_full[rb.slot], p.b_slot_bytes);
+                            tma_load_2d(b_ring + (size_t)rb.slot * p.b_slot_bytes, &p.w_map, &b_full[rb.slot], c * kKChunk,
                                         sl.taps[k].w_tap * p.w_rows_per_tap + t.ns * p.N);
-                            ++it;
+                            rb.advance(p.sb);
                         }
                     }
                 }
-                if (has_gdn) {
+                if (kGdn) {
                     for (int g = 0; g < ps.n_groups * p.n_acc; ++g) {
                         for (int gc = 0; gc < p.N / kKChunk; ++gc) {
-                            const uint32_t slot = it % p.sb, ph = (it / p.sb) & 1u;
-                            mbar_wait(&b_empty[slot], ph ^ 1u);
-                            mbar_arrive_expect_tx(&b_full[slot], p.b_slot_bytes);
-                            tma_load_2d(b_ring + (size_t)slot * p.b_slot_bytes, &p.g_map, &b_full[slot], gc * kKChunk, 0);
-                            ++it;
+                            { PROBE_T0(); mbar_wait(&b_empty[rb.slot], rb.phase ^ 1u); PROBE_ADD(w_wait); }
+                            mbar_arrive_expect_tx(&b_full[rb.slot], p.b_slot_bytes);
+                            tma_load_2d(b_ring + (size_t)rb.slot * p.b_slot_bytes, &p.g_map, &b_full[rb.slot], gc * kKChunk, 0);
+                            rb.advance(p.sb);
                         }
                     }
                 }
@@ -209,10 +221,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         }
     } else if (warp == 2 && lane == 0) {
         // ===================== MMA issuer =====================
+        // One thread issues everything, so the code between two tcgen05.mma must stay well under the
+        // 64 cycles an M128 x N128 x K16 MMA occupies the tensor pipe: descriptors are built once per
+        // tile and advanced by adding to their low word.
         const uint32_t idesc = umma_idesc_bf16(128, p.N);
-        const uint32_t a_ring_addr = smem_u32(a_ring), b_ring_addr = smem_u32(b_ring);
-        const uint32_t staging_addr = smem_u32(staging);
-        uint32_t ita = 0, itb = 0, pit = 0, git = 0;
+        const uint64_t desc_hi = umma_desc_sw128(0);
+        const uint32_t a_ring_addr = smem_u32(a_ring) >> 4, b_ring_addr = smem_u32(b_ring) >> 4;
+        const uint32_t staging_addr = smem_u32(staging) >> 4;
+        const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_slot16 = p.b_slot_bytes >> 4;
+        const uint32_t n_acc = p.n_acc, N = p.N;
+        Ring ra, rb;
+        uint32_t pit = 0, git = 0;
         long long w_a = 0, w_b = 0, w_acc = 0, w_x2 = 0, n_tiles = 0;
         const long long t_begin = p.dbg ? clock64() : 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -225,52 +244,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                 for (int c = 0; c < p.cin_chunks; ++c) {
                     for (int s = 0; s < ps.n_slabs; ++s) {
                         const Slab& sl = ps.slabs[s];
-                        const uint32_t sa_slot = ita % p.sa;
-                        { PROBE_T0(); mbar_wait(&a_full[sa_slot], (ita / p.sa) & 1u); PROBE_ADD(w_a); }
-                        const uint32_t a_slab = a_ring_addr + sa_slot * p.a_slot_bytes;
-                        for (int k = 0; k < sl.n_taps; ++k) {
+                        { PROBE_T0(); mbar_wait(&a_full[ra.slot], ra.phase); PROBE_ADD(w_a); }
+                        const uint32_t a_slab = a_ring_addr + ra.slot * a_slot16;
+                        const int n_taps = sl.n_taps;
+                        for (int k = 0; k < n_taps; ++k) {
                             const Tap tp = sl.taps[k];
-                            const uint32_t sb_slot = itb % p.sb;
-                            { PROBE_T0(); mbar_wait(&b_full[sb_slot], (itb / p.sb) & 1u); PROBE_ADD(w_b); }
+                            { PROBE_T0(); mbar_wait(&b_full[rb.slot], rb.phase); PROBE_ADD(w_b); }
                             tc_fence_after();
-                            const uint32_t b_tile = b_ring_addr + sb_slot * p.b_slot_bytes;
-                            for (int a = 0; a < p.n_acc; ++a) {
-                                const uint32_t acc = (uint32_t)tp.group * p.n_acc + a;
-                                const uint32_t d = tmem_base + acc * p.N;
-                                const uint32_t a_tile = a_slab + (uint32_t)(tp.row_off + a * kAccRows) * kRowBytes;
-#pragma unroll
-                                for (int kk = 0; kk < kKChunk / 16; ++kk) {
-                                    umma_bf16(d, umma_desc_sw128(a_tile + kk * 32), umma_desc_sw128(b_tile + kk * 32),
-                                              idesc, ((touched >> acc) & 1u) | (uint32_t)(kk > 0));
-                                }
+                            const uint64_t bd = desc_hi | (uint64_t)(b_ring_addr + rb.slot * b_slot16);
+                            uint64_t ad = desc_hi | (uint64_t)(a_slab + (uint32_t)tp.row_off * (kRowBytes >> 4));
+                            uint32_t acc = (uint32_t)tp.group * n_acc;
+                            for (uint32_t a = 0; a < n_acc; ++a, ++acc, ad += (kAccRows * kRowBytes) >> 4) {
+                                const uint32_t d = tmem_base + acc * N;
+                                umma_bf16(d, ad, bd, idesc, (touched >> acc) & 1u);
+                                umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+                                umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
+                                umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
                                 touched |= 1u << acc;
                             }
-                            umma_commit(&b_empty[sb_slot]);
-                            ++itb;
+                            umma_commit(&b_empty[rb.slot]);
+                            rb.advance(p.sb);
                         }
-                        umma_commit(&a_empty[sa_slot]);
-                        ++ita;
+                        umma_commit(&a_empty[ra.slot]);
+                        ra.advance(p.sa);
                     }
                 }
                 umma_commit(&acc_full);
-                if (has_gdn) {
-                    const uint32_t d = tmem_base + (uint32_t)(ps.n_groups * p.n_acc) * p.N;
-                    for (int g = 0; g < ps.n_groups * p.n_acc; ++g) {
+                if (kGdn) {
+                    const uint32_t d = tmem_base + (uint32_t)(ps.n_groups * n_acc) * N;
+                    for (int g = 0; g < ps.n_groups * (int)n_acc; ++g) {
                         { PROBE_T0(); mbar_wait(&x2_full, git & 1u); PROBE_ADD(w_x2); }
                         tc_fence_after();
-                        for (int gc = 0; gc < p.N / kKChunk; ++gc) {
-                            const uint32_t sb_slot = itb % p.sb;
-                            { PROBE_T0(); mbar_wait(&b_full[sb_slot], (itb / p.sb) & 1u); PROBE_ADD(w_b); }
+                        for (uint32_t gc = 0; gc < N / kKChunk; ++gc) {
+                            { PROBE_T0(); mbar_wait(&b_full[rb.slot], rb.phase); PROBE_ADD(w_b); }
                             tc_fence_after();
-                            const uint32_t b_tile = b_ring_addr + sb_slot * p.b_slot_bytes;
-                            const uint32_t a_tile = staging_addr + gc * (128 * 128);
-#pragma unroll
-                            for (int kk = 0; kk < kKChunk / 16; ++kk) {
-                                umma_bf16(d, umma_desc_sw128(a_tile + kk * 32), umma_desc_sw128(b_tile + kk * 32), idesc,
-                                          (uint32_t)((gc | kk) > 0));
-                            }
-                            umma_commit(&b_empty[sb_slot]);
-                            ++itb;
+                            const uint64_t bd = desc_hi | (uint64_t)(b_ring_addr + rb.slot * b_slot16);
+                            const uint64_t ad = desc_hi | (uint64_t)(staging_addr + gc * ((128 * 128) >> 4));
+                            umma_bf16(d, ad, bd, idesc, (uint32_t)(gc > 0));
+                            umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+                            umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
+                            umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
+                            umma_commit(&b_empty[rb.slot]);
+                            rb.advance(p.sb);
                         }
                         umma_commit(&norm_full);
                         ++git;
@@ -290,11 +305,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         const uint32_t lane_sel = ((uint32_t)(warp & 3) * 32u) << 16;
         const int th = et / kTileW, tw = et % kTileW;
         uint32_t pit = 0, git = 0;
-        const int n32 = p.N / 32, n16rem = (p.N % 32) / 16;
+        const int n32 = p.N / 32;
         long long e_acc = 0, e_s1 = 0, e_norm = 0, e_s2 = 0, e_store = 0;
         const long long t_begin = p.dbg ? clock64() : 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const TileCoord t = decode_tile(p, tile);
+            const float* bias_t = bias_s + t.ns * p.N;
             for (int pi = 0; pi < p.n_passes; ++pi) {
                 const Pass& ps = p.passes[pi];
                 { PROBE_T0(); mbar_wait(&acc_full, pit & 1u); PROBE_ADD(e_acc); }
@@ -304,22 +320,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                         const uint32_t acc = (uint32_t)g * p.n_acc + a;
                         const uint32_t t_acc = tmem_base + lane_sel + acc * p.N;
                         const uint32_t t_norm = tmem_base + lane_sel + (uint32_t)(ps.n_groups * p.n_acc) * p.N;
-                        const int gh = t.gh0 + a * kAccRows + th, gw = t.gw0 + tw;
-                        const int c_base = t.ns * p.N;
 
-                        if (has_gdn) {
+                        if (OUT_NHWC || kGdn) {
+                            // the previous TMA store must have finished reading `staging` before it is rewritten
+                            const long long _st = p.dbg ? clock64() : 0;
+                            if (OUT_NHWC && et == 0) tma_store_wait_read();
+                            if (OUT_NHWC) named_bar_sync(1, 128);
+                            if (p.dbg) e_store += clock64() - _st;
+                        }
+                        if (kGdn) {
                             // stage 1: v = acc + bias; v^2 (bf16) -> staging as the A operand of the gamma GEMM
                             const long long _s1 = p.dbg ? clock64() : 0;
                             for (int cc = 0; cc < n32; ++cc) {
                                 float v[32];
                                 tmem_ld32(t_acc + cc * 32, v);
                                 tmem_ld_wait();
+                                const float4* b4 = reinterpret_cast<const float4*>(bias_t + cc * 32);
                                 uint32_t pk[16];
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    const float x0 = v[2 * j] + __ldg(p.bias + c_base + cc * 32 + 2 * j);
-                                    const float x1 = v[2 * j + 1] + __ldg(p.bias + c_base + cc * 32 + 2 * j + 1);
-                                    pk[j] = pack_bf16x2(x0 * x0, x1 * x1);
+                                for (int q = 0; q < 8; ++q) {
+                                    const float4 b = b4[q];
+                                    const float x0 = v[4 * q] + b.x, x1 = v[4 * q + 1] + b.y;
+                                    const float x2 = v[4 * q + 2] + b.z, x3 = v[4 * q + 3] + b.w;
+                                    pk[2 * q] = pack_bf16x2(x0 * x0, x1 * x1);
+                                    pk[2 * q + 1] = pack_bf16x2(x2 * x2, x3 * x3);
                                 }
                                 uint8_t* atom = staging + (size_t)((cc * 32) / kKChunk) * (128 * 128);
                                 const uint32_t chunk0 = ((cc * 32) % kKChunk) / 8;
@@ -337,39 +361,46 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                             tc_fence_after();
                             ++git;
                         }
-                        const long long _s2 = p.dbg ? clock64() : 0;
 
                         // stage 2: activation, then write out
-                        for (int cc = 0; cc < n32 + n16rem; ++cc) {
+                        const long long _s2 = p.dbg ? clock64() : 0;
+                        const int gh = t.gh0 + a * kAccRows + th, gw = t.gw0 + tw;
+                        const int oh = gh * p.out_s + ps.dy[g], ow = gw * p.out_s + ps.dx[g];
+                        const bool in_range = gh < p.grid_h && gw < p.grid_w && oh < p.out_h && ow < p.out_w;
+                        const size_t cs = (size_t)p.out_h * p.out_w;
+                        float* o = OUT_NHWC ? nullptr
+                                            : p.out_f32 + ((size_t)t.b * p.out_c * p.out_h + oh) * p.out_w + ow +
+                                                  (size_t)(t.ns * p.N) * cs;
+                        const int c_left = p.out_c - t.ns * p.N;  // valid channels from this split's base
+                        for (int cc = 0; cc < n32; ++cc) {
                             float v[32];
-                            const bool half = (cc == n32);  // trailing 16 columns (N % 32 == 16)
-                            if (!half) {
-                                tmem_ld32(t_acc + cc * 32, v);
-                            } else {
-                                float h16[16];
-                                tmem_ld16(t_acc + cc * 32, h16);
-                                tmem_ld_wait();
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) { v[j] = h16[j]; v[16 + j] = 0.f; }
-                            }
+                            tmem_ld32(t_acc + cc * 32, v);
                             float nrm[32];
-                            if (has_gdn) tmem_ld32(t_norm + cc * 32, nrm);
+                            if (kGdn) tmem_ld32(t_norm + cc * 32, nrm);
                             tmem_ld_wait();
-                            const int ncols = half ? 16 : 32;
+                            const float4* b4 = reinterpret_cast<const float4*>(bias_t + cc * 32);
+                            const float4* e4 = reinterpret_cast<const float4*>(beta_s + cc * 32);
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const int c = c_base + cc * 32 + j;
-                                float x = v[j];
-                                if (j < ncols && c < p.out_c && p.bias) x += __ldg(p.bias + c);
-                                if (has_gdn) {
-                                    const float d = nrm[j] + __ldg(p.beta + c);
-                                    x = (p.epilogue == LICOS_EPI_GDN) ? x * rsqrtf(d) : x * sqrtf(d);
-                                } else if (p.epilogue == LICOS_EPI_RELU) {
-                                    x = fmaxf(x, 0.f);
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 b = b4[q];
+                                float x[4] = {v[4 * q] + b.x, v[4 * q + 1] + b.y, v[4 * q + 2] + b.z, v[4 * q + 3] + b.w};
+                                if (kGdn) {
+                                    const float4 e = e4[q];
+                                    const float d[4] = {nrm[4 * q] + e.x, nrm[4 * q + 1] + e.y, nrm[4 * q + 2] + e.z,
+                                                        nrm[4 * q + 3] + e.w};
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) {
+                                        const float r = rsqrtf(d[i]);
+                                        x[i] *= (EPI == LICOS_EPI_GDN) ? r : d[i] * r;  // d * rsqrt(d) = sqrt(d), d > 0
+                                    }
+                                } else if (EPI == LICOS_EPI_RELU) {
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) x[i] = fmaxf(x[i], 0.f);
                                 }
-                                v[j] = x;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) v[4 * q + i] = x[i];
                             }
-                            if (p.out_layout == LICOS_LAYOUT_NHWC_BF16) {
+                            if (OUT_NHWC) {
                                 uint8_t* atom = staging + (size_t)((cc * 32) / kKChunk) * (128 * 128);
                                 const uint32_t chunk0 = ((cc * 32) % kKChunk) / 8;
 #pragma unroll
@@ -378,22 +409,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                                         make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
                                                    pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
                                 }
-                            } else {
-                                const int oh = gh * p.out_s + ps.dy[g], ow = gw * p.out_s + ps.dx[g];
-                                if (gh < p.grid_h && gw < p.grid_w && oh < p.out_h && ow < p.out_w) {
-                                    float* o = p.out_f32 + ((size_t)t.b * p.out_c * p.out_h + oh) * p.out_w + ow;
-                                    const size_t cs = (size_t)p.out_h * p.out_w;
+                            } else if (in_range) {
 #pragma unroll
-                                    for (int j = 0; j < 32; ++j) {
-                                        const int c = c_base + cc * 32 + j;
-                                        if (j < ncols && c < p.out_c) o[(size_t)c * cs] = v[j];
-                                    }
-                                }
+                                for (int j = 0; j < 32; ++j)
+                                    if (cc * 32 + j < c_left) o[(size_t)(cc * 32 + j) * cs] = v[j];
+                            }
+                        }
+                        if (!OUT_NHWC && (p.N & 16)) {  // trailing 16 columns (N % 32 == 16); never a GDN layer
+                            float h[16];
+                            tmem_ld16(t_acc + n32 * 32, h);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                float x = h[j] + bias_t[n32 * 32 + j];
+                                if (EPI == LICOS_EPI_RELU) x = fmaxf(x, 0.f);
+                                if (in_range && n32 * 32 + j < c_left) o[(size_t)(n32 * 32 + j) * cs] = x;
                             }
                         }
                         if (p.dbg) e_s2 += clock64() - _s2;
-                        const long long _st = p.dbg ? clock64() : 0;
-                        if (p.out_layout == LICOS_LAYOUT_NHWC_BF16) {
+                        if (OUT_NHWC) {
+                            const long long _st = p.dbg ? clock64() : 0;
                             fence_proxy_async();
                             named_bar_sync(1, 128);
                             if (et == 0) {
@@ -402,11 +437,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                                                  at * kKChunk, t.gw0, t.gh0 + a * kAccRows, t.b);
                                 }
                                 tma_store_commit();
-                                tma_store_wait_read();
                             }
-                            named_bar_sync(1, 128);
+                            if (p.dbg) e_store += clock64() - _st;
                         }
-                        if (p.dbg) e_store += clock64() - _st;
                     }
                 }
                 tc_fence_before();
@@ -654,6 +687,7 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     memset(&p, 0, sizeof(p));
 
     const NPlan pl = plan_n(a->out_c);
+    if (pl.rows > 512) return LICOS_ERR_UNSUPPORTED;  // bias staging holds 512 channels
     p.N = pl.N;
     p.n_split = pl.n_split;
     p.w_rows_per_tap = pl.rows;
@@ -860,7 +894,7 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     p.b_slot_bytes = (uint32_t)pl.N * 128u;
     p.staging_bytes = (gdn || a->out_layout == LICOS_LAYOUT_NHWC_BF16) ? (uint32_t)(pl.N / kKChunk) * 128u * 128u : 0u;
     const int64_t b_slot_al = p.b_slot_bytes;  // N is a multiple of 16, so N*128 is a multiple of 2 KB
-    const int64_t budget = 230000 - 1024 - (int64_t)p.staging_bytes;
+    const int64_t budget = kMaxDynSmem - 1024 - (int64_t)p.staging_bytes;
     int sb = 4;
     int sa = (int)((budget - (int64_t)sb * b_slot_al) / p.a_slot_bytes);
     if (sa > kMaxSA) sa = kMaxSA;
@@ -887,15 +921,31 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
         LICOS_CUDA_OK(cudaGetDevice(&dev));
         LICOS_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    static std::once_flag attr_once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(attr_once, []() {
-        attr_err = cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 231000);
-    });
-    LICOS_CUDA_OK(attr_err);
     const int grid = (int)(tiles < sms ? tiles : sms);
-    conv_igemm_kernel<<<grid, kThreads, smem_bytes, s>>>(p);
-    LICOS_CUDA_OK(cudaGetLastError());
+    const bool nhwc = a->out_layout == LICOS_LAYOUT_NHWC_BF16;
+    cudaError_t err = cudaErrorInvalidValue;
+#define LICOS_LAUNCH(E, O)                                                                              \
+    do {                                                                                                \
+        static cudaError_t attr = cudaFuncSetAttribute(conv_igemm_kernel<E, O>,                         \
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                                       kMaxDynSmem);                                    \
+        if (attr != cudaSuccess) { err = attr; break; }                                                 \
+        conv_igemm_kernel<E, O><<<grid, kThreads, smem_bytes, s>>>(p);                                  \
+        err = cudaGetLastError();                                                                       \
+    } while (0)
+    switch (a->epilogue * 2 + (nhwc ? 1 : 0)) {
+        case LICOS_EPI_NONE * 2 + 0: LICOS_LAUNCH(LICOS_EPI_NONE, false); break;
+        case LICOS_EPI_NONE * 2 + 1: LICOS_LAUNCH(LICOS_EPI_NONE, true); break;
+        case LICOS_EPI_GDN * 2 + 0: LICOS_LAUNCH(LICOS_EPI_GDN, false); break;
+        case LICOS_EPI_GDN * 2 + 1: LICOS_LAUNCH(LICOS_EPI_GDN, true); break;
+        case LICOS_EPI_IGDN * 2 + 0: LICOS_LAUNCH(LICOS_EPI_IGDN, false); break;
+        case LICOS_EPI_IGDN * 2 + 1: LICOS_LAUNCH(LICOS_EPI_IGDN, true); break;
+        case LICOS_EPI_RELU * 2 + 0: LICOS_LAUNCH(LICOS_EPI_RELU, false); break;
+        case LICOS_EPI_RELU * 2 + 1: LICOS_LAUNCH(LICOS_EPI_RELU, true); break;
+        default: return LICOS_ERR_INVALID;
+    }
+#undef LICOS_LAUNCH
+    LICOS_CUDA_OK(err);
     return LICOS_OK;
 }
 
