@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     constexpr bool kGdn = (EPI == LICOS_EPI_GDN || EPI == LICOS_EPI_IGDN);
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], b_full[kMaxSB], b_empty[kMaxSB];
-    __shared__ uint64_t acc_full, acc_empty, x2_full, norm_full;
+    __shared__ uint64_t acc_full, acc_empty, x2_full[2], norm_full[2];
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float bias_s[512];
     __shared__ __align__(16) float beta_s[256];
@@ -133,13 +133,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    // Two MMA-issuing threads (one per accumulator sub-tile) when the tile has two sub-tiles: an mbarrier
+    // wait costs the issuing thread ~85 cycles even when already complete and tcgen05.mma cannot be queued far
+    // ahead, so a single issuer leaves the tensor pipe idle at every tap boundary; with two independent
+    // issue streams one thread's wait hides behind the other's MMAs.
+    const uint32_t n_iss = (p.n_acc == 2) ? 2u : 1u;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < p.sa; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < p.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        mbar_init(&acc_full, 1);
+        for (int i = 0; i < p.sa; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], n_iss); }
+        for (int i = 0; i < p.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], n_iss); }
+        mbar_init(&acc_full, n_iss);
         mbar_init(&acc_empty, 128);
-        mbar_init(&x2_full, 128);
-        mbar_init(&norm_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&x2_full[i], 128); mbar_init(&norm_full[i], 1); }
         mbar_fence_init();
     }
     for (int i = threadIdx.x; i < p.N * p.n_split; i += kThreads) bias_s[i] = (p.bias && i < p.out_c) ? p.bias[i] : 0.f;
@@ -203,14 +207,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                         }
                     }
                 }
-                if (kGdn) {
-                    for (int g = 0; g < ps.n_groups * p.n_acc; ++g) {
-                        for (int gc = 0; gc < p.N / kKChunk; ++gc) {
-                            { PROBE_T0(); mbar_wait(&b_empty[rb.slot], rb.phase ^ 1u); PROBE_ADD(w_wait); }
-                            mbar_arrive_expect_tx(&b_full[rb.slot], p.b_slot_bytes);
-                            tma_load_2d(b_ring + (size_t)rb.slot * p.b_slot_bytes, &p.g_map, &b_full[rb.slot], gc * kKChunk, 0);
-                            rb.advance(p.sb);
-                        }
+                if (kGdn) {  // gamma tiles, once per pass: every issuer reads them for its own sub-tile
+                    for (int gc = 0; gc < p.N / kKChunk; ++gc) {
+                        { PROBE_T0(); mbar_wait(&b_empty[rb.slot], rb.phase ^ 1u); PROBE_ADD(w_wait); }
+                        mbar_arrive_expect_tx(&b_full[rb.slot], p.b_slot_bytes);
+                        tma_load_2d(b_ring + (size_t)rb.slot * p.b_slot_bytes, &p.g_map, &b_full[rb.slot], gc * kKChunk, 0);
+                        rb.advance(p.sb);
                     }
                 }
             }
@@ -219,8 +221,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             p.dbg[blockIdx.x * 16 + DBG_PB_WAIT] = w_wait;
             p.dbg[blockIdx.x * 16 + DBG_PB_TOTAL] = clock64() - t_begin;
         }
-    } else if (warp == 2 && lane == 0) {
-        // ===================== MMA issuer =====================
+    } else if ((warp == 2 || (warp == 3 && n_iss == 2)) && lane == 0) {
+        // ===================== MMA issuer(s) =====================
+        const uint32_t iss = (uint32_t)warp - 2u;
         // One thread issues everything, so the code between two tcgen05.mma must stay well under the
         // 64 cycles an M128 x N128 x K16 MMA occupies the tensor pipe: descriptors are built once per
         // tile and advanced by adding to their low word.
@@ -230,8 +233,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         const uint32_t staging_addr = smem_u32(staging) >> 4;
         const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_slot16 = p.b_slot_bytes >> 4;
         const uint32_t n_acc = p.n_acc, N = p.N;
+        const uint32_t my_accs = (n_iss == 2) ? 1u : n_acc;  // accumulators of a group this thread drives
         Ring ra, rb;
-        uint32_t pit = 0, git = 0;
+        uint32_t pit = 0;
         long long w_a = 0, w_b = 0, w_acc = 0, w_x2 = 0, n_tiles = 0;
         const long long t_begin = p.dbg ? clock64() : 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -252,9 +256,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                             { PROBE_T0(); mbar_wait(&b_full[rb.slot], rb.phase); PROBE_ADD(w_b); }
                             tc_fence_after();
                             const uint64_t bd = desc_hi | (uint64_t)(b_ring_addr + rb.slot * b_slot16);
-                            uint64_t ad = desc_hi | (uint64_t)(a_slab + (uint32_t)tp.row_off * (kRowBytes >> 4));
-                            uint32_t acc = (uint32_t)tp.group * n_acc;
-                            for (uint32_t a = 0; a < n_acc; ++a, ++acc, ad += (kAccRows * kRowBytes) >> 4) {
+                            uint64_t ad = desc_hi | (uint64_t)(a_slab + ((uint32_t)tp.row_off + iss * kAccRows) * (kRowBytes >> 4));
+                            uint32_t acc = (uint32_t)tp.group * n_acc + iss;
+                            for (uint32_t a = 0; a < my_accs; ++a, ++acc, ad += (kAccRows * kRowBytes) >> 4) {
                                 const uint32_t d = tmem_base + acc * N;
                                 umma_bf16(d, ad, bd, idesc, (touched >> acc) & 1u);
                                 umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
@@ -270,31 +274,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                     }
                 }
                 umma_commit(&acc_full);
-                if (kGdn) {
-                    const uint32_t d = tmem_base + (uint32_t)(ps.n_groups * n_acc) * N;
-                    for (int g = 0; g < ps.n_groups * (int)n_acc; ++g) {
-                        { PROBE_T0(); mbar_wait(&x2_full, git & 1u); PROBE_ADD(w_x2); }
+                if (kGdn) {  // (GDN layers have one accumulator group; sub-tile `iss` is this thread's)
+                    const uint32_t d = tmem_base + n_acc * N;
+                    { PROBE_T0(); mbar_wait(&x2_full[iss], pit & 1u); PROBE_ADD(w_x2); }
+                    tc_fence_after();
+                    for (uint32_t gc = 0; gc < N / kKChunk; ++gc) {
+                        { PROBE_T0(); mbar_wait(&b_full[rb.slot], rb.phase); PROBE_ADD(w_b); }
                         tc_fence_after();
-                        for (uint32_t gc = 0; gc < N / kKChunk; ++gc) {
-                            { PROBE_T0(); mbar_wait(&b_full[rb.slot], rb.phase); PROBE_ADD(w_b); }
-                            tc_fence_after();
-                            const uint64_t bd = desc_hi | (uint64_t)(b_ring_addr + rb.slot * b_slot16);
-                            const uint64_t ad = desc_hi | (uint64_t)(staging_addr + gc * ((128 * 128) >> 4));
-                            umma_bf16(d, ad, bd, idesc, (uint32_t)(gc > 0));
-                            umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
-                            umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
-                            umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
-                            umma_commit(&b_empty[rb.slot]);
-                            rb.advance(p.sb);
-                        }
-                        umma_commit(&norm_full);
-                        ++git;
+                        const uint64_t bd = desc_hi | (uint64_t)(b_ring_addr + rb.slot * b_slot16);
+                        const uint64_t ad = desc_hi | (uint64_t)(staging_addr + gc * ((128 * 128) >> 4));
+                        umma_bf16(d, ad, bd, idesc, (uint32_t)(gc > 0));
+                        umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+                        umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
+                        umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
+                        umma_commit(&b_empty[rb.slot]);
+                        rb.advance(p.sb);
                     }
+                    umma_commit(&norm_full[iss]);
                 }
                 ++pit;
             }
         }
-        if (p.dbg) {
+        if (p.dbg && iss == 0) {
             unsigned long long* d = p.dbg + blockIdx.x * 16;
             d[DBG_MMA_A] = w_a; d[DBG_MMA_B] = w_b; d[DBG_MMA_ACC] = w_acc; d[DBG_MMA_X2] = w_x2;
             d[DBG_MMA_TOTAL] = clock64() - t_begin; d[DBG_TILES] = n_tiles;
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         const int et = threadIdx.x - 128;  // == TMEM lane == row of the 128-row sub-tile
         const uint32_t lane_sel = ((uint32_t)(warp & 3) * 32u) << 16;
         const int th = et / kTileW, tw = et % kTileW;
-        uint32_t pit = 0, git = 0;
+        uint32_t pit = 0;
         const int n32 = p.N / 32;
         long long e_acc = 0, e_s1 = 0, e_norm = 0, e_s2 = 0, e_store = 0;
         const long long t_begin = p.dbg ? clock64() : 0;
@@ -355,11 +356,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                             }
                             fence_proxy_async();
                             tc_fence_before();
-                            mbar_arrive(&x2_full);
+                            mbar_arrive(&x2_full[a]);
                             if (p.dbg) e_s1 += clock64() - _s1;
-                            { PROBE_T0(); mbar_wait(&norm_full, git & 1u); PROBE_ADD(e_norm); }
+                            { PROBE_T0(); mbar_wait(&norm_full[a], pit & 1u); PROBE_ADD(e_norm); }
                             tc_fence_after();
-                            ++git;
                         }
 
                         // stage 2: activation, then write out
