@@ -246,7 +246,8 @@ def run_b200(args):
         sync_all()
 
         sampler = ClockSampler(local)
-        sampler.start()
+        if not os.environ.get("LICOS_BENCH_NOSAMPLER"):
+            sampler.start()
         launches["n"] = 0
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         enc_ms = dec_ms = 0.0

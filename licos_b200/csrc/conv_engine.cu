@@ -18,6 +18,7 @@
 // each an ordinary tiled TMA descriptor; padding and ragged edges are TMA out-of-bounds zero fill /
 // store clipping.  Replaces SURVEY.md section 8a rows A3, A4, A5.
 #include "common.cuh"
+#include "conv_edge.cuh"
 
 #include <math.h>
 #include <mutex>
@@ -595,6 +596,13 @@ static NPlan plan_n(int out_c) {
     pl.rows = pl.N * pl.n_split;
     return pl;
 }
+// g_s[6]-style layer: ConvTranspose2d to <= 4 channels -> GEMM + gather kernel
+static bool use_narrow(int kind, int out_c, int in_c) { return kind == LICOS_DECONV_5X5_S2 && out_c <= kNarrowCpt && in_c % 64 == 0 && in_c <= 256; }
+// g_a[0]-style layer: K = 25 * C_in fits two swizzle atoms -> fused in-kernel im2col
+static bool use_first_direct(int kind, int in_c, int out_c, int out_layout) {
+    return kind == LICOS_CONV_5X5_S2 && in_c * 25 <= 128 && out_layout == LICOS_LAYOUT_NHWC_BF16 && out_c % 64 == 0 &&
+           out_c <= 256;
+}
 static int taps_of(int kind) { return kind == LICOS_CONV_3X3_S1 ? 9 : 25; }
 static int first_kpad(int in_c) { return (in_c * 25 + 63) / 64 * 64; }
 
@@ -610,6 +618,127 @@ static void set_tap(Slab& s, int i, int row_off, int group, int w_tap) {
     s.taps[i].row_off = (int8_t)row_off;
     s.taps[i].group = (int8_t)group;
     s.taps[i].w_tap = (int16_t)w_tap;
+}
+
+static int sm_count_of(const licos_conv_args* a, int* sms) {
+    *sms = a->sm_count;
+    if (*sms <= 0) {
+        int dev = 0;
+        LICOS_CUDA_OK(cudaGetDevice(&dev));
+        LICOS_CUDA_OK(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    return LICOS_OK;
+}
+
+static int launch_first(const licos_conv_args* a, cudaStream_t s) {
+    const bool gdn = (a->epilogue == LICOS_EPI_GDN || a->epilogue == LICOS_EPI_IGDN);
+    FirstParams p;
+    memset(&p, 0, sizeof(p));
+    p.x = (const float*)a->in;
+    p.bias = a->bias;
+    p.beta = a->beta;
+    p.B = a->batch; p.C = a->in_c; p.H = a->in_h; p.W = a->in_w;
+    p.OH = (a->in_h + 1) / 2; p.OW = (a->in_w + 1) / 2;
+    p.N = a->out_c; p.K = a->in_c * 25; p.k_pad = first_kpad(a->in_c);
+    p.tiles_h = (p.OH + 7) / 8; p.tiles_w = (p.OW + 15) / 16;
+    const int64_t tiles = (int64_t)a->batch * p.tiles_h * p.tiles_w;
+    if (tiles > 0x7fffffff) return LICOS_ERR_UNSUPPORTED;
+    p.total_tiles = (int)tiles;
+    const int need_cols = gdn ? 2 * p.N : p.N;
+    p.tmem_cols = need_cols <= 128 ? 128u : (need_cols <= 256 ? 256u : 512u);
+    {
+        const uint64_t dims[2] = {(uint64_t)p.k_pad, (uint64_t)p.N};
+        const uint64_t strides[1] = {(uint64_t)p.k_pad};
+        const uint32_t box[2] = {64, (uint32_t)p.N};
+        if (!make_map(&p.w_map, a->weight, 2, dims, strides, box)) return LICOS_ERR_CUDA;
+    }
+    if (gdn) {
+        const uint64_t dims[2] = {(uint64_t)p.N, (uint64_t)p.N};
+        const uint64_t strides[1] = {(uint64_t)p.N};
+        const uint32_t box[2] = {64, (uint32_t)p.N};
+        if (!make_map(&p.g_map, a->gamma, 2, dims, strides, box)) return LICOS_ERR_CUDA;
+    } else {
+        p.g_map = p.w_map;
+    }
+    {
+        const uint64_t OC = (uint64_t)p.N, OH = (uint64_t)p.OH, OW = (uint64_t)p.OW;
+        const uint64_t dims[4] = {OC, OW, OH, (uint64_t)a->batch};
+        const uint64_t strides[3] = {OC, OW * OC, OH * OW * OC};
+        const uint32_t box[4] = {64, 16, 8, 1};
+        if (!make_map(&p.out_map, a->out, 4, dims, strides, box)) return LICOS_ERR_CUDA;
+    }
+    const int k_atoms = p.k_pad / 64, n_atoms = p.N / 64;
+    const int as_atoms = k_atoms > n_atoms ? k_atoms : n_atoms;
+    const size_t smem = 1024 + (size_t)k_atoms * p.N * 128 + (gdn ? (size_t)n_atoms * p.N * 128 : 0) +
+                        (size_t)as_atoms * 128 * 128 + (size_t)p.C * kPatchRows * kPatchPitch * 4;
+    if (smem > (size_t)kMaxDynSmem) return LICOS_ERR_UNSUPPORTED;
+    int sms = 0;
+    const int rc = sm_count_of(a, &sms);
+    if (rc != LICOS_OK) return rc;
+    const int per_sm = (smem <= 113000 && p.tmem_cols <= 256) ? 2 : 1;
+    const int grid = (int)(tiles < (int64_t)sms * per_sm ? tiles : (int64_t)sms * per_sm);
+    cudaError_t err = cudaErrorInvalidValue;
+#define LICOS_LAUNCH_FIRST(E)                                                                                       \
+    do {                                                                                                            \
+        static cudaError_t attr =                                                                                   \
+            cudaFuncSetAttribute(conv_first_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);   \
+        if (attr != cudaSuccess) { err = attr; break; }                                                             \
+        conv_first_kernel<E><<<grid, kEdgeThreads, smem, s>>>(p);                                                   \
+        err = cudaGetLastError();                                                                                   \
+    } while (0)
+    switch (a->epilogue) {
+        case LICOS_EPI_NONE: LICOS_LAUNCH_FIRST(LICOS_EPI_NONE); break;
+        case LICOS_EPI_GDN: LICOS_LAUNCH_FIRST(LICOS_EPI_GDN); break;
+        case LICOS_EPI_IGDN: LICOS_LAUNCH_FIRST(LICOS_EPI_IGDN); break;
+        case LICOS_EPI_RELU: LICOS_LAUNCH_FIRST(LICOS_EPI_RELU); break;
+        default: return LICOS_ERR_INVALID;
+    }
+#undef LICOS_LAUNCH_FIRST
+    LICOS_CUDA_OK(err);
+    return LICOS_OK;
+}
+
+static int launch_narrow(const licos_conv_args* a, cudaStream_t s) {
+    NarrowParams p;
+    memset(&p, 0, sizeof(p));
+    p.out = (float*)a->out;
+    p.bias = a->bias;
+    p.B = a->batch; p.H = a->in_h; p.W = a->in_w; p.C = a->in_c; p.out_c = a->out_c;
+    p.OH = 2 * a->in_h; p.OW = 2 * a->in_w;
+    p.chunks = a->in_c / 64;
+    p.relu = a->epilogue == LICOS_EPI_RELU;
+    p.tiles_h = (a->in_h + kNarrowRows - 1) / kNarrowRows;
+    p.tiles_w = (a->in_w + kNarrowCols - 1) / kNarrowCols;
+    const int64_t tiles = (int64_t)a->batch * p.tiles_h * p.tiles_w;
+    if (tiles > 0x7fffffff) return LICOS_ERR_UNSUPPORTED;
+    p.total_tiles = (int)tiles;
+    {
+        const uint64_t C = (uint64_t)a->in_c, H = (uint64_t)a->in_h, W = (uint64_t)a->in_w;
+        const uint64_t dims[4] = {C, W, H, (uint64_t)a->batch};
+        const uint64_t strides[3] = {C, W * C, H * W * C};
+        const uint32_t box[4] = {64, 16, 8, 1};
+        if (!make_map(&p.in_map, a->in, 4, dims, strides, box)) return LICOS_ERR_CUDA;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)a->in_c, (uint64_t)kNarrowN};
+        const uint64_t strides[1] = {(uint64_t)a->in_c};
+        const uint32_t box[2] = {64, (uint32_t)kNarrowN};
+        if (!make_map(&p.w_map, a->weight, 2, dims, strides, box)) return LICOS_ERR_CUDA;
+    }
+    const size_t w_bytes = ((size_t)p.chunks * kNarrowN * 128 + 1023) & ~(size_t)1023;
+    const size_t a_bytes = (size_t)p.chunks * 128 * 128, z_bytes = (size_t)128 * kZPitch * 4;
+    const size_t smem = 1024 + w_bytes + (a_bytes > z_bytes ? a_bytes : z_bytes);
+    int sms = 0;
+    const int rc = sm_count_of(a, &sms);
+    if (rc != LICOS_OK) return rc;
+    const int per_sm = smem <= 113000 ? 2 : 1;
+    const int grid = (int)(tiles < (int64_t)sms * per_sm ? tiles : (int64_t)sms * per_sm);
+    static cudaError_t attr =
+        cudaFuncSetAttribute(deconv_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    LICOS_CUDA_OK(attr);
+    deconv_narrow_kernel<<<grid, kEdgeThreads, smem, s>>>(p);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
 }
 
 }  // namespace licos
@@ -632,6 +761,7 @@ int64_t licos_packed_weight_bytes(int kind, int out_c, int in_c, int in_layout) 
         return (int64_t)pl.rows * first_kpad(in_c) * 2;
     }
     const int cin_pad = (in_c + 63) / 64 * 64;
+    if (use_narrow(kind, out_c, in_c)) return (int64_t)kNarrowN * cin_pad * 2;
     return (int64_t)taps_of(kind) * pl.rows * cin_pad * 2;
 }
 
@@ -645,6 +775,10 @@ int licos_pack_conv_weight(const float* w, int kind, int out_c, int in_c, int in
         const int kp = first_kpad(in_c);
         pack_weight_first_kernel<<<ew_grid((int64_t)pl.rows * kp), 256, 0, s>>>(w, out_c, in_c * 25, pl.rows, kp,
                                                                                (__nv_bfloat16*)packed);
+    } else if (use_narrow(kind, out_c, in_c)) {
+        const int cin_pad = (in_c + 63) / 64 * 64;
+        pack_weight_narrow_kernel<<<ew_grid((int64_t)kNarrowN * cin_pad), 256, 0, s>>>(w, out_c, in_c, cin_pad,
+                                                                                     (__nv_bfloat16*)packed);
     } else {
         const int cin_pad = (in_c + 63) / 64 * 64;
         const int K = kind == LICOS_CONV_3X3_S1 ? 3 : 5;
@@ -669,6 +803,7 @@ void licos_debug_set_conv_probe(unsigned long long* device_buf) { g_conv_probe =
 int64_t licos_conv_workspace_bytes(const licos_conv_args* a) {
     if (!a) return LICOS_ERR_INVALID;
     if (a->in_layout != LICOS_LAYOUT_NCHW_F32) return 0;
+    if (use_first_direct(a->kind, a->in_c, a->out_c, a->out_layout)) return 0;
     const int oh = (a->in_h + 1) / 2, ow = (a->in_w + 1) / 2;
     return (int64_t)a->batch * oh * ow * first_kpad(a->in_c) * 2;
 }
@@ -682,6 +817,13 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     if (gdn && (!a->beta || !a->gamma || !a->bias)) return LICOS_ERR_INVALID;
     if (a->out_layout != LICOS_LAYOUT_NCHW_F32 && a->out_layout != LICOS_LAYOUT_NHWC_BF16) return LICOS_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
+
+    if (a->in_layout == LICOS_LAYOUT_NCHW_F32 && use_first_direct(a->kind, a->in_c, a->out_c, a->out_layout))
+        return launch_first(a, s);
+    if (a->in_layout == LICOS_LAYOUT_NHWC_BF16 && use_narrow(a->kind, a->out_c, a->in_c)) {
+        if (a->out_layout != LICOS_LAYOUT_NCHW_F32 || gdn) return LICOS_ERR_UNSUPPORTED;
+        return launch_narrow(a, s);
+    }
 
     ConvParams p;  // ~3.3 KB of plain data, passed by value as a __grid_constant__ kernel parameter
     memset(&p, 0, sizeof(p));

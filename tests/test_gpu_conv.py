@@ -131,6 +131,16 @@ def test_deconv_last_layer_narrow(cuda):
         _run(cuda, _lib.DECONV_5X5_S2, 2, 128, cout, 32, 32, out_nchw=True)
 
 
+def test_edge_kernels_ragged_and_relu(cuda):
+    # fused-im2col first layer and GEMM+gather last layer on sizes that are not tile multiples
+    _run(cuda, _lib.CONV_5X5_S2, 2, 3, 128, 33, 31, epi=_lib.EPI_GDN, first=True)
+    _run(cuda, _lib.CONV_5X5_S2, 1, 1, 192, 70, 18, epi=_lib.EPI_GDN, first=True)
+    _run(cuda, _lib.CONV_5X5_S2, 1, 3, 128, 256, 256, epi=_lib.EPI_NONE, first=True)
+    _run(cuda, _lib.DECONV_5X5_S2, 2, 128, 3, 20, 9, out_nchw=True)
+    _run(cuda, _lib.DECONV_5X5_S2, 1, 192, 1, 7, 45, epi=_lib.EPI_RELU, out_nchw=True)
+    _run(cuda, _lib.DECONV_5X5_S2, 3, 128, 3, 128, 128, out_nchw=True)
+
+
 def test_deconv_to_nchw_wide(cuda):
     _run(cuda, _lib.DECONV_5X5_S2, 1, 128, 192, 8, 8, out_nchw=True)
 
