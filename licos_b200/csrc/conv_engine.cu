@@ -21,6 +21,7 @@
 #include "conv_edge.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <mutex>
 #include <string.h>
 
@@ -82,7 +83,8 @@ struct ConvParams {
     const float* bias;
     const float* beta;
     int sa, sb;
-    uint32_t a_slot_bytes, b_slot_bytes, staging_bytes;
+    uint32_t a_slot_bytes, b_slot_bytes, staging_bytes, gamma_bytes;
+    int n_buf;  // TMEM accumulator sets (2 = the epilogue of pass p overlaps the mainloop of pass p+1)
     int total_tiles;
     unsigned long long* dbg;  // optional per-CTA cycle probes (licos_debug_set_conv_probe)
 };
@@ -115,12 +117,13 @@ struct Ring {
     }
 };
 
-template <int EPI, bool OUT_NHWC>
+// XC = number of 32-channel chunks the epilogue is unrolled for (4: N <= 128, 6: N <= 192, 8: N <= 256)
+template <int EPI, bool OUT_NHWC, int XC>
 __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
     constexpr bool kGdn = (EPI == LICOS_EPI_GDN || EPI == LICOS_EPI_IGDN);
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], b_full[kMaxSB], b_empty[kMaxSB];
-    __shared__ uint64_t acc_full, acc_empty, x2_full[2], norm_full[2];
+    __shared__ uint64_t acc_full[2], acc_empty[2], norm_full, g_full;
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float bias_s[512];
     __shared__ __align__(16) float beta_s[256];
@@ -130,6 +133,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     uint8_t* a_ring = smem;
     uint8_t* b_ring = a_ring + (size_t)p.sa * p.a_slot_bytes;
     uint8_t* staging = b_ring + (size_t)p.sb * p.b_slot_bytes;
+    uint8_t* gamma_s = staging + p.staging_bytes;  // resident gamma: (N / 64) atoms of [N][64] bf16
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -142,9 +146,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.sa; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], n_iss); }
         for (int i = 0; i < p.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], n_iss); }
-        mbar_init(&acc_full, n_iss);
-        mbar_init(&acc_empty, 128);
-        for (int i = 0; i < 2; ++i) { mbar_init(&x2_full[i], 128); mbar_init(&norm_full[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], n_iss); mbar_init(&acc_empty[i], 128); }
+        mbar_init(&norm_full, 1);
+        mbar_init(&g_full, 1);
         mbar_fence_init();
     }
     for (int i = threadIdx.x; i < p.N * p.n_split; i += kThreads) bias_s[i] = (p.bias && i < p.out_c) ? p.bias[i] : 0.f;
@@ -188,7 +192,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     } else if (warp == 1 && lane == 0) {
         // ===================== B producer =====================
         tma_prefetch_desc(&p.w_map);
-        if (kGdn) tma_prefetch_desc(&p.g_map);
+        if (kGdn) {  // gamma stays resident for the whole kernel
+            tma_prefetch_desc(&p.g_map);
+            mbar_arrive_expect_tx(&g_full, p.gamma_bytes);
+            for (int gc = 0; gc < p.N / kKChunk; ++gc)
+                tma_load_2d(gamma_s + (size_t)gc * p.N * 128, &p.g_map, &g_full, gc * kKChunk, 0);
+        }
         Ring rb;
         long long w_wait = 0;
         const long long t_begin = p.dbg ? clock64() : 0;
@@ -208,14 +217,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                         }
                     }
                 }
-                if (kGdn) {  // gamma tiles, once per pass: every issuer reads them for its own sub-tile
-                    for (int gc = 0; gc < p.N / kKChunk; ++gc) {
-                        { PROBE_T0(); mbar_wait(&b_empty[rb.slot], rb.phase ^ 1u); PROBE_ADD(w_wait); }
-                        mbar_arrive_expect_tx(&b_full[rb.slot], p.b_slot_bytes);
-                        tma_load_2d(b_ring + (size_t)rb.slot * p.b_slot_bytes, &p.g_map, &b_full[rb.slot], gc * kKChunk, 0);
-                        rb.advance(p.sb);
-                    }
-                }
             }
         }
         if (p.dbg) {
@@ -231,7 +232,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         const uint32_t idesc = umma_idesc_bf16(128, p.N);
         const uint64_t desc_hi = umma_desc_sw128(0);
         const uint32_t a_ring_addr = smem_u32(a_ring) >> 4, b_ring_addr = smem_u32(b_ring) >> 4;
-        const uint32_t staging_addr = smem_u32(staging) >> 4;
         const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_slot16 = p.b_slot_bytes >> 4;
         const uint32_t n_acc = p.n_acc, N = p.N;
         const uint32_t my_accs = (n_iss == 2) ? 1u : n_acc;  // accumulators of a group this thread drives
@@ -243,8 +243,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             ++n_tiles;
             for (int pi = 0; pi < p.n_passes; ++pi) {
                 const Pass& ps = p.passes[pi];
-                { PROBE_T0(); mbar_wait(&acc_empty, (pit & 1u) ^ 1u); PROBE_ADD(w_acc); }
+                const uint32_t buf = pit % (uint32_t)p.n_buf;
+                { PROBE_T0(); mbar_wait(&acc_empty[buf], ((pit / (uint32_t)p.n_buf) & 1u) ^ 1u); PROBE_ADD(w_acc); }
                 tc_fence_after();
+                const uint32_t tmem_set = tmem_base + buf * (uint32_t)(ps.n_groups * (int)n_acc) * N;
                 uint32_t touched = 0;
                 for (int c = 0; c < p.cin_chunks; ++c) {
                     for (int s = 0; s < ps.n_slabs; ++s) {
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                             uint64_t ad = desc_hi | (uint64_t)(a_slab + ((uint32_t)tp.row_off + iss * kAccRows) * (kRowBytes >> 4));
                             uint32_t acc = (uint32_t)tp.group * n_acc + iss;
                             for (uint32_t a = 0; a < my_accs; ++a, ++acc, ad += (kAccRows * kRowBytes) >> 4) {
-                                const uint32_t d = tmem_base + acc * N;
+                                const uint32_t d = tmem_set + acc * N;
                                 umma_bf16(d, ad, bd, idesc, (touched >> acc) & 1u);
                                 umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
                                 umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
@@ -274,25 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                         ra.advance(p.sa);
                     }
                 }
-                umma_commit(&acc_full);
-                if (kGdn) {  // (GDN layers have one accumulator group; sub-tile `iss` is this thread's)
-                    const uint32_t d = tmem_base + n_acc * N;
-                    { PROBE_T0(); mbar_wait(&x2_full[iss], pit & 1u); PROBE_ADD(w_x2); }
-                    tc_fence_after();
-                    for (uint32_t gc = 0; gc < N / kKChunk; ++gc) {
-                        { PROBE_T0(); mbar_wait(&b_full[rb.slot], rb.phase); PROBE_ADD(w_b); }
-                        tc_fence_after();
-                        const uint64_t bd = desc_hi | (uint64_t)(b_ring_addr + rb.slot * b_slot16);
-                        const uint64_t ad = desc_hi | (uint64_t)(staging_addr + gc * ((128 * 128) >> 4));
-                        umma_bf16(d, ad, bd, idesc, (uint32_t)(gc > 0));
-                        umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
-                        umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
-                        umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
-                        umma_commit(&b_empty[rb.slot]);
-                        rb.advance(p.sb);
-                    }
-                    umma_commit(&norm_full[iss]);
-                }
+                umma_commit(&acc_full[buf]);
                 ++pit;
             }
         }
@@ -306,8 +290,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         const int et = threadIdx.x - 128;  // == TMEM lane == row of the 128-row sub-tile
         const uint32_t lane_sel = ((uint32_t)(warp & 3) * 32u) << 16;
         const int th = et / kTileW, tw = et % kTileW;
-        uint32_t pit = 0;
+        uint32_t pit = 0, nit = 0;
         const int n32 = p.N / 32;
+        const uint32_t idesc = umma_idesc_bf16(128, p.N);
+        const uint64_t desc_hi = umma_desc_sw128(0);
+        const uint32_t staging16 = smem_u32(staging) >> 4, gamma16 = smem_u32(gamma_s) >> 4;
+        bool gamma_ready = false;
         long long e_acc = 0, e_s1 = 0, e_norm = 0, e_s2 = 0, e_store = 0;
         const long long t_begin = p.dbg ? clock64() : 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -315,52 +303,73 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             const float* bias_t = bias_s + t.ns * p.N;
             for (int pi = 0; pi < p.n_passes; ++pi) {
                 const Pass& ps = p.passes[pi];
-                { PROBE_T0(); mbar_wait(&acc_full, pit & 1u); PROBE_ADD(e_acc); }
+                const uint32_t buf = pit % (uint32_t)p.n_buf;
+                { PROBE_T0(); mbar_wait(&acc_full[buf], (pit / (uint32_t)p.n_buf) & 1u); PROBE_ADD(e_acc); }
                 tc_fence_after();
+                const uint32_t tmem_set = tmem_base + lane_sel + buf * (uint32_t)(ps.n_groups * p.n_acc) * p.N;
                 for (int g = 0; g < ps.n_groups; ++g) {
                     for (int a = 0; a < p.n_acc; ++a) {
                         const uint32_t acc = (uint32_t)g * p.n_acc + a;
-                        const uint32_t t_acc = tmem_base + lane_sel + acc * p.N;
-                        const uint32_t t_norm = tmem_base + lane_sel + (uint32_t)(ps.n_groups * p.n_acc) * p.N;
+                        const uint32_t t_acc = tmem_set + acc * p.N;
 
-                        if (OUT_NHWC || kGdn) {
+                        if (OUT_NHWC) {
                             // the previous TMA store must have finished reading `staging` before it is rewritten
                             const long long _st = p.dbg ? clock64() : 0;
-                            if (OUT_NHWC && et == 0) tma_store_wait_read();
-                            if (OUT_NHWC) named_bar_sync(1, 128);
+                            if (et == 0) tma_store_wait_read();
+                            named_bar_sync(1, 128);
                             if (p.dbg) e_store += clock64() - _st;
                         }
+                        uint32_t xs[kGdn ? XC * 16 : 1];  // v = acc + bias kept as packed bf16 pairs
                         if (kGdn) {
-                            // stage 1: v = acc + bias; v^2 (bf16) -> staging as the A operand of the gamma GEMM
+                            // stage 1: v^2 (bf16) -> staging = A operand of the gamma GEMM; the GEMM then overwrites
+                            // the accumulator IN PLACE with the norm (no second TMEM region -> room to double-buffer)
                             const long long _s1 = p.dbg ? clock64() : 0;
-                            for (int cc = 0; cc < n32; ++cc) {
-                                float v[32];
-                                tmem_ld32(t_acc + cc * 32, v);
-                                tmem_ld_wait();
-                                const float4* b4 = reinterpret_cast<const float4*>(bias_t + cc * 32);
-                                uint32_t pk[16];
 #pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    const float4 b = b4[q];
-                                    const float x0 = v[4 * q] + b.x, x1 = v[4 * q + 1] + b.y;
-                                    const float x2 = v[4 * q + 2] + b.z, x3 = v[4 * q + 3] + b.w;
-                                    pk[2 * q] = pack_bf16x2(x0 * x0, x1 * x1);
-                                    pk[2 * q + 1] = pack_bf16x2(x2 * x2, x3 * x3);
-                                }
-                                uint8_t* atom = staging + (size_t)((cc * 32) / kKChunk) * (128 * 128);
-                                const uint32_t chunk0 = ((cc * 32) % kKChunk) / 8;
+                            for (int cc = 0; cc < XC; ++cc) {
+                                if (cc < n32) {
+                                    float v[32];
+                                    tmem_ld32(t_acc + cc * 32, v);
+                                    tmem_ld_wait();
+                                    const float4* b4 = reinterpret_cast<const float4*>(bias_t + cc * 32);
+                                    uint32_t pk[16];
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    *reinterpret_cast<uint4*>(atom + sw128_offset(et, chunk0 + q)) =
-                                        make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                                    for (int q = 0; q < 8; ++q) {
+                                        const float4 b = b4[q];
+                                        const float x0 = v[4 * q] + b.x, x1 = v[4 * q + 1] + b.y;
+                                        const float x2 = v[4 * q + 2] + b.z, x3 = v[4 * q + 3] + b.w;
+                                        xs[cc * 16 + 2 * q] = pack_bf16x2(x0, x1);
+                                        xs[cc * 16 + 2 * q + 1] = pack_bf16x2(x2, x3);
+                                        pk[2 * q] = pack_bf16x2(x0 * x0, x1 * x1);
+                                        pk[2 * q + 1] = pack_bf16x2(x2 * x2, x3 * x3);
+                                    }
+                                    uint8_t* atom = staging + (size_t)((cc * 32) / kKChunk) * (128 * 128);
+                                    const uint32_t chunk0 = ((cc * 32) % kKChunk) / 8;
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        *reinterpret_cast<uint4*>(atom + sw128_offset(et, chunk0 + q)) =
+                                            make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                                    }
                                 }
                             }
                             fence_proxy_async();
                             tc_fence_before();
-                            mbar_arrive(&x2_full[a]);
+                            named_bar_sync(1, 128);
+                            if (et == 0) {
+                                if (!gamma_ready) { mbar_wait(&g_full, 0); gamma_ready = true; }
+                                tc_fence_after();
+                                const uint32_t d = tmem_set - lane_sel + acc * p.N;
+                                for (uint32_t ks = 0; ks < (uint32_t)p.N / 16; ++ks) {
+                                    const uint32_t atom = ks >> 2, off = (ks & 3) * 2;
+                                    umma_bf16(d, desc_hi | (uint64_t)(staging16 + atom * 1024 + off),
+                                              desc_hi | (uint64_t)(gamma16 + atom * ((uint32_t)p.N * 8) + off), idesc,
+                                              (uint32_t)(ks > 0));
+                                }
+                                umma_commit(&norm_full);
+                            }
                             if (p.dbg) e_s1 += clock64() - _s1;
-                            { PROBE_T0(); mbar_wait(&norm_full[a], pit & 1u); PROBE_ADD(e_norm); }
+                            { PROBE_T0(); mbar_wait(&norm_full, nit & 1u); PROBE_ADD(e_norm); }
                             tc_fence_after();
+                            ++nit;
                         }
 
                         // stage 2: activation, then write out
@@ -373,50 +382,50 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                                             : p.out_f32 + ((size_t)t.b * p.out_c * p.out_h + oh) * p.out_w + ow +
                                                   (size_t)(t.ns * p.N) * cs;
                         const int c_left = p.out_c - t.ns * p.N;  // valid channels from this split's base
-                        for (int cc = 0; cc < n32; ++cc) {
-                            float v[32];
-                            tmem_ld32(t_acc + cc * 32, v);
-                            float nrm[32];
-                            if (kGdn) tmem_ld32(t_norm + cc * 32, nrm);
-                            tmem_ld_wait();
-                            const float4* b4 = reinterpret_cast<const float4*>(bias_t + cc * 32);
-                            const float4* e4 = reinterpret_cast<const float4*>(beta_s + cc * 32);
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const float4 b = b4[q];
-                                float x[4] = {v[4 * q] + b.x, v[4 * q + 1] + b.y, v[4 * q + 2] + b.z, v[4 * q + 3] + b.w};
-                                if (kGdn) {
-                                    const float4 e = e4[q];
-                                    const float d[4] = {nrm[4 * q] + e.x, nrm[4 * q + 1] + e.y, nrm[4 * q + 2] + e.z,
-                                                        nrm[4 * q + 3] + e.w};
+                        for (int cc = 0; cc < XC; ++cc) {
+                            if (cc < n32) {
+                                float v[32];
+                                tmem_ld32(t_acc + cc * 32, v);  // GDN: the norm; otherwise the accumulator
+                                tmem_ld_wait();
+                                const float4* b4 = reinterpret_cast<const float4*>((kGdn ? beta_s : bias_t) + cc * 32);
 #pragma unroll
-                                    for (int i = 0; i < 4; ++i) {
-                                        const float r = rsqrtf(d[i]);
-                                        x[i] *= (EPI == LICOS_EPI_GDN) ? r : d[i] * r;  // d * rsqrt(d) = sqrt(d), d > 0
+                                for (int q = 0; q < 8; ++q) {
+                                    const float4 b = b4[q];
+                                    float x[4] = {v[4 * q] + b.x, v[4 * q + 1] + b.y, v[4 * q + 2] + b.z, v[4 * q + 3] + b.w};
+                                    if (kGdn) {
+                                        const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&xs[cc * 16 + 2 * q]);
+                                        const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&xs[cc * 16 + 2 * q + 1]);
+                                        const float xv[4] = {__low2float(p0), __high2float(p0), __low2float(p1), __high2float(p1)};
+#pragma unroll
+                                        for (int i = 0; i < 4; ++i) {
+                                            const float r = rsqrtf(x[i]);  // x[i] = norm + beta > 0
+                                            x[i] = xv[i] * ((EPI == LICOS_EPI_GDN) ? r : x[i] * r);  // d*rsqrt(d) = sqrt(d)
+                                        }
+                                    } else if (EPI == LICOS_EPI_RELU) {
+#pragma unroll
+                                        for (int i = 0; i < 4; ++i) x[i] = fmaxf(x[i], 0.f);
                                     }
-                                } else if (EPI == LICOS_EPI_RELU) {
 #pragma unroll
-                                    for (int i = 0; i < 4; ++i) x[i] = fmaxf(x[i], 0.f);
+                                    for (int i = 0; i < 4; ++i) v[4 * q + i] = x[i];
                                 }
+                                if (OUT_NHWC) {
+                                    uint8_t* atom = staging + (size_t)((cc * 32) / kKChunk) * (128 * 128);
+                                    const uint32_t chunk0 = ((cc * 32) % kKChunk) / 8;
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) v[4 * q + i] = x[i];
-                            }
-                            if (OUT_NHWC) {
-                                uint8_t* atom = staging + (size_t)((cc * 32) / kKChunk) * (128 * 128);
-                                const uint32_t chunk0 = ((cc * 32) % kKChunk) / 8;
+                                    for (int q = 0; q < 4; ++q) {
+                                        *reinterpret_cast<uint4*>(atom + sw128_offset(et, chunk0 + q)) =
+                                            make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                                                       pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+                                    }
+                                } else if (in_range) {
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    *reinterpret_cast<uint4*>(atom + sw128_offset(et, chunk0 + q)) =
-                                        make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                                                   pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+                                    for (int j = 0; j < 32; ++j)
+                                        if (cc * 32 + j < c_left) o[(size_t)(cc * 32 + j) * cs] = v[j];
                                 }
-                            } else if (in_range) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (cc * 32 + j < c_left) o[(size_t)(cc * 32 + j) * cs] = v[j];
                             }
                         }
-                        if (!OUT_NHWC && (p.N & 16)) {  // trailing 16 columns (N % 32 == 16); never a GDN layer
+                        if (!OUT_NHWC && !kGdn && (p.N & 16)) {  // trailing 16 columns (N % 32 == 16)
                             float h[16];
                             tmem_ld16(t_acc + n32 * 32, h);
                             tmem_ld_wait();
@@ -444,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                     }
                 }
                 tc_fence_before();
-                mbar_arrive(&acc_empty);
+                mbar_arrive(&acc_empty[buf]);
                 ++pit;
             }
         }
@@ -892,11 +901,18 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     const int groups = merged ? 4 : 1;
 
     // accumulators per tile
+    // GDN accumulates its norm in place, so TMEM holds only accumulators; two sets when they fit so that the
+    // epilogue of one pass overlaps the mainloop of the next
     int n_acc = 2;
-    if ((groups * 2 + (gdn ? 1 : 0)) * pl.N > (int)kTmemCols) n_acc = 1;
+    if (groups * 2 * pl.N > (int)kTmemCols) n_acc = 1;
     if (p.grid_h <= kAccRows) n_acc = 1;
-    if ((groups * n_acc + (gdn ? 1 : 0)) * pl.N > (int)kTmemCols) return LICOS_ERR_UNSUPPORTED;
+    if (n_acc == 2 && 2 * groups * 2 * pl.N > (int)kTmemCols && 2 * groups * pl.N <= (int)kTmemCols &&
+        !getenv("LICOS_PREFER_NACC2"))
+        n_acc = 1;  // one double-buffered accumulator beats two single-buffered ones that share weight tiles
+    if (groups * n_acc * pl.N > (int)kTmemCols) return LICOS_ERR_UNSUPPORTED;
     p.n_acc = n_acc;
+    p.n_buf = (2 * groups * n_acc * pl.N <= (int)kTmemCols) ? 2 : 1;
+    if (getenv("LICOS_NBUF1")) p.n_buf = 1;
     const int TH = kAccRows * n_acc;
     const int R = TH + 2;
 
@@ -1035,19 +1051,24 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     p.a_slot_bytes = (uint32_t)R * kRowBytes;
     p.b_slot_bytes = (uint32_t)pl.N * 128u;
     p.staging_bytes = (gdn || a->out_layout == LICOS_LAYOUT_NHWC_BF16) ? (uint32_t)(pl.N / kKChunk) * 128u * 128u : 0u;
+    p.gamma_bytes = gdn ? (uint32_t)(pl.N / kKChunk) * (uint32_t)pl.N * 128u : 0u;
     const int64_t b_slot_al = p.b_slot_bytes;  // N is a multiple of 16, so N*128 is a multiple of 2 KB
-    const int64_t budget = kMaxDynSmem - 1024 - (int64_t)p.staging_bytes;
-    int sb = 4;
-    int sa = (int)((budget - (int64_t)sb * b_slot_al) / p.a_slot_bytes);
-    if (sa > kMaxSA) sa = kMaxSA;
-    if (sa < 2) { sb = 3; sa = (int)((budget - (int64_t)sb * b_slot_al) / p.a_slot_bytes); }
+    const int64_t budget = kMaxDynSmem - 1024 - (int64_t)p.staging_bytes - (int64_t)p.gamma_bytes;
+    int sb = 5, sa = 0;
+    while (sa < 2 && sb > 2) {  // prefer >= 4 weight slots, give them up when the resident gamma leaves no room
+        --sb;
+        sa = (int)((budget - (int64_t)sb * b_slot_al) / p.a_slot_bytes);
+    }
     if (sa < 2) return LICOS_ERR_UNSUPPORTED;
     if (sa > kMaxSA) sa = kMaxSA;
     int64_t left = budget - (int64_t)sa * p.a_slot_bytes - (int64_t)sb * b_slot_al;
     while (sb < kMaxSB && left >= b_slot_al) { ++sb; left -= b_slot_al; }
+    if (const char* e = getenv("LICOS_SA")) { const int v = atoi(e); if (v >= 2 && v <= kMaxSA) sa = v; }
+    if (const char* e = getenv("LICOS_SB")) { const int v = atoi(e); if (v >= 2 && v <= kMaxSB) sb = v; }
     p.sa = sa;
     p.sb = sb;
-    size_t smem_bytes = 1024 + (size_t)sa * p.a_slot_bytes + (size_t)sb * b_slot_al + p.staging_bytes;
+    size_t smem_bytes = 1024 + (size_t)sa * p.a_slot_bytes + (size_t)sb * b_slot_al + p.staging_bytes + p.gamma_bytes;
+    if (smem_bytes > (size_t)kMaxDynSmem) return LICOS_ERR_UNSUPPORTED;
     if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;  // one CTA per SM: each CTA owns all 512 TMEM columns
 
     p.tiles_h = (p.grid_h + TH - 1) / TH;
@@ -1066,14 +1087,20 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     const int grid = (int)(tiles < sms ? tiles : sms);
     const bool nhwc = a->out_layout == LICOS_LAYOUT_NHWC_BF16;
     cudaError_t err = cudaErrorInvalidValue;
-#define LICOS_LAUNCH(E, O)                                                                              \
+#define LICOS_LAUNCH_X(E, O, X)                                                                         \
     do {                                                                                                \
-        static cudaError_t attr = cudaFuncSetAttribute(conv_igemm_kernel<E, O>,                         \
+        static cudaError_t attr = cudaFuncSetAttribute(conv_igemm_kernel<E, O, X>,                      \
                                                        cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                                        kMaxDynSmem);                                    \
         if (attr != cudaSuccess) { err = attr; break; }                                                 \
-        conv_igemm_kernel<E, O><<<grid, kThreads, smem_bytes, s>>>(p);                                  \
+        conv_igemm_kernel<E, O, X><<<grid, kThreads, smem_bytes, s>>>(p);                               \
         err = cudaGetLastError();                                                                       \
+    } while (0)
+#define LICOS_LAUNCH(E, O)                                                                              \
+    do {                                                                                                \
+        if (pl.N <= 128) LICOS_LAUNCH_X(E, O, 4);                                                       \
+        else if (pl.N <= 192) LICOS_LAUNCH_X(E, O, 6);                                                  \
+        else LICOS_LAUNCH_X(E, O, 8);                                                                   \
     } while (0)
     switch (a->epilogue * 2 + (nhwc ? 1 : 0)) {
         case LICOS_EPI_NONE * 2 + 0: LICOS_LAUNCH(LICOS_EPI_NONE, false); break;
@@ -1087,6 +1114,7 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
         default: return LICOS_ERR_INVALID;
     }
 #undef LICOS_LAUNCH
+#undef LICOS_LAUNCH_X
     LICOS_CUDA_OK(err);
     return LICOS_OK;
 }
