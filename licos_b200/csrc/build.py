@@ -34,7 +34,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in SOURCES:
         obj = os.path.join(PKG, "lib", os.path.splitext(src)[0] + ".o")
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(HERE, src), "-o", obj]
+        cmd = [NVCC, *FLAGS, *os.environ.get("LICOS_NVCC_EXTRA", "").split(), "-c", os.path.join(HERE, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

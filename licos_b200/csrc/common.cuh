@@ -69,6 +69,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a pipeline bug becomes a trap (reported as a CUDA error) instead of a hung GPU.
+#ifdef LICOS_DEBUG_TRAP
+#include <stdio.h>
+#define mbar_wait(bar, parity) mbar_wait_dbg(bar, parity, __LINE__)
+static __device__ __noinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity, int line) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 400000000LL) {
+            printf("HANG block %d thread %d line %d bar_off %u parity %u\n", blockIdx.x, threadIdx.x, line, smem_u32(bar), parity);
+            __trap();
+        }
+    }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
@@ -76,6 +90,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > 8000000000LL) __trap();
     }
 }
+#endif
 
 // ----------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor, tiled mode)

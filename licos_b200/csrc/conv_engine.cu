@@ -19,6 +19,7 @@
 // store clipping.  Replaces SURVEY.md section 8a rows A3, A4, A5.
 #include "common.cuh"
 #include "conv_edge.cuh"
+#include "conv_first2.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -707,6 +708,103 @@ static int launch_first(const licos_conv_args* a, cudaStream_t s) {
     return LICOS_OK;
 }
 
+// fp32 tensor, 4 dims, innermost contiguous, no swizzle (input patches of the fused first layer)
+static bool make_map_f32(CUtensorMap* m, const void* base, const uint64_t* dims, const uint64_t* strides_elems,
+                         const uint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdims[4], gstrides[3];
+    cuuint32_t gbox[4], estr[4];
+    for (int i = 0; i < 4; ++i) { gdims[i] = dims[i]; gbox[i] = box[i]; estr[i] = 1; }
+    for (int i = 0; i < 3; ++i) gstrides[i] = strides_elems[i] * 4;
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdims, gstrides, gbox, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// pipelined first layer (conv_first2.cuh): 1 or 3 bands, N in {64, 128}, rows of x 16-byte aligned (TMA)
+static bool use_first2(const licos_conv_args* a) {
+    return (a->in_c == 1 || a->in_c == 3) && (a->out_c == 64 || a->out_c == 128) && a->in_w % 4 == 0 &&
+           ((uintptr_t)a->in & 15) == 0 && !getenv("LICOS_FIRST_V1");
+}
+
+static int launch_first2(const licos_conv_args* a, cudaStream_t s) {
+    const bool gdn = (a->epilogue == LICOS_EPI_GDN || a->epilogue == LICOS_EPI_IGDN);
+    First2Params p;
+    memset(&p, 0, sizeof(p));
+    p.w = (const __nv_bfloat16*)a->weight;
+    p.bias = a->bias;
+    p.beta = a->beta;
+    p.N = a->out_c;
+    p.k_pad = first_kpad(a->in_c);
+    const int OH = (a->in_h + 1) / 2, OW = (a->in_w + 1) / 2;
+    p.tiles_h = (OH + 7) / 8; p.tiles_w = (OW + 15) / 16;
+    const int64_t tiles = (int64_t)a->batch * p.tiles_h * p.tiles_w;
+    if (tiles > 0x7fffffff) return LICOS_ERR_UNSUPPORTED;
+    p.total_tiles = (int)tiles;
+    p.tmem_cols = 4u * (uint32_t)p.N;
+    {
+        const uint64_t W = (uint64_t)a->in_w, H = (uint64_t)a->in_h, C = (uint64_t)a->in_c;
+        const uint64_t dims[4] = {W, H, C, (uint64_t)a->batch};
+        const uint64_t strides[3] = {W, H * W, C * H * W};
+        const uint32_t box[4] = {(uint32_t)kF2PatchPitch, (uint32_t)kF2PatchRows, (uint32_t)a->in_c, 1};
+        if (!make_map_f32(&p.x_map, a->in, dims, strides, box)) return LICOS_ERR_CUDA;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)p.k_pad, (uint64_t)p.N};
+        const uint64_t strides[1] = {(uint64_t)p.k_pad};
+        const uint32_t box[2] = {64, (uint32_t)p.N};
+        if (!make_map(&p.w_map, a->weight, 2, dims, strides, box)) return LICOS_ERR_CUDA;
+    }
+    if (gdn) {
+        const uint64_t dims[2] = {(uint64_t)p.N, (uint64_t)p.N};
+        const uint64_t strides[1] = {(uint64_t)p.N};
+        const uint32_t box[2] = {64, (uint32_t)p.N};
+        if (!make_map(&p.g_map, a->gamma, 2, dims, strides, box)) return LICOS_ERR_CUDA;
+    } else {
+        p.g_map = p.w_map;
+    }
+    {
+        const uint64_t OC = (uint64_t)p.N;
+        const uint64_t dims[4] = {OC, (uint64_t)OW, (uint64_t)OH, (uint64_t)a->batch};
+        const uint64_t strides[3] = {OC, OW * OC, (uint64_t)OH * OW * OC};
+        const uint32_t box[4] = {64, 16, 8, 1};
+        if (!make_map(&p.out_map, a->out, 4, dims, strides, box)) return LICOS_ERR_CUDA;
+    }
+    size_t smem = first2_smem_bytes(a->in_c, p.N, gdn);
+    if (smem > (size_t)kMaxDynSmem) return LICOS_ERR_UNSUPPORTED;
+    if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM (TMEM is sized for that)
+    int sms = 0;
+    const int rc = sm_count_of(a, &sms);
+    if (rc != LICOS_OK) return rc;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    cudaError_t err = cudaErrorInvalidValue;
+#define LICOS_LAUNCH_F2(E, C)                                                                                        \
+    do {                                                                                                             \
+        static cudaError_t attr =                                                                                    \
+            cudaFuncSetAttribute(conv_first2_kernel<E, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem); \
+        if (attr != cudaSuccess) { err = attr; break; }                                                              \
+        conv_first2_kernel<E, C><<<grid, kF2Threads, smem, s>>>(p);                                                  \
+        err = cudaGetLastError();                                                                                    \
+    } while (0)
+#define LICOS_LAUNCH_F2E(E)                                             \
+    do {                                                                \
+        if (a->in_c == 1) LICOS_LAUNCH_F2(E, 1); else LICOS_LAUNCH_F2(E, 3); \
+    } while (0)
+    switch (a->epilogue) {
+        case LICOS_EPI_NONE: LICOS_LAUNCH_F2E(LICOS_EPI_NONE); break;
+        case LICOS_EPI_GDN: LICOS_LAUNCH_F2E(LICOS_EPI_GDN); break;
+        case LICOS_EPI_IGDN: LICOS_LAUNCH_F2E(LICOS_EPI_IGDN); break;
+        case LICOS_EPI_RELU: LICOS_LAUNCH_F2E(LICOS_EPI_RELU); break;
+        default: return LICOS_ERR_INVALID;
+    }
+#undef LICOS_LAUNCH_F2E
+#undef LICOS_LAUNCH_F2
+    LICOS_CUDA_OK(err);
+    return LICOS_OK;
+}
+
 static int launch_narrow(const licos_conv_args* a, cudaStream_t s) {
     NarrowParams p;
     memset(&p, 0, sizeof(p));
@@ -828,7 +926,7 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
 
     if (a->in_layout == LICOS_LAYOUT_NCHW_F32 && use_first_direct(a->kind, a->in_c, a->out_c, a->out_layout))
-        return launch_first(a, s);
+        return use_first2(a) ? launch_first2(a, s) : launch_first(a, s);
     if (a->in_layout == LICOS_LAYOUT_NHWC_BF16 && use_narrow(a->kind, a->out_c, a->in_c)) {
         if (a->out_layout != LICOS_LAYOUT_NCHW_F32 || gdn) return LICOS_ERR_UNSUPPORTED;
         return launch_narrow(a, s);

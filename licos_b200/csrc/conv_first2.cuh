@@ -1,0 +1,337 @@
+// g_a[0] for the reference's band counts (1 = raw split, 3 = RGB):
+// Conv2d(C_in -> N, 5x5, stride 2) + bias + GDN / ReLU, fp32 NCHW in, bf16 NHWC out, as a pipelined,
+// warp-specialised kernel (one persistent CTA per SM, 14 warps):
+//
+//   warp 0      patch loader   TMA (tiled, fp32, zero fill = the conv padding) of the (2*8+3) x 40 x C_in input
+//                              patch of the next 8 x 16 output tile into a 3-slot ring
+//   warp 1      MMA issuer     conv GEMM [128 px] x [K = 25 C_in + 2] x [N]: 2 (C_in = 1) or 5 (C_in = 3) tcgen05.mma;
+//                              the two extra K columns carry the bias as a bf16 hi + lo pair against A = 1.0
+//   warps 2-5   im2col         two 64-thread teams (alternate tiles); a thread builds the K-major, 128-byte-swizzled
+//                              rows of two neighbouring output pixels from 16-byte shared loads of the patch
+//                              (fusing fp32 -> bf16 and NCHW -> NHWC into the build)
+//   warps 6-9   epilogue 0     alternate tiles: TMEM -> x (packed bf16 in registers), x^2 -> smem -> gamma GEMM (in
+//   warps 10-13 epilogue 1     place over the accumulator) -> x * rsqrt(beta + norm) -> bf16 -> TMA store
+//
+// Four TMEM accumulators (4 x N <= 512 columns), so the conv GEMM of tile t+2 never waits for the epilogue of tile t.
+#pragma once
+
+#include "common.cuh"
+#include "epilogue.cuh"
+
+namespace licos {
+
+constexpr int kF2Threads = 14 * 32;
+constexpr int kF2Slots = 3;
+// patch = input rows 2*oh0-2 .. +18, columns 2*ow0-4 .. +39: a TMA box must start on a 16-byte boundary of the
+// innermost dimension (measured: an unaligned start coordinate raises an illegal-instruction fault)
+constexpr int kF2PatchRows = 19, kF2PatchPitch = 40;
+
+struct First2Params {
+    CUtensorMap x_map;    // fp32 (W, H, C, B), box (40, 19, C, 1), no swizzle
+    CUtensorMap w_map;    // [N][k_pad] bf16, box (64, N): K columns 0..63
+    CUtensorMap g_map;    // gamma [N][N] bf16, box (64, N)
+    CUtensorMap out_map;  // NHWC bf16 (N, OW, OH, B), box (64, 16, 8, 1)
+    const __nv_bfloat16* w;  // packed weight [N][k_pad] (K columns 64.. are copied by hand)
+    const float* bias;
+    const float* beta;
+    int k_pad;
+    int N;
+    int tiles_h, tiles_w, total_tiles;
+    uint32_t tmem_cols;
+};
+
+template <int CIN>
+struct First2Geom {
+    static_assert(CIN == 1 || CIN == 3, "fused first layer is built for 1 and 3 bands");
+    static constexpr int kK = CIN * 25;               // real K; columns kK, kK+1 carry the bias
+    static constexpr int kSteps = (kK + 2 + 15) / 16;  // tcgen05.mma K steps: 2 or 5
+    static constexpr int kPk = kSteps * 8;            // packed bf16 pairs per pixel row
+    static constexpr bool kTail = kSteps > 4;         // K step 4 lives in the shared tail atom
+    static constexpr uint32_t kPatchBytes = CIN * kF2PatchRows * kF2PatchPitch * 4;
+    static constexpr uint32_t kPatchSlot = (kPatchBytes + 127u) & ~127u;
+};
+
+__host__ __device__ constexpr size_t first2_smem_bytes(int cin, int N, bool gdn) {
+    const size_t n_atoms = N / 64;
+    const size_t patch = ((size_t)cin * kF2PatchRows * kF2PatchPitch * 4 + 127) & ~(size_t)127;
+    return 1024 + (size_t)N * 128                       // W atom 0
+           + (cin == 3 ? 16384 : 0)                     // shared tail atom (A K-step 4 of every slot + W K-step 4)
+           + (gdn ? n_atoms * N * 128 : 0)              // gamma
+           + (size_t)kF2Slots * 16384                   // A ring
+           + 2 * n_atoms * 16384                        // staging, one per epilogue team
+           + kF2Slots * patch;
+}
+
+template <int EPI, int CIN>
+__global__ void __launch_bounds__(kF2Threads, 1) conv_first2_kernel(const __grid_constant__ First2Params p) {
+    using G = First2Geom<CIN>;
+    constexpr bool kGdn = (EPI == LICOS_EPI_GDN || EPI == LICOS_EPI_IGDN);
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t patch_full[kF2Slots], patch_empty[kF2Slots], a_full[kF2Slots], a_empty[kF2Slots];
+    __shared__ uint64_t acc_full[4], acc_empty[4], norm_full[2], w_bar;
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float beta_s[128];
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int N = p.N, n_atoms = N / 64;
+    uint8_t* w_s = smem;
+    uint8_t* tail_s = w_s + (size_t)N * 128;
+    uint8_t* g_s = tail_s + (G::kTail ? 16384 : 0);
+    uint8_t* a_s = g_s + (kGdn ? (size_t)n_atoms * N * 128 : 0);
+    uint8_t* stg_s = a_s + (size_t)kF2Slots * 16384;
+    uint8_t* patch_s = stg_s + (size_t)2 * n_atoms * 16384;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < kF2Slots; ++i) {
+            mbar_init(&patch_full[i], 1); mbar_init(&patch_empty[i], 64);
+            mbar_init(&a_full[i], 64); mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        mbar_init(&norm_full[0], 1); mbar_init(&norm_full[1], 1);
+        mbar_init(&w_bar, 1);
+        mbar_fence_init();
+    }
+    if (kGdn)
+        for (int i = tid; i < N; i += kF2Threads) beta_s[i] = p.beta[i];
+    if (warp == 1) {
+        tmem_alloc(&tmem_base_smem, p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    // ---- resident operands: W (K columns 0..63 by TMA, the rest by hand with the bias folded in), gamma ----
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&w_bar, (uint32_t)N * 128u + (kGdn ? (uint32_t)n_atoms * N * 128u : 0u));
+        tma_load_2d(w_s, &p.w_map, &w_bar, 0, 0);
+        if (kGdn)
+            for (int a = 0; a < n_atoms; ++a) tma_load_2d(g_s + (size_t)a * N * 128, &p.g_map, &w_bar, a * 64, 0);
+    }
+    if (G::kTail) {
+        if (tid < N) {  // K columns 64..79 of row n -> logical chunks 6, 7 of the tail atom
+            const uint4* src = reinterpret_cast<const uint4*>(p.w + (size_t)tid * p.k_pad + 64);
+            uint4 c0 = src[0], c1 = src[1];
+            const float b = p.bias ? p.bias[tid] : 0.f;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(b), lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+            __nv_bfloat16 e[16];
+            *reinterpret_cast<uint4*>(e) = c0;
+            *reinterpret_cast<uint4*>(e + 8) = c1;
+            e[G::kK - 64] = hi;
+            e[G::kK - 64 + 1] = lo;
+            *reinterpret_cast<uint4*>(tail_s + sw128_offset(tid, 6)) = *reinterpret_cast<uint4*>(e);
+            *reinterpret_cast<uint4*>(tail_s + sw128_offset(tid, 7)) = *reinterpret_cast<uint4*>(e + 8);
+        }
+    } else {
+        mbar_wait(&w_bar, 0);  // patch the bias pair into the TMA-written atom
+        if (tid < N) {
+            const float b = p.bias ? p.bias[tid] : 0.f;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(b), lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+            __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(w_s + sw128_offset(tid, G::kK / 8));
+            row[G::kK % 8] = hi;
+            row[G::kK % 8 + 1] = lo;
+        }
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    const int grid = gridDim.x;
+    if (warp == 0) {
+        // ===================== patch loader =====================
+        if (lane == 0) {
+            tma_prefetch_desc(&p.x_map);
+            int lt = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid, ++lt) {
+                const int slot = lt % kF2Slots;
+                const uint32_t par = (uint32_t)(lt / kF2Slots) & 1u;
+                int r = tile;
+                const int ow0 = (r % p.tiles_w) * 16;
+                r /= p.tiles_w;
+                const int oh0 = (r % p.tiles_h) * 8;
+                const int b = r / p.tiles_h;
+                mbar_wait(&patch_empty[slot], par ^ 1u);
+                mbar_arrive_expect_tx(&patch_full[slot], G::kPatchBytes);
+                tma_load_4d(patch_s + (size_t)slot * G::kPatchSlot, &p.x_map, &patch_full[slot], 2 * ow0 - 4, 2 * oh0 - 2, 0, b);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            mbar_wait(&w_bar, 0);
+            const uint32_t idesc = umma_idesc_bf16(128, N);
+            const uint64_t desc_hi = umma_desc_sw128(0);
+            const uint32_t a16 = smem_u32(a_s) >> 4, w16 = smem_u32(w_s) >> 4, t16 = smem_u32(tail_s) >> 4;
+            int lt = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid, ++lt) {
+                const int slot = lt % kF2Slots, buf = lt & 3;
+                mbar_wait(&a_full[slot], (uint32_t)(lt / kF2Slots) & 1u);
+                mbar_wait(&acc_empty[buf], ((uint32_t)(lt >> 2) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)buf * (uint32_t)N;
+#pragma unroll
+                for (int ks = 0; ks < G::kSteps; ++ks) {
+                    const uint64_t ad = desc_hi | (uint64_t)(ks < 4 ? a16 + slot * 1024 + 2 * ks : t16 + 2 * slot);
+                    const uint64_t bd = desc_hi | (uint64_t)(ks < 4 ? w16 + 2 * ks : t16 + 6);
+                    umma_bf16(d, ad, bd, idesc, (uint32_t)(ks > 0));
+                }
+                umma_commit(&a_empty[slot]);
+                umma_commit(&acc_full[buf]);
+            }
+        }
+    } else if (warp < 6) {
+        // ===================== im2col builders =====================
+        const int team = (warp - 2) >> 1;
+        const int u = tid - 64 - team * 64;  // 0..63 inside the team
+        const int th = u >> 3, q = u & 7;
+        const int m0 = th * 16 + 2 * q;      // rows (pixels) m0, m0 + 1 of the tile
+        for (int lt = team;; lt += 2) {
+            const int tile = blockIdx.x + lt * grid;
+            if (tile >= p.total_tiles) break;
+            const int slot = lt % kF2Slots;
+            const uint32_t par = (uint32_t)(lt / kF2Slots) & 1u;
+            mbar_wait(&patch_full[slot], par);
+            const float* pt = reinterpret_cast<const float*>(patch_s + (size_t)slot * G::kPatchSlot) + (2 * th) * kF2PatchPitch + 4 * q;
+            uint32_t pa[G::kPk], pb[G::kPk];
+            float pend_a = 0.f, pend_b = 0.f;
+#pragma unroll
+            for (int r = 0; r < CIN * 5; ++r) {  // r = c * 5 + kh: one patch row per (channel, row tap)
+                const int c = r / 5, kh = r % 5;
+                const float* pr = pt + (c * kF2PatchRows + kh) * kF2PatchPitch;  // patch columns 4q+2 .. 4q+8
+                const float2 f0 = *reinterpret_cast<const float2*>(pr + 2);
+                const float4 f1 = *reinterpret_cast<const float4*>(pr + 4);
+                const float f[7] = {f0.x, f0.y, f1.x, f1.y, f1.z, f1.w, pr[8]};
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const int k = r * 5 + j;
+                    if (k & 1) {
+                        pa[k >> 1] = pack_bf16x2(pend_a, f[j]);
+                        pb[k >> 1] = pack_bf16x2(pend_b, f[j + 2]);
+                    } else {
+                        pend_a = f[j];
+                        pend_b = f[j + 2];
+                    }
+                }
+            }
+            // K (odd) .. : 1.0 against the bias hi / lo rows of W, then zeros
+            pa[G::kK >> 1] = pack_bf16x2(pend_a, 1.f);
+            pb[G::kK >> 1] = pack_bf16x2(pend_b, 1.f);
+            pa[(G::kK >> 1) + 1] = pb[(G::kK >> 1) + 1] = pack_bf16x2(1.f, 0.f);
+#pragma unroll
+            for (int i = (G::kK >> 1) + 2; i < G::kPk; ++i) pa[i] = pb[i] = 0u;
+            mbar_arrive(&patch_empty[slot]);  // the patch is in registers now
+
+            mbar_wait(&a_empty[slot], par ^ 1u);
+            uint8_t* a0 = a_s + (size_t)slot * 16384;
+#pragma unroll
+            for (int g = 0; g < G::kSteps * 2; ++g) {
+                uint8_t* base = (g < 8) ? a0 : tail_s;
+                const uint32_t chunk = (g < 8) ? (uint32_t)g : (uint32_t)(2 * slot + (g - 8));
+                *reinterpret_cast<uint4*>(base + sw128_offset(m0, chunk)) = make_uint4(pa[4 * g], pa[4 * g + 1], pa[4 * g + 2], pa[4 * g + 3]);
+                *reinterpret_cast<uint4*>(base + sw128_offset(m0 + 1, chunk)) = make_uint4(pb[4 * g], pb[4 * g + 1], pb[4 * g + 2], pb[4 * g + 3]);
+            }
+            fence_proxy_async();
+            mbar_arrive(&a_full[slot]);
+        }
+    } else {
+        // ===================== epilogue teams =====================
+        const int team = (warp - 6) >> 2;
+        const int row = (warp & 3) * 32 + lane;  // TMEM lane == row of the tile; warp % 4 selects the lane quadrant
+        const uint32_t lane_sel = ((uint32_t)(warp & 3) * 32u) << 16;
+        const bool leader = (warp & 3) == 0 && lane == 0;
+        uint8_t* stg = stg_s + (size_t)team * n_atoms * 16384;
+        const uint32_t idesc = umma_idesc_bf16(128, N);
+        const uint64_t desc_hi = umma_desc_sw128(0);
+        const uint32_t stg16 = smem_u32(stg) >> 4, g16 = smem_u32(g_s) >> 4;
+        const int n32 = N / 32;
+        uint32_t nit = 0;
+        for (int lt = team;; lt += 2) {
+            const int tile = blockIdx.x + lt * grid;
+            if (tile >= p.total_tiles) break;
+            int r = tile;
+            const int ow0 = (r % p.tiles_w) * 16;
+            r /= p.tiles_w;
+            const int oh0 = (r % p.tiles_h) * 8;
+            const int b = r / p.tiles_h;
+            const int buf = lt & 3;
+            const uint32_t t_acc = tmem_base + lane_sel + (uint32_t)buf * (uint32_t)N;
+
+            if (leader) tma_store_wait_read();  // this team's previous store has read the staging tile
+            named_bar_sync(1 + team, 128);
+            mbar_wait(&acc_full[buf], (uint32_t)(lt >> 2) & 1u);
+            tc_fence_after();
+
+            uint32_t xs[kGdn ? 64 : 1];
+            if (kGdn) {
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    if (cc < n32) {
+                        float v[32];
+                        tmem_ld32(t_acc + cc * 32, v);
+                        tmem_ld_wait();
+                        uint32_t sq[16];
+                        gdn_stage1_32<false>(v, nullptr, xs + cc * 16, sq);
+                        store_row32(stg, row, cc, sq);
+                    }
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                named_bar_sync(1 + team, 128);
+                if (leader) {
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + (uint32_t)buf * (uint32_t)N;
+                    for (uint32_t ks = 0; ks < (uint32_t)N / 16; ++ks) {
+                        const uint32_t atom = ks >> 2, off = (ks & 3) * 2;
+                        umma_bf16(d, desc_hi | (uint64_t)(stg16 + atom * 1024 + off),
+                                  desc_hi | (uint64_t)(g16 + atom * ((uint32_t)N * 8) + off), idesc, (uint32_t)(ks > 0));
+                    }
+                    umma_commit(&norm_full[team]);
+                }
+                mbar_wait(&norm_full[team], nit & 1u);
+                tc_fence_after();
+                ++nit;
+            }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                if (cc < n32) {
+                    float v[32];
+                    tmem_ld32(t_acc + cc * 32, v);
+                    tmem_ld_wait();
+                    uint32_t out[16];
+                    if (kGdn) {
+                        gdn_stage2_32<EPI == LICOS_EPI_IGDN>(v, beta_s + cc * 32, xs + cc * 16, out);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float x0 = v[2 * i], x1 = v[2 * i + 1];
+                            if (EPI == LICOS_EPI_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                            out[i] = pack_bf16x2(x0, x1);
+                        }
+                    }
+                    store_row32(stg, row, cc, out);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[buf]);
+            fence_proxy_async();
+            named_bar_sync(1 + team, 128);
+            if (leader) {
+                for (int at = 0; at < n_atoms; ++at)
+                    tma_store_4d(&p.out_map, stg + (size_t)at * 16384, at * 64, ow0, oh0, b);
+                tma_store_commit();
+            }
+        }
+        if (leader) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+}  // namespace licos

@@ -1,0 +1,97 @@
+// Register-level pieces of the fused conv epilogue shared by the conv kernels: packed fp32x2 arithmetic
+// (sm_100 FADD2 / FMUL2), TMEM -> bf16 staging conversion, and the two stages of the fused GDN / IGDN
+// (SURVEY.md section 8a row A5):
+//   stage 1   x = acc (+ bias);   x kept in registers as packed bf16;   x^2 (bf16) -> swizzled smem tile that is the
+//             A operand of the gamma GEMM, which overwrites the accumulator in place with gamma . x^2
+//   stage 2   d = norm + beta;    out = x * rsqrt(d)  (GDN)   or   x * d * rsqrt(d) = x * sqrt(d)  (IGDN)
+#pragma once
+
+#include "common.cuh"
+
+namespace licos {
+
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// bf16x2 from an fp32 pair (lo -> low half)
+__device__ __forceinline__ uint32_t f2_to_bf16x2(uint64_t v) {
+    float lo, hi;
+    f2_unpack(v, lo, hi);
+    return pack_bf16x2(lo, hi);
+}
+// fp32 pair from a bf16x2 (exact)
+__device__ __forceinline__ uint64_t bf16x2_to_f2(uint32_t v) {
+    return f2_pack(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+
+__device__ __forceinline__ float fast_rsqrt(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// 16 packed bf16 pairs (32 consecutive channels of one row) -> the four 16-byte chunks of the swizzled tile
+__device__ __forceinline__ void store_row32(uint8_t* tile_base, int row, int col32, const uint32_t (&pk)[16]) {
+    uint8_t* atom = tile_base + (size_t)((col32 * 32) / 64) * (128 * 128);
+    const uint32_t chunk0 = ((col32 * 32) % 64) / 8;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(atom + sw128_offset(row, chunk0 + q)) =
+            make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+}
+
+// stage 1 for 32 channels: v (fp32 accumulator columns, bias optional) -> xs (packed x), sq (packed x^2)
+template <bool ADD_BIAS>
+__device__ __forceinline__ void gdn_stage1_32(const float (&v)[32], const float* bias32, uint32_t* xs16, uint32_t (&sq)[16]) {
+    const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(bias32);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        uint64_t x0 = f2_pack(v[4 * q], v[4 * q + 1]), x1 = f2_pack(v[4 * q + 2], v[4 * q + 3]);
+        if (ADD_BIAS) {
+            const ulonglong2 b = b2[q];
+            x0 = f2_add(x0, b.x);
+            x1 = f2_add(x1, b.y);
+        }
+        xs16[2 * q] = f2_to_bf16x2(x0);
+        xs16[2 * q + 1] = f2_to_bf16x2(x1);
+        sq[2 * q] = f2_to_bf16x2(f2_mul(x0, x0));
+        sq[2 * q + 1] = f2_to_bf16x2(f2_mul(x1, x1));
+    }
+}
+
+// stage 2 for 32 channels: v = norm columns, beta32 in smem, xs16 = packed x -> out (packed bf16)
+template <bool INVERSE>
+__device__ __forceinline__ void gdn_stage2_32(const float (&v)[32], const float* beta32, const uint32_t* xs16,
+                                              uint32_t (&out)[16]) {
+    const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(beta32);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const ulonglong2 b = b2[q];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint64_t d = f2_add(f2_pack(v[4 * q + 2 * h], v[4 * q + 2 * h + 1]), h ? b.y : b.x);
+            float d0, d1;
+            f2_unpack(d, d0, d1);
+            uint64_t r = f2_pack(fast_rsqrt(d0), fast_rsqrt(d1));
+            if (INVERSE) r = f2_mul(r, d);  // d * rsqrt(d) = sqrt(d)
+            out[2 * q + h] = f2_to_bf16x2(f2_mul(bf16x2_to_f2(xs16[2 * q + h]), r));
+        }
+    }
+}
+
+}  // namespace licos
