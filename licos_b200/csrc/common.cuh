@@ -69,8 +69,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a pipeline bug becomes a trap (reported as a CUDA error) instead of a hung GPU.
-#ifdef LICOS_DEBUG_TRAP
 #include <stdio.h>
+#ifdef LICOS_DEBUG_TRAP
 #define mbar_wait(bar, parity) mbar_wait_dbg(bar, parity, __LINE__)
 static __device__ __noinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity, int line) {
     if (mbar_try_wait(bar, parity)) return;
@@ -83,6 +83,8 @@ static __device__ __noinline__ void mbar_wait_dbg(uint64_t* bar, uint32_t parity
     }
 }
 #else
+// (no printf here: a call on the cold path costs the single-thread issue loops ~5 %; build with
+// LICOS_NVCC_EXTRA=-DLICOS_DEBUG_TRAP to find out which barrier timed out)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();

@@ -1,16 +1,12 @@
-// Dedicated kernels for the two "edge" layers whose GEMM is degenerate:
+// Generic fused-im2col first layer (any C_in with 25 C_in <= 128, any width): the fallback of conv_first2.cuh for band
+// counts and row pitches its TMA patch loader does not cover.
 //
 //   conv_first_kernel     g_a[0]: Conv2d(C_in <= 5 -> N, 5x5, s2) + GDN/ReLU, fp32 NCHW in, bf16 NHWC out.
 //                         K = 25*C_in <= 128.  The im2col tile is built in shared memory by the CTA itself from
 //                         a staged input patch (the fp32 -> bf16 / NCHW -> NHWC conversion is fused into it),
 //                         then one short tcgen05 GEMM and the same fused GDN epilogue as the main engine.
-//   deconv_narrow_kernel  g_s[6]: ConvTranspose2d(C -> C_out <= 4, 5x5, s2), bf16 NHWC in, fp32 NCHW out.
-//                         Z[pixel, (tap, c_out)] = X[pixel, :] . W[:, (tap, c_out)] is ONE GEMM with N = 25*4
-//                         (8 MMAs per 128 pixels instead of 25 taps x 4 parities of N = 16 MMAs); the transposed
-//                         convolution is then a deterministic gather of <= 9 Z values per output pixel from
-//                         shared memory (col2im without atomics), written straight to fp32 NCHW.
 //
-// Both are plain (not warp-specialised) loops sized so that two CTAs share an SM and overlap each other.
+// A plain (not warp-specialised) loop sized so that two CTAs share an SM and overlap each other.
 #pragma once
 
 #include "common.cuh"
@@ -250,163 +246,6 @@ __global__ void __launch_bounds__(kEdgeThreads, 2) conv_first_kernel(const __gri
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base_smem, p.tmem_cols);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// last layer
-// ------------------------------------------------------------------------------------------------
-constexpr int kNarrowCpt = 4;                    // channel slots per tap in Z
-constexpr int kNarrowN = 112;                    // 25 taps x 4, rounded up to a multiple of 16
-constexpr int kZPitch = 116;                     // floats per Z row: 16-byte aligned and bank-conflict free
-constexpr int kNarrowRows = 6, kNarrowCols = 14; // interior of the 8 x 16 (one-pixel halo) input tile
-
-struct NarrowParams {
-    CUtensorMap in_map;  // NHWC bf16 (C, W, H, B), box (64, 16, 8, 1)
-    CUtensorMap w_map;   // [112][C] bf16, box (64, 112)
-    float* out;
-    const float* bias;
-    int B, H, W, C, out_c, OH, OW;
-    int chunks;
-    int tiles_h, tiles_w, total_tiles;
-    int relu;
-};
-
-__global__ void __launch_bounds__(kEdgeThreads, 2) deconv_narrow_kernel(const __grid_constant__ NarrowParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t w_bar, a_bar, mma_bar;
-    __shared__ uint32_t tmem_base_smem;
-    __shared__ float bias_s[kNarrowCpt];
-
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t w_atom_bytes = kNarrowN * 128u;
-    uint8_t* w_s = smem;                                             // chunks x [112][64] bf16
-    uint8_t* a_s = w_s + (((size_t)p.chunks * w_atom_bytes + 1023) & ~(size_t)1023);  // chunks x [128][64] bf16
-    float* z_s = reinterpret_cast<float*>(a_s);                      // aliases A: [128][kZPitch] fp32
-
-    const int tid = threadIdx.x, warp = tid >> 5;
-    if (tid == 0) {
-        mbar_init(&w_bar, 1);
-        mbar_init(&a_bar, 1);
-        mbar_init(&mma_bar, 1);
-        mbar_fence_init();
-    }
-    if (tid < kNarrowCpt) bias_s[tid] = (p.bias && tid < p.out_c) ? p.bias[tid] : 0.f;
-    if (warp == 1) {
-        tmem_alloc(&tmem_base_smem, 128);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_acc = tmem_base_smem;
-    if (tid == 0) {
-        mbar_arrive_expect_tx(&w_bar, (uint32_t)p.chunks * w_atom_bytes);
-        for (int c = 0; c < p.chunks; ++c) tma_load_2d(w_s + (size_t)c * w_atom_bytes, &p.w_map, &w_bar, c * 64, 0);
-    }
-    const uint32_t idesc = umma_idesc_bf16(128, kNarrowN);
-    const uint64_t desc_hi = umma_desc_sw128(0);
-    const uint32_t lane_sel = ((uint32_t)(warp & 3) * 32u) << 16;
-    uint32_t phase = 0;
-    bool first = true;
-
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int r = tile;
-        const int j0 = (r % p.tiles_w) * kNarrowCols;
-        r /= p.tiles_w;
-        const int i0 = (r % p.tiles_h) * kNarrowRows;
-        const int b = r / p.tiles_h;
-
-        // Z (aliasing A) of the previous tile has been consumed by every thread
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        if (tid == 0) {
-            mbar_arrive_expect_tx(&a_bar, (uint32_t)p.chunks * (128 * 128));
-            for (int c = 0; c < p.chunks; ++c)
-                tma_load_4d(a_s + (size_t)c * (128 * 128), &p.in_map, &a_bar, c * 64, j0 - 1, i0 - 1, b);
-            if (first) mbar_wait(&w_bar, 0);
-            mbar_wait(&a_bar, phase);
-            tc_fence_after();
-            const uint32_t a16 = smem_u32(a_s) >> 4, w16 = smem_u32(w_s) >> 4;
-            for (int c = 0; c < p.chunks; ++c)
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16(tmem_acc, desc_hi | (uint64_t)(a16 + c * 1024 + kk * 2),
-                              desc_hi | (uint64_t)(w16 + c * (w_atom_bytes >> 4) + kk * 2), idesc, (uint32_t)((c | kk) > 0));
-            umma_commit(&mma_bar);
-        }
-        first = false;
-
-        // ---- Z: TMEM -> shared (fp32), one row per pixel of the 8 x 16 tile ----
-        if (warp < 4) {
-            mbar_wait(&mma_bar, phase);
-            tc_fence_after();
-            float* zrow = z_s + (size_t)tid * kZPitch;
-            const uint32_t t_acc = tmem_acc + lane_sel;
-#pragma unroll
-            for (int cc = 0; cc < 3; ++cc) {
-                float v[32];
-                tmem_ld32(t_acc + cc * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    *reinterpret_cast<float4*>(zrow + cc * 32 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            }
-            float h[16];
-            tmem_ld16(t_acc + 96, h);
-            tmem_ld_wait();
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<float4*>(zrow + 96 + 4 * q) = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
-        }
-        phase ^= 1u;
-        tc_fence_before();
-        __syncthreads();
-
-        // ---- col2im as a gather: each output pixel sums the <= 9 taps that reach it ----
-        for (int o = tid; o < 2 * kNarrowRows * 2 * kNarrowCols; o += kEdgeThreads) {
-            const int oy = o / (2 * kNarrowCols), ox = o - oy * (2 * kNarrowCols);
-            const int Y = 2 * i0 + oy, X = 2 * j0 + ox;
-            if (Y >= p.OH || X >= p.OW) continue;
-            const int a = oy & 1, ii = oy >> 1, bq = ox & 1, jj = ox >> 1;
-            float acc[4] = {bias_s[0], bias_s[1], bias_s[2], bias_s[3]};
-            for (int kh = a; kh < 5; kh += 2) {
-                const int rr = 1 + ii + (a + 2 - kh) / 2;
-                for (int kw = bq; kw < 5; kw += 2) {
-                    const int cc = 1 + jj + (bq + 2 - kw) / 2;
-                    const float4 z = *reinterpret_cast<const float4*>(z_s + (size_t)(rr * 16 + cc) * kZPitch + (kh * 5 + kw) * kNarrowCpt);
-                    acc[0] += z.x; acc[1] += z.y; acc[2] += z.z; acc[3] += z.w;
-                }
-            }
-            float* o_ptr = p.out + ((size_t)b * p.out_c * p.OH + Y) * p.OW + X;
-            const size_t cs = (size_t)p.OH * p.OW;
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch)
-                if (ch < p.out_c) o_ptr[ch * cs] = p.relu ? fmaxf(acc[ch], 0.f) : acc[ch];
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base_smem, 128);
-    }
-}
-
-// packed[(tap * 4 + c)][cin_pad] for the narrow deconv; w is the ConvTranspose2d weight (in_c, out_c, 5, 5)
-__global__ void pack_weight_narrow_kernel(const float* __restrict__ w, int out_c, int in_c, int cin_pad,
-                                          __nv_bfloat16* __restrict__ packed) {
-    const int64_t total = (int64_t)kNarrowN * cin_pad;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        const int i = (int)(e % cin_pad);
-        const int row = (int)(e / cin_pad);
-        const int tap = row / kNarrowCpt, c = row % kNarrowCpt;
-        float v = 0.f;
-        if (tap < 25 && c < out_c && i < in_c) v = w[((size_t)i * out_c + c) * 25 + tap];
-        packed[e] = __float2bfloat16_rn(v);
     }
 }
 

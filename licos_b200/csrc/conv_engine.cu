@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "conv_edge.cuh"
 #include "conv_first2.cuh"
+#include "deconv_narrow2.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -607,7 +608,7 @@ static NPlan plan_n(int out_c) {
     return pl;
 }
 // g_s[6]-style layer: ConvTranspose2d to <= 4 channels -> GEMM + gather kernel
-static bool use_narrow(int kind, int out_c, int in_c) { return kind == LICOS_DECONV_5X5_S2 && out_c <= kNarrowCpt && in_c % 64 == 0 && in_c <= 256; }
+static bool use_narrow(int kind, int out_c, int in_c) { return kind == LICOS_DECONV_5X5_S2 && out_c <= kN2Cpt && in_c % 64 == 0 && in_c <= 256; }
 // g_a[0]-style layer: K = 25 * C_in fits two swizzle atoms -> fused in-kernel im2col
 static bool use_first_direct(int kind, int in_c, int out_c, int out_layout) {
     return kind == LICOS_CONV_5X5_S2 && in_c * 25 <= 128 && out_layout == LICOS_LAYOUT_NHWC_BF16 && out_c % 64 == 0 &&
@@ -806,7 +807,7 @@ static int launch_first2(const licos_conv_args* a, cudaStream_t s) {
 }
 
 static int launch_narrow(const licos_conv_args* a, cudaStream_t s) {
-    NarrowParams p;
+    Narrow2Params p;
     memset(&p, 0, sizeof(p));
     p.out = (float*)a->out;
     p.bias = a->bias;
@@ -814,36 +815,40 @@ static int launch_narrow(const licos_conv_args* a, cudaStream_t s) {
     p.OH = 2 * a->in_h; p.OW = 2 * a->in_w;
     p.chunks = a->in_c / 64;
     p.relu = a->epilogue == LICOS_EPI_RELU;
-    p.tiles_h = (a->in_h + kNarrowRows - 1) / kNarrowRows;
-    p.tiles_w = (a->in_w + kNarrowCols - 1) / kNarrowCols;
-    const int64_t tiles = (int64_t)a->batch * p.tiles_h * p.tiles_w;
-    if (tiles > 0x7fffffff) return LICOS_ERR_UNSUPPORTED;
-    p.total_tiles = (int)tiles;
+    p.strip_rows = a->in_h < 32 ? a->in_h : 32;
+    p.strips = (a->in_h + p.strip_rows - 1) / p.strip_rows;
+    p.segs = (a->in_w + kN2SegPx - 1) / kN2SegPx;
+    const int64_t units = (int64_t)a->batch * p.strips * p.segs;
+    if (units > 0x7fffffff) return LICOS_ERR_UNSUPPORTED;
+    p.total_units = (int)units;
     {
         const uint64_t C = (uint64_t)a->in_c, H = (uint64_t)a->in_h, W = (uint64_t)a->in_w;
         const uint64_t dims[4] = {C, W, H, (uint64_t)a->batch};
         const uint64_t strides[3] = {C, W * C, H * W * C};
-        const uint32_t box[4] = {64, 16, 8, 1};
+        const uint32_t box[4] = {64, (uint32_t)kN2BoxPx, 1, 1};
         if (!make_map(&p.in_map, a->in, 4, dims, strides, box)) return LICOS_ERR_CUDA;
     }
     {
-        const uint64_t dims[2] = {(uint64_t)a->in_c, (uint64_t)kNarrowN};
+        const uint64_t dims[2] = {(uint64_t)a->in_c, (uint64_t)(3 * kN2N)};
         const uint64_t strides[1] = {(uint64_t)a->in_c};
-        const uint32_t box[2] = {64, (uint32_t)kNarrowN};
+        const uint32_t box[2] = {64, (uint32_t)kN2N};
         if (!make_map(&p.w_map, a->weight, 2, dims, strides, box)) return LICOS_ERR_CUDA;
     }
-    const size_t w_bytes = ((size_t)p.chunks * kNarrowN * 128 + 1023) & ~(size_t)1023;
-    const size_t a_bytes = (size_t)p.chunks * 128 * 128, z_bytes = (size_t)128 * kZPitch * 4;
-    const size_t smem = 1024 + w_bytes + (a_bytes > z_bytes ? a_bytes : z_bytes);
+    const size_t w_bytes = (size_t)3 * p.chunks * kN2WTile, slot_bytes = (size_t)p.chunks * kN2ChunkStride;
+    int slots = (int)(((size_t)kMaxDynSmem - 1024 - w_bytes) / slot_bytes);
+    if (slots > kN2MaxSlots) slots = kN2MaxSlots;
+    if (slots < 2) return LICOS_ERR_UNSUPPORTED;
+    p.slots = slots;
+    size_t smem = 1024 + w_bytes + (size_t)slots * slot_bytes;
+    if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM: the accumulator ring owns all of TMEM
     int sms = 0;
     const int rc = sm_count_of(a, &sms);
     if (rc != LICOS_OK) return rc;
-    const int per_sm = smem <= 113000 ? 2 : 1;
-    const int grid = (int)(tiles < (int64_t)sms * per_sm ? tiles : (int64_t)sms * per_sm);
+    const int grid = (int)(units < sms ? units : sms);
     static cudaError_t attr =
-        cudaFuncSetAttribute(deconv_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+        cudaFuncSetAttribute(deconv_narrow2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     LICOS_CUDA_OK(attr);
-    deconv_narrow_kernel<<<grid, kEdgeThreads, smem, s>>>(p);
+    deconv_narrow2_kernel<<<grid, kN2Threads, smem, s>>>(p);
     LICOS_CUDA_OK(cudaGetLastError());
     return LICOS_OK;
 }
@@ -868,7 +873,7 @@ int64_t licos_packed_weight_bytes(int kind, int out_c, int in_c, int in_layout) 
         return (int64_t)pl.rows * first_kpad(in_c) * 2;
     }
     const int cin_pad = (in_c + 63) / 64 * 64;
-    if (use_narrow(kind, out_c, in_c)) return (int64_t)kNarrowN * cin_pad * 2;
+    if (use_narrow(kind, out_c, in_c)) return (int64_t)3 * kN2N * cin_pad * 2;
     return (int64_t)taps_of(kind) * pl.rows * cin_pad * 2;
 }
 
@@ -884,8 +889,8 @@ int licos_pack_conv_weight(const float* w, int kind, int out_c, int in_c, int in
                                                                                (__nv_bfloat16*)packed);
     } else if (use_narrow(kind, out_c, in_c)) {
         const int cin_pad = (in_c + 63) / 64 * 64;
-        pack_weight_narrow_kernel<<<ew_grid((int64_t)kNarrowN * cin_pad), 256, 0, s>>>(w, out_c, in_c, cin_pad,
-                                                                                     (__nv_bfloat16*)packed);
+        pack_weight_narrow2_kernel<<<ew_grid((int64_t)3 * kN2N * cin_pad), 256, 0, s>>>(w, out_c, in_c, cin_pad,
+                                                                                      (__nv_bfloat16*)packed);
     } else {
         const int cin_pad = (in_c + 63) / 64 * 64;
         const int K = kind == LICOS_CONV_3X3_S1 ? 3 : 5;

@@ -6,14 +6,15 @@
 //                              patch of the next 8 x 16 output tile into a 3-slot ring
 //   warp 1      MMA issuer     conv GEMM [128 px] x [K = 25 C_in + 2] x [N]: 2 (C_in = 1) or 5 (C_in = 3) tcgen05.mma;
 //                              the two extra K columns carry the bias as a bf16 hi + lo pair against A = 1.0
-//   warps 2-5   im2col         two 64-thread teams (alternate tiles); a thread builds the K-major, 128-byte-swizzled
-//                              rows of two neighbouring output pixels from 16-byte shared loads of the patch
-//                              (fusing fp32 -> bf16 and NCHW -> NHWC into the build)
+//   warps 2-5   im2col         128 threads build the K-major, 128-byte-swizzled A tile of every output tile from 8/16-byte
+//                              shared loads of the patch (fusing fp32 -> bf16 and NCHW -> NHWC into the build)
 //   warps 6-9   epilogue 0     alternate tiles: TMEM -> x (packed bf16 in registers), x^2 -> smem -> gamma GEMM (in
 //   warps 10-13 epilogue 1     place over the accumulator) -> x * rsqrt(beta + norm) -> bf16 -> TMA store
 //
 // Four TMEM accumulators (4 x N <= 512 columns), so the conv GEMM of tile t+2 never waits for the epilogue of tile t.
 #pragma once
+
+#include <type_traits>
 
 #include "common.cuh"
 #include "epilogue.cuh"
@@ -85,8 +86,8 @@ __global__ void __launch_bounds__(kF2Threads, 1) conv_first2_kernel(const __grid
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int i = 0; i < kF2Slots; ++i) {
-            mbar_init(&patch_full[i], 1); mbar_init(&patch_empty[i], 64);
-            mbar_init(&a_full[i], 64); mbar_init(&a_empty[i], 1);
+            mbar_init(&patch_full[i], 1); mbar_init(&patch_empty[i], 128);
+            mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1);
         }
         for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
         mbar_init(&norm_full[0], 1); mbar_init(&norm_full[1], 1);
@@ -183,54 +184,93 @@ __global__ void __launch_bounds__(kF2Threads, 1) conv_first2_kernel(const __grid
         }
     } else if (warp < 6) {
         // ===================== im2col builders =====================
-        const int team = (warp - 2) >> 1;
-        const int u = tid - 64 - team * 64;  // 0..63 inside the team
-        const int th = u >> 3, q = u & 7;
-        const int m0 = th * 16 + 2 * q;      // rows (pixels) m0, m0 + 1 of the tile
-        for (int lt = team;; lt += 2) {
-            const int tile = blockIdx.x + lt * grid;
-            if (tile >= p.total_tiles) break;
+        // All 128 threads work on every tile, so every thread passes through every phase of the ring barriers (a
+        // waiter that skipped phases could not tell them apart by parity).  C_in = 3: a thread builds HALF of the K
+        // range (K columns 0..39 or 40..79 = chunks 0..4 / 5..9) of two neighbouring pixels; C_in = 1: one pixel.
+        const int u = tid - 64;  // 0..127
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid, ++lt) {
             const int slot = lt % kF2Slots;
             const uint32_t par = (uint32_t)(lt / kF2Slots) & 1u;
+            uint8_t* a0 = a_s + (size_t)slot * 16384;
+            const float* patch = reinterpret_cast<const float*>(patch_s + (size_t)slot * G::kPatchSlot);
             mbar_wait(&patch_full[slot], par);
-            const float* pt = reinterpret_cast<const float*>(patch_s + (size_t)slot * G::kPatchSlot) + (2 * th) * kF2PatchPitch + 4 * q;
-            uint32_t pa[G::kPk], pb[G::kPk];
-            float pend_a = 0.f, pend_b = 0.f;
+            if constexpr (CIN == 3) {
+                const int half = u >> 6, th = (u >> 3) & 7, q = u & 7;
+                const int m0 = th * 16 + 2 * q;  // rows (pixels) m0, m0 + 1 of the tile
+                const float* pt = patch + (2 * th) * kF2PatchPitch + 4 * q;
+                uint32_t pa[20], pb[20];
+                float pend_a = 0.f, pend_b = 0.f;
+                auto rows = [&](auto first_row, auto n_rows) {
+                    constexpr int R0 = decltype(first_row)::value, NR = decltype(n_rows)::value;
 #pragma unroll
-            for (int r = 0; r < CIN * 5; ++r) {  // r = c * 5 + kh: one patch row per (channel, row tap)
-                const int c = r / 5, kh = r % 5;
-                const float* pr = pt + (c * kF2PatchRows + kh) * kF2PatchPitch;  // patch columns 4q+2 .. 4q+8
-                const float2 f0 = *reinterpret_cast<const float2*>(pr + 2);
-                const float4 f1 = *reinterpret_cast<const float4*>(pr + 4);
-                const float f[7] = {f0.x, f0.y, f1.x, f1.y, f1.z, f1.w, pr[8]};
+                    for (int r = R0; r < R0 + NR; ++r) {  // r = c * 5 + kh: one patch row per (channel, row tap)
+                        const int c = r / 5, kh = r % 5;
+                        const float* pr = pt + (c * kF2PatchRows + kh) * kF2PatchPitch;  // patch columns 4q+2 .. 4q+8
+                        const float2 f0 = *reinterpret_cast<const float2*>(pr + 2);
+                        const float4 f1 = *reinterpret_cast<const float4*>(pr + 4);
+                        const float f[7] = {f0.x, f0.y, f1.x, f1.y, f1.z, f1.w, pr[8]};
 #pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    const int k = r * 5 + j;
-                    if (k & 1) {
-                        pa[k >> 1] = pack_bf16x2(pend_a, f[j]);
-                        pb[k >> 1] = pack_bf16x2(pend_b, f[j + 2]);
-                    } else {
-                        pend_a = f[j];
-                        pend_b = f[j + 2];
+                        for (int j = 0; j < 5; ++j) {
+                            const int k = (r - R0) * 5 + j;  // K column relative to this half (both halves start even)
+                            if (k & 1) {
+                                pa[k >> 1] = pack_bf16x2(pend_a, f[j]);
+                                pb[k >> 1] = pack_bf16x2(pend_b, f[j + 2]);
+                            } else {
+                                pend_a = f[j];
+                                pend_b = f[j + 2];
+                            }
+                        }
+                    }
+                };
+                if (half == 0) {
+                    rows(std::integral_constant<int, 0>{}, std::integral_constant<int, 8>{});  // K 0..39
+                } else {
+                    rows(std::integral_constant<int, 8>{}, std::integral_constant<int, 7>{});  // K 40..74
+                    // K 75, 76: 1.0 against the bias hi / lo rows of W, then zeros
+                    pa[17] = pack_bf16x2(pend_a, 1.f);
+                    pb[17] = pack_bf16x2(pend_b, 1.f);
+                    pa[18] = pb[18] = pack_bf16x2(1.f, 0.f);
+                    pa[19] = pb[19] = 0u;
+                }
+                mbar_arrive(&patch_empty[slot]);  // the patch is in registers now
+                mbar_wait(&a_empty[slot], par ^ 1u);
+#pragma unroll
+                for (int gg = 0; gg < 5; ++gg) {
+                    const int g = half * 5 + gg;  // 16-byte chunk of the 80-column row
+                    uint8_t* base = (g < 8) ? a0 : tail_s;
+                    const uint32_t chunk = (g < 8) ? (uint32_t)g : (uint32_t)(2 * slot + (g - 8));
+                    *reinterpret_cast<uint4*>(base + sw128_offset(m0, chunk)) =
+                        make_uint4(pa[4 * gg], pa[4 * gg + 1], pa[4 * gg + 2], pa[4 * gg + 3]);
+                    *reinterpret_cast<uint4*>(base + sw128_offset(m0 + 1, chunk)) =
+                        make_uint4(pb[4 * gg], pb[4 * gg + 1], pb[4 * gg + 2], pb[4 * gg + 3]);
+                }
+            } else {
+                const int th = u >> 4, tw = u & 15;  // thread == pixel (row u of the tile)
+                const float* pt = patch + (2 * th) * kF2PatchPitch + 2 * tw;
+                uint32_t pa[16];
+                float pend = 0.f;
+#pragma unroll
+                for (int kh = 0; kh < 5; ++kh) {
+                    const float* pr = pt + kh * kF2PatchPitch;  // patch columns 2tw+2 .. 2tw+6
+                    const float2 f0 = *reinterpret_cast<const float2*>(pr + 2);
+                    const float2 f1 = *reinterpret_cast<const float2*>(pr + 4);
+                    const float f[5] = {f0.x, f0.y, f1.x, f1.y, pr[6]};
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        const int k = kh * 5 + j;
+                        if (k & 1) pa[k >> 1] = pack_bf16x2(pend, f[j]);
+                        else pend = f[j];
                     }
                 }
-            }
-            // K (odd) .. : 1.0 against the bias hi / lo rows of W, then zeros
-            pa[G::kK >> 1] = pack_bf16x2(pend_a, 1.f);
-            pb[G::kK >> 1] = pack_bf16x2(pend_b, 1.f);
-            pa[(G::kK >> 1) + 1] = pb[(G::kK >> 1) + 1] = pack_bf16x2(1.f, 0.f);
+                pa[12] = pack_bf16x2(pend, 1.f);  // K 24, then 1.0 (bias hi)
+                pa[13] = pack_bf16x2(1.f, 0.f);   // 1.0 (bias lo), zeros
+                pa[14] = pa[15] = 0u;
+                mbar_arrive(&patch_empty[slot]);
+                mbar_wait(&a_empty[slot], par ^ 1u);
 #pragma unroll
-            for (int i = (G::kK >> 1) + 2; i < G::kPk; ++i) pa[i] = pb[i] = 0u;
-            mbar_arrive(&patch_empty[slot]);  // the patch is in registers now
-
-            mbar_wait(&a_empty[slot], par ^ 1u);
-            uint8_t* a0 = a_s + (size_t)slot * 16384;
-#pragma unroll
-            for (int g = 0; g < G::kSteps * 2; ++g) {
-                uint8_t* base = (g < 8) ? a0 : tail_s;
-                const uint32_t chunk = (g < 8) ? (uint32_t)g : (uint32_t)(2 * slot + (g - 8));
-                *reinterpret_cast<uint4*>(base + sw128_offset(m0, chunk)) = make_uint4(pa[4 * g], pa[4 * g + 1], pa[4 * g + 2], pa[4 * g + 3]);
-                *reinterpret_cast<uint4*>(base + sw128_offset(m0 + 1, chunk)) = make_uint4(pb[4 * g], pb[4 * g + 1], pb[4 * g + 2], pb[4 * g + 3]);
+                for (int g = 0; g < 4; ++g)
+                    *reinterpret_cast<uint4*>(a0 + sw128_offset(u, g)) = make_uint4(pa[4 * g], pa[4 * g + 1], pa[4 * g + 2], pa[4 * g + 3]);
             }
             fence_proxy_async();
             mbar_arrive(&a_full[slot]);

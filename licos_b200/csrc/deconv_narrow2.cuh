@@ -1,0 +1,219 @@
+// g_s[6]: ConvTranspose2d(C -> C_out <= 4, 5x5, stride 2, padding 2, output_padding 1), bf16 NHWC in, fp32 NCHW out
+// (the model's last layer).  HBM-bound: it reads the largest activation of the model.
+//
+// o = 2i - 2 + k  =>  output (Y, X) = (2i' + a, 2j + b) takes row taps kh = a + 2 - 2dh from input row i' + dh and
+// column taps kw = b + 2 - 2dw from input column j + dw, dh, dw in {-1, 0, 1}.  The kernel splits the two directions:
+//
+//   columns  in the tensor core.  One GEMM per input row segment of 128 pixels, M = 128 pixels, N = 48 = (kh, b, c_out)
+//            [40 used], K = 3 shifts x C: the three column shifts dw are three views of ONE TMA-loaded row of 130
+//            pixels -- a SWIZZLE_128B K-major operand may start at any 128-byte row (the swizzle is a function of the
+//            absolute shared-memory address; tools/desc_test.cu) -- each against its own weight slice.
+//   rows     in the epilogue, for free.  The accumulators of consecutive input rows sit in a ring of 8 TMEM slots; the
+//            thread that owns pixel j (TMEM lane j) sums the <= 3 row taps from the slots of rows i'-1, i', i'+1 --
+//            all in its own lane -- adds the bias and stores the 2 x 2 x C_out outputs of its pixel as float2 pairs
+//            (a warp store = 256 contiguous bytes of one NCHW output row).
+//
+// No im2col, no shared-memory staging of partial sums, no atomics; every input byte is fetched from L2 once per strip.
+#pragma once
+
+#include "common.cuh"
+
+namespace licos {
+
+constexpr int kN2Threads = 6 * 32;       // warp 0 loader, warp 1 MMA issuer, warps 2-5 epilogue
+constexpr int kN2N = 48;                 // MMA N: 5 row taps x 2 column parities x 4 channel slots = 40, padded
+constexpr int kN2Cpt = 4;                // channel slots
+constexpr int kN2SegPx = 128;            // pixels per row segment (= MMA M)
+constexpr int kN2BoxPx = kN2SegPx + 2;   // one halo pixel either side
+constexpr uint32_t kN2ChunkStride = 17408;  // 130 rows x 128 B rounded up to a multiple of 1024
+constexpr uint32_t kN2WTile = kN2N * 128;   // one [48][64] bf16 weight tile
+constexpr int kN2AccSlots = 8, kN2AccStride = 64;
+constexpr int kN2MaxSlots = 4;
+
+struct Narrow2Params {
+    CUtensorMap in_map;  // NHWC bf16 (C, W, H, B), box (64, 130, 1, 1)
+    CUtensorMap w_map;   // [3 shifts x 48][C] bf16, box (64, 48)
+    float* out;
+    const float* bias;
+    int B, H, W, C, out_c, OH, OW;
+    int chunks;          // C / 64
+    int strip_rows, strips, segs, total_units;
+    int slots;           // A ring depth
+    int relu;
+};
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(kN2Threads, 1) deconv_narrow2_kernel(const __grid_constant__ Narrow2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t a_full[kN2MaxSlots], a_empty[kN2MaxSlots], acc_full[kN2AccSlots], acc_empty[kN2AccSlots], w_bar;
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ float bias_s[kN2Cpt];
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    uint8_t* w_s = smem;                                        // [shift][chunk] tiles of [48][64]
+    uint8_t* a_s = w_s + (size_t)3 * p.chunks * kN2WTile;       // ring of `slots` x chunks x [130][64]
+    const uint32_t slot_bytes = (uint32_t)p.chunks * kN2ChunkStride;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < kN2MaxSlots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < kN2AccSlots; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        mbar_init(&w_bar, 1);
+        mbar_fence_init();
+    }
+    if (tid < kN2Cpt) bias_s[tid] = (p.bias && tid < p.out_c) ? p.bias[tid] : 0.f;
+    if (warp == 1) {
+        tmem_alloc(&tmem_base_smem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    const int S = p.strip_rows;
+
+    if (warp == 0) {
+        // ===================== loader =====================
+        if (lane == 0) {
+            tma_prefetch_desc(&p.in_map);
+            mbar_arrive_expect_tx(&w_bar, 3u * (uint32_t)p.chunks * kN2WTile);
+            for (int s = 0; s < 3; ++s)
+                for (int c = 0; c < p.chunks; ++c)
+                    tma_load_2d(w_s + (size_t)(s * p.chunks + c) * kN2WTile, &p.w_map, &w_bar, c * 64, s * kN2N);
+            uint32_t n = 0;
+            for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
+                int r = unit;
+                const int j0 = (r % p.segs) * kN2SegPx;
+                r /= p.segs;
+                const int r0 = (r % p.strips) * S;
+                const int b = r / p.strips;
+                for (int t = 0; t < S + 2; ++t, ++n) {
+                    const uint32_t slot = n % (uint32_t)p.slots;
+                    mbar_wait(&a_empty[slot], ((n / (uint32_t)p.slots) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(&a_full[slot], (uint32_t)p.chunks * (kN2BoxPx * 128u));
+                    for (int c = 0; c < p.chunks; ++c)
+                        tma_load_4d(a_s + (size_t)slot * slot_bytes + (size_t)c * kN2ChunkStride, &p.in_map, &a_full[slot],
+                                    c * 64, j0 - 1, r0 - 1 + t, b);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            mbar_wait(&w_bar, 0);
+            const uint32_t idesc = umma_idesc_bf16(128, kN2N);
+            const uint64_t desc_hi = umma_desc_sw128(0);
+            const uint32_t a16 = smem_u32(a_s) >> 4, w16 = smem_u32(w_s) >> 4;
+            uint32_t n = 0;
+            for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
+                for (int t = 0; t < S + 2; ++t, ++n) {
+                    const uint32_t slot = n % (uint32_t)p.slots, acc = n % kN2AccSlots;
+                    mbar_wait(&a_full[slot], (n / (uint32_t)p.slots) & 1u);
+                    mbar_wait(&acc_empty[acc], ((n / kN2AccSlots) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + acc * kN2AccStride;
+                    uint32_t accumulate = 0;
+                    for (int s = 0; s < 3; ++s) {        // column shift dw = s - 1: the operand starts s pixels in
+                        for (int c = 0; c < p.chunks; ++c) {
+                            const uint32_t ab = a16 + ((slot * slot_bytes + (uint32_t)c * kN2ChunkStride + (uint32_t)s * 128u) >> 4);
+                            const uint32_t wb = w16 + (((uint32_t)(s * p.chunks + c) * kN2WTile) >> 4);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                umma_bf16(d, desc_hi | (uint64_t)(ab + 2 * k), desc_hi | (uint64_t)(wb + 2 * k), idesc, accumulate);
+                                accumulate = 1;
+                            }
+                        }
+                    }
+                    umma_commit(&a_empty[slot]);
+                    umma_commit(&acc_full[acc]);
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue: row taps + bias, straight to NCHW =====================
+        const int m = (warp & 3) * 32 + lane;  // pixel of the segment == TMEM lane
+        const uint32_t lane_sel = ((uint32_t)(warp & 3) * 32u) << 16;
+        const float b0 = bias_s[0], b1 = bias_s[1], b2 = bias_s[2], b3 = bias_s[3];
+        const size_t cs = (size_t)p.OH * p.OW;
+        uint32_t n0 = 0;
+        for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
+            int r = unit;
+            const int j = (r % p.segs) * kN2SegPx + m;
+            r /= p.segs;
+            const int r0 = (r % p.strips) * S;
+            const int b = r / p.strips;
+            for (int k = 0; k < S; ++k) {
+                const uint32_t g_lo = n0 + k, g_mid = g_lo + 1, g_up = g_lo + 2;  // GEMMs of rows i-1, i, i+1
+                mbar_wait(&acc_full[g_up % kN2AccSlots], (g_up / kN2AccSlots) & 1u);
+                tc_fence_after();
+                float up[16], mid[16], lo[8];
+                tmem_ld16(tmem_base + lane_sel + (g_up % kN2AccSlots) * kN2AccStride, up);         // kh = 0, 1
+                tmem_ld16(tmem_base + lane_sel + (g_mid % kN2AccSlots) * kN2AccStride + 16, mid);  // kh = 2, 3
+                tmem_ld8(tmem_base + lane_sel + (g_lo % kN2AccSlots) * kN2AccStride + 32, lo);     // kh = 4
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&acc_empty[g_lo % kN2AccSlots]);
+                const int i = r0 + k;
+                if (i < p.H && j < p.W) {
+                    // columns are [kh][b][c]: a = 0 <- kh 0 (up), 2 (mid), 4 (lo);  a = 1 <- kh 1 (up), 3 (mid)
+                    float o0[8], o1[8];
+                    const float bb[4] = {b0, b1, b2, b3};
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        o0[q] = up[q] + mid[q] + lo[q] + bb[q & 3];
+                        o1[q] = up[8 + q] + mid[8 + q] + bb[q & 3];
+                        if (p.relu) { o0[q] = fmaxf(o0[q], 0.f); o1[q] = fmaxf(o1[q], 0.f); }
+                    }
+                    float* o = p.out + ((size_t)b * p.out_c * p.OH + 2 * i) * p.OW + 2 * j;
+#pragma unroll
+                    for (int c = 0; c < kN2Cpt; ++c) {
+                        if (c < p.out_c) {
+                            *reinterpret_cast<float2*>(o + c * cs) = make_float2(o0[c], o0[4 + c]);
+                            *reinterpret_cast<float2*>(o + c * cs + p.OW) = make_float2(o1[c], o1[4 + c]);
+                        }
+                    }
+                }
+            }
+            // the two trailing rows of the strip are not the "row i-1" of any iteration: release them here
+            tc_fence_before();
+            mbar_arrive(&acc_empty[(n0 + S) % kN2AccSlots]);
+            mbar_arrive(&acc_empty[(n0 + S + 1) % kN2AccSlots]);
+            n0 += S + 2;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// packed[s][n][cin_pad]: s = dw + 1, n = kh * 8 + b * 4 + c; kw = b + 2 - 2 dw.  w is the ConvTranspose2d weight
+// (in_c, out_c, 5, 5).
+__global__ void pack_weight_narrow2_kernel(const float* __restrict__ w, int out_c, int in_c, int cin_pad,
+                                           __nv_bfloat16* __restrict__ packed) {
+    const int64_t total = (int64_t)3 * kN2N * cin_pad;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int i = (int)(e % cin_pad);
+        const int n = (int)((e / cin_pad) % kN2N);
+        const int s = (int)(e / ((int64_t)cin_pad * kN2N));
+        const int kh = n / 8, b = (n / 4) % 2, c = n % 4;
+        const int kw = b + 2 - 2 * (s - 1);
+        float v = 0.f;
+        if (kh < 5 && kw >= 0 && kw < 5 && c < out_c && i < in_c) v = w[((size_t)i * out_c + c) * 25 + kh * 5 + kw];
+        packed[e] = __float2bfloat16_rn(v);
+    }
+}
+
+}  // namespace licos
