@@ -94,6 +94,49 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 #endif
 
+// Whole-warp wait for warp-uniform issue loops: the vote makes the loop condition provably uniform, so the compiler
+// keeps the loop state of the caller in uniform registers (a per-thread spin makes everything after it "divergent").
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+    }
+}
+
+// Raw shared-address forms for the issue loops (the address is computed once, outside the loop).
+__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// non-blocking probe (no hardware suspend): used to look ahead at ring slots that may not be filled yet
+__device__ __forceinline__ bool mbar_test_wait_addr(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_warp_addr(uint32_t bar, uint32_t parity) {
+    while (!__all_sync(0xffffffffu, mbar_try_wait_addr(bar, parity))) {
+    }
+}
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor, tiled mode)
 // ----------------------------------------------------------------------------------------------

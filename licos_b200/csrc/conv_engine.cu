@@ -19,6 +19,7 @@
 // store clipping.  Replaces SURVEY.md section 8a rows A3, A4, A5.
 #include "common.cuh"
 #include "conv_edge.cuh"
+#include "epilogue.cuh"
 #include "conv_first2.cuh"
 #include "deconv_narrow2.cuh"
 
@@ -36,7 +37,7 @@ constexpr int kTileW = 16;    // tile columns
 constexpr int kAccRows = 8;   // tile rows per accumulator: 8 x 16 = 128 = MMA M
 constexpr int kKChunk = 64;   // channels per K chunk = one 128-byte swizzle atom of bf16
 constexpr uint32_t kRowBytes = kTileW * kKChunk * 2;  // one slab row: 2 KB
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;  // A producer, B producer, MMA issuer, (idle), 2 x 4 epilogue warps
 constexpr int kMaxSA = 4, kMaxSB = 8;
 constexpr uint32_t kTmemCols = 512;
 constexpr int kMaxDynSmem = 228000;  // 227 KB opt-in limit minus ~3.4 KB of static shared memory
@@ -86,9 +87,14 @@ struct ConvParams {
     const float* beta;
     int sa, sb;
     uint32_t a_slot_bytes, b_slot_bytes, staging_bytes, gamma_bytes;
+    unsigned long long pass_info[kMaxPasses];  // lean issue loop: per slab 5 bits {n_taps-1 : 2, first row_off : 2, descending : 1}
+    int lean;           // 1 = every slab's taps walk consecutive slab rows (pass_info valid), 0 = generic per-tap table walk
+    int n_teams;        // epilogue teams that take jobs (2, or 1 when two staging tiles do not fit in shared memory)
+    int jobs_per_pass;  // accumulators per pass (n_groups * n_acc): each is one epilogue job
     int n_buf;  // TMEM accumulator sets (2 = the epilogue of pass p overlaps the mainloop of pass p+1)
     int total_tiles;
     unsigned long long* dbg;  // optional per-CTA cycle probes (licos_debug_set_conv_probe)
+    int dbg_flags;            // LICOS_DBG_FLAGS experiments: 1 = A slabs loaded only once per ring slot, 2 = same for weights
 };
 
 // probe slots (per CTA, 16 x u64)
@@ -125,37 +131,46 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     constexpr bool kGdn = (EPI == LICOS_EPI_GDN || EPI == LICOS_EPI_IGDN);
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], b_full[kMaxSB], b_empty[kMaxSB];
-    __shared__ uint64_t acc_full[2], acc_empty[2], norm_full, g_full;
+    __shared__ uint64_t acc_full[2], acc_empty[2], norm_full[2], g_full;
     __shared__ uint32_t tmem_base_smem;
     __shared__ __align__(16) float bias_s[512];
     __shared__ __align__(16) float beta_s[256];
+    __shared__ int16_t w_taps_s[kMaxPasses][kMaxSlabs * kMaxTaps];  // weight tap of the i-th B tile of a pass (per chunk)
+    __shared__ int n_taps_s[kMaxPasses];
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
     uint8_t* a_ring = smem;
     uint8_t* b_ring = a_ring + (size_t)p.sa * p.a_slot_bytes;
-    uint8_t* staging = b_ring + (size_t)p.sb * p.b_slot_bytes;
-    uint8_t* gamma_s = staging + p.staging_bytes;  // resident gamma: (N / 64) atoms of [N][64] bf16
+    uint8_t* staging_all = b_ring + (size_t)p.sb * p.b_slot_bytes;  // one tile per epilogue team
+    uint8_t* gamma_s = staging_all + (size_t)p.n_teams * p.staging_bytes;   // resident gamma: (N / 64) atoms of [N][64] bf16
 
-    const int warp = threadIdx.x >> 5;
+    // the warp index through a shuffle: the compiler then knows the role branches are warp-uniform and keeps the
+    // issue loops' state in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
 
-    // Two MMA-issuing threads (one per accumulator sub-tile) when the tile has two sub-tiles: an mbarrier
-    // wait costs the issuing thread ~85 cycles even when already complete and tcgen05.mma cannot be queued far
-    // ahead, so a single issuer leaves the tensor pipe idle at every tap boundary; with two independent
-    // issue streams one thread's wait hides behind the other's MMAs.
-    const uint32_t n_iss = (p.n_acc == 2) ? 2u : 1u;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < p.sa; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], n_iss); }
-        for (int i = 0; i < p.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], n_iss); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], n_iss); mbar_init(&acc_empty[i], 128); }
-        mbar_init(&norm_full, 1);
+        for (int i = 0; i < p.sa; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < p.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 128u * (uint32_t)p.jobs_per_pass);
+            mbar_init(&norm_full[i], 1);
+        }
         mbar_init(&g_full, 1);
         mbar_fence_init();
     }
     for (int i = threadIdx.x; i < p.N * p.n_split; i += kThreads) bias_s[i] = (p.bias && i < p.out_c) ? p.bias[i] : 0.f;
     if (kGdn)
         for (int i = threadIdx.x; i < p.N; i += kThreads) beta_s[i] = p.beta[i];
+    if (threadIdx.x < p.n_passes) {
+        const Pass& ps = p.passes[threadIdx.x];
+        int n = 0;
+        for (int sl = 0; sl < ps.n_slabs; ++sl)
+            for (int k = 0; k < ps.slabs[sl].n_taps; ++k) w_taps_s[threadIdx.x][n++] = ps.slabs[sl].taps[k].w_tap;
+        n_taps_s[threadIdx.x] = n;
+    }
     if (warp == 2) {
         tmem_alloc(&tmem_base_smem, kTmemCols);
         tmem_relinquish();
@@ -169,6 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         // ===================== A producer =====================
         for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.in_maps[i]);
         Ring ra;
+        int n_loaded = 0;
         long long w_wait = 0;
         const long long t_begin = p.dbg ? clock64() : 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -179,6 +195,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                     for (int s = 0; s < ps.n_slabs; ++s) {
                         const Slab& sl = ps.slabs[s];
                         { PROBE_T0(); mbar_wait(&a_empty[ra.slot], ra.phase ^ 1u); PROBE_ADD(w_wait); }
+                        if ((p.dbg_flags & 1) && n_loaded >= p.sa) { mbar_arrive(&a_full[ra.slot]); ra.advance(p.sa); continue; }
+                        ++n_loaded;
                         mbar_arrive_expect_tx(&a_full[ra.slot], p.a_slot_bytes);
                         tma_load_4d(a_ring + (size_t)ra.slot * p.a_slot_bytes, &p.in_maps[sl.in_map], &a_full[ra.slot],
                                     c * kKChunk, t.gw0 + sl.dw, t.gh0 - 1, t.b);
@@ -191,172 +209,229 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             p.dbg[blockIdx.x * 16 + DBG_PA_WAIT] = w_wait;
             p.dbg[blockIdx.x * 16 + DBG_PA_TOTAL] = clock64() - t_begin;
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===================== B producer =====================
-        tma_prefetch_desc(&p.w_map);
-        if (kGdn) {  // gamma stays resident for the whole kernel
-            tma_prefetch_desc(&p.g_map);
-            mbar_arrive_expect_tx(&g_full, p.gamma_bytes);
-            for (int gc = 0; gc < p.N / kKChunk; ++gc)
-                tma_load_2d(gamma_s + (size_t)gc * p.N * 128, &p.g_map, &g_full, gc * kKChunk, 0);
+    } else if (warp == 1) {
+        // ===================== B producer (warp-uniform loop, one elected lane issues the TMA) =====================
+        if (lane == 0) {
+            tma_prefetch_desc(&p.w_map);
+            if (kGdn) {  // gamma stays resident for the whole kernel
+                tma_prefetch_desc(&p.g_map);
+                mbar_arrive_expect_tx(&g_full, p.gamma_bytes);
+                for (int gc = 0; gc < p.N / kKChunk; ++gc)
+                    tma_load_2d(gamma_s + (size_t)gc * p.N * 128, &p.g_map, &g_full, gc * kKChunk, 0);
+            }
         }
-        Ring rb;
-        long long w_wait = 0;
-        const long long t_begin = p.dbg ? clock64() : 0;
+        __syncwarp();
+        uint32_t slot = 0, phase = 0;
+        int n_loaded = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const TileCoord t = decode_tile(p, tile);
+            const int ns_row = (tile % p.n_split) * p.N;
             for (int pi = 0; pi < p.n_passes; ++pi) {
-                const Pass& ps = p.passes[pi];
+                const int nt = n_taps_s[pi];
                 for (int c = 0; c < p.cin_chunks; ++c) {
-                    for (int s = 0; s < ps.n_slabs; ++s) {
-                        const Slab& sl = ps.slabs[s];
-                        for (int k = 0; k < sl.n_taps; ++k) {
-                            { PROBE_T0(); mbar_wait(&b_empty[rb.slot], rb.phase ^ 1u); PROBE_ADD(w_wait); }
-                            mbar_arrive_expect_tx(&b_full[rb.slot], p.b_slot_bytes);
-                            tma_load_2d(b_ring + (size_t)rb.slot * p.b_slot_bytes, &p.w_map, &b_full[rb.slot], c * kKChunk,
-                                        sl.taps[k].w_tap * p.w_rows_per_tap + t.ns * p.N);
-                            rb.advance(p.sb);
+                    for (int i = 0; i < nt; ++i) {
+                        const int row = (int)w_taps_s[pi][i] * p.w_rows_per_tap + ns_row;
+                        mbar_wait_warp(&b_empty[slot], phase ^ 1u);
+                        if (elect_one()) {
+                            if ((p.dbg_flags & 2) && n_loaded >= p.sb) {
+                                mbar_arrive(&b_full[slot]);
+                            } else {
+                                mbar_arrive_expect_tx(&b_full[slot], p.b_slot_bytes);
+                                tma_load_2d(b_ring + (size_t)slot * p.b_slot_bytes, &p.w_map, &b_full[slot], c * kKChunk, row);
+                            }
                         }
+                        __syncwarp();
+                        ++n_loaded;
+                        slot = (slot + 1 == (uint32_t)p.sb) ? 0u : slot + 1;
+                        phase ^= (slot == 0u) ? 1u : 0u;
                     }
                 }
             }
         }
-        if (p.dbg) {
-            p.dbg[blockIdx.x * 16 + DBG_PB_WAIT] = w_wait;
-            p.dbg[blockIdx.x * 16 + DBG_PB_TOTAL] = clock64() - t_begin;
-        }
-    } else if ((warp == 2 || (warp == 3 && n_iss == 2)) && lane == 0) {
-        // ===================== MMA issuer(s) =====================
-        const uint32_t iss = (uint32_t)warp - 2u;
-        // One thread issues everything, so the code between two tcgen05.mma must stay well under the
-        // 64 cycles an M128 x N128 x K16 MMA occupies the tensor pipe: descriptors are built once per
-        // tile and advanced by adding to their low word.
+    } else if (warp == 2) {
+        // ===================== MMA issuer =====================
+        // Measured (tools/mma_bench3-6.cu): tcgen05.mma issue is synchronous with the issuing thread's instruction
+        // stream.  The pipe sustains its 64-cycle rate (M128 N128 K16) only while the next MMA is presented within a few
+        // cycles; every instruction of the issuing thread between two MMAs -- ring bookkeeping, descriptor arithmetic,
+        // ~90 cycles per (completed) mbarrier wait -- runs at full latency (one warp, nothing to hide it behind) and
+        // idles the pipe, while a commit is free.  So: a WARP-UNIFORM loop with the MMAs of a tap issued back to back by the
+        // elected lane (no R2UR / ELECT sequence per MMA), alternating between the two accumulators; descriptors advance
+        // by register adds (the taps of a slab walk consecutive slab rows: pass_info); no table loads, no probes.
+        // Variants that were measured and dropped: two issuers, one per accumulator (fall into lock-step on the shared
+        // barriers); 2 / 4 issuers taking alternate taps with a shared turn counter (the hand-over costs as much as the
+        // bookkeeping it hides); one test_wait probing all ring slots at once (the waits were not the bottleneck).
         const uint32_t idesc = umma_idesc_bf16(128, p.N);
         const uint64_t desc_hi = umma_desc_sw128(0);
         const uint32_t a_ring_addr = smem_u32(a_ring) >> 4, b_ring_addr = smem_u32(b_ring) >> 4;
         const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_slot16 = p.b_slot_bytes >> 4;
-        const uint32_t n_acc = p.n_acc, N = p.N;
-        const uint32_t my_accs = (n_iss == 2) ? 1u : n_acc;  // accumulators of a group this thread drives
-        Ring ra, rb;
-        uint32_t pit = 0;
-        long long w_a = 0, w_b = 0, w_acc = 0, w_x2 = 0, n_tiles = 0;
+        const uint32_t n_acc = p.n_acc, N = p.N, sa = p.sa, sb = p.sb;
+        constexpr uint32_t kAccStep16 = (kAccRows * kRowBytes) >> 4;
+        uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0, pit = 0;
         const long long t_begin = p.dbg ? clock64() : 0;
+        long long n_tiles = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             ++n_tiles;
-            for (int pi = 0; pi < p.n_passes; ++pi) {
+            for (int pi = 0; pi < p.n_passes; ++pi, ++pit) {
                 const Pass& ps = p.passes[pi];
                 const uint32_t buf = pit % (uint32_t)p.n_buf;
-                { PROBE_T0(); mbar_wait(&acc_empty[buf], ((pit / (uint32_t)p.n_buf) & 1u) ^ 1u); PROBE_ADD(w_acc); }
+                mbar_wait_warp(&acc_empty[buf], ((pit / (uint32_t)p.n_buf) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t tmem_set = tmem_base + buf * (uint32_t)(ps.n_groups * (int)n_acc) * N;
-                uint32_t touched = 0;
-                for (int c = 0; c < p.cin_chunks; ++c) {
-                    for (int s = 0; s < ps.n_slabs; ++s) {
-                        const Slab& sl = ps.slabs[s];
-                        { PROBE_T0(); mbar_wait(&a_full[ra.slot], ra.phase); PROBE_ADD(w_a); }
-                        const uint32_t a_slab = a_ring_addr + ra.slot * a_slot16;
-                        const int n_taps = sl.n_taps;
-                        for (int k = 0; k < n_taps; ++k) {
-                            const Tap tp = sl.taps[k];
-                            { PROBE_T0(); mbar_wait(&b_full[rb.slot], rb.phase); PROBE_ADD(w_b); }
-                            tc_fence_after();
-                            const uint64_t bd = desc_hi | (uint64_t)(b_ring_addr + rb.slot * b_slot16);
-                            uint64_t ad = desc_hi | (uint64_t)(a_slab + ((uint32_t)tp.row_off + iss * kAccRows) * (kRowBytes >> 4));
-                            uint32_t acc = (uint32_t)tp.group * n_acc + iss;
-                            for (uint32_t a = 0; a < my_accs; ++a, ++acc, ad += (kAccRows * kRowBytes) >> 4) {
-                                const uint32_t d = tmem_set + acc * N;
-                                umma_bf16(d, ad, bd, idesc, (touched >> acc) & 1u);
-                                umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
-                                umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
-                                umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
-                                touched |= 1u << acc;
+                if (p.lean) {
+                    const int n_slabs = ps.n_slabs;
+                    uint32_t accumulate = 0;
+                    for (int c = 0; c < p.cin_chunks; ++c) {
+                        unsigned long long info = p.pass_info[pi];
+                        for (int s = 0; s < n_slabs; ++s) {
+                            const int nt = (int)(info & 3u) + 1;
+                            uint32_t a_lo = a_ring_addr + a_slot * a_slot16 + ((uint32_t)(info >> 2) & 3u) * (kRowBytes >> 4);
+                            const uint32_t a_step = (info & 16u) ? 0u - (kRowBytes >> 4) : (kRowBytes >> 4);
+                            info >>= 5;
+                            mbar_wait_warp(&a_full[a_slot], a_phase);
+                            for (int k = 0; k < nt; ++k) {
+                                mbar_wait_warp(&b_full[b_slot], b_phase);
+                                tc_fence_after();
+                                const uint64_t bd = desc_hi | (uint64_t)(b_ring_addr + b_slot * b_slot16);
+                                const uint64_t ad = desc_hi | (uint64_t)a_lo;
+                                if (elect_one()) {
+                                    if (n_acc == 2) {
+                                        umma_bf16(tmem_set, ad, bd, idesc, accumulate);
+                                        umma_bf16(tmem_set + N, ad + kAccStep16, bd, idesc, accumulate);
+#pragma unroll
+                                        for (uint32_t ks = 1; ks < 4; ++ks) {
+                                            umma_bf16(tmem_set, ad + 2 * ks, bd + 2 * ks, idesc, 1u);
+                                            umma_bf16(tmem_set + N, ad + kAccStep16 + 2 * ks, bd + 2 * ks, idesc, 1u);
+                                        }
+                                    } else {
+                                        umma_bf16(tmem_set, ad, bd, idesc, accumulate);
+#pragma unroll
+                                        for (uint32_t ks = 1; ks < 4; ++ks) umma_bf16(tmem_set, ad + 2 * ks, bd + 2 * ks, idesc, 1u);
+                                    }
+                                    umma_commit(&b_empty[b_slot]);
+                                }
+                                __syncwarp();
+                                accumulate = 1;
+                                a_lo += a_step;
+                                b_slot = (b_slot + 1 == sb) ? 0u : b_slot + 1;
+                                b_phase ^= (b_slot == 0u) ? 1u : 0u;
                             }
-                            umma_commit(&b_empty[rb.slot]);
-                            rb.advance(p.sb);
+                            if (elect_one()) umma_commit(&a_empty[a_slot]);
+                            __syncwarp();
+                            a_slot = (a_slot + 1 == sa) ? 0u : a_slot + 1;
+                            a_phase ^= (a_slot == 0u) ? 1u : 0u;
                         }
-                        umma_commit(&a_empty[ra.slot]);
-                        ra.advance(p.sa);
+                    }
+                } else {
+                    // generic walk of the tap table (merged multi-group passes): rare shapes, not tuned
+                    uint32_t touched = 0;
+                    for (int c = 0; c < p.cin_chunks; ++c) {
+                        for (int s = 0; s < ps.n_slabs; ++s) {
+                            const Slab& sl = ps.slabs[s];
+                            mbar_wait_warp(&a_full[a_slot], a_phase);
+                            const uint32_t a_slab = a_ring_addr + a_slot * a_slot16;
+                            const int n_taps = sl.n_taps;
+                            for (int k = 0; k < n_taps; ++k) {
+                                const Tap tp = sl.taps[k];
+                                mbar_wait_warp(&b_full[b_slot], b_phase);
+                                tc_fence_after();
+                                const uint64_t bd = desc_hi | (uint64_t)(b_ring_addr + b_slot * b_slot16);
+                                uint64_t ad = desc_hi | (uint64_t)(a_slab + (uint32_t)tp.row_off * (kRowBytes >> 4));
+                                uint32_t acc = (uint32_t)tp.group * n_acc;
+                                if (elect_one()) {
+                                    for (uint32_t a = 0; a < n_acc; ++a, ++acc, ad += kAccStep16) {
+                                        const uint32_t d = tmem_set + acc * N;
+                                        umma_bf16(d, ad, bd, idesc, (touched >> acc) & 1u);
+                                        umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+                                        umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
+                                        umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
+                                    }
+                                    umma_commit(&b_empty[b_slot]);
+                                }
+                                __syncwarp();
+                                for (uint32_t a = 0; a < n_acc; ++a) touched |= 1u << ((uint32_t)tp.group * n_acc + a);
+                                b_slot = (b_slot + 1 == sb) ? 0u : b_slot + 1;
+                                b_phase ^= (b_slot == 0u) ? 1u : 0u;
+                            }
+                            if (elect_one()) umma_commit(&a_empty[a_slot]);
+                            __syncwarp();
+                            a_slot = (a_slot + 1 == sa) ? 0u : a_slot + 1;
+                            a_phase ^= (a_slot == 0u) ? 1u : 0u;
+                        }
                     }
                 }
-                umma_commit(&acc_full[buf]);
-                ++pit;
+                if (elect_one()) umma_commit(&acc_full[buf]);
+                __syncwarp();
             }
         }
-        if (p.dbg && iss == 0) {
+        if (p.dbg && lane == 0) {
             unsigned long long* d = p.dbg + blockIdx.x * 16;
-            d[DBG_MMA_A] = w_a; d[DBG_MMA_B] = w_b; d[DBG_MMA_ACC] = w_acc; d[DBG_MMA_X2] = w_x2;
+            d[DBG_MMA_A] = 0; d[DBG_MMA_B] = 0; d[DBG_MMA_ACC] = 0; d[DBG_MMA_X2] = 0;
             d[DBG_MMA_TOTAL] = clock64() - t_begin; d[DBG_TILES] = n_tiles;
         }
     } else if (warp >= 4) {
-        // ===================== epilogue =====================
-        const int et = threadIdx.x - 128;  // == TMEM lane == row of the 128-row sub-tile
+        // ===================== epilogue: two teams of 4 warps, alternate accumulators =====================
+        const int team = (warp - 4) >> 2;
+        const int et = (warp & 3) * 32 + lane;  // == TMEM lane == row of the 128-row sub-tile
         const uint32_t lane_sel = ((uint32_t)(warp & 3) * 32u) << 16;
+        const bool leader = et == 0;
         const int th = et / kTileW, tw = et % kTileW;
-        uint32_t pit = 0, nit = 0;
+        uint8_t* staging = staging_all + (size_t)team * p.staging_bytes;
+        uint32_t pit = 0, nit = 0, job = 0;
         const int n32 = p.N / 32;
         const uint32_t idesc = umma_idesc_bf16(128, p.N);
         const uint64_t desc_hi = umma_desc_sw128(0);
         const uint32_t staging16 = smem_u32(staging) >> 4, gamma16 = smem_u32(gamma_s) >> 4;
         bool gamma_ready = false;
+        const bool probe = p.dbg && leader && team == 0;
         long long e_acc = 0, e_s1 = 0, e_norm = 0, e_s2 = 0, e_store = 0;
-        const long long t_begin = p.dbg ? clock64() : 0;
+        const long long t_begin = probe ? clock64() : 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const TileCoord t = decode_tile(p, tile);
             const float* bias_t = bias_s + t.ns * p.N;
-            for (int pi = 0; pi < p.n_passes; ++pi) {
+            for (int pi = 0; pi < p.n_passes; ++pi, ++pit) {
                 const Pass& ps = p.passes[pi];
                 const uint32_t buf = pit % (uint32_t)p.n_buf;
-                { PROBE_T0(); mbar_wait(&acc_full[buf], (pit / (uint32_t)p.n_buf) & 1u); PROBE_ADD(e_acc); }
-                tc_fence_after();
                 const uint32_t tmem_set = tmem_base + lane_sel + buf * (uint32_t)(ps.n_groups * p.n_acc) * p.N;
+                bool waited = false;
                 for (int g = 0; g < ps.n_groups; ++g) {
                     for (int a = 0; a < p.n_acc; ++a) {
+                        if (((job++) & (uint32_t)(p.n_teams - 1)) != (uint32_t)team) continue;
+                        if (!waited) {
+                            const long long _t = probe ? clock64() : 0;
+                            mbar_wait(&acc_full[buf], (pit / (uint32_t)p.n_buf) & 1u);
+                            if (probe) e_acc += clock64() - _t;
+                            tc_fence_after();
+                            waited = true;
+                        }
                         const uint32_t acc = (uint32_t)g * p.n_acc + a;
                         const uint32_t t_acc = tmem_set + acc * p.N;
 
-                        if (OUT_NHWC) {
-                            // the previous TMA store must have finished reading `staging` before it is rewritten
-                            const long long _st = p.dbg ? clock64() : 0;
-                            if (et == 0) tma_store_wait_read();
-                            named_bar_sync(1, 128);
-                            if (p.dbg) e_store += clock64() - _st;
+                        if (OUT_NHWC || kGdn) {
+                            // this team's previous TMA store must have finished reading `staging` before it is rewritten
+                            const long long _st = probe ? clock64() : 0;
+                            if (OUT_NHWC && leader) tma_store_wait_read();
+                            named_bar_sync(1 + team, 128);
+                            if (probe) e_store += clock64() - _st;
                         }
                         uint32_t xs[kGdn ? XC * 16 : 1];  // v = acc + bias kept as packed bf16 pairs
                         if (kGdn) {
                             // stage 1: v^2 (bf16) -> staging = A operand of the gamma GEMM; the GEMM then overwrites
                             // the accumulator IN PLACE with the norm (no second TMEM region -> room to double-buffer)
-                            const long long _s1 = p.dbg ? clock64() : 0;
+                            const long long _s1 = probe ? clock64() : 0;
 #pragma unroll
                             for (int cc = 0; cc < XC; ++cc) {
                                 if (cc < n32) {
                                     float v[32];
                                     tmem_ld32(t_acc + cc * 32, v);
                                     tmem_ld_wait();
-                                    const float4* b4 = reinterpret_cast<const float4*>(bias_t + cc * 32);
-                                    uint32_t pk[16];
-#pragma unroll
-                                    for (int q = 0; q < 8; ++q) {
-                                        const float4 b = b4[q];
-                                        const float x0 = v[4 * q] + b.x, x1 = v[4 * q + 1] + b.y;
-                                        const float x2 = v[4 * q + 2] + b.z, x3 = v[4 * q + 3] + b.w;
-                                        xs[cc * 16 + 2 * q] = pack_bf16x2(x0, x1);
-                                        xs[cc * 16 + 2 * q + 1] = pack_bf16x2(x2, x3);
-                                        pk[2 * q] = pack_bf16x2(x0 * x0, x1 * x1);
-                                        pk[2 * q + 1] = pack_bf16x2(x2 * x2, x3 * x3);
-                                    }
-                                    uint8_t* atom = staging + (size_t)((cc * 32) / kKChunk) * (128 * 128);
-                                    const uint32_t chunk0 = ((cc * 32) % kKChunk) / 8;
-#pragma unroll
-                                    for (int q = 0; q < 4; ++q) {
-                                        *reinterpret_cast<uint4*>(atom + sw128_offset(et, chunk0 + q)) =
-                                            make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-                                    }
+                                    uint32_t sq[16];
+                                    gdn_stage1_32<true>(v, bias_t + cc * 32, xs + cc * 16, sq);
+                                    store_row32(staging, et, cc, sq);
                                 }
                             }
                             fence_proxy_async();
                             tc_fence_before();
-                            named_bar_sync(1, 128);
-                            if (et == 0) {
+                            named_bar_sync(1 + team, 128);
+                            if (leader) {
                                 if (!gamma_ready) { mbar_wait(&g_full, 0); gamma_ready = true; }
                                 tc_fence_after();
                                 const uint32_t d = tmem_set - lane_sel + acc * p.N;
@@ -366,16 +441,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                                               desc_hi | (uint64_t)(gamma16 + atom * ((uint32_t)p.N * 8) + off), idesc,
                                               (uint32_t)(ks > 0));
                                 }
-                                umma_commit(&norm_full);
+                                umma_commit(&norm_full[team]);
                             }
-                            if (p.dbg) e_s1 += clock64() - _s1;
-                            { PROBE_T0(); mbar_wait(&norm_full, nit & 1u); PROBE_ADD(e_norm); }
+                            if (probe) e_s1 += clock64() - _s1;
+                            const long long _n = probe ? clock64() : 0;
+                            mbar_wait(&norm_full[team], nit & 1u);
+                            if (probe) e_norm += clock64() - _n;
                             tc_fence_after();
                             ++nit;
                         }
 
                         // stage 2: activation, then write out
-                        const long long _s2 = p.dbg ? clock64() : 0;
+                        const long long _s2 = probe ? clock64() : 0;
                         const int gh = t.gh0 + a * kAccRows + th, gw = t.gw0 + tw;
                         const int oh = gh * p.out_s + ps.dy[g], ow = gw * p.out_s + ps.dx[g];
                         const bool in_range = gh < p.grid_h && gw < p.grid_w && oh < p.out_h && ow < p.out_w;
@@ -390,40 +467,39 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                                 float v[32];
                                 tmem_ld32(t_acc + cc * 32, v);  // GDN: the norm; otherwise the accumulator
                                 tmem_ld_wait();
-                                const float4* b4 = reinterpret_cast<const float4*>((kGdn ? beta_s : bias_t) + cc * 32);
+                                if (kGdn) {
+                                    uint32_t out[16];
+                                    gdn_stage2_32<EPI == LICOS_EPI_IGDN>(v, beta_s + cc * 32, xs + cc * 16, out);
+                                    if (OUT_NHWC) {
+                                        store_row32(staging, et, cc, out);
+                                    } else if (in_range) {
 #pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    const float4 b = b4[q];
-                                    float x[4] = {v[4 * q] + b.x, v[4 * q + 1] + b.y, v[4 * q + 2] + b.z, v[4 * q + 3] + b.w};
-                                    if (kGdn) {
-                                        const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&xs[cc * 16 + 2 * q]);
-                                        const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&xs[cc * 16 + 2 * q + 1]);
-                                        const float xv[4] = {__low2float(p0), __high2float(p0), __low2float(p1), __high2float(p1)};
-#pragma unroll
-                                        for (int i = 0; i < 4; ++i) {
-                                            const float r = rsqrtf(x[i]);  // x[i] = norm + beta > 0
-                                            x[i] = xv[i] * ((EPI == LICOS_EPI_GDN) ? r : x[i] * r);  // d*rsqrt(d) = sqrt(d)
+                                        for (int j = 0; j < 16; ++j) {
+                                            if (cc * 32 + 2 * j < c_left) o[(size_t)(cc * 32 + 2 * j) * cs] = __uint_as_float(out[j] << 16);
+                                            if (cc * 32 + 2 * j + 1 < c_left) o[(size_t)(cc * 32 + 2 * j + 1) * cs] = __uint_as_float(out[j] & 0xffff0000u);
                                         }
-                                    } else if (EPI == LICOS_EPI_RELU) {
-#pragma unroll
-                                        for (int i = 0; i < 4; ++i) x[i] = fmaxf(x[i], 0.f);
                                     }
+                                } else {
+                                    const float4* b4 = reinterpret_cast<const float4*>(bias_t + cc * 32);
 #pragma unroll
-                                    for (int i = 0; i < 4; ++i) v[4 * q + i] = x[i];
-                                }
-                                if (OUT_NHWC) {
-                                    uint8_t* atom = staging + (size_t)((cc * 32) / kKChunk) * (128 * 128);
-                                    const uint32_t chunk0 = ((cc * 32) % kKChunk) / 8;
+                                    for (int q = 0; q < 8; ++q) {
+                                        const float4 b = b4[q];
+                                        v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+                                        if (EPI == LICOS_EPI_RELU) {
 #pragma unroll
-                                    for (int q = 0; q < 4; ++q) {
-                                        *reinterpret_cast<uint4*>(atom + sw128_offset(et, chunk0 + q)) =
-                                            make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                                                       pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+                                            for (int i = 0; i < 4; ++i) v[4 * q + i] = fmaxf(v[4 * q + i], 0.f);
+                                        }
                                     }
-                                } else if (in_range) {
+                                    if (OUT_NHWC) {
+                                        uint32_t out[16];
 #pragma unroll
-                                    for (int j = 0; j < 32; ++j)
-                                        if (cc * 32 + j < c_left) o[(size_t)(cc * 32 + j) * cs] = v[j];
+                                        for (int i = 0; i < 16; ++i) out[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+                                        store_row32(staging, et, cc, out);
+                                    } else if (in_range) {
+#pragma unroll
+                                        for (int j = 0; j < 32; ++j)
+                                            if (cc * 32 + j < c_left) o[(size_t)(cc * 32 + j) * cs] = v[j];
+                                    }
                                 }
                             }
                         }
@@ -438,29 +514,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                                 if (in_range && n32 * 32 + j < c_left) o[(size_t)(n32 * 32 + j) * cs] = x;
                             }
                         }
-                        if (p.dbg) e_s2 += clock64() - _s2;
+                        // this accumulator has been read: hand it back to the MMA issuer
+                        tc_fence_before();
+                        mbar_arrive(&acc_empty[buf]);
+                        if (probe) e_s2 += clock64() - _s2;
                         if (OUT_NHWC) {
-                            const long long _st = p.dbg ? clock64() : 0;
+                            const long long _st = probe ? clock64() : 0;
                             fence_proxy_async();
-                            named_bar_sync(1, 128);
-                            if (et == 0) {
+                            named_bar_sync(1 + team, 128);
+                            if (leader) {
                                 for (int at = 0; at < p.N / kKChunk; ++at) {
                                     tma_store_4d(&p.out_maps[ps.out_map[g]], staging + (size_t)at * (128 * 128),
                                                  at * kKChunk, t.gw0, t.gh0 + a * kAccRows, t.b);
                                 }
                                 tma_store_commit();
                             }
-                            if (p.dbg) e_store += clock64() - _st;
+                            if (probe) e_store += clock64() - _st;
                         }
                     }
                 }
-                tc_fence_before();
-                mbar_arrive(&acc_empty[buf]);
-                ++pit;
             }
         }
-        if (et == 0) tma_store_wait_all();
-        if (p.dbg && et == 0) {
+        if (leader) tma_store_wait_all();
+        if (probe) {
             unsigned long long* d = p.dbg + blockIdx.x * 16;
             d[DBG_EPI_ACC] = e_acc; d[DBG_EPI_S1] = e_s1; d[DBG_EPI_NORM] = e_norm; d[DBG_EPI_S2] = e_s2;
             d[DBG_EPI_STORE] = e_store; d[DBG_EPI_TOTAL] = clock64() - t_begin;
@@ -1015,7 +1091,7 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     if (groups * n_acc * pl.N > (int)kTmemCols) return LICOS_ERR_UNSUPPORTED;
     p.n_acc = n_acc;
     p.n_buf = (2 * groups * n_acc * pl.N <= (int)kTmemCols) ? 2 : 1;
-    if (getenv("LICOS_NBUF1")) p.n_buf = 1;
+    p.jobs_per_pass = groups * n_acc;
     const int TH = kAccRows * n_acc;
     const int R = TH + 2;
 
@@ -1097,6 +1173,23 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
         }
     }
 
+    // ---- lean issue-loop encoding: the taps of every slab must walk consecutive slab rows, one group ----
+    p.lean = groups == 1;
+    for (int pi = 0; pi < p.n_passes && p.lean; ++pi) {
+        const Pass& ps = p.passes[pi];
+        unsigned long long info = 0;
+        for (int sidx = 0; sidx < ps.n_slabs && p.lean; ++sidx) {
+            const Slab& sl = ps.slabs[sidx];
+            const int nt = sl.n_taps, r0 = sl.taps[0].row_off;
+            const int step = nt > 1 ? sl.taps[1].row_off - r0 : 1;
+            if (nt < 1 || nt > 4 || r0 < 0 || r0 > 3 || (step != 1 && step != -1)) p.lean = 0;
+            for (int k = 1; k < nt; ++k)
+                if (sl.taps[k].row_off != r0 + k * step || sl.taps[k].group != 0) p.lean = 0;
+            info |= (unsigned long long)((nt - 1) | (r0 << 2) | ((step < 0 ? 1 : 0) << 4)) << (5 * sidx);
+        }
+        p.pass_info[pi] = info;
+    }
+
     // ---- tensor maps ---------------------------------------------------------------------------
     const uint64_t C = (uint64_t)cin_pad, H = (uint64_t)in_h, W = (uint64_t)in_w, B = (uint64_t)a->batch;
     const uint32_t in_box[4] = {(uint32_t)kKChunk, (uint32_t)kTileW, (uint32_t)R, 1};
@@ -1156,21 +1249,27 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     p.staging_bytes = (gdn || a->out_layout == LICOS_LAYOUT_NHWC_BF16) ? (uint32_t)(pl.N / kKChunk) * 128u * 128u : 0u;
     p.gamma_bytes = gdn ? (uint32_t)(pl.N / kKChunk) * (uint32_t)pl.N * 128u : 0u;
     const int64_t b_slot_al = p.b_slot_bytes;  // N is a multiple of 16, so N*128 is a multiple of 2 KB
-    const int64_t budget = kMaxDynSmem - 1024 - (int64_t)p.staging_bytes - (int64_t)p.gamma_bytes;
-    int sb = 5, sa = 0;
-    while (sa < 2 && sb > 2) {  // prefer >= 4 weight slots, give them up when the resident gamma leaves no room
-        --sb;
-        sa = (int)((budget - (int64_t)sb * b_slot_al) / p.a_slot_bytes);
+    int sa = 0, sb = 0;
+    for (p.n_teams = 2; p.n_teams >= 1; --p.n_teams) {
+        const int64_t budget = kMaxDynSmem - 1024 - (int64_t)p.n_teams * p.staging_bytes - (int64_t)p.gamma_bytes;
+        sb = 5;
+        sa = 0;
+        while (sa < 2 && sb > 2) {  // prefer >= 4 weight slots, give them up when the resident gamma leaves no room
+            --sb;
+            sa = (int)((budget - (int64_t)sb * b_slot_al) / p.a_slot_bytes);
+        }
+        if (sa < 2) continue;
+        if (sa > kMaxSA) sa = kMaxSA;
+        int64_t left = budget - (int64_t)sa * p.a_slot_bytes - (int64_t)sb * b_slot_al;
+        while (sb < kMaxSB && left >= b_slot_al) { ++sb; left -= b_slot_al; }
+        break;
     }
-    if (sa < 2) return LICOS_ERR_UNSUPPORTED;
-    if (sa > kMaxSA) sa = kMaxSA;
-    int64_t left = budget - (int64_t)sa * p.a_slot_bytes - (int64_t)sb * b_slot_al;
-    while (sb < kMaxSB && left >= b_slot_al) { ++sb; left -= b_slot_al; }
+    if (p.n_teams < 1) return LICOS_ERR_UNSUPPORTED;
     if (const char* e = getenv("LICOS_SA")) { const int v = atoi(e); if (v >= 2 && v <= kMaxSA) sa = v; }
     if (const char* e = getenv("LICOS_SB")) { const int v = atoi(e); if (v >= 2 && v <= kMaxSB) sb = v; }
     p.sa = sa;
     p.sb = sb;
-    size_t smem_bytes = 1024 + (size_t)sa * p.a_slot_bytes + (size_t)sb * b_slot_al + p.staging_bytes + p.gamma_bytes;
+    size_t smem_bytes = 1024 + (size_t)sa * p.a_slot_bytes + (size_t)sb * b_slot_al + (size_t)p.n_teams * p.staging_bytes + p.gamma_bytes;
     if (smem_bytes > (size_t)kMaxDynSmem) return LICOS_ERR_UNSUPPORTED;
     if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;  // one CTA per SM: each CTA owns all 512 TMEM columns
 
@@ -1180,6 +1279,7 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     if (tiles > 0x7fffffff) return LICOS_ERR_UNSUPPORTED;
     p.total_tiles = (int)tiles;
     p.dbg = g_conv_probe;
+    if (const char* e = getenv("LICOS_DBG_FLAGS")) p.dbg_flags = atoi(e);
 
     int sms = a->sm_count;
     if (sms <= 0) {

@@ -26,6 +26,9 @@ LAYERS = [  # kind, cin, cout, H, W (input), epilogue, first, out_nchw
     ("plain 128->128 (no GDN)", _lib.CONV_5X5_S2, 128, 128, 128, 128, _lib.EPI_NONE, False, False),
 ]
 probe = torch.zeros(16 * 160, dtype=torch.int64, device=dev)
+SEL = os.environ.get("LAYERS")
+if SEL:
+    LAYERS = [LAYERS[int(i)] for i in SEL.split(",")]
 for name, kind, cin, cout, H, W, epi, first, nchw in LAYERS:
     kk = 5
     x = torch.randn(B, cin, H, W, generator=g)
