@@ -378,7 +378,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         uint32_t pit = 0, nit = 0, job = 0;
         const int n32 = p.N / 32;
         const uint32_t idesc = umma_idesc_bf16(128, p.N);
-        const uint64_t desc_hi = umma_desc_sw128(0);
         const uint32_t staging16 = smem_u32(staging) >> 4, gamma16 = smem_u32(gamma_s) >> 4;
         bool gamma_ready = false;
         const bool probe = p.dbg && leader && team == 0;
@@ -431,17 +430,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                             fence_proxy_async();
                             tc_fence_before();
                             named_bar_sync(1 + team, 128);
-                            if (leader) {
+                            if ((warp & 3) == 0) {  // the team's first warp, converged after the barrier
                                 if (!gamma_ready) { mbar_wait(&g_full, 0); gamma_ready = true; }
                                 tc_fence_after();
-                                const uint32_t d = tmem_set - lane_sel + acc * p.N;
-                                for (uint32_t ks = 0; ks < (uint32_t)p.N / 16; ++ks) {
-                                    const uint32_t atom = ks >> 2, off = (ks & 3) * 2;
-                                    umma_bf16(d, desc_hi | (uint64_t)(staging16 + atom * 1024 + off),
-                                              desc_hi | (uint64_t)(gamma16 + atom * ((uint32_t)p.N * 8) + off), idesc,
-                                              (uint32_t)(ks > 0));
+                                if (elect_one()) {
+                                    issue_gamma_gemm_n(tmem_set - lane_sel + acc * p.N, staging16, gamma16, (uint32_t)p.N, idesc);
+                                    umma_commit(&norm_full[team]);
                                 }
-                                umma_commit(&norm_full[team]);
+                                __syncwarp();
                             }
                             if (probe) e_s1 += clock64() - _s1;
                             const long long _n = probe ? clock64() : 0;

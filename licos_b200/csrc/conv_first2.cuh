@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(kF2Threads, 1) conv_first2_kernel(const __grid
     uint8_t* stg_s = a_s + (size_t)kF2Slots * 16384;
     uint8_t* patch_s = stg_s + (size_t)2 * n_atoms * 16384;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform role dispatch
     if (tid == 0) {
         for (int i = 0; i < kF2Slots; ++i) {
             mbar_init(&patch_full[i], 1); mbar_init(&patch_empty[i], 128);
@@ -283,7 +284,6 @@ __global__ void __launch_bounds__(kF2Threads, 1) conv_first2_kernel(const __grid
         const bool leader = (warp & 3) == 0 && lane == 0;
         uint8_t* stg = stg_s + (size_t)team * n_atoms * 16384;
         const uint32_t idesc = umma_idesc_bf16(128, N);
-        const uint64_t desc_hi = umma_desc_sw128(0);
         const uint32_t stg16 = smem_u32(stg) >> 4, g16 = smem_u32(g_s) >> 4;
         const int n32 = N / 32;
         uint32_t nit = 0;
@@ -319,15 +319,13 @@ __global__ void __launch_bounds__(kF2Threads, 1) conv_first2_kernel(const __grid
                 fence_proxy_async();
                 tc_fence_before();
                 named_bar_sync(1 + team, 128);
-                if (leader) {
+                if ((warp & 3) == 0) {  // the team's first warp, converged after the barrier
                     tc_fence_after();
-                    const uint32_t d = tmem_base + (uint32_t)buf * (uint32_t)N;
-                    for (uint32_t ks = 0; ks < (uint32_t)N / 16; ++ks) {
-                        const uint32_t atom = ks >> 2, off = (ks & 3) * 2;
-                        umma_bf16(d, desc_hi | (uint64_t)(stg16 + atom * 1024 + off),
-                                  desc_hi | (uint64_t)(g16 + atom * ((uint32_t)N * 8) + off), idesc, (uint32_t)(ks > 0));
+                    if (elect_one()) {
+                        issue_gamma_gemm_n(tmem_base + (uint32_t)buf * (uint32_t)N, stg16, g16, (uint32_t)N, idesc);
+                        umma_commit(&norm_full[team]);
                     }
-                    umma_commit(&norm_full[team]);
+                    __syncwarp();
                 }
                 mbar_wait(&norm_full[team], nit & 1u);
                 tc_fence_after();

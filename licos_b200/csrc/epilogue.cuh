@@ -94,4 +94,27 @@ __device__ __forceinline__ void gdn_stage2_32(const float (&v)[32], const float*
     }
 }
 
+// The gamma GEMM of the fused GDN: D[tmem] = A (x^2 staging tile, K-major, 128-byte swizzle, atoms of 64 channels)
+// x B (resident gamma, same layout), KS = C / 16 MMAs issued back to back.  Call from ONE elected lane of a converged
+// warp: inside an elect_one() block the compiler keeps the operands in uniform registers (no per-MMA R2UR / ELECT loop).
+template <int KS>
+__device__ __forceinline__ void issue_gamma_gemm(uint32_t d_tmem, uint32_t stg16, uint32_t gamma16, uint32_t n_rows,
+                                                 uint32_t idesc) {
+    const uint64_t desc_hi = umma_desc_sw128(0);
+#pragma unroll
+    for (uint32_t ks = 0; ks < (uint32_t)KS; ++ks) {
+        const uint32_t atom = ks >> 2, off = (ks & 3) * 2;
+        umma_bf16(d_tmem, desc_hi | (uint64_t)(stg16 + atom * 1024 + off), desc_hi | (uint64_t)(gamma16 + atom * (n_rows * 8) + off),
+                  idesc, (uint32_t)(ks > 0));
+    }
+}
+__device__ __forceinline__ void issue_gamma_gemm_n(uint32_t d_tmem, uint32_t stg16, uint32_t gamma16, uint32_t N, uint32_t idesc) {
+    switch (N) {
+        case 64: issue_gamma_gemm<4>(d_tmem, stg16, gamma16, N, idesc); break;
+        case 128: issue_gamma_gemm<8>(d_tmem, stg16, gamma16, N, idesc); break;
+        case 192: issue_gamma_gemm<12>(d_tmem, stg16, gamma16, N, idesc); break;
+        default: issue_gamma_gemm<16>(d_tmem, stg16, gamma16, N, idesc); break;  // 256
+    }
+}
+
 }  // namespace licos
