@@ -31,6 +31,13 @@ TILE = (3, 256, 256)
 # 2 x MACs of conv + deconv + GDN for one 3x256x256 tile (5.528 GFLOP each way)
 FLOP_PER_TILE_ENCODE = 2 * 2764.05e6
 FLOP_PER_TILE_DECODE = 2 * 2764.05e6
+# The dominant kernel (conv_igemm_kernel) runs g_a[2], g_a[4], g_a[6], g_s[0], g_s[2], g_s[4] with their fused GDN / IGDN:
+# MACs per tile = conv + gamma GEMM = (1677.7 + 67.1) + (419.4 + 16.8) + 157.3 + (157.3 + 16.8) + (419.4 + 67.1) + (1677.7 + 268.4) M
+FLOP_PER_TILE_ENGINE = 2 * 4945.0e6
+# HBM-bound kernels: algorithmic bytes per tile (every tensor read once, written once)
+BYTES_PER_TILE_FIRST = 3 * 256 * 256 * 4 + 128 * 128 * 128 * 2   # g_a[0]: fp32 NCHW x in, bf16 NHWC out
+BYTES_PER_TILE_LAST = 128 * 128 * 128 * 2 + 3 * 256 * 256 * 4    # g_s[6]: bf16 NHWC in, fp32 NCHW x_hat out
+BYTES_PER_TILE_EB = 192 * 16 * 16 * 12                           # y in, y_hat + likelihoods out (12 B / latent element)
 
 
 def parse():
@@ -224,9 +231,18 @@ def run_b200(args):
 
     ops.conv_forward = counted_conv
 
+    eb_ms = {"events": None}
+
     def encode(xb):
         y = net.g_a(xb)
-        y_hat, lik = eb(y)
+        if eb_ms["events"] is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            y_hat, lik = eb(y)
+            e1.record()
+            eb_ms["events"].append((e0, e1))
+        else:
+            y_hat, lik = eb(y)
         sym = eb.symbols(y)
         return y, y_hat, lik, sym
 
@@ -279,19 +295,30 @@ def run_b200(args):
 
         # ---- per-launch durations of the dominant kernel (conv igemm), live, CUDA events on this stream ----
         conv_ms["events"] = []
-        inst_steps = 3
+        eb_ms["events"] = []
+        inst_steps = 5
         for _ in range(inst_steps):
             step(x)
         torch.cuda.synchronize()
         per_layer = {}
-        conv_total_ms = 0.0
+        conv_total_ms = engine_total_ms = first_total_ms = last_total_ms = 0.0
         for e0, e1, kind, cin, cout, shape in conv_ms["events"]:
             ms = e0.elapsed_time(e1)
             conv_total_ms += ms
+            if cin <= 16:
+                first_total_ms += ms          # conv_first2_kernel
+            elif cout <= 4:
+                last_total_ms += ms           # deconv_narrow2_kernel
+            else:
+                engine_total_ms += ms         # conv_igemm_kernel
             key = f"{['conv5s2', 'deconv5s2', 'conv3s1'][kind]}_{cin}->{cout}_{shape[-2] if len(shape) == 4 else ''}"
             per_layer.setdefault(key, []).append(ms)
+        eb_total_ms = sum(e0.elapsed_time(e1) for e0, e1 in eb_ms["events"])
         conv_ms["events"] = None
+        eb_ms["events"] = None
         conv_ms_per_step = conv_total_ms / inst_steps
+        engine_ms_per_step = engine_total_ms / inst_steps
+        first_ms, last_ms, eb_ms_step = first_total_ms / inst_steps, last_total_ms / inst_steps, eb_total_ms / inst_steps
 
         # ---- end to end through the public model API with HOST buffers ----
         if args.no_e2e:
@@ -300,18 +327,22 @@ def run_b200(args):
             e2e = run_e2e(net, eb, x, args, torch, device, world)
 
     # max over ranks
-    t = torch.tensor([total_ms, enc_ms, dec_ms, conv_ms_per_step, e2e["ms_per_step"]], dtype=torch.float64,
-                     device=device)
+    t = torch.tensor([total_ms, enc_ms, dec_ms, conv_ms_per_step, e2e["ms_per_step"], engine_ms_per_step, first_ms,
+                      last_ms, eb_ms_step], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, enc_ms, dec_ms, conv_ms_per_step, e2e_ms = t.tolist()
+    total_ms, enc_ms, dec_ms, conv_ms_per_step, e2e_ms, engine_ms_per_step, first_ms, last_ms, eb_ms_step = t.tolist()
 
     pix_per_step = B * TILE[1] * TILE[2] * world
     ms_per_step = total_ms / args.steps
     value = pix_per_step / (ms_per_step * 1e-3) / 1e6
     pk = peaks()
-    flop_per_step_gpu = B * (FLOP_PER_TILE_ENCODE + FLOP_PER_TILE_DECODE)
-    achieved_tflops = flop_per_step_gpu / (conv_ms_per_step * 1e-3) / 1e12
+    achieved_tflops = B * FLOP_PER_TILE_ENGINE / (engine_ms_per_step * 1e-3) / 1e12
+
+    def hbm(name, bytes_per_tile, ms, note):
+        gbs = B * bytes_per_tile / (ms * 1e-3) / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": gbs / pk["hbm_gbs"], "ms_per_launch": round(ms, 4), "note": note}
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
@@ -339,12 +370,22 @@ def run_b200(args):
                     "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                     "path": "pinned host x -> model.g_a / entropy_bottleneck / g_s -> x_hat, symbols, bpp on host"},
             "gpu_launches": n_launch,
-            "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (8 launches per step: 4 conv + 4 deconv layers, GDN/IGDN fused)",
+            "roofline": {"bound": "tensor",
+                         "kernel": "conv_igemm_kernel (6 launches per step: g_a[2,4,6], g_s[0,2,4], GDN/IGDN fused)",
                          "achieved": achieved_tflops, "peak": pk["tflops"], "unit": "TFLOP/s",
                          "frac": achieved_tflops / pk["tflops"], "traffic": traffic,
                          "peak_source": pk["source"],
+                         "algorithmic": "2 x (conv + gamma-GEMM MACs) of the 6 layers = 9.89 GFLOP per tile, summed over "
+                                        "the 6 launches / their summed CUDA-event durations (an instrumented pass)",
                          "per_launch_ms": {k: round(statistics.mean(v), 4) for k, v in per_layer.items()},
+                         "share_of_step": engine_ms_per_step / ms_per_step,
                          "conv_share_of_step": conv_ms_per_step / ms_per_step},
+            "roofline_hbm": [
+                hbm("conv_first2_kernel (g_a[0] + GDN)", BYTES_PER_TILE_FIRST, first_ms, "fp32 NCHW x in, bf16 NHWC out"),
+                hbm("deconv_narrow2_kernel (g_s[6])", BYTES_PER_TILE_LAST, last_ms, "bf16 NHWC in, fp32 NCHW x_hat out"),
+                hbm("eb_lut_kernel + eb_eval_kernel (quantise + likelihoods)", BYTES_PER_TILE_EB, eb_ms_step,
+                    "12 B per latent element (two launches)"),
+            ],
         }
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -364,45 +405,49 @@ def run_e2e(net, eb, x_dev, args, torch, device, world):
     ysz = (B, eb.channels, TILE[1] // 16, TILE[2] // 16)
     xhat_host = torch.empty(x_host.shape, dtype=torch.float32).pin_memory()
     sym_host = torch.empty(ysz, dtype=torch.int32).pin_memory()
-    bpp_host = torch.empty(1, dtype=torch.float64).pin_memory()
+    bpp_host = torch.empty(16, dtype=torch.float64).pin_memory()
     chunk = max(1, min(args.e2e_chunk, B))
     streams = [torch.cuda.Stream(device=device) for _ in range(3)]
     steps = max(3, min(args.steps, 10))
 
-    def one():
-        accs = [torch.zeros(1, dtype=torch.float64, device=device) for _ in streams]
+    # Tiles stream through three CUDA streams, chunk by chunk, continuously across steps (no join between steps: a
+    # deployed coder does not drain its pipeline every 256 tiles).  Every step's inputs are copied from pinned host
+    # memory and its x_hat, symbols and bpp land in pinned host memory inside the timed region.
+    def run(n_steps):
+        accs = torch.zeros(n_steps, len(streams), dtype=torch.float64, device=device)
         main = torch.cuda.current_stream()
         for s in streams:
             s.wait_stream(main)
-        for i, lo in enumerate(range(0, B, chunk)):
-            hi = min(B, lo + chunk)
-            s = streams[i % len(streams)]
-            with torch.cuda.stream(s):
-                xb = x_host[lo:hi].to(device, non_blocking=True)
-                y = net.g_a(xb)
-                y_hat, lik = eb(y)
-                sym = eb.symbols(y)
-                x_hat = net.g_s(y_hat)
-                ops.sum_log(lik, accs[i % len(streams)])  # per-stream accumulator, summed after the join
-                xhat_host[lo:hi].copy_(x_hat, non_blocking=True)
-                sym_host[lo:hi].copy_(sym, non_blocking=True)
+        k = 0
+        for it in range(n_steps):
+            for lo in range(0, B, chunk):
+                hi = min(B, lo + chunk)
+                si = k % len(streams)
+                k += 1
+                with torch.cuda.stream(streams[si]):
+                    xb = x_host[lo:hi].to(device, non_blocking=True)
+                    y = net.g_a(xb)
+                    y_hat, lik = eb(y)
+                    sym = eb.symbols(y)
+                    x_hat = net.g_s(y_hat)
+                    ops.sum_log(lik, accs[it, si:si + 1])  # per-(step, stream) accumulator, summed after the join
+                    xhat_host[lo:hi].copy_(x_hat, non_blocking=True)
+                    sym_host[lo:hi].copy_(sym, non_blocking=True)
         for s in streams:
             main.wait_stream(s)
-        total = accs[0] + accs[1] + accs[2]
-        bpp_host.copy_(total / (-math.log(2) * B * TILE[1] * TILE[2]), non_blocking=True)
+        bpp = accs.sum(dim=1) / (-math.log(2) * B * TILE[1] * TILE[2])
+        bpp_host[:n_steps].copy_(bpp, non_blocking=True)
 
-    for _ in range(2):
-        one()
+    run(2)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        one()
+    run(steps)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / steps
     return {"ms_per_step": dt * 1e3, "h2d": x_host.numel() * 4,
-            "d2h": xhat_host.numel() * 4 + sym_host.numel() * 4 + 8, "bpp": float(bpp_host.item())}
+            "d2h": xhat_host.numel() * 4 + sym_host.numel() * 4 + 8, "bpp": float(bpp_host[0].item())}
 
 
 if __name__ == "__main__":
