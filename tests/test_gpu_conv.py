@@ -158,3 +158,58 @@ def test_unsupported_shapes_fail_loudly(cuda):
                          weight=w, bias=None)
     with pytest.raises(RuntimeError):
         ops.nchw_to_nhwc_bf16(torch.zeros(1, 3, 4, 4))
+
+
+def test_first_layer_pipelined_variants(cuda):
+    # conv_first2_kernel: both band counts, both widths, every epilogue, partial tiles (OH, OW not multiples of 8 / 16),
+    # more tiles than SMs (ring slots and TMEM buffers wrap many times)
+    _run(cuda, _lib.CONV_5X5_S2, 1, 1, 64, 32, 36, epi=_lib.EPI_GDN, first=True)
+    _run(cuda, _lib.CONV_5X5_S2, 2, 3, 64, 40, 24, epi=_lib.EPI_RELU, first=True)
+    _run(cuda, _lib.CONV_5X5_S2, 1, 3, 128, 40, 24, epi=_lib.EPI_IGDN, first=True)
+    _run(cuda, _lib.CONV_5X5_S2, 1, 1, 128, 24, 52, epi=_lib.EPI_NONE, first=True)
+    _run(cuda, _lib.CONV_5X5_S2, 6, 3, 128, 128, 128, epi=_lib.EPI_GDN, first=True)
+    _run(cuda, _lib.CONV_5X5_S2, 5, 1, 128, 128, 160, epi=_lib.EPI_GDN, first=True)
+
+
+def test_last_layer_segments_strips_and_widths(cuda):
+    # deconv_narrow2_kernel: two 128-pixel row segments, a ragged last strip (H = 32 + 1), 3- and 4-chunk inputs,
+    # more strips than SMs (TMEM slot ring wraps), out_c = 2 and 4
+    _run(cuda, _lib.DECONV_5X5_S2, 1, 128, 3, 40, 200, out_nchw=True)
+    _run(cuda, _lib.DECONV_5X5_S2, 1, 256, 2, 33, 20, out_nchw=True)
+    _run(cuda, _lib.DECONV_5X5_S2, 2, 192, 4, 9, 130, epi=_lib.EPI_RELU, out_nchw=True)
+    _run(cuda, _lib.DECONV_5X5_S2, 40, 64, 1, 128, 16, out_nchw=True)
+
+
+def test_kernels_are_safe_under_concurrent_streams(cuda):
+    # bench.py's host-buffer leg runs three streams at once: results must not depend on what else is on the GPU
+    g = torch.Generator().manual_seed(3)
+    jobs = []
+    for kind, cin, cout, H, W, epi, first, nchw in [
+            (_lib.CONV_5X5_S2, 3, 128, 64, 64, _lib.EPI_GDN, True, False),
+            (_lib.CONV_5X5_S2, 128, 128, 32, 32, _lib.EPI_GDN, False, False),
+            (_lib.DECONV_5X5_S2, 128, 128, 16, 16, _lib.EPI_IGDN, False, False),
+            (_lib.DECONV_5X5_S2, 128, 3, 32, 32, _lib.EPI_NONE, False, True)]:
+        x = torch.randn(24, cin, H, W, generator=g)
+        wshape = (cin, cout, 5, 5) if kind == _lib.DECONV_5X5_S2 else (cout, cin, 5, 5)
+        w = torch.randn(wshape, generator=g) / (cin * 25) ** 0.5
+        in_layout = _lib.LAYOUT_NCHW_F32 if first else _lib.LAYOUT_NHWC_BF16
+        out_layout = _lib.LAYOUT_NCHW_F32 if nchw else _lib.LAYOUT_NHWC_BF16
+        xd = x.to(cuda) if first else x.permute(0, 2, 3, 1).contiguous().bfloat16().to(cuda)
+        packed = ops.pack_conv_weight(w.to(cuda), kind, cout, cin, in_layout)
+        bh = gh = None
+        if epi in (_lib.EPI_GDN, _lib.EPI_IGDN):
+            bh, gh = ops.gdn_pack(torch.ones(cout, device=cuda), (0.1 * torch.eye(cout)).sqrt().to(cuda), 0.0, 0.0, 0.0)
+        kw = dict(kind=kind, epilogue=epi, in_layout=in_layout, out_layout=out_layout, in_c=cin, out_c=cout,
+                  weight=packed, bias=torch.zeros(cout, device=cuda), beta=bh, gamma=gh)
+        jobs.append((xd, kw, ops.conv_forward(xd, **kw).float().clone()))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(device=cuda) for _ in range(3)]
+    for it in range(30):
+        outs = []
+        for s in streams:
+            with torch.cuda.stream(s):
+                for xd, kw, ref in jobs:
+                    outs.append((ops.conv_forward(xd, **kw), ref))
+        torch.cuda.synchronize()
+        for o, ref in outs:
+            assert torch.equal(o.float(), ref), "a kernel's result changed under concurrent load"
