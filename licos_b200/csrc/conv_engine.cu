@@ -798,7 +798,7 @@ static bool make_map_f32(CUtensorMap* m, const void* base, const uint64_t* dims,
 
 // pipelined first layer (conv_first2.cuh): 1 or 3 bands, N in {64, 128}, rows of x 16-byte aligned (TMA)
 static bool use_first2(const licos_conv_args* a) {
-    return (a->in_c == 1 || a->in_c == 3) && (a->out_c == 64 || a->out_c == 128) && a->in_w % 4 == 0 &&
+    return (a->in_c == 1 || a->in_c == 3) && (a->out_c == 64 || a->out_c == 128 || a->out_c == 192) && a->in_w % 4 == 0 &&
            ((uintptr_t)a->in & 15) == 0 && !getenv("LICOS_FIRST_V1");
 }
 
@@ -816,7 +816,9 @@ static int launch_first2(const licos_conv_args* a, cudaStream_t s) {
     const int64_t tiles = (int64_t)a->batch * p.tiles_h * p.tiles_w;
     if (tiles > 0x7fffffff) return LICOS_ERR_UNSUPPORTED;
     p.total_tiles = (int)tiles;
-    p.tmem_cols = 4u * (uint32_t)p.N;
+    const int teams = p.N <= 128 ? 2 : 1;
+    p.tmem_cols = 512u;
+    if (p.N == 64) p.tmem_cols = 256u;
     {
         const uint64_t W = (uint64_t)a->in_w, H = (uint64_t)a->in_h, C = (uint64_t)a->in_c;
         const uint64_t dims[4] = {W, H, C, (uint64_t)a->batch};
@@ -845,7 +847,7 @@ static int launch_first2(const licos_conv_args* a, cudaStream_t s) {
         const uint32_t box[4] = {64, 16, 8, 1};
         if (!make_map(&p.out_map, a->out, 4, dims, strides, box)) return LICOS_ERR_CUDA;
     }
-    size_t smem = first2_smem_bytes(a->in_c, p.N, gdn);
+    size_t smem = first2_smem_bytes(a->in_c, p.N, gdn, teams);
     if (smem > (size_t)kMaxDynSmem) return LICOS_ERR_UNSUPPORTED;
     if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM (TMEM is sized for that)
     int sms = 0;
@@ -853,17 +855,21 @@ static int launch_first2(const licos_conv_args* a, cudaStream_t s) {
     if (rc != LICOS_OK) return rc;
     const int grid = (int)(tiles < sms ? tiles : sms);
     cudaError_t err = cudaErrorInvalidValue;
-#define LICOS_LAUNCH_F2(E, C)                                                                                        \
-    do {                                                                                                             \
-        static cudaError_t attr =                                                                                    \
-            cudaFuncSetAttribute(conv_first2_kernel<E, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem); \
-        if (attr != cudaSuccess) { err = attr; break; }                                                              \
-        conv_first2_kernel<E, C><<<grid, kF2Threads, smem, s>>>(p);                                                  \
-        err = cudaGetLastError();                                                                                    \
+#define LICOS_LAUNCH_F2(E, C, T)                                                                                        \
+    do {                                                                                                                \
+        static cudaError_t attr =                                                                                       \
+            cudaFuncSetAttribute(conv_first2_kernel<E, C, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem); \
+        if (attr != cudaSuccess) { err = attr; break; }                                                                 \
+        conv_first2_kernel<E, C, T><<<grid, first2_threads(T), smem, s>>>(p);                                           \
+        err = cudaGetLastError();                                                                                       \
     } while (0)
-#define LICOS_LAUNCH_F2E(E)                                             \
-    do {                                                                \
-        if (a->in_c == 1) LICOS_LAUNCH_F2(E, 1); else LICOS_LAUNCH_F2(E, 3); \
+#define LICOS_LAUNCH_F2E(E)                                                          \
+    do {                                                                             \
+        if (teams == 2) {                                                            \
+            if (a->in_c == 1) LICOS_LAUNCH_F2(E, 1, 2); else LICOS_LAUNCH_F2(E, 3, 2); \
+        } else {                                                                     \
+            if (a->in_c == 1) LICOS_LAUNCH_F2(E, 1, 1); else LICOS_LAUNCH_F2(E, 3, 1); \
+        }                                                                            \
     } while (0)
     switch (a->epilogue) {
         case LICOS_EPI_NONE: LICOS_LAUNCH_F2E(LICOS_EPI_NONE); break;

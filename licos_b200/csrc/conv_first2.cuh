@@ -21,8 +21,11 @@
 
 namespace licos {
 
-constexpr int kF2Threads = 14 * 32;
-constexpr int kF2Slots = 3;
+// TEAMS = 2: N <= 128, 14 warps, 3 ring slots, 4 TMEM accumulators.  TEAMS = 1: N = 192 (gamma alone is 72 KB of shared
+// memory), 10 warps, 2 ring slots, 2 accumulators.
+__host__ __device__ constexpr int first2_threads(int teams) { return (6 + 4 * teams) * 32; }
+__host__ __device__ constexpr int first2_slots(int teams) { return teams == 2 ? 3 : 2; }
+__host__ __device__ constexpr int first2_bufs(int teams) { return teams == 2 ? 4 : 2; }
 // patch = input rows 2*oh0-2 .. +18, columns 2*ow0-4 .. +39: a TMA box must start on a 16-byte boundary of the
 // innermost dimension (measured: an unaligned start coordinate raises an illegal-instruction fault)
 constexpr int kF2PatchRows = 19, kF2PatchPitch = 40;
@@ -52,36 +55,38 @@ struct First2Geom {
     static constexpr uint32_t kPatchSlot = (kPatchBytes + 127u) & ~127u;
 };
 
-__host__ __device__ constexpr size_t first2_smem_bytes(int cin, int N, bool gdn) {
+__host__ __device__ constexpr size_t first2_smem_bytes(int cin, int N, bool gdn, int teams) {
     const size_t n_atoms = N / 64;
     const size_t patch = ((size_t)cin * kF2PatchRows * kF2PatchPitch * 4 + 127) & ~(size_t)127;
-    return 1024 + (size_t)N * 128                       // W atom 0
-           + (cin == 3 ? 16384 : 0)                     // shared tail atom (A K-step 4 of every slot + W K-step 4)
-           + (gdn ? n_atoms * N * 128 : 0)              // gamma
-           + (size_t)kF2Slots * 16384                   // A ring
-           + 2 * n_atoms * 16384                        // staging, one per epilogue team
-           + kF2Slots * patch;
+    return 1024 + (size_t)N * 128                                  // W atom 0
+           + (cin == 3 ? (size_t)(N > 128 ? N : 128) * 128 : 0)    // shared tail atom (A K-step 4 of every slot + W K-step 4)
+           + (gdn ? n_atoms * N * 128 : 0)                         // gamma
+           + (size_t)first2_slots(teams) * 16384                   // A ring
+           + (size_t)teams * n_atoms * 16384                       // staging, one per epilogue team
+           + first2_slots(teams) * patch;
 }
 
-template <int EPI, int CIN>
-__global__ void __launch_bounds__(kF2Threads, 1) conv_first2_kernel(const __grid_constant__ First2Params p) {
+template <int EPI, int CIN, int TEAMS>
+__global__ void __launch_bounds__(first2_threads(TEAMS), 1) conv_first2_kernel(const __grid_constant__ First2Params p) {
     using G = First2Geom<CIN>;
+    constexpr int kF2Threads = first2_threads(TEAMS), kF2Slots = first2_slots(TEAMS), kBufs = first2_bufs(TEAMS);
+    constexpr int kXC = TEAMS == 2 ? 4 : 6;  // 32-channel chunks the epilogue is unrolled for
     constexpr bool kGdn = (EPI == LICOS_EPI_GDN || EPI == LICOS_EPI_IGDN);
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t patch_full[kF2Slots], patch_empty[kF2Slots], a_full[kF2Slots], a_empty[kF2Slots];
     __shared__ uint64_t acc_full[4], acc_empty[4], norm_full[2], w_bar;
     __shared__ uint32_t tmem_base_smem;
-    __shared__ __align__(16) float beta_s[128];
+    __shared__ __align__(16) float beta_s[256];
 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
     const int N = p.N, n_atoms = N / 64;
     uint8_t* w_s = smem;
     uint8_t* tail_s = w_s + (size_t)N * 128;
-    uint8_t* g_s = tail_s + (G::kTail ? 16384 : 0);
+    uint8_t* g_s = tail_s + (G::kTail ? (size_t)(N > 128 ? N : 128) * 128 : 0);
     uint8_t* a_s = g_s + (kGdn ? (size_t)n_atoms * N * 128 : 0);
     uint8_t* stg_s = a_s + (size_t)kF2Slots * 16384;
-    uint8_t* patch_s = stg_s + (size_t)2 * n_atoms * 16384;
+    uint8_t* patch_s = stg_s + (size_t)TEAMS * n_atoms * 16384;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform role dispatch
@@ -168,9 +173,9 @@ __global__ void __launch_bounds__(kF2Threads, 1) conv_first2_kernel(const __grid
             const uint32_t a16 = smem_u32(a_s) >> 4, w16 = smem_u32(w_s) >> 4, t16 = smem_u32(tail_s) >> 4;
             int lt = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid, ++lt) {
-                const int slot = lt % kF2Slots, buf = lt & 3;
+                const int slot = lt % kF2Slots, buf = lt % kBufs;
                 mbar_wait(&a_full[slot], (uint32_t)(lt / kF2Slots) & 1u);
-                mbar_wait(&acc_empty[buf], ((uint32_t)(lt >> 2) & 1u) ^ 1u);
+                mbar_wait(&acc_empty[buf], ((uint32_t)(lt / kBufs) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)buf * (uint32_t)N;
 #pragma unroll
@@ -287,7 +292,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) conv_first2_kernel(const __grid
         const uint32_t stg16 = smem_u32(stg) >> 4, g16 = smem_u32(g_s) >> 4;
         const int n32 = N / 32;
         uint32_t nit = 0;
-        for (int lt = team;; lt += 2) {
+        for (int lt = team;; lt += TEAMS) {
             const int tile = blockIdx.x + lt * grid;
             if (tile >= p.total_tiles) break;
             int r = tile;
@@ -295,18 +300,18 @@ __global__ void __launch_bounds__(kF2Threads, 1) conv_first2_kernel(const __grid
             r /= p.tiles_w;
             const int oh0 = (r % p.tiles_h) * 8;
             const int b = r / p.tiles_h;
-            const int buf = lt & 3;
+            const int buf = lt % kBufs;
             const uint32_t t_acc = tmem_base + lane_sel + (uint32_t)buf * (uint32_t)N;
 
             if (leader) tma_store_wait_read();  // this team's previous store has read the staging tile
             named_bar_sync(1 + team, 128);
-            mbar_wait(&acc_full[buf], (uint32_t)(lt >> 2) & 1u);
+            mbar_wait(&acc_full[buf], (uint32_t)(lt / kBufs) & 1u);
             tc_fence_after();
 
-            uint32_t xs[kGdn ? 64 : 1];
+            uint32_t xs[kGdn ? kXC * 16 : 1];
             if (kGdn) {
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
+                for (int cc = 0; cc < kXC; ++cc) {
                     if (cc < n32) {
                         float v[32];
                         tmem_ld32(t_acc + cc * 32, v);
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(kF2Threads, 1) conv_first2_kernel(const __grid
                 ++nit;
             }
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < kXC; ++cc) {
                 if (cc < n32) {
                     float v[32];
                     tmem_ld32(t_acc + cc * 32, v);

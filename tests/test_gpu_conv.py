@@ -169,6 +169,10 @@ def test_first_layer_pipelined_variants(cuda):
     _run(cuda, _lib.CONV_5X5_S2, 1, 1, 128, 24, 52, epi=_lib.EPI_NONE, first=True)
     _run(cuda, _lib.CONV_5X5_S2, 6, 3, 128, 128, 128, epi=_lib.EPI_GDN, first=True)
     _run(cuda, _lib.CONV_5X5_S2, 5, 1, 128, 128, 160, epi=_lib.EPI_GDN, first=True)
+    # N = 192 (hyperprior widths): one epilogue team, two TMEM accumulators
+    _run(cuda, _lib.CONV_5X5_S2, 2, 3, 192, 64, 72, epi=_lib.EPI_GDN, first=True)
+    _run(cuda, _lib.CONV_5X5_S2, 1, 1, 192, 40, 32, epi=_lib.EPI_RELU, first=True)
+    _run(cuda, _lib.CONV_5X5_S2, 3, 3, 192, 160, 128, epi=_lib.EPI_GDN, first=True)
 
 
 def test_last_layer_segments_strips_and_widths(cuda):
