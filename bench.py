@@ -37,7 +37,7 @@ FLOP_PER_TILE_ENGINE = 2 * 4945.0e6
 # HBM-bound kernels: algorithmic bytes per tile (every tensor read once, written once)
 BYTES_PER_TILE_FIRST = 3 * 256 * 256 * 4 + 128 * 128 * 128 * 2   # g_a[0]: fp32 NCHW x in, bf16 NHWC out
 BYTES_PER_TILE_LAST = 128 * 128 * 128 * 2 + 3 * 256 * 256 * 4    # g_s[6]: bf16 NHWC in, fp32 NCHW x_hat out
-BYTES_PER_TILE_EB = 192 * 16 * 16 * 12                           # y in, y_hat + likelihoods out (12 B / latent element)
+BYTES_PER_TILE_EB = 192 * 16 * 16 * 18                           # y in; y_hat, likelihoods, int32 symbols, bf16 NHWC y_hat out
 
 
 def parse():
@@ -238,19 +238,18 @@ def run_b200(args):
         if eb_ms["events"] is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            y_hat, lik = eb(y)
+            y_hat, lik, sym, y_nhwc = eb.forward_fused(y, want_symbols=True, want_nhwc=True)
             e1.record()
             eb_ms["events"].append((e0, e1))
         else:
-            y_hat, lik = eb(y)
-        sym = eb.symbols(y)
-        return y, y_hat, lik, sym
+            y_hat, lik, sym, y_nhwc = eb.forward_fused(y, want_symbols=True, want_nhwc=True)
+        return y, y_hat, lik, sym, y_nhwc
 
     def step(xb):
-        y, y_hat, lik, sym = encode(xb)
-        x_hat = net.g_s(y_hat)
-        # kernels besides the convs: EB table + gather, symbols, NCHW->NHWC of y_hat
-        launches["n"] += 4
+        y, y_hat, lik, sym, y_nhwc = encode(xb)
+        x_hat = net.g_s(y_hat, nhwc=y_nhwc)
+        # kernels besides the convs: EB likelihood table + the fused quantise / likelihood / symbols / NHWC pass
+        launches["n"] += 2
         return y_hat, lik, sym, x_hat
 
     def sync_all():
@@ -278,11 +277,11 @@ def run_b200(args):
         for _ in range(args.steps):
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             e0.record()
-            y, y_hat, lik, sym = encode(x)
+            y, y_hat, lik, sym, y_nhwc = encode(x)
             e1.record()
-            x_hat = net.g_s(y_hat)
+            x_hat = net.g_s(y_hat, nhwc=y_nhwc)
             e2.record()
-            launches["n"] += 4
+            launches["n"] += 2
             marks.append((e0, e1, e2))
         t_end.record()
         sync_all()
@@ -383,8 +382,8 @@ def run_b200(args):
             "roofline_hbm": [
                 hbm("conv_first2_kernel (g_a[0] + GDN)", BYTES_PER_TILE_FIRST, first_ms, "fp32 NCHW x in, bf16 NHWC out"),
                 hbm("deconv_narrow2_kernel (g_s[6])", BYTES_PER_TILE_LAST, last_ms, "bf16 NHWC in, fp32 NCHW x_hat out"),
-                hbm("eb_lut_kernel + eb_eval_kernel (quantise + likelihoods)", BYTES_PER_TILE_EB, eb_ms_step,
-                    "12 B per latent element (two launches)"),
+                hbm("eb_lut_kernel + eb_eval_tile_kernel (quantise + likelihoods + symbols + NHWC copy)", BYTES_PER_TILE_EB,
+                    eb_ms_step, "18 B per latent element (two launches; 12 B for forward() alone)"),
             ],
         }
         if cpu is not None:
@@ -427,9 +426,8 @@ def run_e2e(net, eb, x_dev, args, torch, device, world):
                 with torch.cuda.stream(streams[si]):
                     xb = x_host[lo:hi].to(device, non_blocking=True)
                     y = net.g_a(xb)
-                    y_hat, lik = eb(y)
-                    sym = eb.symbols(y)
-                    x_hat = net.g_s(y_hat)
+                    y_hat, lik, sym, y_nhwc = eb.forward_fused(y, want_symbols=True, want_nhwc=True)
+                    x_hat = net.g_s(y_hat, nhwc=y_nhwc)
                     ops.sum_log(lik, accs[it, si:si + 1])  # per-(step, stream) accumulator, summed after the join
                     xhat_host[lo:hi].copy_(x_hat, non_blocking=True)
                     sym_host[lo:hi].copy_(sym, non_blocking=True)

@@ -140,6 +140,11 @@ int64_t licos_eb_lut_floats(int channels); /* size of the eval-mode workspace, i
  * x, y_hat, lik: fp32 [batch][channels][hw].  lut_ws: licos_eb_lut_floats(channels) floats. */
 int licos_eb_forward_eval(const licos_eb_params* p, const float* x, int batch, int64_t hw, float* lut_ws,
                           float* y_hat, float* lik, void* stream);
+/* The same, in ONE pass over x, optionally also producing what the callers of forward() ask for next:
+ * symbols (EntropyModel.quantize(x, "symbols", medians), int32 [batch][channels][hw], may be NULL) and a bf16 NHWC
+ * copy of y_hat (the layout licos_conv_forward reads, may be NULL).  hw % 4 == 0, channels even. */
+int licos_eb_forward_eval_fused(const licos_eb_params* p, const float* x, int batch, int64_t hw, float* lut_ws,
+                                float* y_hat, float* lik, int32_t* symbols, void* y_hat_nhwc_bf16, void* stream);
 /* EntropyBottleneck.forward(x, training=True): y_hat = x + noise.  noise == NULL draws U(-0.5, 0.5)
  * from an in-kernel Philox stream keyed by (seed, element index). */
 int licos_eb_forward_noise(const licos_eb_params* p, const float* x, const float* noise, uint64_t seed,

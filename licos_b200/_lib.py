@@ -63,6 +63,8 @@ SIGNATURES = {
     "licos_debug_set_conv_probe": (None, [c_vp]),
     "licos_eb_lut_floats": (c_i64, [c_int]),
     "licos_eb_forward_eval": (c_int, [ctypes.POINTER(EbParams), c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "licos_eb_forward_eval_fused": (c_int, [ctypes.POINTER(EbParams), c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                            c_vp]),
     "licos_eb_forward_noise": (c_int, [ctypes.POINTER(EbParams), c_vp, c_vp, c_u64, c_int, c_i64, c_vp, c_vp, c_vp]),
     "licos_eb_symbols": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp]),
     "licos_eb_dequantize": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_vp]),

@@ -130,6 +130,61 @@ __global__ void eb_eval_kernel(EbMeta m, const float* __restrict__ x, const floa
     }
 }
 
+// One pass over the latent for the whole eval-mode bottleneck (A9 + A10): y_hat, likelihoods, optionally the integer
+// symbols and optionally a bf16 NHWC copy of y_hat (the layout g_s / h_s read), so y is read from HBM once and the
+// separate symbols and layout-conversion launches disappear.  A block owns one image and 64 consecutive positions of
+// all C channels: coalesced 256-byte rows in and out for the NCHW tensors, a [C][66] bf16 tile in shared memory that
+// is read back transposed (pitch 66 -> conflict-free) for 4-byte-per-thread NHWC rows.  hw % 4 == 0.
+constexpr int kEbTileHw = 64, kEbTilePitch = 66;
+__global__ void __launch_bounds__(256) eb_eval_tile_kernel(EbMeta m, const float* __restrict__ x,
+                                                           const float* __restrict__ packed, const float* __restrict__ med,
+                                                           const float* __restrict__ lut, int C, int hw,
+                                                           float* __restrict__ y_hat, float* __restrict__ lik,
+                                                           int32_t* __restrict__ sym, __nv_bfloat16* __restrict__ nhwc) {
+    extern __shared__ __nv_bfloat16 tile[];  // [C][kEbTilePitch]
+    const int tiles_per_img = (hw + kEbTileHw - 1) / kEbTileHw;
+    const int b = blockIdx.x / tiles_per_img, hw0 = (blockIdx.x % tiles_per_img) * kEbTileHw;
+    const int n_hw = min(kEbTileHw, hw - hw0);  // multiple of 4
+    const int vecs = n_hw / 4;                   // float4 groups per channel row
+    const size_t img = (size_t)b * C * hw;
+    for (int idx = threadIdx.x; idx < C * 16; idx += 256) {
+        const int c = idx >> 4, v = idx & 15;
+        if (v >= vecs) continue;
+        const size_t off = img + (size_t)c * hw + hw0 + 4 * v;
+        const float4 t = __ldcs(reinterpret_cast<const float4*>(x + off));
+        const float md = __ldg(med + c);
+        const float xv[4] = {t.x, t.y, t.z, t.w};
+        float yv[4], lv[4];
+        int sv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float r = rintf(xv[j] - md);
+            yv[j] = r + md;
+            sv[j] = (int)r;
+            lv[j] = (fabsf(r) <= (float)kLutR) ? __ldg(lut + (size_t)c * kLutN + ((int)r + kLutR))
+                                               : eb_likelihood_slow(packed, m, c, yv[j]);
+        }
+        __stcs(reinterpret_cast<float4*>(y_hat + off), make_float4(yv[0], yv[1], yv[2], yv[3]));
+        __stcs(reinterpret_cast<float4*>(lik + off), make_float4(lv[0], lv[1], lv[2], lv[3]));
+        if (sym) __stcs(reinterpret_cast<int4*>(sym + off), make_int4(sv[0], sv[1], sv[2], sv[3]));
+        if (nhwc) {
+            __nv_bfloat162* row = reinterpret_cast<__nv_bfloat162*>(tile + c * kEbTilePitch + 4 * v);
+            row[0] = __floats2bfloat162_rn(yv[0], yv[1]);
+            row[1] = __floats2bfloat162_rn(yv[2], yv[3]);
+        }
+    }
+    if (!nhwc) return;
+    __syncthreads();
+    const int half_c = C / 2;  // C is even (checked by the host)
+    for (int idx = threadIdx.x; idx < n_hw * half_c; idx += 256) {
+        const int p = idx / half_c, cp = idx - p * half_c;
+        __nv_bfloat162 v2;
+        v2.x = tile[(2 * cp) * kEbTilePitch + p];
+        v2.y = tile[(2 * cp + 1) * kEbTilePitch + p];
+        *reinterpret_cast<__nv_bfloat162*>(nhwc + ((size_t)b * hw + hw0 + p) * C + 2 * cp) = v2;
+    }
+}
+
 // Philox4x32-10, one draw per element: counter = element index, key = seed.
 __device__ __forceinline__ uint32_t philox_u32(uint64_t seed, uint64_t idx) {
     uint32_t c0 = (uint32_t)idx, c1 = (uint32_t)(idx >> 32), c2 = 0x6c69636fu, c3 = 0x73623230u;
@@ -414,6 +469,31 @@ int licos_eb_forward_eval(const licos_eb_params* p, const float* x, int batch, i
         eb_eval_kernel<1><<<grid_for(n, 256), 256, 0, s>>>(m, x, p->packed, p->medians, lut_ws, p->channels, hw, n,
                                                           y_hat, lik);
     }
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_eb_forward_eval_fused(const licos_eb_params* p, const float* x, int batch, int64_t hw, float* lut_ws,
+                                float* y_hat, float* lik, int32_t* symbols, void* y_hat_nhwc_bf16, void* stream) {
+    EbMeta m;
+    int max_w;
+    if (!make_meta(p, m, max_w) || !x || !lut_ws || !y_hat || !lik || batch < 0 || hw < 0) return LICOS_ERR_INVALID;
+    if (hw % 4 != 0 || hw > 0x7fffffff || p->channels % 2 != 0 || p->channels > 512) return LICOS_ERR_UNSUPPORTED;
+    if ((((uintptr_t)x | (uintptr_t)y_hat | (uintptr_t)lik | (uintptr_t)symbols) % 16) != 0) return LICOS_ERR_UNSUPPORTED;
+    const int64_t n = (int64_t)batch * p->channels * hw;
+    if (n == 0) return LICOS_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t sm = (size_t)m.ppc * sizeof(float);
+    if (max_w <= 3) eb_lut_kernel<3><<<p->channels, 288, sm, s>>>(m, p->packed, p->medians, lut_ws);
+    else eb_lut_kernel<16><<<p->channels, 288, sm, s>>>(m, p->packed, p->medians, lut_ws);
+    LICOS_CUDA_OK(cudaGetLastError());
+    const int64_t blocks = (int64_t)batch * ((hw + kEbTileHw - 1) / kEbTileHw);
+    if (blocks > 0x7fffffff) return LICOS_ERR_UNSUPPORTED;
+    const size_t tile_bytes = y_hat_nhwc_bf16 ? (size_t)p->channels * kEbTilePitch * sizeof(__nv_bfloat16) : 0;
+    static cudaError_t attr = cudaFuncSetAttribute(eb_eval_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    LICOS_CUDA_OK(attr);
+    eb_eval_tile_kernel<<<(int)blocks, 256, tile_bytes, s>>>(m, x, p->packed, p->medians, lut_ws, p->channels, (int)hw, y_hat,
+                                                            lik, symbols, (__nv_bfloat16*)y_hat_nhwc_bf16);
     LICOS_CUDA_OK(cudaGetLastError());
     return LICOS_OK;
 }

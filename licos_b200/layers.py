@@ -138,12 +138,14 @@ class FusedSequential(nn.Sequential):
     def _eager_forward(self, x: Tensor) -> Tensor:
         return super().forward(x)
 
-    def forward(self, x: Tensor, take_abs: bool = False) -> Tensor:
+    def forward(self, x: Tensor, take_abs: bool = False, nhwc: Optional[Tensor] = None) -> Tensor:
+        """``nhwc``: optional bf16 (B, H, W, C) copy of ``x`` that a fused producer already wrote
+        (``EntropyBottleneck.forward_fused``); saves the layout-conversion launch on the fused path."""
         if not x.is_cuda:
             raise RuntimeError("licos_b200: g_a / g_s / h_a / h_s need CUDA tensors on a B200 (no CPU path exists)")
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             return self._eager_forward(torch.abs(x) if take_abs else x)
-        return self.fused_forward(x, take_abs=take_abs)
+        return self.fused_forward(x, take_abs=take_abs, nhwc=nhwc)
 
     # -- caches of kernel-layout parameters, rebuilt when a parameter's version or storage changes --
     def _packed_weight(self, m: nn.Module, kind: int, in_layout: int):
@@ -171,7 +173,7 @@ class FusedSequential(nn.Sequential):
                 float(g.beta_reparam.pedestal))
         return slot.tensors
 
-    def fused_forward(self, x: Tensor, take_abs: bool = False) -> Tensor:
+    def fused_forward(self, x: Tensor, take_abs: bool = False, nhwc: Optional[Tensor] = None) -> Tensor:
         """x: fp32 (B, C, H, W) on a B200.  Returns fp32 NCHW like the module chain would."""
         if not x.is_cuda:
             raise RuntimeError("licos_b200: the fused path needs CUDA tensors (no CPU fallback exists)")
@@ -200,7 +202,12 @@ class FusedSequential(nn.Sequential):
         first = steps[0][0]
         direct_first = (steps[0][1] == _lib.CONV_5X5_S2 and first.in_channels <= 16 and not take_abs)
         if not direct_first:
-            cur = ops.nchw_to_nhwc_bf16(cur, take_abs=take_abs)
+            if nhwc is not None and not take_abs:
+                if nhwc.dtype != torch.bfloat16 or tuple(nhwc.shape) != (x.shape[0], x.shape[2], x.shape[3], x.shape[1]):
+                    raise ValueError("nhwc must be the bf16 (B, H, W, C) copy of x")
+                cur = nhwc.contiguous()
+            else:
+                cur = ops.nchw_to_nhwc_bf16(cur, take_abs=take_abs)
             layout = _lib.LAYOUT_NHWC_BF16
         for n, (m, kind, epi, gdn) in enumerate(steps):
             last = n == len(steps) - 1

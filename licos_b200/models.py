@@ -83,8 +83,14 @@ class FactorizedPrior(CompressionModel):
 
     def forward(self, x: Tensor) -> Dict:
         y = self.g_a(x)
-        y_hat, y_likelihoods = self.entropy_bottleneck(y)
-        x_hat = self.g_s(y_hat)
+        eb = self.entropy_bottleneck
+        if not eb.training and not torch.is_grad_enabled() and y.is_cuda:
+            # inference: quantise + likelihoods + the bf16 NHWC copy g_s reads, in one pass over y
+            y_hat, y_likelihoods, _, y_nhwc = eb.forward_fused(y, want_symbols=False, want_nhwc=True)
+            x_hat = self.g_s(y_hat, nhwc=y_nhwc)
+        else:
+            y_hat, y_likelihoods = eb(y)
+            x_hat = self.g_s(y_hat)
         return {"x_hat": x_hat, "likelihoods": {"y": y_likelihoods}}
 
     @classmethod

@@ -165,6 +165,28 @@ def eb_forward_eval(ebp: EbPacked, x: torch.Tensor):
     return y_hat, lik
 
 
+def eb_forward_eval_fused(ebp: EbPacked, x: torch.Tensor, want_symbols: bool = False, want_nhwc: bool = False):
+    """One pass: (y_hat, likelihoods, symbols | None, bf16 NHWC y_hat | None).  Falls back to the separate kernels
+    for shapes the tiled kernel does not take (hw % 4 != 0, odd channel counts)."""
+    _need_cuda(_f32(x))
+    B, C = x.shape[0], x.shape[1]
+    if C != ebp.p.channels:
+        raise ValueError("channel mismatch")
+    hw = x.numel() // max(B * C, 1)
+    if x.numel() == 0 or hw % 4 != 0 or C % 2 != 0 or C > 512 or x.dim() != 4:
+        y_hat, lik = eb_forward_eval(ebp, x)
+        sym = eb_symbols(x, ebp.medians) if want_symbols else None
+        return y_hat, lik, sym, (nchw_to_nhwc_bf16(y_hat) if want_nhwc and x.dim() == 4 and x.numel() else None)
+    x = x.contiguous()
+    y_hat, lik = torch.empty_like(x), torch.empty_like(x)
+    sym = torch.empty(x.shape, dtype=torch.int32, device=x.device) if want_symbols else None
+    nhwc = torch.empty((B, x.shape[2], x.shape[3], C), dtype=torch.bfloat16, device=x.device) if want_nhwc else None
+    lut = torch.empty(int(lib.licos_eb_lut_floats(C)), dtype=torch.float32, device=x.device)
+    check(lib.licos_eb_forward_eval_fused(ctypes.byref(ebp.p), x.data_ptr(), B, hw, lut.data_ptr(), y_hat.data_ptr(),
+                                          lik.data_ptr(), _ptr(sym), _ptr(nhwc), _stream()), "eb_forward_eval_fused")
+    return y_hat, lik, sym, nhwc
+
+
 def eb_forward_noise(ebp: EbPacked, x: torch.Tensor, noise: Optional[torch.Tensor], seed: int = 0):
     _need_cuda(_f32(x), noise)
     B, C = x.shape[0], x.shape[1]

@@ -49,7 +49,7 @@ def test_error_strings_and_status_mapping():
     assert _lib.lib.licos_packed_weight_bytes(_lib.CONV_5X5_S2, 128, 128, _lib.LAYOUT_NHWC_BF16) == 25 * 128 * 128 * 2
     assert _lib.lib.licos_packed_weight_bytes(_lib.CONV_5X5_S2, 320, 192, _lib.LAYOUT_NHWC_BF16) == 25 * 320 * 192 * 2
     assert _lib.lib.licos_packed_weight_bytes(_lib.CONV_5X5_S2, 128, 3, _lib.LAYOUT_NCHW_F32) == 128 * 128 * 2
-    assert _lib.lib.licos_packed_weight_bytes(_lib.DECONV_5X5_S2, 3, 128, _lib.LAYOUT_NHWC_BF16) == 112 * 128 * 2
+    assert _lib.lib.licos_packed_weight_bytes(_lib.DECONV_5X5_S2, 3, 128, _lib.LAYOUT_NHWC_BF16) == 3 * 48 * 128 * 2
     assert _lib.lib.licos_packed_weight_bytes(_lib.DECONV_5X5_S2, 13, 128, _lib.LAYOUT_NHWC_BF16) == 25 * 16 * 128 * 2
 
 

@@ -162,3 +162,37 @@ def test_federated_pair_merge_on_device(cuda):
     exp = R.federated_average(cpu(a.state_dict()), cpu(b.state_dict()), loss=3.0, best_loss=1.0)
     for k, v in exp.items():
         assert torch.equal(got[k].cpu(), v), k  # same two roundings as `w*a; += w*b`
+
+
+@pytest.mark.parametrize("tag,in_ch", [("rgb", 3), ("split", 1)])
+def test_eb_forward_fused_equals_separate_kernels_and_golden(cuda, tag, in_ch):
+    # one pass over y: y_hat / likelihoods / symbols bit-identical to the separate kernels (and to the golden vectors),
+    # the bf16 NHWC copy equal to the rounded, transposed y_hat; ties, escapes, a partial 64-position tile, odd channels
+    z = np.load(os.path.join(GOLD, f"factorized_{tag}.npz"))
+    net, _ = _pair(in_ch, cuda)
+    eb = net.entropy_bottleneck
+    y = torch.from_numpy(z["y"]).to(cuda)
+    with torch.no_grad():
+        y_hat, lik, sym, nhwc = eb.forward_fused(y, want_symbols=True, want_nhwc=True)
+        y_hat0, lik0 = eb(y)
+    assert np.array_equal(sym.cpu().numpy(), z["symbols"])
+    assert np.array_equal(y_hat.cpu().numpy(), z["y_hat"])
+    assert torch.equal(lik, lik0) and torch.equal(y_hat, y_hat0)
+    assert torch.equal(nhwc, y_hat.permute(0, 2, 3, 1).contiguous().bfloat16())
+
+    med = eb.quantiles[:, 0, 1].detach().reshape(1, -1, 1, 1)
+    g = torch.Generator().manual_seed(1)
+    for shape in [(3, 192, 12, 20), (2, 192, 2, 2), (1, 192, 5, 3)]:   # 240 = 3 tiles + 48; 4; 15 (falls back)
+        yy = (torch.randn(shape, generator=g) * 40).to(cuda)
+        yy[0, :, 0, 0] = med[0, :, 0, 0] + 0.5           # ties
+        yy[0, :, 0, 1] = med[0, :, 0, 0] - 1.5
+        yy[-1, :, -1, -1] = 500.0                        # beyond the likelihood table
+        with torch.no_grad():
+            a = eb.forward_fused(yy, want_symbols=True, want_nhwc=True)
+            b = eb(yy)
+            s = eb.symbols(yy)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], s)
+        assert torch.equal(a[3], b[0].permute(0, 2, 3, 1).contiguous().bfloat16())
+    with torch.no_grad():
+        out = net(synth.make_input("rgb256" if in_ch == 3 else "raw512", 2).to(cuda))   # model.forward uses the fused pass
+    assert out["x_hat"].shape[0] == 2
