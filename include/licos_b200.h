@@ -204,6 +204,20 @@ int licos_rans_decode_batch(const uint8_t* const* encoded, const int64_t* n_byte
                             int n_cdfs, int cdf_stride, const int32_t* cdf_sizes, const int32_t* offsets,
                             int32_t* symbols, int threads);
 
+/* Device-resident rANS ENCODER (same bitstream as licos_rans_encode; replaces the symbol D2H copy + host coding of
+ * EntropyModel.compress).  One thread per image; symbols, indexes and the integer tables are device pointers.
+ *   indexes == NULL: index of symbol i is i / n_spatial (EntropyBottleneck: one table per channel), otherwise an int32
+ *   array [batch][n] (index_stride = n) or [n] shared by every image (index_stride = 0).
+ *   rcp_ws: n_cdfs * cdf_stride uint64 of scratch.  work: batch * cap_words uint32 of scratch; image b's stream is the
+ *   last lengths[b] words of its row (lengths[b] = -1: cap_words too small or an invalid index -> use the host coder). */
+int licos_rans_encode_device(const int32_t* symbols, const int32_t* indexes, int64_t index_stride, int batch, int64_t n,
+                             int64_t n_spatial, const int32_t* cdfs, int n_cdfs, int cdf_stride, const int32_t* cdf_sizes,
+                             const int32_t* offsets, uint64_t* rcp_ws, uint32_t* work, int64_t cap_words, int32_t* lengths,
+                             void* stream);
+/* Packs the streams back to back: out[word_offsets[b] .. + lengths[b]) = stream b (word_offsets: exclusive prefix sum). */
+int licos_rans_pack_device(const uint32_t* work, int64_t cap_words, const int32_t* lengths, const int64_t* word_offsets,
+                           int batch, uint32_t* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* Federated merge (licos/federation_utils.py:47-53)                                           */
 /* ------------------------------------------------------------------------------------------ */

@@ -70,7 +70,7 @@ int64_t encode_one(const int32_t* symbols, const int32_t* indexes, int64_t n, co
         steps.push_back({(uint16_t)cdf[v], (uint16_t)(cdf[v + 1] - cdf[v])});
         if (v == escape) {
             uint32_t nibbles = 0;
-            while ((raw >> (nibbles * kBypassBits)) != 0) ++nibbles;
+            while (nibbles < 8 && (raw >> (nibbles * kBypassBits)) != 0) ++nibbles;  // (a shift by 32 is undefined)
             uint32_t count = nibbles;  // nibble count, base-15 "unary" prefix
             while (count >= kBypassMax) {
                 steps.push_back({(uint16_t)kBypassMax, 0});

@@ -1,0 +1,212 @@
+// Device-resident front end of compress() (SURVEY.md section 8f rows N1 stretch / N2): the rANS ENCODER on the GPU,
+// bitstream-identical to csrc/host_codec.cpp (and therefore to compressai.ans: 64-bit state, 32-bit renormalisation
+// words, 16-bit precision, 4-bit bypass nibbles with the base-15 count prefix, symbols coded in reverse), so that the
+// symbols never leave the device: only the finished byte strings are copied to the host.
+//
+// A rANS stream is sequential in its state, and the CompressAI format has ONE stream per image, so the parallelism is
+// across the images of a batch: one thread per image, one warp per block so the streams spread over up to `batch / 32`
+// SMs.  The exact 64-by-16-bit division the coder needs (x / range, x % range) is one mul.hi.u64 + a correction against
+// a per-table-entry reciprocal (floor((2^64 - 1) / range), rans_rcp_kernel); symbols and their table entries are fetched 16
+// at a time ahead of the sequential state updates, so the walk pays one DRAM latency per 16 symbols.  Words are pushed from the end of a per-image scratch row
+// (the stream is written back to front); a second kernel packs the rows into one contiguous buffer.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/licos_b200.h"
+#include "common.cuh"
+
+namespace licos {
+
+constexpr uint32_t kRansPrecision = 16, kRansBypassBits = 4, kRansBypassMax = 15;
+constexpr uint64_t kRansLow = 1ull << 31;
+
+// The coder state is kept as two 32-bit halves: after the renormalisation test the update needs x / range and
+// x % range (64 by 16 bit).  With rcp = floor((2^64 - 1) / range): q0 = mulhi64(x, rcp) is q or q - 1, and the
+// remainder is below 2^17, so it is computed in 32-bit arithmetic.  The new low word is (q_lo << 16) | (r + start):
+// r + start < 2^16, no carry.  Everything is straight-line, predicated code: a lone warp per SM pays the full latency of
+// every dependent instruction and every convergence barrier, so the loop body is kept short and branch-free.
+struct RansState {
+    uint32_t lo, hi;
+    uint32_t* wp;  // words are pushed downwards from the end of this image's scratch row: *--wp
+};
+
+__device__ __forceinline__ void rans_put_symbol(RansState& s, uint32_t start, uint32_t range, uint64_t rcp) {
+    const bool ren = s.hi >= (range << 15);  // x >= ((L >> 16) << 32) * range = range << 47
+    if (ren) {
+        *--s.wp = s.lo;
+        s.lo = s.hi;
+        s.hi = 0;
+    }
+    const uint64_t x = ((uint64_t)s.hi << 32) | s.lo;
+    uint64_t q = __umul64hi(x, rcp);
+    uint32_t r = s.lo - (uint32_t)q * range;  // the true remainder (plus at most one range) fits 32 bits
+    if (r >= range) { r -= range; ++q; }
+    s.hi = (uint32_t)(q >> 16);               // x' = (q << 16) + r + start
+    s.lo = ((uint32_t)q << 16) | (r + start);
+}
+
+__device__ __forceinline__ void rans_put_nibble(RansState& s, uint32_t nib) {
+    if (s.hi >= (1u << 27)) {  // x >= ((L >> 16) << 32) * 2^(16 - 4) = 2^59
+        *--s.wp = s.lo;
+        s.lo = s.hi;
+        s.hi = 0;
+    }
+    s.hi = (s.hi << kRansBypassBits) | (s.lo >> (32 - kRansBypassBits));
+    s.lo = (s.lo << kRansBypassBits) | nib;
+}
+
+// reciprocal of every table frequency, once per call: rcp[ci][v] = floor((2^64 - 1) / (cdf[v+1] - cdf[v]))
+__global__ void rans_rcp_kernel(const int32_t* __restrict__ cdfs, int n_cdfs, int stride, const int32_t* __restrict__ sizes,
+                                uint64_t* __restrict__ rcp) {
+    const int64_t total = (int64_t)n_cdfs * stride;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int ci = (int)(e / stride), v = (int)(e % stride);
+        uint64_t r = 0;
+        if (v + 1 < sizes[ci]) {
+            const uint32_t f = (uint32_t)(cdfs[e + 1] - cdfs[e]);
+            if (f > 0) r = 0xFFFFFFFFFFFFFFFFull / f;
+        }
+        rcp[e] = r;
+    }
+}
+
+// symbols [batch][n] int32; indexes: explicit [batch][n] (or [n] shared: idx_stride 0), or NULL -> index = i / n_spatial
+__global__ void __launch_bounds__(32) rans_encode_kernel(const int32_t* __restrict__ symbols, const int32_t* __restrict__ indexes,
+                                                         int64_t idx_stride, int batch, int64_t n, int64_t n_spatial,
+                                                         const int32_t* __restrict__ cdfs, int n_cdfs, int stride,
+                                                         const int32_t* __restrict__ sizes, const int32_t* __restrict__ offsets,
+                                                         const uint64_t* __restrict__ rcp, uint32_t* __restrict__ work,
+                                                         int64_t cap_words, int32_t* __restrict__ lengths) {
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    if (b >= batch) return;
+    const int32_t* sym = symbols + (size_t)b * n;
+    const int32_t* idx = indexes ? indexes + (size_t)b * idx_stride : nullptr;
+    uint32_t* const row = work + (size_t)b * cap_words;
+    RansState st{(uint32_t)kRansLow, 0u, row + cap_words};
+    bool bad = false;
+    // Walk the symbols backwards in chunks of 16.  Phase A (independent of the coder state): fetch the symbols and look
+    // up (start, range, reciprocal) for all 16 -- the loads overlap, one DRAM latency per chunk.  Phase B: the
+    // sequential state updates, from registers.  Out-of-support symbols (bypass nibbles) are re-derived in phase B.
+    constexpr int kChunk = 16;
+    const bool vec = ((((uintptr_t)sym) | (uintptr_t)(n * 4)) & 15) == 0;  // every full chunk start is 16-byte aligned
+    int64_t i = n;
+    // channel index of the chunk start without a division per symbol (index == NULL: symbol i belongs to table i / n_spatial)
+    int64_t first = n - (n % kChunk ? n % kChunk : (n ? kChunk : 0));
+    int32_t ci_b = (int32_t)(first / n_spatial);
+    int64_t rem_b = first % n_spatial;
+    while (i > 0) {
+        const int cnt = (int)(i % kChunk ? i % kChunk : kChunk);  // the ragged chunk comes first: the rest are full and aligned
+        const int64_t base = i - cnt;
+        if (st.wp - row < 4 * kChunk * 3) { bad = true; break; }  // scratch row nearly full: give up, the host coder takes over
+        int32_t sv[kChunk];
+        if (vec && cnt == kChunk) {
+#pragma unroll
+            for (int q = 0; q < kChunk / 4; ++q) {
+                const int4 t = __ldg(reinterpret_cast<const int4*>(sym + base) + q);
+                sv[4 * q] = t.x; sv[4 * q + 1] = t.y; sv[4 * q + 2] = t.z; sv[4 * q + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kChunk; ++k) sv[k] = k < cnt ? __ldg(sym + base + k) : 0;
+        }
+        uint32_t sta[kChunk], rg[kChunk];  // start; range (0 = invalid) | bit 31 = out of support (nibbles follow)
+        uint64_t rc[kChunk];
+        int32_t ci = ci_b;
+        int64_t rem = rem_b;
+#pragma unroll
+        for (int k = 0; k < kChunk; ++k) {
+            sta[k] = 0; rg[k] = 0; rc[k] = 0;
+            if (k < cnt) {
+                const int32_t c = idx ? __ldg(idx + base + k) : ci;
+                if (c >= 0 && c < n_cdfs) {
+                    const int32_t escape = __ldg(sizes + c) - 2;
+                    int32_t v = sv[k] - __ldg(offsets + c);
+                    uint32_t raw = 0;
+                    bool esc = false;
+                    if (v < 0) { raw = (uint32_t)(-2 * v - 1); v = escape; esc = true; }
+                    else if (v >= escape) { raw = (uint32_t)(2 * (v - escape)); v = escape; esc = true; }
+                    const uint32_t e = (uint32_t)c * (uint32_t)stride + (uint32_t)v;
+                    const uint32_t s0 = (uint32_t)__ldg(cdfs + e), s1 = (uint32_t)__ldg(cdfs + e + 1);
+                    sta[k] = s0;
+                    rg[k] = (s1 > s0 ? s1 - s0 : 0u) | (esc ? 0x80000000u : 0u);
+                    rc[k] = __ldg(rcp + e);
+                    if (esc) sv[k] = (int32_t)raw;  // keep the raw value for phase B
+                }
+                if (++rem >= n_spatial) { rem = 0; ++ci; }
+            }
+        }
+#pragma unroll
+        for (int k = kChunk - 1; k >= 0; --k) {
+            if (k < cnt) {
+                const uint32_t range = rg[k] & 0x7fffffffu;
+                if (range == 0) { bad = true; continue; }
+                if (rg[k] & 0x80000000u) {
+                    // forward order is [symbol][count prefix: 15, 15, .., rest][nibbles low to high]; coding runs in reverse
+                    const uint32_t raw = (uint32_t)sv[k];
+                    uint32_t nibbles = 0;
+                    while (nibbles < 8 && (raw >> (nibbles * kRansBypassBits)) != 0) ++nibbles;  // (a shift by 32 is undefined)
+                    for (uint32_t j = nibbles; j-- > 0;) rans_put_nibble(st, (raw >> (j * kRansBypassBits)) & kRansBypassMax);
+                    rans_put_nibble(st, nibbles % kRansBypassMax);
+                    for (uint32_t c15 = nibbles / kRansBypassMax; c15 > 0; --c15) rans_put_nibble(st, kRansBypassMax);
+                }
+                rans_put_symbol(st, sta[k], range, rc[k]);
+            }
+        }
+        i -= cnt;
+        // the next chunk starts kChunk positions earlier
+        rem_b -= kChunk;
+        while (rem_b < 0) { rem_b += n_spatial; --ci_b; }
+    }
+    *--st.wp = st.hi;
+    *--st.wp = st.lo;
+    lengths[b] = bad ? -1 : (int32_t)(row + cap_words - st.wp);
+}
+
+// out[offsets[b] .. offsets[b] + lengths[b]) (words) = the used tail of scratch row b
+__global__ void rans_pack_kernel(const uint32_t* __restrict__ work, int64_t cap_words, const int32_t* __restrict__ lengths,
+                                 const int64_t* __restrict__ offsets, uint32_t* __restrict__ out) {
+    const int b = blockIdx.x;
+    const int32_t len = lengths[b];
+    if (len <= 0) return;
+    const uint32_t* src = work + (size_t)b * cap_words + (cap_words - len);
+    uint32_t* dst = out + offsets[b];
+    for (int32_t k = threadIdx.x; k < len; k += blockDim.x) dst[k] = src[k];
+}
+
+}  // namespace licos
+
+using namespace licos;
+
+extern "C" {
+
+int licos_rans_encode_device(const int32_t* symbols, const int32_t* indexes, int64_t index_stride, int batch, int64_t n,
+                             int64_t n_spatial, const int32_t* cdfs, int n_cdfs, int cdf_stride, const int32_t* cdf_sizes,
+                             const int32_t* offsets, uint64_t* rcp_ws, uint32_t* work, int64_t cap_words, int32_t* lengths,
+                             void* stream) {
+    if (!symbols || !cdfs || !cdf_sizes || !offsets || !rcp_ws || !work || !lengths || batch < 0 || n < 0 || cap_words < 2 ||
+        n_cdfs < 1 || cdf_stride < 2)
+        return LICOS_ERR_INVALID;
+    if (!indexes && n_spatial < 1) return LICOS_ERR_INVALID;
+    if (batch == 0) return LICOS_OK;
+    const int64_t entries = (int64_t)n_cdfs * cdf_stride;
+    rans_rcp_kernel<<<(int)((entries + 255) / 256 < 1184 ? (entries + 255) / 256 : 1184), 256, 0, (cudaStream_t)stream>>>(
+        cdfs, n_cdfs, cdf_stride, cdf_sizes, rcp_ws);
+    LICOS_CUDA_OK(cudaGetLastError());
+    rans_encode_kernel<<<(batch + 31) / 32, 32, 0, (cudaStream_t)stream>>>(symbols, indexes, index_stride, batch, n,
+                                                                            n_spatial > 0 ? n_spatial : 1, cdfs, n_cdfs,
+                                                                            cdf_stride, cdf_sizes, offsets, rcp_ws, work,
+                                                                            cap_words, lengths);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_rans_pack_device(const uint32_t* work, int64_t cap_words, const int32_t* lengths, const int64_t* word_offsets,
+                           int batch, uint32_t* out, void* stream) {
+    if (!work || !lengths || !word_offsets || !out || batch < 0) return LICOS_ERR_INVALID;
+    if (batch == 0) return LICOS_OK;
+    rans_pack_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(work, cap_words, lengths, word_offsets, out);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+}  // extern "C"

@@ -53,6 +53,7 @@ class EntropyModel(nn.Module):
         self.register_buffer("_quantized_cdf", torch.IntTensor())
         self.register_buffer("_cdf_length", torch.IntTensor())
         self.coder_threads = 0  # 0 = all host cores
+        self.device_coder = True  # compress(): rANS-encode on the GPU (same bitstream); False = host threads
 
     offset = property(lambda self: self._offset)
     quantized_cdf = property(lambda self: self._quantized_cdf)
@@ -123,6 +124,12 @@ class EntropyModel(nn.Module):
         self._check_tables()
         symbols = self.quantize(inputs, "symbols", means)
         B = symbols.size(0)
+        if symbols.is_cuda and self.device_coder:
+            # device-resident front end: symbols and indexes never leave the GPU, only the byte strings do
+            out = ops.rans_encode_device(symbols.reshape(B, -1), indexes.reshape(B, -1), 1, self._quantized_cdf,
+                                         self._cdf_length, self._offset)
+            if out is not None:
+                return out
         sym = symbols.reshape(B, -1).cpu().numpy()
         idx = indexes.reshape(B, -1).int().cpu().numpy()
         cdf, lengths, offsets = self._host_tables()
@@ -340,7 +347,13 @@ class EntropyBottleneck(EntropyModel):
         self._check_tables()
         B, C = x.size(0), x.size(1)
         n_spatial = int(np.prod(x.shape[2:])) if x.dim() > 2 else 1
-        sym = self.symbols(x).reshape(B, -1).cpu().numpy()
+        sym_dev = self.symbols(x)
+        if self.device_coder:
+            out = ops.rans_encode_device(sym_dev.reshape(B, -1), None, n_spatial, self._quantized_cdf, self._cdf_length,
+                                         self._offset)
+            if out is not None:
+                return out
+        sym = sym_dev.reshape(B, -1).cpu().numpy()
         idx = np.repeat(np.arange(C, dtype=np.int32), n_spatial)  # same index plane for every image
         cdf, lengths, offsets = self._host_tables()
         return ops.rans_encode_batch(sym, idx, cdf, lengths, offsets, threads=self.coder_threads)

@@ -359,6 +359,47 @@ def rans_encode_batch(symbols: np.ndarray, indexes: np.ndarray, cdfs, cdf_sizes,
     return [out[i, : sizes[i]].tobytes() for i in range(B)]
 
 
+def rans_encode_device(symbols: torch.Tensor, indexes: Optional[torch.Tensor], n_spatial: int, cdfs: torch.Tensor,
+                       cdf_sizes: torch.Tensor, offsets: torch.Tensor):
+    """Device-resident rANS encoder.  symbols: int32 (B, ...) on the GPU; indexes: None (index = position // n_spatial),
+    an int32 tensor shaped like symbols, or like one image (shared).  cdfs / cdf_sizes / offsets: int32 device tensors.
+    Returns list[bytes], or None when a stream did not fit the scratch row (callers then use the host coder)."""
+    _need_cuda(symbols, indexes, cdfs, cdf_sizes, offsets)
+    B = symbols.shape[0]
+    if B == 0:
+        return []
+    sym = symbols.reshape(B, -1).contiguous()
+    n = sym.shape[1]
+    idx, stride = None, 0
+    if indexes is not None:
+        idx = indexes.to(torch.int32).contiguous()
+        stride = n if idx.numel() == sym.numel() else 0
+        if idx.numel() not in (sym.numel(), n):
+            raise ValueError("indexes must match symbols or one image of symbols")
+    cdfs, cdf_sizes, offsets = cdfs.contiguous(), cdf_sizes.contiguous(), offsets.contiguous()
+    dev = sym.device
+    cap = n + 1024                                     # words per image: 32 bits per symbol + slack
+    work = torch.empty((B, cap), dtype=torch.int32, device=dev)
+    rcp = torch.empty(cdfs.numel(), dtype=torch.int64, device=dev)
+    lengths = torch.empty(B, dtype=torch.int32, device=dev)
+    check(lib.licos_rans_encode_device(sym.data_ptr(), _ptr(idx), stride, B, n, int(n_spatial), cdfs.data_ptr(),
+                                       cdfs.shape[0], cdfs.shape[1], cdf_sizes.data_ptr(), offsets.data_ptr(),
+                                       rcp.data_ptr(), work.data_ptr(), cap, lengths.data_ptr(), _stream()),
+          "rans_encode_device")
+    offs = torch.cumsum(lengths.clamp(min=0).to(torch.int64), 0)
+    word_offsets = offs - lengths.clamp(min=0)
+    host = torch.stack([lengths.to(torch.int64), word_offsets]).cpu()   # one small D2H (and the sync point)
+    lens, starts = host[0].tolist(), host[1].tolist()
+    if min(lens) < 0:
+        return None
+    total = int(starts[-1] + lens[-1])
+    packed = torch.empty(total, dtype=torch.int32, device=dev)
+    check(lib.licos_rans_pack_device(work.data_ptr(), cap, lengths.data_ptr(), word_offsets.data_ptr(), B,
+                                     packed.data_ptr(), _stream()), "rans_pack_device")
+    raw = packed.cpu().numpy().tobytes()
+    return [raw[4 * s: 4 * (s + l)] for s, l in zip(starts, lens)]
+
+
 def rans_decode_batch(strings, indexes: np.ndarray, n: int, cdfs, cdf_sizes, offsets, threads: int = 0) -> np.ndarray:
     B = len(strings)
     indexes = _i32(indexes)

@@ -196,3 +196,33 @@ def test_eb_forward_fused_equals_separate_kernels_and_golden(cuda, tag, in_ch):
     with torch.no_grad():
         out = net(synth.make_input("rgb256" if in_ch == 3 else "raw512", 2).to(cuda))   # model.forward uses the fused pass
     assert out["x_hat"].shape[0] == 2
+
+
+def test_device_rans_encoder_is_bitstream_identical(cuda):
+    # the GPU encoder against the host coder (itself pinned to the C / Python oracle twins): same bytes for ordinary
+    # symbols, out-of-support symbols (bypass nibbles, long base-15 prefixes), a shared and a per-image index plane,
+    # odd lengths (scalar tail of the 4-wide backwards walk) and a stream that does not fit its scratch row
+    net, ref = _pair(3, cuda)
+    net.update()
+    eb = net.entropy_bottleneck
+    cdf, lens, offs = eb._quantized_cdf, eb._cdf_length, eb._offset
+    g = torch.Generator().manual_seed(7)
+    for shape, scale in [((5, 192, 16, 16), 6.0), ((3, 192, 3, 5), 30.0), ((33, 192, 4, 4), 2.0), ((2, 192, 1, 1), 2000.0)]:
+        y = (torch.randn(shape, generator=g) * scale).to(cuda)
+        y[0, 0, 0, 0] = 3.0e5                      # 5 nibbles of bypass
+        y[-1, -1, -1, -1] = -1.0e6                 # 6 nibbles
+        sym = eb.symbols(y)
+        B, n_sp = shape[0], shape[2] * shape[3]
+        host = ops.rans_encode_batch(sym.reshape(B, -1).cpu().numpy(),
+                                     np.repeat(np.arange(192, dtype=np.int32), n_sp), cdf.cpu().numpy(), lens.cpu().numpy(),
+                                     offs.cpu().numpy())
+        dev_implicit = ops.rans_encode_device(sym, None, n_sp, cdf, lens, offs)
+        idx_plane = torch.arange(192, dtype=torch.int32, device=cuda).repeat_interleave(n_sp)
+        dev_shared = ops.rans_encode_device(sym, idx_plane, n_sp, cdf, lens, offs)
+        dev_full = ops.rans_encode_device(sym, idx_plane.repeat(B, 1), n_sp, cdf, lens, offs)
+        assert dev_implicit == host and dev_shared == host and dev_full == host
+        eb.device_coder = False
+        via_host = eb.compress(y)
+        eb.device_coder = True
+        assert eb.compress(y) == via_host == host
+        assert torch.equal(eb.decompress(host, shape[2:]), eb(y)[0])
