@@ -214,6 +214,13 @@ int licos_rans_encode_device(const int32_t* symbols, const int32_t* indexes, int
                              int64_t n_spatial, const int32_t* cdfs, int n_cdfs, int cdf_stride, const int32_t* cdf_sizes,
                              const int32_t* offsets, uint64_t* rcp_ws, uint32_t* work, int64_t cap_words, int32_t* lengths,
                              void* stream);
+/* Device-resident rANS DECODER (mirror of licos_rans_decode; one thread per image).  packed: all streams back to back as
+ * 32-bit words (a stream's length is a multiple of 4 bytes), stream b = packed[word_offsets[b] .. + n_words[b]).
+ * symbols: int32 [batch][n] out.  status[b] = 0, or -1 for a malformed stream / invalid index. */
+int licos_rans_decode_device(const uint32_t* packed, const int64_t* word_offsets, const int32_t* n_words, const int32_t* indexes,
+                             int64_t index_stride, int batch, int64_t n, int64_t n_spatial, const int32_t* cdfs, int n_cdfs,
+                             int cdf_stride, const int32_t* cdf_sizes, const int32_t* offsets, int32_t* symbols, int32_t* status,
+                             void* stream);
 /* Packs the streams back to back: out[word_offsets[b] .. + lengths[b]) = stream b (word_offsets: exclusive prefix sum). */
 int licos_rans_pack_device(const uint32_t* work, int64_t cap_words, const int32_t* lengths, const int64_t* word_offsets,
                            int batch, uint32_t* out, void* stream);

@@ -83,6 +83,8 @@ SIGNATURES = {
     "licos_rans_encode_device": (c_int, [c_vp, c_vp, c_i64, c_int, c_i64, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
                                          c_i64, c_vp, c_vp]),
     "licos_rans_pack_device": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_vp, c_vp]),
+    "licos_rans_decode_device": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_vp,
+                                         c_vp, c_vp]),
     "licos_weighted_sum2": (c_int, [c_vp, c_vp, c_f32, c_f32, c_i64, c_vp, c_vp]),
     "licos_scale_inplace": (c_int, [c_vp, c_f32, c_i64, c_vp]),
 }

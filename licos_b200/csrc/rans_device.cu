@@ -173,6 +173,85 @@ __global__ void rans_pack_kernel(const uint32_t* __restrict__ work, int64_t cap_
     for (int32_t k = threadIdx.x; k < len; k += blockDim.x) dst[k] = src[k];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// decoder: one image per thread; mirrors decode_one() in host_codec.cpp
+// ---------------------------------------------------------------------------------------------------------------
+struct RansReader {
+    const uint32_t* words;
+    int64_t n_words, pos;
+    uint32_t lo, hi;
+    __device__ __forceinline__ uint32_t next() { return pos < n_words ? __ldg(words + pos++) : 0u; }
+    __device__ __forceinline__ void refill() {  // if (x < L) x = (x << 32) | next()
+        if (hi == 0 && lo < (uint32_t)kRansLow) { hi = lo; lo = next(); }
+    }
+    __device__ __forceinline__ uint32_t nibble() {
+        const uint32_t v = lo & kRansBypassMax;
+        lo = (lo >> kRansBypassBits) | (hi << (32 - kRansBypassBits));
+        hi >>= kRansBypassBits;
+        refill();
+        return v;
+    }
+};
+
+__global__ void __launch_bounds__(32) rans_decode_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ word_offsets,
+                                                         const int32_t* __restrict__ n_words, const int32_t* __restrict__ indexes,
+                                                         int64_t idx_stride, int batch, int64_t n, int64_t n_spatial,
+                                                         const int32_t* __restrict__ cdfs, int n_cdfs, int stride,
+                                                         const int32_t* __restrict__ sizes, const int32_t* __restrict__ offsets,
+                                                         int32_t* __restrict__ out, int32_t* __restrict__ status) {
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    if (b >= batch) return;
+    RansReader r{packed + word_offsets[b], (int64_t)n_words[b], 0, 0u, 0u};
+    if (r.n_words < 2) { status[b] = -1; return; }
+    r.lo = r.next();
+    r.hi = r.next();
+    const int32_t* idx = indexes ? indexes + (size_t)b * idx_stride : nullptr;
+    int32_t* o = out + (size_t)b * n;
+    int32_t ci_run = 0;
+    int64_t rem = 0;
+    bool bad = false;
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t ci = idx ? __ldg(idx + i) : ci_run;
+        if (++rem >= n_spatial) { rem = 0; ++ci_run; }
+        if (ci < 0 || ci >= n_cdfs) { bad = true; o[i] = 0; continue; }
+        const int32_t* cdf = cdfs + (size_t)ci * stride;
+        const int32_t len = __ldg(sizes + ci), escape = len - 2;
+        const uint32_t target = r.lo & 0xffffu;
+        // first entry strictly above the target (the table is strictly increasing): s = that position - 1
+        int32_t lo_i = 0, hi_i = len;  // search in cdf[0 .. len)
+        while (lo_i < hi_i) {
+            const int32_t mid = (lo_i + hi_i) >> 1;
+            if ((uint32_t)__ldg(cdf + mid) <= target) lo_i = mid + 1; else hi_i = mid;
+        }
+        const int32_t s = lo_i - 1;
+        const uint32_t start = (uint32_t)__ldg(cdf + s), freq = (uint32_t)__ldg(cdf + s + 1) - start;
+        // x = freq * (x >> 16) + (x & 0xffff) - start
+        const uint64_t x = ((uint64_t)r.hi << 32) | r.lo;
+        const uint64_t nx = (uint64_t)freq * (x >> kRansPrecision) + target - start;
+        r.lo = (uint32_t)nx;
+        r.hi = (uint32_t)(nx >> 32);
+        r.refill();
+        int32_t v = s;
+        if (v == escape) {
+            uint32_t d = r.nibble();
+            uint32_t nibbles = d;
+            while (d == kRansBypassMax) {
+                d = r.nibble();
+                nibbles += d;
+            }
+            uint32_t raw = 0;
+            for (uint32_t j = 0; j < nibbles; ++j) {
+                const uint32_t nb = r.nibble();
+                if (j < 8) raw |= nb << (j * kRansBypassBits);
+            }
+            v = (int32_t)(raw >> 1);
+            v = (raw & 1u) ? -v - 1 : v + escape;
+        }
+        o[i] = v + __ldg(offsets + ci);
+    }
+    status[b] = bad ? -1 : 0;
+}
+
 }  // namespace licos
 
 using namespace licos;
@@ -205,6 +284,22 @@ int licos_rans_pack_device(const uint32_t* work, int64_t cap_words, const int32_
     if (!work || !lengths || !word_offsets || !out || batch < 0) return LICOS_ERR_INVALID;
     if (batch == 0) return LICOS_OK;
     rans_pack_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(work, cap_words, lengths, word_offsets, out);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_rans_decode_device(const uint32_t* packed, const int64_t* word_offsets, const int32_t* n_words, const int32_t* indexes,
+                             int64_t index_stride, int batch, int64_t n, int64_t n_spatial, const int32_t* cdfs, int n_cdfs,
+                             int cdf_stride, const int32_t* cdf_sizes, const int32_t* offsets, int32_t* symbols, int32_t* status,
+                             void* stream) {
+    if (!packed || !word_offsets || !n_words || !cdfs || !cdf_sizes || !offsets || !symbols || !status || batch < 0 || n < 0 ||
+        n_cdfs < 1 || cdf_stride < 2)
+        return LICOS_ERR_INVALID;
+    if (!indexes && n_spatial < 1) return LICOS_ERR_INVALID;
+    if (batch == 0 || n == 0) return LICOS_OK;
+    rans_decode_kernel<<<(batch + 31) / 32, 32, 0, (cudaStream_t)stream>>>(packed, word_offsets, n_words, indexes, index_stride,
+                                                                            batch, n, n_spatial > 0 ? n_spatial : 1, cdfs, n_cdfs,
+                                                                            cdf_stride, cdf_sizes, offsets, symbols, status);
     LICOS_CUDA_OK(cudaGetLastError());
     return LICOS_OK;
 }

@@ -152,6 +152,11 @@ class EntropyModel(nn.Module):
                         raise ValueError("Invalid means parameters")
         B = indexes.size(0)
         n = indexes[0].numel() if B else 0
+        if indexes.is_cuda and self.device_coder and B:
+            sym_d = ops.rans_decode_device(list(strings), indexes.reshape(B, -1), n, 1, self._quantized_cdf,
+                                           self._cdf_length, self._offset)
+            if sym_d is not None:
+                return self.dequantize(sym_d.reshape(indexes.size()), means, dtype)
         cdf, lengths, offsets = self._host_tables()
         idx = indexes.reshape(B, -1).int().cpu().numpy()
         sym = ops.rans_decode_batch(list(strings), idx, n, cdf, lengths, offsets, threads=self.coder_threads)
@@ -364,12 +369,19 @@ class EntropyBottleneck(EntropyModel):
         self._check_tables()
         C = self._quantized_cdf.size(0)
         n_spatial = int(np.prod(size)) if len(size) else 1
-        idx = np.repeat(np.arange(C, dtype=np.int32), n_spatial)
-        cdf, lengths, offsets = self._host_tables()
-        sym = ops.rans_decode_batch(list(strings), idx, C * n_spatial, cdf, lengths, offsets,
-                                    threads=self.coder_threads)
         _require_cuda(self.quantiles, "EntropyBottleneck.decompress")
-        symbols = torch.from_numpy(sym).reshape(len(strings), C, *size).to(self.quantiles.device)
+        symbols = None
+        if self.device_coder and len(strings):
+            symbols = ops.rans_decode_device(list(strings), None, C * n_spatial, n_spatial, self._quantized_cdf,
+                                             self._cdf_length, self._offset)
+            if symbols is not None:
+                symbols = symbols.reshape(len(strings), C, *size)
+        if symbols is None:
+            idx = np.repeat(np.arange(C, dtype=np.int32), n_spatial)
+            cdf, lengths, offsets = self._host_tables()
+            sym = ops.rans_decode_batch(list(strings), idx, C * n_spatial, cdf, lengths, offsets,
+                                        threads=self.coder_threads)
+            symbols = torch.from_numpy(sym).reshape(len(strings), C, *size).to(self.quantiles.device)
         return ops.eb_dequantize(symbols.contiguous(), self.packed_params().medians)
 
 

@@ -400,6 +400,41 @@ def rans_encode_device(symbols: torch.Tensor, indexes: Optional[torch.Tensor], n
     return [raw[4 * s: 4 * (s + l)] for s, l in zip(starts, lens)]
 
 
+def rans_decode_device(strings, indexes: Optional[torch.Tensor], n: int, n_spatial: int, cdfs: torch.Tensor,
+                       cdf_sizes: torch.Tensor, offsets: torch.Tensor):
+    """Device-resident rANS decoder: list[bytes] -> int32 (B, n) symbols on the GPU (one H2D copy of the strings).
+    Returns None when a stream is not a whole number of 32-bit words or fails to decode (callers use the host coder)."""
+    _need_cuda(indexes, cdfs, cdf_sizes, offsets)
+    B = len(strings)
+    dev = cdfs.device
+    if B == 0:
+        return torch.empty((0, n), dtype=torch.int32, device=dev)
+    sizes = [len(s) for s in strings]
+    if any(sz % 4 or sz < 8 for sz in sizes):
+        return None
+    words = np.frombuffer(b"".join(strings), dtype=np.uint32)
+    n_words = np.asarray([sz // 4 for sz in sizes], dtype=np.int32)
+    offs = np.zeros(B, dtype=np.int64)
+    np.cumsum(n_words[:-1], out=offs[1:])
+    packed = torch.from_numpy(words.view(np.int32).copy()).to(dev)
+    offs_d, nw_d = torch.from_numpy(offs).to(dev), torch.from_numpy(n_words).to(dev)
+    idx, stride = None, 0
+    if indexes is not None:
+        idx = indexes.to(torch.int32).contiguous()
+        stride = n if idx.numel() == B * n else 0
+        if idx.numel() not in (B * n, n):
+            raise ValueError("indexes must have n entries per image (or n shared entries)")
+    out = torch.empty((B, n), dtype=torch.int32, device=dev)
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    cdfs, cdf_sizes, offsets = cdfs.contiguous(), cdf_sizes.contiguous(), offsets.contiguous()
+    check(lib.licos_rans_decode_device(packed.data_ptr(), offs_d.data_ptr(), nw_d.data_ptr(), _ptr(idx), stride, B, n,
+                                       int(n_spatial), cdfs.data_ptr(), cdfs.shape[0], cdfs.shape[1], cdf_sizes.data_ptr(),
+                                       offsets.data_ptr(), out.data_ptr(), status.data_ptr(), _stream()), "rans_decode_device")
+    if int(status.min().item()) < 0:
+        return None
+    return out
+
+
 def rans_decode_batch(strings, indexes: np.ndarray, n: int, cdfs, cdf_sizes, offsets, threads: int = 0) -> np.ndarray:
     B = len(strings)
     indexes = _i32(indexes)

@@ -226,3 +226,13 @@ def test_device_rans_encoder_is_bitstream_identical(cuda):
         eb.device_coder = True
         assert eb.compress(y) == via_host == host
         assert torch.equal(eb.decompress(host, shape[2:]), eb(y)[0])
+        # the GPU decoder: same symbols back, through every index form; and through the host decoder
+        flat = sym.reshape(B, -1)
+        for ix in (None, idx_plane, idx_plane.repeat(B, 1)):
+            dec = ops.rans_decode_device(host, ix, flat.shape[1], n_sp, cdf, lens, offs)
+            assert dec is not None and torch.equal(dec, flat)
+        eb.device_coder = False
+        y_host = eb.decompress(host, shape[2:])
+        eb.device_coder = True
+        assert torch.equal(eb.decompress(host, shape[2:]), y_host)
+    assert ops.rans_decode_device([b"\x00" * 6], None, 4, 1, cdf, lens, offs) is None   # not a whole number of words
