@@ -65,9 +65,8 @@ class FlatState:
 
     def touch(self) -> None:
         """Bump parameter versions so kernel-layout weight caches are rebuilt after an in-place merge."""
-        with torch.no_grad():
-            for p in self.net.parameters():
-                p.add_(0)
+        for p in self.net.parameters():
+            torch.autograd.graph.increment_version(p)  # no kernel launch (p.add_(0) cost ~150 launches per merge)
 
 
 def federated_average(state: FlatState, loss: float, group: Optional[dist.ProcessGroup] = None,
