@@ -178,6 +178,16 @@ int licos_sum_log(const float* lik, int64_t n, double* acc, void* stream);
 /* acc[0] += sum((a[i]-b[i])^2) */
 int licos_sum_sq_err(const float* a, const float* b, int64_t n, double* acc, void* stream);
 
+/* MS-SSIM building blocks (eval_utils.py:159-169 compute_msssim = pytorch_msssim.ms_ssim): one pyramid level --
+ * sums[2*i] += sum of the SSIM map, sums[2*i+1] += sum of the contrast-structure map of image-channel i over its
+ * (h-10) x (w-10) valid positions (11-tap separable window `win11`, a HOST pointer; c1 = (0.01*L)^2, c2 = (0.03*L)^2).
+ * x, y: fp32 [bc][h][w]; workspace: licos_msssim_workspace_floats(bc, h, w) floats; sums: double [bc][2], caller zeroes. */
+int64_t licos_msssim_workspace_floats(int64_t bc, int h, int w);
+int licos_msssim_level(const float* x, const float* y, int64_t bc, int h, int w, const float* win11, float c1, float c2,
+                       float* workspace, double* sums, void* stream);
+/* F.avg_pool2d(x, 2, padding=(h % 2, w % 2)): out is [bc][(h + 2*(h%2) - 2)/2 + 1][(w + 2*(w%2) - 2)/2 + 1]. */
+int licos_avgpool2(const float* x, int64_t bc, int h, int w, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* Host-side integer path (compressai._CXX.pmf_to_quantized_cdf, compressai.ans)               */
 /* ------------------------------------------------------------------------------------------ */

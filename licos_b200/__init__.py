@@ -4,7 +4,7 @@ Importing the package loads (or builds) the CUDA shared library; there is no CPU
 from . import _lib  # noqa: F401  (fails loudly if liblicos_b200.so cannot be loaded)
 from .entropy_models import EntropyBottleneck, EntropyModel, GaussianConditional, get_scale_table
 from .layers import GDN, FusedSequential, LowerBound, NonNegativeParametrizer, conv, deconv
-from .losses import RateDistortionLoss, compute_bpp, compute_psnr
+from .losses import RateDistortionLoss, compute_bpp, compute_msssim, compute_psnr
 from .models import (CompressionModel, FactorizedPrior, FactorizedPriorReLU, ScaleHyperprior, image_models,
                      model_architectures)
 from .optimizers import net_aux_optimizer

@@ -57,3 +57,10 @@ def compute_psnr(a, b) -> float:
     """eval_utils.py:145-156"""
     acc = ops.sum_sq_err(a.contiguous(), b.contiguous())
     return -10 * math.log10(acc.item() / a.numel())
+
+
+def compute_msssim(a, b) -> float:
+    """/root/reference/eval_utils.py:159-169 (pytorch_msssim.ms_ssim(a, b, data_range=1.0)) on the device."""
+    from . import ops
+
+    return float(ops.ms_ssim(a.float(), b.float(), data_range=1.0).item())

@@ -284,6 +284,45 @@ def sum_sq_err(a: torch.Tensor, b: torch.Tensor, acc: Optional[torch.Tensor] = N
     return acc
 
 
+_MSSSIM_WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)
+
+
+def ms_ssim(a: torch.Tensor, b: torch.Tensor, data_range: float = 1.0) -> torch.Tensor:
+    """pytorch_msssim.ms_ssim(a, b, data_range) on the device (eval_utils.py:159-169): 0-dim fp32 tensor."""
+    _need_cuda(_f32(a), _f32(b))
+    if a.shape != b.shape or a.dim() != 4:
+        raise ValueError("ms_ssim expects two (B, C, H, W) tensors of the same shape")
+    B, C, H, W = a.shape
+    if min(H, W) <= (11 - 1) * 2 ** 4:
+        raise AssertionError("Image size should be larger than 160 due to the 4 downsamplings in ms-ssim")
+    coords = torch.arange(11, dtype=torch.float32) - 5
+    win = torch.exp(-(coords ** 2) / (2 * 1.5 ** 2))
+    win = (win / win.sum()).contiguous()
+    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    x, y = a.contiguous(), b.contiguous()
+    bc = B * C
+    terms = []
+    for level in range(5):
+        h, w = x.shape[-2:]
+        ws = torch.empty(int(lib.licos_msssim_workspace_floats(bc, h, w)), dtype=torch.float32, device=a.device)
+        sums = torch.zeros(bc, 2, dtype=torch.float64, device=a.device)
+        check(lib.licos_msssim_level(x.data_ptr(), y.data_ptr(), bc, h, w, win.data_ptr(), c1, c2, ws.data_ptr(),
+                                     sums.data_ptr(), _stream()), "msssim_level")
+        means = sums / float((h - 10) * (w - 10))
+        terms.append(torch.relu(means[:, 1] if level < 4 else means[:, 0]))
+        if level < 4:
+            ph, pw = h % 2, w % 2
+            ho, wo = (h + 2 * ph - 2) // 2 + 1, (w + 2 * pw - 2) // 2 + 1
+            nx = torch.empty((B, C, ho, wo), dtype=torch.float32, device=a.device)
+            ny = torch.empty_like(nx)
+            check(lib.licos_avgpool2(x.data_ptr(), bc, h, w, nx.data_ptr(), _stream()), "avgpool2")
+            check(lib.licos_avgpool2(y.data_ptr(), bc, h, w, ny.data_ptr(), _stream()), "avgpool2")
+            x, y = nx, ny
+    stack = torch.stack(terms, dim=0)                                  # (5, B*C) float64
+    wts = torch.tensor(_MSSSIM_WEIGHTS, dtype=torch.float64, device=a.device).view(-1, 1)
+    return torch.prod(stack ** wts, dim=0).mean().float()
+
+
 def weighted_sum2(a: torch.Tensor, b: torch.Tensor, wa: float, wb: float, out: Optional[torch.Tensor] = None):
     _need_cuda(_f32(a), _f32(b), out)
     if out is None:

@@ -236,3 +236,23 @@ def test_device_rans_encoder_is_bitstream_identical(cuda):
         eb.device_coder = True
         assert torch.equal(eb.decompress(host, shape[2:]), y_host)
     assert ops.rans_decode_device([b"\x00" * 6], None, 4, 1, cdf, lens, offs) is None   # not a whole number of words
+
+
+def test_ms_ssim_on_device_matches_oracle(cuda):
+    # eval_utils.py:159-169 compute_msssim: device kernels vs the CPU restatement of pytorch_msssim.ms_ssim; odd sizes
+    # exercise the padded average pooling; identical images give exactly 1
+    from oracle import msssim_ref as M
+
+    g = torch.Generator().manual_seed(0)
+    for shape, noise in [((2, 3, 256, 256), 0.05), ((1, 1, 177, 231), 0.2), ((3, 2, 161, 170), 0.01)]:
+        x = torch.rand(shape, generator=g)
+        y = (x + noise * torch.randn(shape, generator=g)).clamp(0, 1)
+        want = M.ms_ssim(x, y, data_range=1.0).item()
+        got = ops.ms_ssim(x.to(cuda), y.to(cuda), data_range=1.0).item()
+        assert abs(got - want) <= 2e-5, (shape, got, want)
+        want255 = M.ms_ssim(x * 255, y * 255, data_range=255.0).item()
+        got255 = ops.ms_ssim((x * 255).to(cuda), (y * 255).to(cuda), data_range=255.0).item()
+        assert abs(got255 - want255) <= 2e-5
+    assert abs(L.compute_msssim(x.to(cuda), x.to(cuda)) - 1.0) <= 1e-6
+    with pytest.raises(AssertionError):
+        ops.ms_ssim(torch.rand(1, 1, 160, 300, device=cuda), torch.rand(1, 1, 160, 300, device=cuda))
