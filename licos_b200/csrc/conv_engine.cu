@@ -697,6 +697,28 @@ static int ew_grid(int64_t n) {
 
 static unsigned long long* g_conv_probe = nullptr;
 
+// Development knobs, read once (tools/probe_conv.py experiments; none is needed in production):
+//   LICOS_FIRST_V1=1       route the first layer to the non-pipelined kernel
+//   LICOS_PREFER_NACC2=1   two single-buffered accumulators instead of one double-buffered one when both do not fit
+//   LICOS_SA / LICOS_SB    force the slab / weight ring depths
+//   LICOS_DBG_FLAGS        bit 0 / 1: load every slab / weight ring slot only once (isolates the mainloop from data movement)
+struct DevKnobs {
+    bool first_v1, prefer_nacc2;
+    int sa, sb, dbg_flags;
+};
+static const DevKnobs& knobs() {
+    static const DevKnobs k = [] {
+        DevKnobs v{};
+        v.first_v1 = getenv("LICOS_FIRST_V1") != nullptr;
+        v.prefer_nacc2 = getenv("LICOS_PREFER_NACC2") != nullptr;
+        if (const char* e = getenv("LICOS_SA")) v.sa = atoi(e);
+        if (const char* e = getenv("LICOS_SB")) v.sb = atoi(e);
+        if (const char* e = getenv("LICOS_DBG_FLAGS")) v.dbg_flags = atoi(e);
+        return v;
+    }();
+    return k;
+}
+
 static void set_tap(Slab& s, int i, int row_off, int group, int w_tap) {
     s.taps[i].row_off = (int8_t)row_off;
     s.taps[i].group = (int8_t)group;
@@ -799,7 +821,7 @@ static bool make_map_f32(CUtensorMap* m, const void* base, const uint64_t* dims,
 // pipelined first layer (conv_first2.cuh): 1 or 3 bands, N in {64, 128}, rows of x 16-byte aligned (TMA)
 static bool use_first2(const licos_conv_args* a) {
     return (a->in_c == 1 || a->in_c == 3) && (a->out_c == 64 || a->out_c == 128 || a->out_c == 192) && a->in_w % 4 == 0 &&
-           ((uintptr_t)a->in & 15) == 0 && !getenv("LICOS_FIRST_V1");
+           ((uintptr_t)a->in & 15) == 0 && !knobs().first_v1;
 }
 
 static int launch_first2(const licos_conv_args* a, cudaStream_t s) {
@@ -1088,7 +1110,7 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     if (groups * 2 * pl.N > (int)kTmemCols) n_acc = 1;
     if (p.grid_h <= kAccRows) n_acc = 1;
     if (n_acc == 2 && 2 * groups * 2 * pl.N > (int)kTmemCols && 2 * groups * pl.N <= (int)kTmemCols &&
-        !getenv("LICOS_PREFER_NACC2"))
+        !knobs().prefer_nacc2)
         n_acc = 1;  // one double-buffered accumulator beats two single-buffered ones that share weight tiles
     if (groups * n_acc * pl.N > (int)kTmemCols) return LICOS_ERR_UNSUPPORTED;
     p.n_acc = n_acc;
@@ -1267,8 +1289,8 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
         break;
     }
     if (p.n_teams < 1) return LICOS_ERR_UNSUPPORTED;
-    if (const char* e = getenv("LICOS_SA")) { const int v = atoi(e); if (v >= 2 && v <= kMaxSA) sa = v; }
-    if (const char* e = getenv("LICOS_SB")) { const int v = atoi(e); if (v >= 2 && v <= kMaxSB) sb = v; }
+    if (knobs().sa >= 2 && knobs().sa <= kMaxSA) sa = knobs().sa;
+    if (knobs().sb >= 2 && knobs().sb <= kMaxSB) sb = knobs().sb;
     p.sa = sa;
     p.sb = sb;
     size_t smem_bytes = 1024 + (size_t)sa * p.a_slot_bytes + (size_t)sb * b_slot_al + (size_t)p.n_teams * p.staging_bytes + p.gamma_bytes;
@@ -1281,7 +1303,7 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     if (tiles > 0x7fffffff) return LICOS_ERR_UNSUPPORTED;
     p.total_tiles = (int)tiles;
     p.dbg = g_conv_probe;
-    if (const char* e = getenv("LICOS_DBG_FLAGS")) p.dbg_flags = atoi(e);
+    p.dbg_flags = knobs().dbg_flags;
 
     int sms = a->sm_count;
     if (sms <= 0) {

@@ -167,3 +167,37 @@ def test_full_size_properties(cuda):
     assert out["x_hat"].shape == x.shape and torch.isfinite(out["x_hat"]).all()
     assert (out["likelihoods"]["y"] >= 1e-9).all() and (out["likelihoods"]["y"] <= 1).all()
     assert (sym != 0).float().mean().item() > 0.5
+
+
+def test_full_size_other_baseline_configs(cuda):
+    """BASELINE configs 3 (raw-split 1x512x512) and 4 (hyperprior N=192 / M=320 on 3x1024x1024) at their tile sizes,
+    reduced batch: size-independent properties -- compress -> decompress round trip through the device coders gives
+    exactly the x_hat of forward (clamped), batch independence, determinism, finite outputs, bounded likelihoods."""
+    torch.manual_seed(42)
+    net3 = L.get_model("bmshj2018-factorized", False, 1, 1)
+    synth.condition_weights(net3)
+    net3.update()
+    net3 = net3.to(cuda).eval()
+    net4 = L.image_models["bmshj2018-hyperprior"](quality=6, pretrained=False)
+    synth.condition_weights(net4)
+    net4.update()
+    net4 = net4.to(cuda).eval()
+    for net, x in ((net3, synth.make_input("raw512", 24, device=cuda)), (net4, synth.make_input("rgb1024", 2, device=cuda))):
+        with torch.no_grad():
+            out = net(x)
+            comp = net.compress(x)
+            dec = net.decompress(comp["strings"], comp["shape"])
+            assert torch.equal(dec["x_hat"], out["x_hat"].clamp(0, 1))
+            part = net(x[1:2])
+            assert torch.equal(part["x_hat"], out["x_hat"][1:2])
+            assert torch.equal(net(x)["x_hat"], out["x_hat"])
+        assert out["x_hat"].shape == x.shape and torch.isfinite(out["x_hat"]).all()
+        for lik in out["likelihoods"].values():
+            assert (lik >= 1e-9).all() and (lik <= 1).all()
+        n_bytes = sum(len(s) for group in comp["strings"] for s in group)
+        bpp_coded = 8 * n_bytes / (x.shape[0] * x.shape[2] * x.shape[3])
+        bpp_model = sum(torch.log(v).sum().item() for v in out["likelihoods"].values()) / (
+            -math.log(2) * x.shape[0] * x.shape[2] * x.shape[3])
+        # the coded size tracks the model's rate (rANS overhead above it; below it where the 1e-9 likelihood floor charges
+        # 30 bits for out-of-support symbols that the bypass nibbles code in fewer)
+        assert 0.7 * bpp_model <= bpp_coded <= 1.1 * bpp_model + 0.05, (bpp_coded, bpp_model)
