@@ -147,30 +147,44 @@ __global__ void __launch_bounds__(256) eb_eval_tile_kernel(EbMeta m, const float
     const int n_hw = min(kEbTileHw, hw - hw0);  // multiple of 4
     const int vecs = n_hw / 4;                   // float4 groups per channel row
     const size_t img = (size_t)b * C * hw;
-    for (int idx = threadIdx.x; idx < C * 16; idx += 256) {
-        const int c = idx >> 4, v = idx & 15;
-        if (v >= vecs) continue;
-        const size_t off = img + (size_t)c * hw + hw0 + 4 * v;
-        const float4 t = __ldcs(reinterpret_cast<const float4*>(x + off));
-        const float md = __ldg(med + c);
-        const float xv[4] = {t.x, t.y, t.z, t.w};
-        float yv[4], lv[4];
-        int sv[4];
+    // four independent 16-byte loads in flight per thread before any dependent table gather
+    constexpr int kUnroll = 4;
+    for (int idx0 = threadIdx.x; idx0 < C * 16; idx0 += 256 * kUnroll) {
+        float4 t[kUnroll];
+        bool live[kUnroll];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float r = rintf(xv[j] - md);
-            yv[j] = r + md;
-            sv[j] = (int)r;
-            lv[j] = (fabsf(r) <= (float)kLutR) ? __ldg(lut + (size_t)c * kLutN + ((int)r + kLutR))
-                                               : eb_likelihood_slow(packed, m, c, yv[j]);
+        for (int u = 0; u < kUnroll; ++u) {
+            const int idx = idx0 + u * 256;
+            const int c = idx >> 4, v = idx & 15;
+            live[u] = idx < C * 16 && v < vecs;
+            if (live[u]) t[u] = __ldcs(reinterpret_cast<const float4*>(x + img + (size_t)c * hw + hw0 + 4 * v));
         }
-        __stcs(reinterpret_cast<float4*>(y_hat + off), make_float4(yv[0], yv[1], yv[2], yv[3]));
-        __stcs(reinterpret_cast<float4*>(lik + off), make_float4(lv[0], lv[1], lv[2], lv[3]));
-        if (sym) __stcs(reinterpret_cast<int4*>(sym + off), make_int4(sv[0], sv[1], sv[2], sv[3]));
-        if (nhwc) {
-            __nv_bfloat162* row = reinterpret_cast<__nv_bfloat162*>(tile + c * kEbTilePitch + 4 * v);
-            row[0] = __floats2bfloat162_rn(yv[0], yv[1]);
-            row[1] = __floats2bfloat162_rn(yv[2], yv[3]);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (!live[u]) continue;
+            const int idx = idx0 + u * 256;
+            const int c = idx >> 4, v = idx & 15;
+            const size_t off = img + (size_t)c * hw + hw0 + 4 * v;
+            const float md = __ldg(med + c);
+            const float xv[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
+            float yv[4], lv[4];
+            int sv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float r = rintf(xv[j] - md);
+                yv[j] = r + md;
+                sv[j] = (int)r;
+                lv[j] = (fabsf(r) <= (float)kLutR) ? __ldg(lut + (size_t)c * kLutN + ((int)r + kLutR))
+                                                   : eb_likelihood_slow(packed, m, c, yv[j]);
+            }
+            __stcs(reinterpret_cast<float4*>(y_hat + off), make_float4(yv[0], yv[1], yv[2], yv[3]));
+            __stcs(reinterpret_cast<float4*>(lik + off), make_float4(lv[0], lv[1], lv[2], lv[3]));
+            if (sym) __stcs(reinterpret_cast<int4*>(sym + off), make_int4(sv[0], sv[1], sv[2], sv[3]));
+            if (nhwc) {
+                __nv_bfloat162* row = reinterpret_cast<__nv_bfloat162*>(tile + c * kEbTilePitch + 4 * v);
+                row[0] = __floats2bfloat162_rn(yv[0], yv[1]);
+                row[1] = __floats2bfloat162_rn(yv[2], yv[3]);
+            }
         }
     }
     if (!nhwc) return;
