@@ -178,6 +178,10 @@ int licos_sum_log(const float* lik, int64_t n, double* acc, void* stream);
 /* acc[0] += sum((a[i]-b[i])^2) */
 int licos_sum_sq_err(const float* a, const float* b, int64_t n, double* acc, void* stream);
 
+/* Raw-tile input scaling (raw_image_folder.py:192-196 `_open_band_`): out = dn / dn_max (dn_max = 4095, raw_utils.py:128),
+ * and, when requant8 != 0 (use_full_range = False), out = rint(out * 255) / 255; evaluated in float64, stored as fp32. */
+int licos_raw_dn_to_unit(const uint16_t* dn, int64_t n, int dn_max, int requant8, float* out, void* stream);
+
 /* MS-SSIM building blocks (eval_utils.py:159-169 compute_msssim = pytorch_msssim.ms_ssim): one pyramid level --
  * sums[2*i] += sum of the SSIM map, sums[2*i+1] += sum of the contrast-structure map of image-channel i over its
  * (h-10) x (w-10) valid positions (11-tap separable window `win11`, a HOST pointer; c1 = (0.01*L)^2, c2 = (0.03*L)^2).

@@ -77,6 +77,7 @@ SIGNATURES = {
     "licos_msssim_workspace_floats": (c_i64, [c_i64, c_int, c_int]),
     "licos_msssim_level": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_vp]),
     "licos_avgpool2": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
+    "licos_raw_dn_to_unit": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
     "licos_rans_encode": (c_i64, [c_vp, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_i64]),
     "licos_rans_decode": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
     "licos_rans_encode_batch": (c_int, [c_vp, c_vp, c_int, c_i64, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_vp,

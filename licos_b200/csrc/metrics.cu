@@ -97,6 +97,16 @@ __global__ void avgpool2_kernel(const float* __restrict__ x, int64_t BC, int H, 
     }
 }
 
+// Raw Sentinel-2 digital numbers -> model input (/root/reference/licos/raw_image_folder.py:192-196, raw_utils.py:128):
+// band = dn / 4095 (float64); unless use_full_range: band = rint(band * 255) / 255 (skimage.img_as_ubyte); float32.
+__global__ void raw_dn_kernel(const uint16_t* __restrict__ dn, int64_t n, double inv_max, int requant8, float* __restrict__ out) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        double v = (double)dn[e] * inv_max;
+        if (requant8) v = rint(v * 255.0) / 255.0;
+        out[e] = (float)v;
+    }
+}
+
 static int grid_cap(int64_t n) {
     int64_t g = (n + 255) / 256;
     if (g > 148 * 16) g = 148 * 16;
@@ -130,6 +140,14 @@ int licos_msssim_level(const float* x, const float* y, int64_t bc, int h, int w,
     if (gx < 1) gx = 1;
     if (bc > 65535) return LICOS_ERR_UNSUPPORTED;
     msssim_v_kernel<<<dim3(gx, (unsigned)bc), 256, 0, s>>>(workspace, (int)bc, h, wo, g, c1, c2, sums);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_raw_dn_to_unit(const uint16_t* dn, int64_t n, int dn_max, int requant8, float* out, void* stream) {
+    if (!dn || !out || n < 0 || dn_max < 1) return LICOS_ERR_INVALID;
+    if (n == 0) return LICOS_OK;
+    raw_dn_kernel<<<grid_cap(n), 256, 0, (cudaStream_t)stream>>>(dn, n, 1.0 / (double)dn_max, requant8, out);
     LICOS_CUDA_OK(cudaGetLastError());
     return LICOS_OK;
 }

@@ -284,6 +284,18 @@ def sum_sq_err(a: torch.Tensor, b: torch.Tensor, acc: Optional[torch.Tensor] = N
     return acc
 
 
+def raw_dn_to_unit(dn: torch.Tensor, dn_max: int = 4095, use_full_range: bool = False) -> torch.Tensor:
+    """raw_image_folder.py:192-196: 12-bit digital numbers (uint16 / int16 storage, any shape) -> fp32 in [0, 1]."""
+    _need_cuda(dn)
+    if dn.dtype not in (torch.uint16, torch.int16):
+        raise ValueError("raw digital numbers must be 16-bit integers")
+    dn = dn.contiguous()
+    out = torch.empty(dn.shape, dtype=torch.float32, device=dn.device)
+    check(lib.licos_raw_dn_to_unit(dn.data_ptr(), dn.numel(), int(dn_max), 0 if use_full_range else 1, out.data_ptr(),
+                                   _stream()), "raw_dn_to_unit")
+    return out
+
+
 _MSSSIM_WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)
 
 

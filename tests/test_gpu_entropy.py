@@ -256,3 +256,15 @@ def test_ms_ssim_on_device_matches_oracle(cuda):
     assert abs(L.compute_msssim(x.to(cuda), x.to(cuda)) - 1.0) <= 1e-6
     with pytest.raises(AssertionError):
         ops.ms_ssim(torch.rand(1, 1, 160, 300, device=cuda), torch.rand(1, 1, 160, 300, device=cuda))
+
+
+def test_raw_dn_scaling_matches_reference_arithmetic(cuda):
+    # raw_image_folder.py:192-196: band = dn / 4095 in float64; img_as_ubyte(band) / 255 unless use_full_range; float32
+    dn = np.arange(0, 4096, dtype=np.uint16)
+    dn = np.concatenate([dn, np.random.default_rng(0).integers(0, 4096, 10000).astype(np.uint16)])
+    band = dn / 4095
+    want_full = band.astype(np.float32)
+    want_8bit = (np.clip(np.rint(band * 255), 0, 255).astype(np.uint8) / 255).astype(np.float32)
+    t = torch.from_numpy(dn.view(np.int16)).to(cuda)
+    assert np.array_equal(ops.raw_dn_to_unit(t, use_full_range=True).cpu().numpy(), want_full)
+    assert np.array_equal(ops.raw_dn_to_unit(t, use_full_range=False).cpu().numpy(), want_8bit)
