@@ -22,6 +22,27 @@ extern "C" void licos_set_last_cuda_error(int code);
 
 namespace licos {
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: remember (kernel, device) pairs so a process
+// that drives several GPUs sets it on each of them, once.
+inline cudaError_t ensure_max_dynamic_smem(const void* kernel, int bytes) {
+    struct Entry { const void* k; int dev; };
+    static Entry done[256];
+    static int n_done = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const int n = n_done;  // (racing first calls at worst set the attribute twice)
+    for (int i = 0; i < n; ++i)
+        if (done[i].k == kernel && done[i].dev == dev) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && n_done < 256) {
+        done[n_done].k = kernel;
+        done[n_done].dev = dev;
+        ++n_done;
+    }
+    return e;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -785,8 +785,7 @@ static int launch_first(const licos_conv_args* a, cudaStream_t s) {
     cudaError_t err = cudaErrorInvalidValue;
 #define LICOS_LAUNCH_FIRST(E)                                                                                       \
     do {                                                                                                            \
-        static cudaError_t attr =                                                                                   \
-            cudaFuncSetAttribute(conv_first_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);   \
+        const cudaError_t attr = ensure_max_dynamic_smem((const void*)conv_first_kernel<E>, kMaxDynSmem);          \
         if (attr != cudaSuccess) { err = attr; break; }                                                             \
         conv_first_kernel<E><<<grid, kEdgeThreads, smem, s>>>(p);                                                   \
         err = cudaGetLastError();                                                                                   \
@@ -879,8 +878,7 @@ static int launch_first2(const licos_conv_args* a, cudaStream_t s) {
     cudaError_t err = cudaErrorInvalidValue;
 #define LICOS_LAUNCH_F2(E, C, T)                                                                                        \
     do {                                                                                                                \
-        static cudaError_t attr =                                                                                       \
-            cudaFuncSetAttribute(conv_first2_kernel<E, C, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem); \
+        const cudaError_t attr = ensure_max_dynamic_smem((const void*)conv_first2_kernel<E, C, T>, kMaxDynSmem);       \
         if (attr != cudaSuccess) { err = attr; break; }                                                                 \
         conv_first2_kernel<E, C, T><<<grid, first2_threads(T), smem, s>>>(p);                                           \
         err = cudaGetLastError();                                                                                       \
@@ -945,9 +943,7 @@ static int launch_narrow(const licos_conv_args* a, cudaStream_t s) {
     const int rc = sm_count_of(a, &sms);
     if (rc != LICOS_OK) return rc;
     const int grid = (int)(units < sms ? units : sms);
-    static cudaError_t attr =
-        cudaFuncSetAttribute(deconv_narrow2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-    LICOS_CUDA_OK(attr);
+    LICOS_CUDA_OK(ensure_max_dynamic_smem((const void*)deconv_narrow2_kernel, kMaxDynSmem));
     deconv_narrow2_kernel<<<grid, kN2Threads, smem, s>>>(p);
     LICOS_CUDA_OK(cudaGetLastError());
     return LICOS_OK;
@@ -1316,9 +1312,8 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     cudaError_t err = cudaErrorInvalidValue;
 #define LICOS_LAUNCH_X(E, O, X)                                                                         \
     do {                                                                                                \
-        static cudaError_t attr = cudaFuncSetAttribute(conv_igemm_kernel<E, O, X>,                      \
-                                                       cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                                       kMaxDynSmem);                                    \
+        const cudaError_t attr = ensure_max_dynamic_smem((const void*)conv_igemm_kernel<E, O, X>,      \
+                                                         kMaxDynSmem);                                  \
         if (attr != cudaSuccess) { err = attr; break; }                                                 \
         conv_igemm_kernel<E, O, X><<<grid, kThreads, smem_bytes, s>>>(p);                               \
         err = cudaGetLastError();                                                                       \

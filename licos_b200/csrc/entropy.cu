@@ -504,8 +504,7 @@ int licos_eb_forward_eval_fused(const licos_eb_params* p, const float* x, int ba
     const int64_t blocks = (int64_t)batch * ((hw + kEbTileHw - 1) / kEbTileHw);
     if (blocks > 0x7fffffff) return LICOS_ERR_UNSUPPORTED;
     const size_t tile_bytes = y_hat_nhwc_bf16 ? (size_t)p->channels * kEbTilePitch * sizeof(__nv_bfloat16) : 0;
-    static cudaError_t attr = cudaFuncSetAttribute(eb_eval_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    LICOS_CUDA_OK(attr);
+    LICOS_CUDA_OK(ensure_max_dynamic_smem((const void*)eb_eval_tile_kernel, 96 * 1024));
     eb_eval_tile_kernel<<<(int)blocks, 256, tile_bytes, s>>>(m, x, p->packed, p->medians, lut_ws, p->channels, (int)hw, y_hat,
                                                             lik, symbols, (__nv_bfloat16*)y_hat_nhwc_bf16);
     LICOS_CUDA_OK(cudaGetLastError());
