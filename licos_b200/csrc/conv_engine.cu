@@ -1,22 +1,26 @@
 // Implicit-GEMM convolution engine for sm_100a: strided 5x5 conv, 5x5 stride-2 transposed conv (as four
 // output-parity sub-convolutions), 3x3 stride-1 conv, each with its epilogue (bias, GDN / IGDN, ReLU)
-// fused.  One persistent, warp-specialised kernel:
+// fused.  One persistent, warp-specialised kernel, one CTA per SM, 12 warps:
 //
-//   warp 0  A producer   TMA loads "slabs" of the NHWC bf16 activation: for one column tap kw and one
-//                        64-channel chunk, a box of (TH+2) rows x 16 columns x 64 channels.  Every row
-//                        tap kh that shares this kw reads the SAME slab at a row offset (a multiple of
-//                        2 KB, so the 128-byte swizzle phase is unchanged) -> each activation byte is
-//                        fetched 5x (not 25x) per 5x5 layer.
-//   warp 1  B producer   TMA loads one [N x 64] weight tile per (tap, chunk); for GDN layers also the
-//                        gamma tiles, through the same ring.
-//   warp 2  MMA issuer   tcgen05.mma (M=128, N<=256, K=16) into TMEM accumulators; also issues the
-//                        second, chained GEMM of the GDN epilogue (gamma x v^2).
-//   warps 4-7 epilogue   TMEM -> registers -> (+bias, square) -> smem -> [gamma MMA] -> rsqrt/sqrt ->
-//                        bf16 NHWC via TMA store, or fp32 NCHW direct stores.
+//   warp 0     A producer   TMA loads "slabs" of the NHWC bf16 activation: for one column tap kw and one
+//                           64-channel chunk, a box of (TH+2) rows x 16 columns x 64 channels.  Every row
+//                           tap kh that shares this kw reads the SAME slab at a row offset (a multiple of
+//                           2 KB, so the 128-byte swizzle phase is unchanged) -> each activation byte is
+//                           fetched 5x (not 25x) per 5x5 layer.
+//   warp 1     B producer   TMA loads one [N x 64] weight tile per (tap, chunk) (warp-uniform loop, tap list in
+//                           shared memory); loads gamma once, resident for the whole kernel.
+//   warp 2     MMA issuer   warp-uniform loop; the elected lane issues the tcgen05.mma (M=128, N<=256, K=16) of a
+//                           tap back to back into two TMEM accumulators (two accumulator SETS: the epilogue of one
+//                           pass overlaps the mainloop of the next).
+//   warps 4-11 epilogue     two teams of 4 warps taking alternate accumulators: TMEM -> registers -> (+bias,
+//                           square) -> smem -> gamma GEMM in place over the accumulator -> rsqrt / sqrt -> bf16
+//                           NHWC via TMA store, or fp32 NCHW direct stores.
 //
 // Stride-2 addressing is done with four parity views of the input (conv) or output (deconv) tensor,
 // each an ordinary tiled TMA descriptor; padding and ragged edges are TMA out-of-bounds zero fill /
-// store clipping.  Replaces SURVEY.md section 8a rows A3, A4, A5.
+// store clipping.  The first layer (fp32 NCHW in, K = 25 C_in) and the last layer (<= 4 output channels) have
+// their own kernels (conv_first2.cuh, deconv_narrow2.cuh; conv_edge.cuh is the generic first-layer fallback).
+// Replaces SURVEY.md section 8a rows A3, A4, A5.  DESIGN.md section 4.0 lists the measurements behind the structure.
 #include "common.cuh"
 #include "conv_edge.cuh"
 #include "epilogue.cuh"
