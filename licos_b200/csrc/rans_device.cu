@@ -55,6 +55,17 @@ __device__ __forceinline__ void rans_put_nibble(RansState& s, uint32_t nib) {
     s.lo = (s.lo << kRansBypassBits) | nib;
 }
 
+// Bypass coding of an out-of-support symbol.  Forward order is [symbol][count prefix: 15, 15, .., rest][nibbles low to
+// high]; coding runs in reverse.  Out of line: the hot loop is unrolled 16 times and must stay small (a lone warp per
+// SM is at the mercy of the instruction cache).
+__device__ __noinline__ void rans_put_escape(RansState& st, uint32_t raw) {
+    uint32_t nibbles = 0;
+    while (nibbles < 8 && (raw >> (nibbles * kRansBypassBits)) != 0) ++nibbles;  // (a shift by 32 is undefined)
+    for (uint32_t j = nibbles; j-- > 0;) rans_put_nibble(st, (raw >> (j * kRansBypassBits)) & kRansBypassMax);
+    rans_put_nibble(st, nibbles % kRansBypassMax);
+    for (uint32_t c15 = nibbles / kRansBypassMax; c15 > 0; --c15) rans_put_nibble(st, kRansBypassMax);
+}
+
 // reciprocal of every table frequency, once per call: rcp[ci][v] = floor((2^64 - 1) / (cdf[v+1] - cdf[v]))
 __global__ void rans_rcp_kernel(const int32_t* __restrict__ cdfs, int n_cdfs, int stride, const int32_t* __restrict__ sizes,
                                 uint64_t* __restrict__ rcp) {
@@ -140,15 +151,7 @@ __global__ void __launch_bounds__(32) rans_encode_kernel(const int32_t* __restri
             if (k < cnt) {
                 const uint32_t range = rg[k] & 0x7fffffffu;
                 if (range == 0) { bad = true; continue; }
-                if (rg[k] & 0x80000000u) {
-                    // forward order is [symbol][count prefix: 15, 15, .., rest][nibbles low to high]; coding runs in reverse
-                    const uint32_t raw = (uint32_t)sv[k];
-                    uint32_t nibbles = 0;
-                    while (nibbles < 8 && (raw >> (nibbles * kRansBypassBits)) != 0) ++nibbles;  // (a shift by 32 is undefined)
-                    for (uint32_t j = nibbles; j-- > 0;) rans_put_nibble(st, (raw >> (j * kRansBypassBits)) & kRansBypassMax);
-                    rans_put_nibble(st, nibbles % kRansBypassMax);
-                    for (uint32_t c15 = nibbles / kRansBypassMax; c15 > 0; --c15) rans_put_nibble(st, kRansBypassMax);
-                }
+                if (rg[k] & 0x80000000u) rans_put_escape(st, (uint32_t)sv[k]);  // rare: kept out of line
                 rans_put_symbol(st, sta[k], range, rc[k]);
             }
         }
