@@ -59,6 +59,7 @@ int licos_nhwc_bf16_to_nchw_f32(const void* in, float* out, int batch, int chann
 #define LICOS_CONV_5X5_S2 0   /* compressai.models.utils.conv:   Conv2d(k=5, s=2, p=2)          */
 #define LICOS_DECONV_5X5_S2 1 /* compressai.models.utils.deconv: ConvTranspose2d(k=5,s=2,p=2,op=1) */
 #define LICOS_CONV_3X3_S1 2   /* conv(.., stride=1, kernel_size=3): Conv2d(k=3, s=1, p=1)       */
+#define LICOS_CONV_1X1 3      /* Conv2d(k=1): the GDN channel mix as its own layer (training path) */
 
 #define LICOS_EPI_NONE 0 /* + bias                                                             */
 #define LICOS_EPI_GDN 1  /* + bias, then GDN:  v * rsqrt(beta + gamma . v^2)                    */
@@ -112,6 +113,50 @@ void licos_debug_set_conv_probe(unsigned long long* device_buf);
 /* One conv / deconv layer with its fused epilogue.  Output spatial size:
  * CONV_5X5_S2 -> ceil(in/2), DECONV_5X5_S2 -> 2*in, CONV_3X3_S1 -> in. */
 int licos_conv_forward(const licos_conv_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Backward pass of the transforms (torch autograd of Conv2d / ConvTranspose2d / GDN / ReLU;  */
+/* reached from licos/train.py:193 `out_criterion["loss"].backward()`)                         */
+/* ------------------------------------------------------------------------------------------ */
+/* DATA gradients need no entry point of their own: the gradient of CONV_5X5_S2 with respect to its input is
+ * DECONV_5X5_S2 over the output gradient with the SAME (out_c, in_c, 5, 5) weight read as a ConvTranspose2d weight, and
+ * vice versa; CONV_3X3_S1 takes the flipped, transposed weight.  They run through licos_conv_forward. */
+
+typedef struct licos_wgrad_args {
+    int kind;        /* CONV_5X5_S2 / DECONV_5X5_S2 (`big` has twice the resolution of `small`), CONV_3X3_S1, CONV_1X1 */
+    int batch;
+    int h, w;         /* spatial size of `small_t`                                                  */
+    int big_h, big_w; /* spatial size of `big_t`: h == ceil(big_h / 2) for the stride-2 kinds       */
+    int small_c, big_c; /* channels, multiples of 64                                                */
+    const void* small_t; /* bf16 NHWC: Conv2d -> the OUTPUT gradient; ConvTranspose2d -> the layer INPUT */
+    const void* big_t;   /* bf16 NHWC: Conv2d -> the layer INPUT; ConvTranspose2d -> the OUTPUT gradient */
+    float* out;       /* fp32 [KH*KW][small_c][big_c], ACCUMULATED into with red.add: the caller zeroes it */
+    int sm_count;     /* 0 = query the device                                                      */
+    int reserved;
+} licos_wgrad_args;
+/* out[kh*KW + kw][cs][cb] += sum_{b,i,j} small[b][i][j][cs] * big[b][s*i + kh - pad][s*j + kw - pad][cb]
+ * (s = 2, pad = 2 for the 5x5 kinds; s = 1, pad = 1 for 3x3; a plain [P x cs]^T [P x cb] product for 1x1).
+ * Conv2d.weight.grad[o][i][kh][kw] = out[..][o][i]; ConvTranspose2d.weight.grad[i][o][kh][kw] = out[..][i][o]. */
+int licos_conv_wgrad(const licos_wgrad_args* args, void* stream);
+
+/* GDN backward, elementwise parts over n bf16 elements (n % 8 == 0); the two channel mixes between them are
+ * LICOS_CONV_1X1 layers:  x2 = x^2;  norm = conv1x1(x2, gamma_hat, beta_hat);
+ *   mid:  d_norm = g * dy/dnorm, d_direct = g * dy/dx|norm   (inverse != 0: IGDN)
+ *   t = conv1x1(d_norm, gamma_hat^T);  out:  dx = d_direct + 2 x t  (dx may alias d_direct)
+ *   gamma_hat.grad = licos_conv_wgrad(CONV_1X1, small = d_norm, big = x2);  beta_hat.grad = licos_colsum_bf16(d_norm) */
+int licos_square_bf16(const void* x, void* x2, int64_t n, void* stream);
+int licos_gdn_bwd_mid(const void* x, const void* g, const void* norm, int inverse, int64_t n, void* d_norm, void* d_direct,
+                      void* stream);
+int licos_gdn_bwd_out(const void* x, const void* t, const void* d_direct, int64_t n, void* dx, void* stream);
+/* ReLU backward: dx = y > 0 ? g : 0 (dx may alias g) */
+int licos_relu_bwd(const void* y, const void* g, int64_t n, void* dx, void* stream);
+/* acc[c] += sum over rows of x[row][c]  (bias / beta gradients); x bf16 [rows][channels], channels % 8 == 0, <= 512 */
+int licos_colsum_bf16(const void* x, int64_t rows, int channels, float* acc, void* stream);
+/* Patch matrix of a 5x5 stride-2 window over a fp32 NCHW tensor (weight gradients of g_a[0] and g_s[6]):
+ * rows[(b, oh, ow)][k] = x[b][c][2 oh + kh - 2][2 ow + kw - 2], k = (c*5 + kh)*5 + kw, zero padded to
+ * licos_im2col5x5s2_kpad(channels) bf16 columns. */
+int64_t licos_im2col5x5s2_kpad(int channels);
+int licos_im2col5x5s2(const float* x, int batch, int channels, int h, int w, void* rows, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* EntropyBottleneck (compressai.entropy_models.EntropyBottleneck)   */

@@ -22,6 +22,7 @@ LAYOUT_NHWC_BF16 = 1
 CONV_5X5_S2 = 0
 DECONV_5X5_S2 = 1
 CONV_3X3_S1 = 2
+CONV_1X1 = 3
 EPI_NONE, EPI_GDN, EPI_IGDN, EPI_RELU = 0, 1, 2, 3
 EB_MAX_LAYERS = 8
 EB_FORM_PLAIN, EB_FORM_STABLE = 0, 1
@@ -36,6 +37,14 @@ class ConvArgs(ctypes.Structure):
         ("in_c", c_int), ("out_c", c_int), ("in_layout", c_int), ("out_layout", c_int),
         ("in_", c_vp), ("out", c_vp), ("weight", c_vp), ("bias", c_vp), ("beta", c_vp), ("gamma", c_vp),
         ("workspace", c_vp), ("workspace_bytes", c_i64), ("sm_count", c_int), ("reserved", c_int),
+    ]
+
+
+class WgradArgs(ctypes.Structure):
+    _fields_ = [
+        ("kind", c_int), ("batch", c_int), ("h", c_int), ("w", c_int), ("big_h", c_int), ("big_w", c_int),
+        ("small_c", c_int), ("big_c", c_int), ("small_t", c_vp), ("big_t", c_vp), ("out", c_vp),
+        ("sm_count", c_int), ("reserved", c_int),
     ]
 
 
@@ -61,6 +70,14 @@ SIGNATURES = {
     "licos_conv_workspace_bytes": (c_i64, [ctypes.POINTER(ConvArgs)]),
     "licos_conv_forward": (c_int, [ctypes.POINTER(ConvArgs), c_vp]),
     "licos_debug_set_conv_probe": (None, [c_vp]),
+    "licos_conv_wgrad": (c_int, [ctypes.POINTER(WgradArgs), c_vp]),
+    "licos_square_bf16": (c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "licos_gdn_bwd_mid": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "licos_gdn_bwd_out": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "licos_relu_bwd": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "licos_colsum_bf16": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
+    "licos_im2col5x5s2_kpad": (c_i64, [c_int]),
+    "licos_im2col5x5s2": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "licos_eb_lut_floats": (c_i64, [c_int]),
     "licos_eb_forward_eval": (c_int, [ctypes.POINTER(EbParams), c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "licos_eb_forward_eval_fused": (c_int, [ctypes.POINTER(EbParams), c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp,

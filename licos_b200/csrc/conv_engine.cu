@@ -690,7 +690,7 @@ static bool use_first_direct(int kind, int in_c, int out_c, int out_layout) {
     return kind == LICOS_CONV_5X5_S2 && in_c * 25 <= 128 && out_layout == LICOS_LAYOUT_NHWC_BF16 && out_c % 64 == 0 &&
            out_c <= 256;
 }
-static int taps_of(int kind) { return kind == LICOS_CONV_3X3_S1 ? 9 : 25; }
+static int taps_of(int kind) { return kind == LICOS_CONV_3X3_S1 ? 9 : (kind == LICOS_CONV_1X1 ? 1 : 25); }
 static int first_kpad(int in_c) { return (in_c * 25 + 63) / 64 * 64; }
 
 static int ew_grid(int64_t n) {
@@ -979,7 +979,8 @@ int64_t licos_packed_weight_bytes(int kind, int out_c, int in_c, int in_layout) 
 
 int licos_pack_conv_weight(const float* w, int kind, int out_c, int in_c, int in_layout, void* packed, void* stream) {
     if (!w || !packed || out_c < 1 || in_c < 1) return LICOS_ERR_INVALID;
-    if (kind != LICOS_CONV_5X5_S2 && kind != LICOS_DECONV_5X5_S2 && kind != LICOS_CONV_3X3_S1) return LICOS_ERR_INVALID;
+    if (kind != LICOS_CONV_5X5_S2 && kind != LICOS_DECONV_5X5_S2 && kind != LICOS_CONV_3X3_S1 && kind != LICOS_CONV_1X1)
+        return LICOS_ERR_INVALID;
     const NPlan pl = plan_n(out_c);
     cudaStream_t s = (cudaStream_t)stream;
     if (in_layout == LICOS_LAYOUT_NCHW_F32) {
@@ -993,7 +994,7 @@ int licos_pack_conv_weight(const float* w, int kind, int out_c, int in_c, int in
                                                                                       (__nv_bfloat16*)packed);
     } else {
         const int cin_pad = (in_c + 63) / 64 * 64;
-        const int K = kind == LICOS_CONV_3X3_S1 ? 3 : 5;
+        const int K = kind == LICOS_CONV_3X3_S1 ? 3 : (kind == LICOS_CONV_1X1 ? 1 : 5);
         pack_weight_kernel<<<ew_grid((int64_t)K * K * pl.rows * cin_pad), 256, 0, s>>>(
             w, kind == LICOS_DECONV_5X5_S2, out_c, in_c, K, K, pl.rows, cin_pad, (__nv_bfloat16*)packed);
     }
@@ -1091,7 +1092,7 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
         out_h = (in_h + 1) / 2; out_w = (in_w + 1) / 2; p.grid_h = out_h; p.grid_w = out_w; p.out_s = 1;
     } else if (kind == LICOS_DECONV_5X5_S2) {
         out_h = 2 * in_h; out_w = 2 * in_w; p.grid_h = in_h; p.grid_w = in_w; p.out_s = 2;
-    } else if (kind == LICOS_CONV_3X3_S1) {
+    } else if (kind == LICOS_CONV_3X3_S1 || kind == LICOS_CONV_1X1) {
         out_h = in_h; out_w = in_w; p.grid_h = in_h; p.grid_w = in_w; p.out_s = 1;
     } else {
         return LICOS_ERR_INVALID;
@@ -1120,7 +1121,7 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     const int R = TH + 2;
 
     // ---- passes ------------------------------------------------------------------------------
-    if (pointwise) {
+    if (pointwise || kind == LICOS_CONV_1X1) {
         p.n_passes = 1;
         Pass& ps = p.passes[0];
         ps.n_slabs = 1; ps.n_groups = 1;

@@ -1,0 +1,591 @@
+// Backward-pass kernels of the training step (SURVEY.md section 8a rows A3-A6 differentiated; reached from
+// licos/train.py:193 `out_criterion["loss"].backward()`).
+//
+//   wgrad_kernel        weight gradient of conv 5x5 s2 / deconv 5x5 s2 / conv 3x3 s1 / 1x1 (and the GDN gamma gradient,
+//                       which is a 1x1 weight gradient): out[tap][cs][cb] += sum over pixels of
+//                       small[pixel][cs] * big[pixel shifted by the tap][cb].  The contraction runs over PIXELS, so both
+//                       operands are MN-major UMMA operands read straight from the NHWC bf16 tiles TMA delivers
+//                       (channels contiguous = the M / N dimension).  A CTA keeps up to four taps (four 128 x 128 fp32
+//                       accumulators = all of TMEM) that share one parity view of `big`: one TMA slab with a one-pixel
+//                       halo serves all of them as shifted operand views.  Work is split over (tap group, channel
+//                       block, pixel range) units; a unit ends with a vector red.add flush into the fp32 result.
+//   gdn_bwd_* / relu_bwd / colsum_bf16   the elementwise and reduction pieces around the 1x1 channel mixes of the GDN
+//                       backward pass (the mixes themselves run on the conv engine as LICOS_CONV_1X1 layers).
+//
+// The data gradients (dgrad) need no kernel of their own: dgrad of a stride-2 conv IS the transposed conv with the
+// same weight and vice versa, so they run on conv_engine.cu with re-packed weights.
+#include "common.cuh"
+
+#include <string.h>
+#include <mutex>
+
+namespace licos {
+
+constexpr int kWgTH = 8, kWgTW = 16;            // tile of `small`: 8 rows x 16 columns = 128 pixels = 8 K-steps of 16
+constexpr int kWgSlabRows = 9, kWgSlabCols = 18;  // slab of `big`: the tile + one row and two columns of halo
+constexpr uint32_t kWgSChunk = 128u * 128u;     // [128 pixels][64 channels] bf16
+constexpr uint32_t kWgGBytes = (uint32_t)kWgSlabRows * kWgSlabCols * 128u;  // 20 736 B delivered per slab chunk
+constexpr uint32_t kWgGChunk = 21u * 1024u;     // slab chunk pitch (1 KB aligned)
+constexpr uint32_t kWgStage = 2u * kWgSChunk + 2u * kWgGChunk;
+constexpr int kWgStages = 3;
+constexpr int kWgMaxTaps = 4, kWgMaxGroups = 10, kWgMaxCombos = 96;
+constexpr int kWgThreads = 192;  // producer, MMA issuer, 4 flush warps
+
+struct WgTap {
+    int8_t dr, dc;   // slab row / column of the tile origin for this tap
+    int16_t w_tap;   // index of the [cs][cb] matrix in `out`
+};
+struct WgGroup {
+    int8_t view, r0, n_taps, pad_;
+    WgTap taps[kWgMaxTaps];
+};
+
+struct WgradParams {
+    CUtensorMap s_map;
+    CUtensorMap g_maps[4];
+    WgGroup groups[kWgMaxGroups];
+    int n_groups, m_blocks, n_blocks;
+    int Cs, Cb;
+    int tiles_h, tiles_w, n_tiles;
+    int n_combos, n_units;
+    int unit_begin[kWgMaxCombos + 1];
+    float* out;
+};
+
+struct WgUnit {
+    int g, mb, nb, t0, t1;
+};
+__device__ __forceinline__ WgUnit wg_decode(const WgradParams& p, int u) {
+    int c = 0;
+    while (c + 1 < p.n_combos && u >= p.unit_begin[c + 1]) ++c;
+    const int s = u - p.unit_begin[c], ns = p.unit_begin[c + 1] - p.unit_begin[c];
+    WgUnit w;
+    w.nb = c % p.n_blocks;
+    w.mb = (c / p.n_blocks) % p.m_blocks;
+    w.g = c / (p.n_blocks * p.m_blocks);
+    w.t0 = (int)((long long)s * p.n_tiles / ns);
+    w.t1 = (int)((long long)(s + 1) * p.n_tiles / ns);
+    return w;
+}
+
+// MN-major SWIZZLE_128B operand: 64 channels (128 B) contiguous per pixel row, 8-pixel groups 1 KB apart,
+// the next 64 channels `lbo_bytes` further on.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full[kWgStages], empty[kWgStages], acc_full, acc_empty;
+    __shared__ uint32_t tmem_base_smem;
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kWgStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(&acc_full, 1);
+        mbar_init(&acc_empty, 128);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(&tmem_base_smem, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    const int tiles_per_img = p.tiles_h * p.tiles_w;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== producer =====================
+            tma_prefetch_desc(&p.s_map);
+            for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.g_maps[i]);
+            uint32_t slot = 0, phase = 0;
+            for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+                const WgUnit w = wg_decode(p, u);
+                const WgGroup& g = p.groups[w.g];
+                const int n_g = (p.Cb - w.nb * 128) > 64 ? 2 : 1;
+                const uint32_t bytes = 2u * kWgSChunk + (uint32_t)n_g * kWgGBytes;
+                for (int t = w.t0; t < w.t1; ++t) {
+                    const int b = t / tiles_per_img, r = t % tiles_per_img;
+                    const int h0 = (r / p.tiles_w) * kWgTH, w0 = (r % p.tiles_w) * kWgTW;
+                    mbar_wait(&empty[slot], phase ^ 1u);
+                    uint8_t* st = smem + (size_t)slot * kWgStage;
+                    mbar_arrive_expect_tx(&full[slot], bytes);
+                    for (int j = 0; j < 2; ++j)
+                        tma_load_4d(st + j * kWgSChunk, &p.s_map, &full[slot], (w.mb * 2 + j) * 64, w0, h0, b);
+                    for (int j = 0; j < n_g; ++j)
+                        tma_load_4d(st + 2 * kWgSChunk + j * kWgGChunk, &p.g_maps[g.view], &full[slot], (w.nb * 2 + j) * 64,
+                                    w0 - 1, h0 + g.r0, b);
+                    if (++slot == kWgStages) { slot = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (warp-uniform loop, elected lane issues) =====================
+        const uint64_t a_hi = umma_desc_mn_sw128(kWgSChunk), b_hi = umma_desc_mn_sw128(kWgGChunk);
+        uint32_t slot = 0, phase = 0, n_unit = 0;
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++n_unit) {
+            const WgUnit w = wg_decode(p, u);
+            const WgGroup& g = p.groups[w.g];
+            const int nt = (p.Cb - w.nb * 128) > 64 ? 128 : 64;
+            const uint32_t idesc = umma_idesc_bf16(128, nt) | (1u << 15) | (1u << 16);
+            const int n_taps = g.n_taps;
+            uint32_t b_off[kWgMaxTaps];
+#pragma unroll
+            for (int k = 0; k < kWgMaxTaps; ++k)
+                b_off[k] = (uint32_t)(((int)g.taps[k].dr * kWgSlabCols + (int)g.taps[k].dc) * 128) >> 4;
+            mbar_wait_warp(&acc_empty, (n_unit & 1u) ^ 1u);
+            tc_fence_after();
+            uint32_t accumulate = 0;
+            for (int t = w.t0; t < w.t1; ++t) {
+                mbar_wait_warp(&full[slot], phase);
+                tc_fence_after();
+                const uint32_t st16 = (smem_base + slot * kWgStage) >> 4;
+                const uint32_t g16 = st16 + ((2u * kWgSChunk) >> 4);
+                if (elect_one()) {
+#pragma unroll
+                    for (uint32_t r = 0; r < (uint32_t)kWgTH; ++r) {
+                        const uint64_t ad = a_hi | (uint64_t)(st16 + r * ((kWgTW * 128u) >> 4));
+                        const uint32_t brow = g16 + r * ((kWgSlabCols * 128u) >> 4);
+#pragma unroll
+                        for (int k = 0; k < kWgMaxTaps; ++k)
+                            if (k < n_taps)
+                                umma_bf16(tmem_base + (uint32_t)k * 128u, ad, b_hi | (uint64_t)(brow + b_off[k]), idesc,
+                                          accumulate | r);
+                    }
+                    umma_commit(&empty[slot]);
+                }
+                __syncwarp();
+                accumulate = 1;
+                if (++slot == kWgStages) { slot = 0; phase ^= 1u; }
+            }
+            if (elect_one()) umma_commit(&acc_full);
+            __syncwarp();
+        }
+    } else {
+        // ===================== flush: TMEM -> red.add into the fp32 result =====================
+        const uint32_t q = (uint32_t)(warp & 3);
+        const uint32_t lane_sel = (q * 32u) << 16;
+        const int row = (int)q * 32 + lane;  // TMEM lane == channel of `small` inside the block
+        uint32_t n_unit = 0;
+        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++n_unit) {
+            const WgUnit w = wg_decode(p, u);
+            const WgGroup& g = p.groups[w.g];
+            const int nt = (p.Cb - w.nb * 128) > 64 ? 128 : 64;
+            const int cs = w.mb * 128 + row;
+            mbar_wait(&acc_full, n_unit & 1u);
+            tc_fence_after();
+            for (int k = 0; k < g.n_taps; ++k) {
+                float* o = p.out + ((size_t)g.taps[k].w_tap * p.Cs + cs) * p.Cb + w.nb * 128;
+                for (int cc = 0; cc < nt / 32; ++cc) {
+                    float v[32];
+                    tmem_ld32(tmem_base + lane_sel + (uint32_t)k * 128u + cc * 32, v);
+                    tmem_ld_wait();
+                    if (cs < p.Cs) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) red_add_v4(o + cc * 32 + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// elementwise / reduction kernels of the GDN, ReLU and bias backward passes (bf16 NHWC, 8 channels per thread)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4 u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+__global__ void square_bf16_kernel(const uint4* __restrict__ x, uint4* __restrict__ x2, int64_t n8) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        float a[8];
+        unpack8(__ldg(x + i), a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] *= a[j];
+        x2[i] = pack8(a);
+    }
+}
+
+// norm = beta + gamma . x^2 (from the 1x1 layer).  GDN: y = x * rsqrt(norm); IGDN: y = x * sqrt(norm).
+//   d_direct = g * dy/dx at fixed norm;  d_norm = g * dy/dnorm
+template <bool INVERSE>
+__global__ void gdn_bwd_mid_kernel(const uint4* __restrict__ x, const uint4* __restrict__ g, const uint4* __restrict__ norm,
+                                   uint4* __restrict__ d_norm, uint4* __restrict__ d_direct, int64_t n8) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        float a[8], b[8], c[8], dn[8], dd[8];
+        unpack8(__ldg(x + i), a);
+        unpack8(__ldg(g + i), b);
+        unpack8(__ldg(norm + i), c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (INVERSE) {
+                const float s = sqrtf(c[j]);
+                dd[j] = b[j] * s;
+                dn[j] = 0.5f * b[j] * a[j] / s;
+            } else {
+                const float r = rsqrtf(c[j]);
+                dd[j] = b[j] * r;
+                dn[j] = -0.5f * b[j] * a[j] * r * r * r;
+            }
+        }
+        d_norm[i] = pack8(dn);
+        d_direct[i] = pack8(dd);
+    }
+}
+
+// dx = d_direct + 2 x t, t = gamma^T . d_norm (from the 1x1 layer); in place over d_direct is allowed
+__global__ void gdn_bwd_out_kernel(const uint4* __restrict__ x, const uint4* __restrict__ t, const uint4* d_direct, uint4* dx,
+                                   int64_t n8) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        float a[8], b[8], c[8];
+        unpack8(__ldg(x + i), a);
+        unpack8(__ldg(t + i), b);
+        unpack8(d_direct[i], c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c[j] = fmaf(2.f * a[j], b[j], c[j]);
+        dx[i] = pack8(c);
+    }
+}
+
+__global__ void relu_bwd_kernel(const uint4* __restrict__ y, const uint4* g, uint4* dx, int64_t n8) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        float a[8], b[8];
+        unpack8(__ldg(y + i), a);
+        unpack8(g[i], b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] = a[j] > 0.f ? b[j] : 0.f;
+        dx[i] = pack8(b);
+    }
+}
+
+// acc[c] += sum over rows of x[row][c]; x bf16 [rows][C], C % 8 == 0, C <= 512.  One thread = 8 channels of a row.
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const uint4* __restrict__ x, int64_t rows, int C, float* __restrict__ acc) {
+    __shared__ float part[512];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) part[i] = 0.f;
+    __syncthreads();
+    const int g_per_row = C / 8;
+    const int rows_per_it = blockDim.x / g_per_row;
+    const int my_g = threadIdx.x % g_per_row, my_r = threadIdx.x / g_per_row;
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (my_r < rows_per_it) {
+        for (int64_t r = (int64_t)blockIdx.x * rows_per_it + my_r; r < rows; r += (int64_t)gridDim.x * rows_per_it) {
+            float a[8];
+            unpack8(__ldg(x + r * g_per_row + my_g), a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] += a[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&part[my_g * 8 + j], s[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(acc + i, part[i]);
+}
+
+// rows[(b, oh, ow)][k] = x[b][c][2*oh + kh - 2][2*ow + kw - 2], k = (c*5 + kh)*5 + kw, zero padded to k_pad: the patch
+// matrix of a 5x5 stride-2 window over a fp32 NCHW tensor (first-layer / last-layer weight gradients).
+__global__ void im2col5x5s2_kernel(const float* __restrict__ x, int B, int C, int H, int W, int OH, int OW, int k_pad,
+                                   __nv_bfloat16* __restrict__ rows) {
+    const int groups = k_pad / 8;
+    const int64_t total = (int64_t)B * OH * OW * groups;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int K = C * 25;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int gk = (int)(e % groups);
+        int64_t pix = e / groups;
+        const int ow = (int)(pix % OW);
+        pix /= OW;
+        const int oh = (int)(pix % OH);
+        const int b = (int)(pix / OH);
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = gk * 8 + j;
+            float val = 0.f;
+            if (k < K) {
+                const int c = k / 25, r = k % 25;
+                const int ih = 2 * oh + r / 5 - 2, iw = 2 * ow + r % 5 - 2;
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = __ldg(x + (((size_t)b * C + c) * H + ih) * W + iw);
+            }
+            v[j] = val;
+        }
+        *reinterpret_cast<uint4*>(rows + (size_t)e * 8) = pack8(v);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn wg_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    });
+    return fn;
+}
+static bool wg_make_map(CUtensorMap* m, const void* base, const uint64_t* dims, const uint64_t* strides_elems,
+                        const uint32_t* box) {
+    EncodeTiledFn fn = wg_encode_fn();
+    if (!fn) return false;
+    cuuint64_t gdims[4], gstrides[3];
+    cuuint32_t gbox[4], estr[4];
+    for (int i = 0; i < 4; ++i) {
+        gdims[i] = dims[i];
+        gbox[i] = box[i];
+        estr[i] = 1;
+        if (dims[i] == 0) return false;
+    }
+    for (int i = 0; i < 3; ++i) gstrides[i] = strides_elems[i] * 2;
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdims, gstrides, gbox, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int wg_ew_grid(int64_t n) {
+    int64_t g = (n + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    return (int)(g < 1 ? 1 : g);
+}
+
+static void wg_add_group(WgradParams& p, int view, const int* khs, int n_kh, const int* kws, int n_kw, int KW, bool strided) {
+    WgGroup& g = p.groups[p.n_groups++];
+    memset(&g, 0, sizeof(g));
+    g.view = (int8_t)view;
+    int r0 = 100;
+    for (int i = 0; i < n_kh; ++i) {
+        const int kh = khs[i];
+        const int dh = strided ? (kh - 2 - (kh & 1)) / 2 : kh - KW / 2;
+        if (dh < r0) r0 = dh;
+    }
+    g.r0 = (int8_t)r0;
+    int n = 0;
+    for (int i = 0; i < n_kh; ++i)
+        for (int j = 0; j < n_kw; ++j) {
+            const int kh = khs[i], kw = kws[j];
+            const int dh = strided ? (kh - 2 - (kh & 1)) / 2 : kh - KW / 2;
+            const int dw = strided ? (kw - 2 - (kw & 1)) / 2 : kw - KW / 2;
+            g.taps[n].dr = (int8_t)(dh - r0);
+            g.taps[n].dc = (int8_t)(dw + 1);
+            g.taps[n].w_tap = (int16_t)(kh * KW + kw);
+            ++n;
+        }
+    g.n_taps = (int8_t)n;
+}
+
+}  // namespace licos
+
+using namespace licos;
+
+extern "C" {
+
+int licos_conv_wgrad(const licos_wgrad_args* a, void* stream) {
+    if (!a || !a->small_t || !a->big_t || !a->out) return LICOS_ERR_INVALID;
+    if (a->batch < 0 || a->h < 1 || a->w < 1 || a->small_c < 1 || a->big_c < 1) return LICOS_ERR_INVALID;
+    if (a->batch == 0) return LICOS_OK;
+    if (a->small_c % 64 != 0 || a->big_c % 64 != 0) return LICOS_ERR_UNSUPPORTED;
+    const bool strided = a->kind == LICOS_CONV_5X5_S2 || a->kind == LICOS_DECONV_5X5_S2;
+    if (!strided && a->kind != LICOS_CONV_3X3_S1 && a->kind != LICOS_CONV_1X1) return LICOS_ERR_INVALID;
+    if (strided ? (a->h != (a->big_h + 1) / 2 || a->w != (a->big_w + 1) / 2) : (a->h != a->big_h || a->w != a->big_w))
+        return LICOS_ERR_INVALID;
+
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.Cs = a->small_c;
+    p.Cb = a->big_c;
+    p.out = a->out;
+    p.m_blocks = (a->small_c + 127) / 128;
+    p.n_blocks = (a->big_c + 127) / 128;
+    if (strided) {
+        static const int e02[2] = {0, 2}, e4[1] = {4}, e024[3] = {0, 2, 4}, o13[2] = {1, 3};
+        wg_add_group(p, 0, e02, 2, e02, 2, 5, true);
+        wg_add_group(p, 0, e02, 2, e4, 1, 5, true);
+        wg_add_group(p, 0, e4, 1, e024, 3, 5, true);
+        wg_add_group(p, 1, e02, 2, o13, 2, 5, true);
+        wg_add_group(p, 1, e4, 1, o13, 2, 5, true);
+        wg_add_group(p, 2, o13, 2, e02, 2, 5, true);
+        wg_add_group(p, 2, o13, 2, e4, 1, 5, true);
+        wg_add_group(p, 3, o13, 2, o13, 2, 5, true);
+    } else if (a->kind == LICOS_CONV_3X3_S1) {
+        static const int k012[3] = {0, 1, 2};
+        for (int kh = 0; kh < 3; ++kh) wg_add_group(p, 0, &k012[kh], 1, k012, 3, 3, false);
+    } else {
+        static const int k0[1] = {0};
+        wg_add_group(p, 0, k0, 1, k0, 1, 1, false);
+    }
+    p.n_combos = p.n_groups * p.m_blocks * p.n_blocks;
+    if (p.n_combos > kWgMaxCombos) return LICOS_ERR_UNSUPPORTED;
+
+    p.tiles_h = (a->h + kWgTH - 1) / kWgTH;
+    p.tiles_w = (a->w + kWgTW - 1) / kWgTW;
+    const int64_t n_tiles = (int64_t)a->batch * p.tiles_h * p.tiles_w;
+    if (n_tiles > 0x3fffffff) return LICOS_ERR_UNSUPPORTED;
+    p.n_tiles = (int)n_tiles;
+
+    int sms = a->sm_count;
+    if (sms <= 0) {
+        int dev = 0;
+        LICOS_CUDA_OK(cudaGetDevice(&dev));
+        LICOS_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // units: every (group, m block, n block) splits its pixel tiles into a share proportional to its tap count
+    {
+        int64_t total = 0;
+        for (int g = 0; g < p.n_groups; ++g) total += (int64_t)p.groups[g].n_taps * p.m_blocks * p.n_blocks;
+        const int64_t target = 2 * (int64_t)sms;
+        int n = 0;
+        for (int c = 0; c < p.n_combos; ++c) {
+            const int g = c / (p.m_blocks * p.n_blocks);
+            int64_t s = ((int64_t)p.groups[g].n_taps * target + total / 2) / total;
+            if (s < 1) s = 1;
+            if (s > n_tiles) s = n_tiles;
+            p.unit_begin[c] = n;
+            n += (int)s;
+        }
+        p.unit_begin[p.n_combos] = n;
+        p.n_units = n;
+    }
+
+    {
+        const uint64_t C = (uint64_t)a->small_c, H = (uint64_t)a->h, W = (uint64_t)a->w, B = (uint64_t)a->batch;
+        const uint64_t dims[4] = {C, W, H, B};
+        const uint64_t strides[3] = {C, W * C, H * W * C};
+        const uint32_t box[4] = {64, (uint32_t)kWgTW, (uint32_t)kWgTH, 1};
+        if (!wg_make_map(&p.s_map, a->small_t, dims, strides, box)) return LICOS_ERR_CUDA;
+    }
+    {
+        const uint64_t C = (uint64_t)a->big_c, H = (uint64_t)a->big_h, W = (uint64_t)a->big_w, B = (uint64_t)a->batch;
+        const uint32_t box[4] = {64, (uint32_t)kWgSlabCols, (uint32_t)kWgSlabRows, 1};
+        if (strided) {
+            if (a->big_h < 2 || a->big_w < 2) return LICOS_ERR_UNSUPPORTED;
+            for (int ph = 0; ph < 2; ++ph)
+                for (int pw = 0; pw < 2; ++pw) {
+                    const uint64_t dims[4] = {C, (W - pw + 1) / 2, (H - ph + 1) / 2, B};
+                    const uint64_t strides[3] = {2 * C, 2 * W * C, H * W * C};
+                    const __nv_bfloat16* base = (const __nv_bfloat16*)a->big_t + ((size_t)ph * W + pw) * C;
+                    if (!wg_make_map(&p.g_maps[ph * 2 + pw], base, dims, strides, box)) return LICOS_ERR_CUDA;
+                }
+        } else {
+            const uint64_t dims[4] = {C, W, H, B};
+            const uint64_t strides[3] = {C, W * C, H * W * C};
+            if (!wg_make_map(&p.g_maps[0], a->big_t, dims, strides, box)) return LICOS_ERR_CUDA;
+            for (int i = 1; i < 4; ++i) p.g_maps[i] = p.g_maps[0];
+        }
+    }
+    const size_t smem = 1024 + (size_t)kWgStages * kWgStage;
+    LICOS_CUDA_OK(ensure_max_dynamic_smem((const void*)wgrad_kernel, (int)smem));
+    const int grid = p.n_units < sms ? p.n_units : sms;
+    wgrad_kernel<<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(p);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_square_bf16(const void* x, void* x2, int64_t n, void* stream) {
+    if (!x || !x2 || n < 0 || n % 8 != 0) return LICOS_ERR_INVALID;
+    if (n == 0) return LICOS_OK;
+    square_bf16_kernel<<<wg_ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)x2, n / 8);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_gdn_bwd_mid(const void* x, const void* g, const void* norm, int inverse, int64_t n, void* d_norm, void* d_direct,
+                      void* stream) {
+    if (!x || !g || !norm || !d_norm || !d_direct || n < 0 || n % 8 != 0) return LICOS_ERR_INVALID;
+    if (n == 0) return LICOS_OK;
+    if (inverse)
+        gdn_bwd_mid_kernel<true><<<wg_ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>(
+            (const uint4*)x, (const uint4*)g, (const uint4*)norm, (uint4*)d_norm, (uint4*)d_direct, n / 8);
+    else
+        gdn_bwd_mid_kernel<false><<<wg_ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>(
+            (const uint4*)x, (const uint4*)g, (const uint4*)norm, (uint4*)d_norm, (uint4*)d_direct, n / 8);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_gdn_bwd_out(const void* x, const void* t, const void* d_direct, int64_t n, void* dx, void* stream) {
+    if (!x || !t || !d_direct || !dx || n < 0 || n % 8 != 0) return LICOS_ERR_INVALID;
+    if (n == 0) return LICOS_OK;
+    gdn_bwd_out_kernel<<<wg_ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)t,
+                                                                           (const uint4*)d_direct, (uint4*)dx, n / 8);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_relu_bwd(const void* y, const void* g, int64_t n, void* dx, void* stream) {
+    if (!y || !g || !dx || n < 0 || n % 8 != 0) return LICOS_ERR_INVALID;
+    if (n == 0) return LICOS_OK;
+    relu_bwd_kernel<<<wg_ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)y, (const uint4*)g, (uint4*)dx, n / 8);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_colsum_bf16(const void* x, int64_t rows, int channels, float* acc, void* stream) {
+    if (!x || !acc || rows < 0 || channels < 8 || channels % 8 != 0 || channels > 512) return LICOS_ERR_INVALID;
+    if (rows == 0) return LICOS_OK;
+    const int rows_per_it = 256 / (channels / 8);
+    int64_t grid = (rows + rows_per_it - 1) / rows_per_it;
+    if (grid > 148 * 4) grid = 148 * 4;
+    colsum_bf16_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, rows, channels, acc);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int64_t licos_im2col5x5s2_kpad(int channels) { return channels < 1 ? LICOS_ERR_INVALID : (int64_t)(channels * 25 + 63) / 64 * 64; }
+
+int licos_im2col5x5s2(const float* x, int batch, int channels, int h, int w, void* rows, void* stream) {
+    if (!x || !rows || batch < 0 || channels < 1 || channels > 16 || h < 1 || w < 1) return LICOS_ERR_INVALID;
+    if (batch == 0) return LICOS_OK;
+    const int oh = (h + 1) / 2, ow = (w + 1) / 2;
+    const int kp = (int)licos_im2col5x5s2_kpad(channels);
+    const int64_t groups = (int64_t)batch * oh * ow * (kp / 8);
+    im2col5x5s2_kernel<<<wg_ew_grid(groups), 256, 0, (cudaStream_t)stream>>>(x, batch, channels, h, w, oh, ow, kp,
+                                                                             (__nv_bfloat16*)rows);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+}  // extern "C"

@@ -7,6 +7,7 @@ does arithmetic on every key, eval_script.py:70-71 loads them).
 """
 from __future__ import annotations
 
+import os
 import weakref
 from typing import Optional
 
@@ -114,6 +115,9 @@ def _conv_kind(m: nn.Module) -> int:
     raise NotImplementedError(f"licos_b200 has no kernel for layer {m!r}")
 
 
+_EAGER_AUTOGRAD = bool(int(os.environ.get("LICOS_EAGER_AUTOGRAD", "0")))  # development: compare against cuDNN autograd
+
+
 class _Packed:
     __slots__ = ("key", "tensors")
 
@@ -144,7 +148,10 @@ class FusedSequential(nn.Sequential):
         if not x.is_cuda:
             raise RuntimeError("licos_b200: g_a / g_s / h_a / h_s need CUDA tensors on a B200 (no CPU path exists)")
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            return self._eager_forward(torch.abs(x) if take_abs else x)
+            xin = torch.abs(x) if take_abs else x
+            if _EAGER_AUTOGRAD or not self._native_backward_ok(xin):
+                return self._eager_forward(xin)  # library (cuDNN) autograd: development comparison / odd shapes only
+            return self.train_forward(xin)
         return self.fused_forward(x, take_abs=take_abs, nhwc=nhwc)
 
     # -- caches of kernel-layout parameters, rebuilt when a parameter's version or storage changes --
@@ -172,6 +179,75 @@ class FusedSequential(nn.Sequential):
                 float(g.beta_reparam.lower_bound.bound), float(g.gamma_reparam.lower_bound.bound),
                 float(g.beta_reparam.pedestal))
         return slot.tensors
+
+    def _cached(self, owner: nn.Module, name, params, build):
+        ent = self._packed_cache.setdefault(owner, {})
+        slot = ent.setdefault(name, _Packed())
+        key = _version_key(*params)
+        if slot.key != key:
+            slot.key, slot.tensors = key, build()
+        return slot.tensors
+
+    def _steps(self):
+        mods = list(self)
+        steps = []
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            kind = _conv_kind(m)
+            epi, gdn = _lib.EPI_NONE, None
+            if i + 1 < len(mods):
+                nxt = mods[i + 1]
+                if isinstance(nxt, GDN):
+                    epi, gdn = (_lib.EPI_IGDN if nxt.inverse else _lib.EPI_GDN), nxt
+                    i += 1
+                elif isinstance(nxt, nn.ReLU):
+                    epi = _lib.EPI_RELU
+                    i += 1
+            steps.append((m, kind, epi, gdn))
+            i += 1
+        return steps
+
+    def _native_backward_ok(self, x: Tensor) -> bool:
+        """The native backward covers the shapes the training loop uses: every stride-2 layer sees even sizes (so that
+        the data gradient of a conv is exactly the transposed conv) and channel counts the kernels take."""
+        if x.dim() != 4 or x.dtype != torch.float32 or len(self) == 0:
+            return False
+        try:
+            steps = self._steps()
+        except NotImplementedError:
+            return False
+        h, w = x.shape[2], x.shape[3]
+        for n, (m, kind, epi, gdn) in enumerate(steps):
+            first_direct = n == 0 and kind == _lib.CONV_5X5_S2 and m.in_channels <= 16
+            narrow_last = n == len(steps) - 1 and kind == _lib.DECONV_5X5_S2 and m.out_channels <= 4
+            if not first_direct and m.in_channels % 64 != 0:
+                return False
+            if not narrow_last and m.out_channels % 64 != 0:
+                return False
+            if narrow_last and (epi != _lib.EPI_NONE or m.in_channels > 256):
+                return False
+            if first_direct and m.out_channels not in (64, 128, 192):
+                return False
+            if m.in_channels > 512 or m.out_channels > 512:
+                return False
+            if kind == _lib.CONV_5X5_S2:
+                if h % 2 or w % 2:
+                    return False
+                h, w = h // 2, w // 2
+            elif kind == _lib.DECONV_5X5_S2:
+                h, w = 2 * h, 2 * w
+        return True
+
+    def train_forward(self, x: Tensor) -> Tensor:
+        """Differentiable forward on the sm_100a kernels: forward, data gradients and weight gradients all native."""
+        steps = self._steps()
+        params = []
+        for m, kind, epi, gdn in steps:
+            params += [m.weight, m.bias]
+            if gdn is not None:
+                params += [gdn.beta, gdn.gamma]
+        return _ChainFn.apply(self, steps, x, *params)
 
     def fused_forward(self, x: Tensor, take_abs: bool = False, nhwc: Optional[Tensor] = None) -> Tensor:
         """x: fp32 (B, C, H, W) on a B200.  Returns fp32 NCHW like the module chain would."""
@@ -225,3 +301,171 @@ class FusedSequential(nn.Sequential):
                                    beta=beta, gamma=gamma)
             layout = out_layout
         return cur
+
+
+# ---------------------------------------------------------------------------------------------
+# native training path: one autograd node per transform (g_a / g_s / h_a / h_s)
+# ---------------------------------------------------------------------------------------------
+
+def _reparam(p: Tensor, rp: NonNegativeParametrizer):
+    lb = torch.max(p, rp.lower_bound.bound)
+    return lb, lb * lb - rp.pedestal
+
+
+def _reparam_grad(p: Tensor, rp: NonNegativeParametrizer, lb: Tensor, d_hat: Tensor) -> Tensor:
+    """Gradient through ``max(p, bound)**2 - pedestal`` with the LowerBound rule."""
+    d_lb = d_hat * 2.0 * lb
+    keep = (p >= rp.lower_bound.bound) | (d_lb < 0)
+    return d_lb * keep.to(d_lb.dtype)
+
+
+class _ChainFn(torch.autograd.Function):
+    """forward: conv (+ bias) on the engine with the pre-activation kept, GDN / IGDN as its own 1x1 layer;
+    backward: data gradients on the engine (conv <-> transposed conv with the same weight), weight / gamma gradients on
+    ``licos_conv_wgrad``, bias / beta gradients by column sums.  Activations and their gradients are bf16 NHWC."""
+
+    @staticmethod
+    def forward(ctx, seq: "FusedSequential", steps, x: Tensor, *params):
+        if not x.is_cuda:
+            raise RuntimeError("licos_b200: training needs CUDA tensors on a B200 (no CPU path exists)")
+        L = _lib
+        dev = x.device
+        cur = x.detach().contiguous()
+        layout = L.LAYOUT_NCHW_F32
+        first = steps[0][0]
+        if not (steps[0][1] == L.CONV_5X5_S2 and first.in_channels <= 16):
+            cur = ops.nchw_to_nhwc_bf16(cur)
+            layout = L.LAYOUT_NHWC_BF16
+        saved = []
+        for n, (m, kind, epi, gdn) in enumerate(steps):
+            last = n == len(steps) - 1
+            out_layout = L.LAYOUT_NCHW_F32 if last else L.LAYOUT_NHWC_BF16
+            packed, bias = seq._packed_weight(m, kind, layout)
+            rec = {"in": cur, "in_layout": layout}
+            if gdn is not None:
+                C = m.out_channels
+                if bias is None:
+                    bias = torch.zeros(C, dtype=torch.float32, device=dev)
+                v = ops.conv_forward(cur, kind=kind, epilogue=L.EPI_NONE, in_layout=layout, out_layout=L.LAYOUT_NHWC_BF16,
+                                     in_c=m.in_channels, out_c=C, weight=packed, bias=bias)
+                beta_hat, gamma_hat = seq._packed_gdn(gdn)
+                eye = _identity_1x1(C, dev)
+                cur = ops.conv_forward(v, kind=L.CONV_1X1, epilogue=epi, in_layout=L.LAYOUT_NHWC_BF16, out_layout=out_layout,
+                                       in_c=C, out_c=C, weight=eye, bias=_zeros(C, dev), beta=beta_hat, gamma=gamma_hat)
+                rec["v"] = v
+            else:
+                cur = ops.conv_forward(cur, kind=kind, epilogue=epi, in_layout=layout, out_layout=out_layout,
+                                       in_c=m.in_channels, out_c=m.out_channels, weight=packed, bias=bias)
+                if epi == L.EPI_RELU:
+                    rec["y"] = cur
+            layout = out_layout
+            saved.append(rec)
+        ctx.seq, ctx.steps, ctx.saved = seq, steps, saved
+        ctx.x_needs_grad = x.requires_grad
+        ctx.param_needs = [p is not None and p.requires_grad for p in params]
+        return cur
+
+    @staticmethod
+    def backward(ctx, g_out: Tensor):
+        L = _lib
+        seq, steps, saved = ctx.seq, ctx.steps, ctx.saved
+        grads = []  # per step, in order: weight, bias, [beta, gamma]
+        g = g_out.contiguous()
+        g_layout = L.LAYOUT_NCHW_F32
+        for n in range(len(steps) - 1, -1, -1):
+            m, kind, epi, gdn = steps[n]
+            rec = saved[n]
+            a_in, in_layout = rec["in"], rec["in_layout"]
+            narrow = g_layout == L.LAYOUT_NCHW_F32 and kind == L.DECONV_5X5_S2 and m.out_channels <= 4
+            need_dgrad = n > 0 or ctx.x_needs_grad
+            step_grads = []
+            if narrow:
+                # g_s[6]: 128 -> C_img transposed conv, gradient arrives as fp32 NCHW
+                Ci, Co = m.in_channels, m.out_channels
+                patches = ops.im2col5x5s2(g)
+                dw = ops.conv_wgrad(a_in, patches, L.CONV_1X1)[0][:, :Co * 25].reshape(Ci, Co, 5, 5)
+                db = g.sum(dim=(0, 2, 3)) if m.bias is not None else None
+                step_grads = [dw, db]
+                if need_dgrad:
+                    wd = seq._cached(m, ("wd", L.LAYOUT_NCHW_F32), (m.weight,), lambda: ops.pack_conv_weight(
+                        m.weight.detach().contiguous(), L.CONV_5X5_S2, Ci, Co, L.LAYOUT_NCHW_F32))
+                    g = ops.conv_forward(g, kind=L.CONV_5X5_S2, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NCHW_F32,
+                                         out_layout=L.LAYOUT_NHWC_BF16, in_c=Co, out_c=Ci, weight=wd, bias=None)
+                    g_layout = L.LAYOUT_NHWC_BF16
+                grads.append(step_grads)
+                continue
+            if g_layout == L.LAYOUT_NCHW_F32:
+                if epi == L.EPI_RELU:
+                    g = g * (rec["y"] > 0).to(g.dtype)  # last layer of h_s: fp32 NCHW output
+                g = ops.nchw_to_nhwc_bf16(g)
+                g_layout = L.LAYOUT_NHWC_BF16
+            elif epi == L.EPI_RELU:
+                g = ops.relu_bwd(rec["y"], g)
+            d_beta = d_gamma = None
+            if gdn is not None:
+                C = m.out_channels
+                v = rec["v"]
+                lb_b, beta_hat = _reparam(gdn.beta.detach(), gdn.beta_reparam)
+                lb_g, gamma_hat = _reparam(gdn.gamma.detach(), gdn.gamma_reparam)
+                w_g, w_gt = seq._cached(gdn, "gdn1x1", (gdn.gamma,), lambda: (
+                    ops.pack_conv_weight(gamma_hat.reshape(C, C, 1, 1).contiguous(), L.CONV_1X1, C, C, L.LAYOUT_NHWC_BF16),
+                    ops.pack_conv_weight(gamma_hat.t().reshape(C, C, 1, 1).contiguous(), L.CONV_1X1, C, C, L.LAYOUT_NHWC_BF16)))
+                x2 = ops.square_bf16(v)
+                norm = ops.conv_forward(x2, kind=L.CONV_1X1, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NHWC_BF16,
+                                        out_layout=L.LAYOUT_NHWC_BF16, in_c=C, out_c=C, weight=w_g, bias=beta_hat.contiguous())
+                d_norm, d_direct = ops.gdn_bwd_mid(v, g, norm, gdn.inverse)
+                t = ops.conv_forward(d_norm, kind=L.CONV_1X1, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NHWC_BF16,
+                                     out_layout=L.LAYOUT_NHWC_BF16, in_c=C, out_c=C, weight=w_gt, bias=None)
+                g = ops.gdn_bwd_out(v, t, d_direct)
+                d_gamma = _reparam_grad(gdn.gamma.detach(), gdn.gamma_reparam, lb_g, ops.conv_wgrad(d_norm, x2, L.CONV_1X1)[0])
+                d_beta = _reparam_grad(gdn.beta.detach(), gdn.beta_reparam, lb_b, ops.colsum_bf16(d_norm))
+            # g is now the gradient with respect to conv + bias
+            db = ops.colsum_bf16(g) if m.bias is not None else None
+            Co, Ci = m.out_channels, m.in_channels
+            if in_layout == L.LAYOUT_NCHW_F32:  # g_a[0]: image in, K = 25 C_in
+                patches = ops.im2col5x5s2(a_in)
+                dw = ops.conv_wgrad(g, patches, L.CONV_1X1)[0][:, :Ci * 25].reshape(Co, Ci, 5, 5)
+            elif kind == L.DECONV_5X5_S2:
+                dw = ops.conv_wgrad(a_in, g, kind).permute(1, 2, 0).reshape(Ci, Co, 5, 5)
+            else:
+                k = 3 if kind == L.CONV_3X3_S1 else 5
+                dw = ops.conv_wgrad(g, a_in, kind).permute(1, 2, 0).reshape(Co, Ci, k, k)
+            step_grads = [dw, db] + ([d_beta, d_gamma] if gdn is not None else [])
+            grads.append(step_grads)
+            if need_dgrad:
+                out_layout = L.LAYOUT_NHWC_BF16 if n > 0 else L.LAYOUT_NCHW_F32
+                w = m.weight.detach()
+                if kind == L.CONV_5X5_S2:
+                    dk, build = L.DECONV_5X5_S2, (lambda: ops.pack_conv_weight(w.contiguous(), L.DECONV_5X5_S2, Ci, Co, L.LAYOUT_NHWC_BF16))
+                elif kind == L.DECONV_5X5_S2:
+                    dk, build = L.CONV_5X5_S2, (lambda: ops.pack_conv_weight(w.contiguous(), L.CONV_5X5_S2, Ci, Co, L.LAYOUT_NHWC_BF16))
+                else:
+                    dk, build = L.CONV_3X3_S1, (lambda: ops.pack_conv_weight(w.flip(2, 3).transpose(0, 1).contiguous(), L.CONV_3X3_S1, Ci, Co,
+                                                                              L.LAYOUT_NHWC_BF16))
+                wd = seq._cached(m, ("wd", L.LAYOUT_NHWC_BF16), (m.weight,), build)
+                g = ops.conv_forward(g, kind=dk, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NHWC_BF16, out_layout=out_layout,
+                                     in_c=Co, out_c=Ci, weight=wd, bias=None)
+                g_layout = out_layout
+        grads.reverse()
+        flat = [t for sg in grads for t in sg]
+        flat = [t if need else None for t, need in zip(flat, ctx.param_needs)]
+        gx = g if ctx.x_needs_grad else None
+        return (None, None, gx, *flat)
+
+
+_CONST_CACHE = {}
+
+
+def _identity_1x1(C: int, dev) -> Tensor:
+    key = ("eye", C, str(dev))
+    if key not in _CONST_CACHE:
+        _CONST_CACHE[key] = ops.pack_conv_weight(torch.eye(C, device=dev).reshape(C, C, 1, 1).contiguous(), _lib.CONV_1X1, C, C,
+                                                 _lib.LAYOUT_NHWC_BF16)
+    return _CONST_CACHE[key]
+
+
+def _zeros(C: int, dev) -> Tensor:
+    key = ("zeros", C, str(dev))
+    if key not in _CONST_CACHE:
+        _CONST_CACHE[key] = torch.zeros(C, dtype=torch.float32, device=dev)
+    return _CONST_CACHE[key]

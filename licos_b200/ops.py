@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ConvArgs, EbParams, check, lib
+from ._lib import ConvArgs, EbParams, WgradArgs, check, lib
 
 
 def _stream() -> int:
@@ -126,6 +126,82 @@ def conv_forward(x: torch.Tensor, *, kind: int, epilogue: int, in_layout: int, o
         a.workspace, a.workspace_bytes = ws.data_ptr(), nws
     check(lib.licos_conv_forward(ctypes.byref(a), _stream()), "conv_forward")
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# backward pass of the transforms
+# ---------------------------------------------------------------------------------------------
+
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.bfloat16:
+        raise TypeError(f"expected bfloat16, got {t.dtype}")
+    return t
+
+
+def conv_wgrad(small: torch.Tensor, big: torch.Tensor, kind: int, sm_count: int = 0) -> torch.Tensor:
+    """fp32 [taps][small_c][big_c] = sum over pixels of small (x) big shifted by the tap; both bf16 NHWC.
+    Conv2d: small = output gradient, big = layer input; ConvTranspose2d: small = layer input, big = output gradient."""
+    _need_cuda(_bf16(small), _bf16(big))
+    B, h, w, cs = small.shape
+    B2, H, W, cb = big.shape
+    if B != B2:
+        raise ValueError("batch mismatch")
+    taps = {_lib.CONV_5X5_S2: 25, _lib.DECONV_5X5_S2: 25, _lib.CONV_3X3_S1: 9, _lib.CONV_1X1: 1}[kind]
+    out = torch.zeros((taps, cs, cb), dtype=torch.float32, device=small.device)
+    a = WgradArgs()
+    a.kind, a.batch, a.h, a.w, a.big_h, a.big_w, a.small_c, a.big_c = kind, B, h, w, H, W, cs, cb
+    a.small_t, a.big_t, a.out, a.sm_count = small.data_ptr(), big.data_ptr(), out.data_ptr(), sm_count
+    check(lib.licos_conv_wgrad(ctypes.byref(a), _stream()), "conv_wgrad")
+    return out
+
+
+def square_bf16(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(_bf16(x))
+    out = torch.empty_like(x)
+    check(lib.licos_square_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "square_bf16")
+    return out
+
+
+def gdn_bwd_mid(x: torch.Tensor, g: torch.Tensor, norm: torch.Tensor, inverse: bool):
+    _need_cuda(_bf16(x), _bf16(g), _bf16(norm))
+    d_norm, d_direct = torch.empty_like(x), torch.empty_like(x)
+    check(lib.licos_gdn_bwd_mid(x.data_ptr(), g.data_ptr(), norm.data_ptr(), int(inverse), x.numel(), d_norm.data_ptr(),
+                                d_direct.data_ptr(), _stream()), "gdn_bwd_mid")
+    return d_norm, d_direct
+
+
+def gdn_bwd_out(x: torch.Tensor, t: torch.Tensor, d_direct: torch.Tensor) -> torch.Tensor:
+    """dx = d_direct + 2 x t, written over d_direct."""
+    _need_cuda(_bf16(x), _bf16(t), _bf16(d_direct))
+    check(lib.licos_gdn_bwd_out(x.data_ptr(), t.data_ptr(), d_direct.data_ptr(), x.numel(), d_direct.data_ptr(), _stream()),
+          "gdn_bwd_out")
+    return d_direct
+
+
+def relu_bwd(y: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    _need_cuda(_bf16(y), _bf16(g))
+    dx = torch.empty_like(g)
+    check(lib.licos_relu_bwd(y.data_ptr(), g.data_ptr(), y.numel(), dx.data_ptr(), _stream()), "relu_bwd")
+    return dx
+
+
+def colsum_bf16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [C] = sum over all leading dimensions of a bf16 (..., C) tensor."""
+    _need_cuda(_bf16(x))
+    C = x.shape[-1]
+    acc = torch.zeros(C, dtype=torch.float32, device=x.device)
+    check(lib.licos_colsum_bf16(x.data_ptr(), x.numel() // C, C, acc.data_ptr(), _stream()), "colsum_bf16")
+    return acc
+
+
+def im2col5x5s2(x: torch.Tensor) -> torch.Tensor:
+    """fp32 (B, C, H, W) -> bf16 (B, ceil(H/2), ceil(W/2), k_pad) patch matrix, k = (c*5 + kh)*5 + kw."""
+    _need_cuda(_f32(x))
+    B, C, H, W = x.shape
+    kp = int(lib.licos_im2col5x5s2_kpad(C))
+    rows = torch.empty((B, (H + 1) // 2, (W + 1) // 2, kp), dtype=torch.bfloat16, device=x.device)
+    check(lib.licos_im2col5x5s2(x.data_ptr(), B, C, H, W, rows.data_ptr(), _stream()), "im2col5x5s2")
+    return rows
 
 
 # ---------------------------------------------------------------------------------------------

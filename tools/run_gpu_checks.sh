@@ -11,8 +11,8 @@ pass=0; fail=0
 for n in $NODES; do
   out=$(timeout 300 python -m pytest "$n" -x -q -s -m gpu 2>&1)
   rc=$?
-  if [ $rc -eq 0 ]; then pass=$((pass+1)); echo "PASS $n" >> $LOG; echo "$out" | grep -E "max\|err\||PSNR|agreement|smoke" >> $LOG
-  else fail=$((fail+1)); echo "FAIL($rc) $n" >> $LOG; echo "$out" | tail -40 >> $LOG; fi
+  if [ $rc -eq 0 ]; then pass=$((pass+1)); echo "PASS $n" >> $LOG; echo "$out" | grep -E "max\|err\||PSNR|agreement|smoke|worst cos|^loss " >> $LOG
+  else fail=$((fail+1)); echo "FAIL($rc) $n" >> $LOG; echo "$out" | grep -E "^grad " | tail -40 >> $LOG; echo "$out" | tail -25 >> $LOG; fi
 done
 echo "SUMMARY pass=$pass fail=$fail" >> $LOG
 tail -5 $LOG
