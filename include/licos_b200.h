@@ -194,6 +194,12 @@ int licos_eb_forward_eval_fused(const licos_eb_params* p, const float* x, int ba
  * from an in-kernel Philox stream keyed by (seed, element index). */
 int licos_eb_forward_noise(const licos_eb_params* p, const float* x, const float* noise, uint64_t seed,
                            int batch, int64_t hw, float* y_hat, float* lik, void* stream);
+/* Backward of EntropyBottleneck.forward(x, training=True) (train.py:193): y_hat is the forward's output (x + noise).
+ *   d_x[e] = g_yhat[e] + g_lik[e] * d likelihood / d y_hat   (either gradient may be NULL = zero; LowerBound's rule applied)
+ *   d_packed[c][:] += gradient with respect to the PACKED parameter block of channel c (softplus(_matrix), _bias,
+ *   tanh(_factor) as laid out in licos_eb_params.packed); the caller zeroes it and applies d softplus / d tanh. */
+int licos_eb_backward(const licos_eb_params* p, const float* y_hat, const float* g_lik, const float* g_yhat, int batch,
+                      int64_t hw, float* d_x, float* d_packed, void* stream);
 /* EntropyModel.quantize(x, "symbols", medians) and EntropyBottleneck._build_indexes.
  * symbols / indexes: int32 [batch][channels][hw]; indexes may be NULL. */
 int licos_eb_symbols(const float* x, const float* medians, int batch, int channels, int64_t hw,
@@ -222,6 +228,11 @@ int licos_gc_symbols(const float* y, const float* means, int64_t n, int32_t* sym
 int licos_sum_log(const float* lik, int64_t n, double* acc, void* stream);
 /* acc[0] += sum((a[i]-b[i])^2) */
 int licos_sum_sq_err(const float* a, const float* b, int64_t n, double* acc, void* stream);
+
+/* Their backward (RateDistortionLoss under autograd, train.py:192-193); g_dev is a DEVICE scalar, the incoming gradient:
+ * out[i] = coef * g_dev[0] / lik[i]   and   out[i] = coef * g_dev[0] * (a[i] - b[i]). */
+int licos_scaled_reciprocal(const float* lik, int64_t n, float coef, const float* g_dev, float* out, void* stream);
+int licos_scaled_diff(const float* a, const float* b, int64_t n, float coef, const float* g_dev, float* out, void* stream);
 
 /* Raw-tile input scaling (raw_image_folder.py:192-196 `_open_band_`): out = dn / dn_max (dn_max = 4095, raw_utils.py:128),
  * and, when requant8 != 0 (use_full_range = False), out = rint(out * 255) / 255; evaluated in float64, stored as fp32. */

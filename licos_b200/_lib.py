@@ -83,6 +83,7 @@ SIGNATURES = {
     "licos_eb_forward_eval_fused": (c_int, [ctypes.POINTER(EbParams), c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp,
                                             c_vp]),
     "licos_eb_forward_noise": (c_int, [ctypes.POINTER(EbParams), c_vp, c_vp, c_u64, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "licos_eb_backward": (c_int, [ctypes.POINTER(EbParams), c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
     "licos_eb_symbols": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp]),
     "licos_eb_dequantize": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_vp]),
     "licos_gc_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_u64, c_i64, c_int, c_f32, c_f32, c_vp, c_vp, c_vp]),
@@ -90,6 +91,8 @@ SIGNATURES = {
     "licos_gc_symbols": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "licos_sum_log": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "licos_sum_sq_err": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "licos_scaled_reciprocal": (c_int, [c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),
+    "licos_scaled_diff": (c_int, [c_vp, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),
     "licos_pmf_to_quantized_cdf": (c_int, [c_vp, c_int, c_int, c_vp]),
     "licos_msssim_workspace_floats": (c_i64, [c_i64, c_int, c_int]),
     "licos_msssim_level": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_vp]),

@@ -239,6 +239,136 @@ __global__ void eb_noise_kernel(EbMeta m, const float* __restrict__ x, const flo
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// EntropyBottleneck training backward (SURVEY.md 8a rows A8, A9 differentiated; train.py:193)
+// ----------------------------------------------------------------------------------------------
+// One path (v - 0.5 or v + 0.5) of the density network: forward with the activations kept, then the reverse sweep.
+// `acc` receives the gradient with respect to the PACKED parameters (softplus / tanh already applied), the return
+// value is d logits / d input times `seed`.  W bounds the layer widths; arrays are indexed at run time (local memory):
+// the latent is 1/256 of the pixels, this kernel is not bandwidth-relevant.
+template <int W>
+__device__ __forceinline__ float eb_logits_fwd_keep(const float* __restrict__ p, const EbMeta& m, float x,
+                                                    float (&ins)[LICOS_EB_MAX_LAYERS][W], float (&ths)[LICOS_EB_MAX_LAYERS][W]) {
+    float cur[W], nxt[W];
+    for (int k = 0; k < W; ++k) cur[k] = 0.f;
+    cur[0] = x;
+    int off = 0;
+    for (int i = 0; i < m.n_layers; ++i) {
+        const int fi = m.widths[i], fo = m.widths[i + 1];
+        const float* M = p + off;
+        const float* b = M + fo * fi;
+        const float* t = b + fo;
+        const bool last = (i == m.n_layers - 1);
+        for (int k = 0; k < fi; ++k) ins[i][k] = cur[k];
+        for (int o = 0; o < fo; ++o) {
+            float acc = 0.f;
+            for (int k = 0; k < fi; ++k) acc += M[o * fi + k] * cur[k];
+            acc += b[o];
+            float th = 0.f;
+            if (!last) { th = tanhf(acc); acc += t[o] * th; }
+            ths[i][o] = th;
+            nxt[o] = acc;
+        }
+        for (int k = 0; k < fo; ++k) cur[k] = nxt[k];
+        off += fo * fi + fo + (last ? 0 : fo);
+    }
+    return cur[0];
+}
+
+template <int W>
+__device__ __forceinline__ float eb_logits_bwd(const float* __restrict__ p, const EbMeta& m, float seed,
+                                               const float (&ins)[LICOS_EB_MAX_LAYERS][W],
+                                               const float (&ths)[LICOS_EB_MAX_LAYERS][W], float* __restrict__ acc) {
+    float d_out[W], d_in[W];
+    d_out[0] = seed;
+    int off = m.ppc;
+    for (int i = m.n_layers - 1; i >= 0; --i) {
+        const int fi = m.widths[i], fo = m.widths[i + 1];
+        const bool last = (i == m.n_layers - 1);
+        off -= fo * fi + fo + (last ? 0 : fo);
+        const float* M = p + off;
+        const float* t = M + fo * fi + fo;
+        float* gM = acc + off;
+        float* gb = gM + fo * fi;
+        float* gt = gb + fo;
+        for (int k = 0; k < fi; ++k) d_in[k] = 0.f;
+        for (int o = 0; o < fo; ++o) {
+            float da = d_out[o];
+            if (!last) {
+                const float th = ths[i][o];
+                gt[o] += d_out[o] * th;
+                da = d_out[o] * (1.f + t[o] * (1.f - th * th));
+            }
+            gb[o] += da;
+            for (int k = 0; k < fi; ++k) {
+                gM[o * fi + k] += da * ins[i][k];
+                d_in[k] += M[o * fi + k] * da;
+            }
+        }
+        for (int k = 0; k < fi; ++k) d_out[k] = d_in[k];
+    }
+    return d_out[0];
+}
+
+constexpr int kEbMaxPpc = 320;  // filters (13,13,3,3) need 298
+
+// blockIdx.y = channel.  d_x = g_yhat + g_lik * d lik / d y_hat; d_packed[c][:] += sum over the channel's elements.
+template <int W>
+__global__ void __launch_bounds__(128) eb_train_bwd_kernel(EbMeta m, const float* __restrict__ y_hat, const float* __restrict__ g_lik,
+                                                           const float* __restrict__ g_yhat, const float* __restrict__ packed,
+                                                           int B, int C, int64_t hw, float* __restrict__ d_x,
+                                                           float* __restrict__ d_packed) {
+    extern __shared__ float sp[];  // [ppc] parameters, [ppc] block accumulators
+    float* sacc = sp + m.ppc;
+    const int c = blockIdx.y;
+    for (int i = threadIdx.x; i < m.ppc; i += blockDim.x) { sp[i] = packed[(size_t)c * m.ppc + i]; sacc[i] = 0.f; }
+    __syncthreads();
+    float acc[kEbMaxPpc];
+    for (int i = 0; i < m.ppc; ++i) acc[i] = 0.f;
+    float ins_u[LICOS_EB_MAX_LAYERS][W], ths_u[LICOS_EB_MAX_LAYERS][W], ins_l[LICOS_EB_MAX_LAYERS][W], ths_l[LICOS_EB_MAX_LAYERS][W];
+    const int64_t n = (int64_t)B * hw;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const int64_t b = j / hw, i = j - b * hw;
+        const int64_t e = (b * C + c) * hw + i;
+        const float v = y_hat[e];
+        const float lower = eb_logits_fwd_keep<W>(sp, m, v - 0.5f, ins_l, ths_l);
+        const float upper = eb_logits_fwd_keep<W>(sp, m, v + 0.5f, ins_u, ths_u);
+        float g = g_lik ? g_lik[e] : 0.f;
+        float su, sl, lik;  // d lik / d upper, d lik / d lower
+        if (m.form == LICOS_EB_FORM_PLAIN) {
+            const float a = sigmoidf_(upper), bq = sigmoidf_(lower);
+            lik = a - bq;
+            su = a * (1.f - a);
+            sl = -bq * (1.f - bq);
+        } else {
+            const float sum = lower + upper;
+            const float s = (sum > 0.f) ? -1.f : ((sum < 0.f) ? 1.f : 0.f);
+            const float a = sigmoidf_(s * upper), bq = sigmoidf_(s * lower);
+            const float d = a - bq;
+            lik = fabsf(d);
+            const float sg = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+            su = sg * s * a * (1.f - a);
+            sl = -sg * s * bq * (1.f - bq);
+        }
+        if (m.bound > 0.f && !(lik >= m.bound || g < 0.f)) g = 0.f;  // LowerBound's gradient rule
+        float dv = 0.f;
+        if (g != 0.f) {
+            dv = eb_logits_bwd<W>(sp, m, g * su, ins_u, ths_u, acc);
+            dv += eb_logits_bwd<W>(sp, m, g * sl, ins_l, ths_l, acc);
+        }
+        d_x[e] = dv + (g_yhat ? g_yhat[e] : 0.f);
+    }
+    for (int i = 0; i < m.ppc; ++i) {
+        float a = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[i], a);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m.ppc; i += blockDim.x) atomicAdd(d_packed + (size_t)c * m.ppc + i, sacc[i]);
+}
+
 __global__ void eb_symbols_kernel(const float* __restrict__ x, const float* __restrict__ med, int C, int64_t hw,
                                   int64_t n, int32_t* __restrict__ sym, int32_t* __restrict__ idx) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -357,6 +487,21 @@ __global__ void sum_sq_err_kernel(const float* __restrict__ a, const float* __re
     }
     s += (double)part;
     block_accumulate(s, acc);
+}
+
+// backward of the two reductions of RateDistortionLoss: out = coef * g[0] / lik  and  out = coef * g[0] * (a - b);
+// g is a DEVICE scalar (the incoming gradient of the bpp / mse term), so nothing synchronises.
+__global__ void scaled_reciprocal_kernel(const float* __restrict__ lik, int64_t n, float coef, const float* __restrict__ g,
+                                         float* __restrict__ out) {
+    const float k = coef * g[0];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = k / lik[i];
+}
+__global__ void scaled_diff_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, float coef,
+                                   const float* __restrict__ g, float* __restrict__ out) {
+    const float k = coef * g[0];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = k * (a[i] - b[i]);
 }
 
 __global__ void weighted_sum2_kernel(const float* __restrict__ a, const float* __restrict__ b, float wa, float wb,
@@ -531,6 +676,27 @@ int licos_eb_forward_noise(const licos_eb_params* p, const float* x, const float
     return LICOS_OK;
 }
 
+int licos_eb_backward(const licos_eb_params* p, const float* y_hat, const float* g_lik, const float* g_yhat, int batch,
+                      int64_t hw, float* d_x, float* d_packed, void* stream) {
+    EbMeta m;
+    int max_w;
+    if (!make_meta(p, m, max_w) || !y_hat || !d_x || !d_packed || batch < 0 || hw < 0) return LICOS_ERR_INVALID;
+    if (m.ppc > kEbMaxPpc) return LICOS_ERR_UNSUPPORTED;
+    const int64_t n = (int64_t)batch * hw;
+    if (n == 0) return LICOS_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t sm = (size_t)m.ppc * 2 * sizeof(float);
+    int gx = (int)((n + 127) / 128);
+    const int cap = (148 * 8 + p->channels - 1) / p->channels;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, p->channels);
+    if (max_w <= 3) eb_train_bwd_kernel<3><<<grid, 128, sm, s>>>(m, y_hat, g_lik, g_yhat, p->packed, batch, p->channels, hw, d_x, d_packed);
+    else eb_train_bwd_kernel<16><<<grid, 128, sm, s>>>(m, y_hat, g_lik, g_yhat, p->packed, batch, p->channels, hw, d_x, d_packed);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
 int licos_eb_symbols(const float* x, const float* medians, int batch, int channels, int64_t hw, int32_t* symbols,
                      int32_t* indexes, void* stream) {
     if (!x || !medians || !symbols || batch < 0 || channels < 1 || hw < 0) return LICOS_ERR_INVALID;
@@ -592,6 +758,22 @@ int licos_sum_sq_err(const float* a, const float* b, int64_t n, double* acc, voi
     if (!a || !b || !acc || n < 0) return LICOS_ERR_INVALID;
     if (n == 0) return LICOS_OK;
     sum_sq_err_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(a, b, n, acc);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_scaled_reciprocal(const float* lik, int64_t n, float coef, const float* g_dev, float* out, void* stream) {
+    if (!lik || !g_dev || !out || n < 0) return LICOS_ERR_INVALID;
+    if (n == 0) return LICOS_OK;
+    scaled_reciprocal_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(lik, n, coef, g_dev, out);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_scaled_diff(const float* a, const float* b, int64_t n, float coef, const float* g_dev, float* out, void* stream) {
+    if (!a || !b || !g_dev || !out || n < 0) return LICOS_ERR_INVALID;
+    if (n == 0) return LICOS_OK;
+    scaled_diff_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n, coef, g_dev, out);
     LICOS_CUDA_OK(cudaGetLastError());
     return LICOS_OK;
 }

@@ -7,11 +7,13 @@ Division of labour:
   * update() -> host logic exactly as upstream (torch CPU ops for the tiny PMF tables) + the C++
     licos_pmf_to_quantized_cdf; run once per model (eval_script.py:72,88);
   * compress()/decompress() -> symbols on the GPU, one D2H per batch, C++ rANS on host threads;
-  * forward() with autograd on -> the differentiable torch expression (training step, train.py:190-193).
+  * forward(training=True) with autograd on -> the noise kernel + licos_eb_backward (training step, train.py:190-193);
+    the eval-mode-with-autograd corner and GaussianConditional keep the differentiable torch expression.
 """
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -36,6 +38,51 @@ def _wants_grad(module: nn.Module, *tensors: Optional[Tensor]) -> bool:
     if any(t is not None and t.requires_grad for t in tensors):
         return True
     return any(p.requires_grad for p in module.parameters())
+
+
+_EAGER_AUTOGRAD = bool(int(os.environ.get("LICOS_EAGER_AUTOGRAD", "0")))  # development: torch-expression autograd
+
+
+class _EbTrainFn(torch.autograd.Function):
+    """EntropyBottleneck.forward(x, training=True) with its backward on the device: the forward is the noise kernel, the
+    backward one kernel that re-evaluates the density network per element and sweeps it in reverse (d x, and the
+    per-channel parameter gradients reduced in the block)."""
+
+    @staticmethod
+    def forward(ctx, eb, x, noise, seed, *raw):
+        ebp = eb.packed_params()
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if noise is None else 0
+        y_hat, lik = ops.eb_forward_noise(ebp, x.detach().contiguous(), None if noise is None else noise.contiguous(), seed)
+        ctx.eb, ctx.ebp = eb, ebp
+        ctx.save_for_backward(y_hat, *raw)
+        return y_hat, lik
+
+    @staticmethod
+    def backward(ctx, g_yhat, g_lik):
+        eb = ctx.eb
+        y_hat, *raw = ctx.saved_tensors
+        g_yhat = None if g_yhat is None else g_yhat.contiguous()
+        g_lik = None if g_lik is None else g_lik.contiguous()
+        d_x, d_packed = ops.eb_backward(ctx.ebp, y_hat, g_lik, g_yhat)
+        grads, off, C = [], 0, eb.channels
+        n_layers = len(eb.filters) + 1
+        k = 0
+        for i in range(n_layers):
+            matrix, bias = raw[k], raw[k + 1]
+            k += 2
+            nm, nb = matrix[0].numel(), bias[0].numel()
+            grads.append(d_packed[:, off:off + nm].reshape(matrix.shape) * torch.sigmoid(matrix))  # d softplus
+            off += nm
+            grads.append(d_packed[:, off:off + nb].reshape(bias.shape))
+            off += nb
+            if i < n_layers - 1:
+                factor = raw[k]
+                k += 1
+                th = torch.tanh(factor)
+                grads.append(d_packed[:, off:off + nb].reshape(factor.shape) * (1 - th * th))
+                off += nb
+        return (None, d_x, None, None, *grads)
 
 
 class EntropyModel(nn.Module):
@@ -292,6 +339,8 @@ class EntropyBottleneck(EntropyModel):
             training = self.training
         _require_cuda(x, "EntropyBottleneck.forward")
         if _wants_grad(self, x):
+            if training and x.dim() >= 2 and x.dtype == torch.float32 and not _EAGER_AUTOGRAD:
+                return _EbTrainFn.apply(self, x, noise, seed, *self._params()[:-1])
             return self._forward_autograd(x, training, noise)
         x = x.contiguous()
         ebp = self.packed_params()

@@ -11,6 +11,32 @@ import torch.nn as nn
 from . import ops
 
 
+class _RDTermsFn(torch.autograd.Function):
+    """(bpp_loss, mse_loss) with the reductions and their backward on the device kernels (train.py:192-193)."""
+
+    @staticmethod
+    def forward(ctx, x_hat, target, num_pixels, *liks):
+        acc = torch.zeros(2, dtype=torch.float64, device=target.device)
+        liks = [lk.contiguous() for lk in liks]
+        for lk in liks:
+            ops.sum_log(lk, acc[0:1])
+        x_hat, target = x_hat.contiguous(), target.contiguous()
+        ops.sum_sq_err(x_hat, target, acc[1:2])
+        ctx.save_for_backward(x_hat, target, *liks)
+        ctx.num_pixels = num_pixels
+        return (acc[0] / (-math.log(2) * num_pixels)).float(), (acc[1] / target.numel()).float()
+
+    @staticmethod
+    def backward(ctx, g_bpp, g_mse):
+        x_hat, target, *liks = ctx.saved_tensors
+        g_bpp = g_bpp.reshape(1).float().contiguous()
+        g_mse = g_mse.reshape(1).float().contiguous()
+        d_xhat = ops.scaled_diff(x_hat, target, 2.0 / target.numel(), g_mse) if ctx.needs_input_grad[0] else None
+        d_liks = [ops.scaled_reciprocal(lk, 1.0 / (-math.log(2) * ctx.num_pixels), g_bpp) if need else None
+                  for lk, need in zip(liks, ctx.needs_input_grad[3:])]
+        return (d_xhat, None, None, *d_liks)
+
+
 class RateDistortionLoss(nn.Module):
     def __init__(self, lmbda: float = 0.01, metric: str = "mse", return_type: str = "all"):
         super().__init__()
@@ -26,9 +52,8 @@ class RateDistortionLoss(nn.Module):
             output["x_hat"].requires_grad or any(v.requires_grad for v in output["likelihoods"].values()))
         out = {}
         if needs_grad:
-            out["bpp_loss"] = sum(torch.log(lk).sum() / (-math.log(2) * num_pixels)
-                                  for lk in output["likelihoods"].values())
-            out["mse_loss"] = torch.mean((output["x_hat"] - target) ** 2)
+            out["bpp_loss"], out["mse_loss"] = _RDTermsFn.apply(output["x_hat"], target, num_pixels,
+                                                                *output["likelihoods"].values())
         else:
             acc = torch.zeros(2, dtype=torch.float64, device=target.device)
             for lk in output["likelihoods"].values():

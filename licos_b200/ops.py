@@ -277,6 +277,18 @@ def eb_forward_noise(ebp: EbPacked, x: torch.Tensor, noise: Optional[torch.Tenso
     return y_hat, lik
 
 
+def eb_backward(ebp: EbPacked, y_hat: torch.Tensor, g_lik: Optional[torch.Tensor], g_yhat: Optional[torch.Tensor]):
+    """Backward of the training-mode bottleneck: (d_x, d_packed [C][params_per_channel])."""
+    _need_cuda(_f32(y_hat), g_lik, g_yhat)
+    B, C = y_hat.shape[0], y_hat.shape[1]
+    hw = y_hat.numel() // max(B * C, 1)
+    d_x = torch.empty_like(y_hat)
+    d_packed = torch.zeros_like(ebp.packed)
+    check(lib.licos_eb_backward(ctypes.byref(ebp.p), y_hat.data_ptr(), _ptr(g_lik), _ptr(g_yhat), B, hw, d_x.data_ptr(),
+                                d_packed.data_ptr(), _stream()), "eb_backward")
+    return d_x, d_packed
+
+
 def eb_symbols(x: torch.Tensor, medians: torch.Tensor, want_indexes: bool = False):
     _need_cuda(_f32(x), _f32(medians))
     B, C = x.shape[0], x.shape[1]
@@ -358,6 +370,23 @@ def sum_sq_err(a: torch.Tensor, b: torch.Tensor, acc: Optional[torch.Tensor] = N
         acc = torch.zeros(1, dtype=torch.float64, device=a.device)
     check(lib.licos_sum_sq_err(a.data_ptr(), b.data_ptr(), a.numel(), acc.data_ptr(), _stream()), "sum_sq_err")
     return acc
+
+
+def scaled_reciprocal(lik: torch.Tensor, coef: float, g: torch.Tensor) -> torch.Tensor:
+    """coef * g / lik with g a one-element fp32 device tensor (no host sync)."""
+    _need_cuda(_f32(lik), _f32(g))
+    out = torch.empty_like(lik)
+    check(lib.licos_scaled_reciprocal(lik.data_ptr(), lik.numel(), coef, g.data_ptr(), out.data_ptr(), _stream()),
+          "scaled_reciprocal")
+    return out
+
+
+def scaled_diff(a: torch.Tensor, b: torch.Tensor, coef: float, g: torch.Tensor) -> torch.Tensor:
+    _need_cuda(_f32(a), _f32(b), _f32(g))
+    out = torch.empty_like(a)
+    check(lib.licos_scaled_diff(a.data_ptr(), b.data_ptr(), a.numel(), coef, g.data_ptr(), out.data_ptr(), _stream()),
+          "scaled_diff")
+    return out
 
 
 def raw_dn_to_unit(dn: torch.Tensor, dn_max: int = 4095, use_full_range: bool = False) -> torch.Tensor:

@@ -17,5 +17,9 @@ def net_aux_optimizer(net: nn.Module, conf: Dict[str, Dict[str, Any]]) -> Dict[s
     out = {}
     for key in ("net", "aux"):
         kwargs = dict(conf[key])
-        out[key] = getattr(torch.optim, kwargs.pop("type"))(groups[key], **kwargs)
+        kind = kwargs.pop("type")
+        if kind in ("Adam", "AdamW") and "fused" not in kwargs and "foreach" not in kwargs and groups[key] and all(
+                p.is_cuda for p in groups[key]):
+            kwargs["fused"] = True  # same update rule, one multi-tensor launch instead of one per parameter
+        out[key] = getattr(torch.optim, kind)(groups[key], **kwargs)
     return out
