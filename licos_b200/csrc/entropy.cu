@@ -369,6 +369,144 @@ __global__ void __launch_bounds__(128) eb_train_bwd_kernel(EbMeta m, const float
     for (int i = threadIdx.x; i < m.ppc; i += blockDim.x) atomicAdd(d_packed + (size_t)c * m.ppc + i, sacc[i]);
 }
 
+// Fast path for the stock density network (filters (3,3,3,3): widths 1,3,3,3,3,1): every loop bound is a compile-time
+// constant, so activations and the 58 parameter-gradient accumulators live in registers.
+template <int NL, int F>
+struct EbStatic {
+    __host__ __device__ static constexpr int width(int i) { return (i == 0 || i == NL) ? 1 : F; }
+    __host__ __device__ static constexpr int layer_size(int i) { return width(i + 1) * width(i) + width(i + 1) + (i == NL - 1 ? 0 : width(i + 1)); }
+    __host__ __device__ static constexpr int offset(int i) { return i == 0 ? 0 : offset(i - 1) + layer_size(i - 1); }
+    static constexpr int kPpc = offset(NL);
+};
+
+template <int NL, int F>
+__device__ __forceinline__ float eb_static_fwd(const float* __restrict__ p, float x, float (&ins)[NL][F], float (&ths)[NL][F]) {
+    float cur[F];
+#pragma unroll
+    for (int k = 0; k < F; ++k) cur[k] = 0.f;
+    cur[0] = x;
+    int off = 0;  // a running literal after unrolling
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+        const int fi = (i == 0) ? 1 : F, fo = (i == NL - 1) ? 1 : F;
+        float nxt[F];
+#pragma unroll
+        for (int k = 0; k < F; ++k) ins[i][k] = cur[k];
+#pragma unroll
+        for (int o = 0; o < F; ++o) {
+            float acc = 0.f, th = 0.f;
+            if (o < fo) {
+#pragma unroll
+                for (int k = 0; k < F; ++k)
+                    if (k < fi) acc += p[off + o * fi + k] * cur[k];
+                acc += p[off + fo * fi + o];
+                if (i < NL - 1) { th = tanhf(acc); acc += p[off + fo * fi + fo + o] * th; }
+            }
+            ths[i][o] = th;
+            nxt[o] = acc;
+        }
+#pragma unroll
+        for (int k = 0; k < F; ++k) cur[k] = nxt[k];
+        off += fo * fi + fo + (i < NL - 1 ? fo : 0);
+    }
+    return cur[0];
+}
+
+template <int NL, int F>
+__device__ __forceinline__ float eb_static_bwd(const float* __restrict__ p, float seed, const float (&ins)[NL][F],
+                                               const float (&ths)[NL][F], float (&acc)[EbStatic<NL, F>::kPpc]) {
+    using S = EbStatic<NL, F>;
+    float d_out[F];
+#pragma unroll
+    for (int k = 0; k < F; ++k) d_out[k] = 0.f;
+    d_out[0] = seed;
+    int off = S::kPpc;
+#pragma unroll
+    for (int i = NL - 1; i >= 0; --i) {
+        const int fi = (i == 0) ? 1 : F, fo = (i == NL - 1) ? 1 : F;
+        off -= fo * fi + fo + (i < NL - 1 ? fo : 0);
+        float d_in[F];
+#pragma unroll
+        for (int k = 0; k < F; ++k) d_in[k] = 0.f;
+#pragma unroll
+        for (int o = 0; o < F; ++o) {
+            if (o < fo) {
+                float da = d_out[o];
+                if (i < NL - 1) {
+                    const float th = ths[i][o];
+                    acc[off + fo * fi + fo + o] += d_out[o] * th;
+                    da = d_out[o] * (1.f + p[off + fo * fi + fo + o] * (1.f - th * th));
+                }
+                acc[off + fo * fi + o] += da;
+#pragma unroll
+                for (int k = 0; k < F; ++k)
+                    if (k < fi) {
+                        acc[off + o * fi + k] += da * ins[i][k];
+                        d_in[k] += p[off + o * fi + k] * da;
+                    }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < F; ++k) d_out[k] = d_in[k];
+    }
+    return d_out[0];
+}
+
+template <int NL, int F>
+__global__ void __launch_bounds__(128) eb_train_bwd_static_kernel(EbMeta m, const float* __restrict__ y_hat,
+                                                                  const float* __restrict__ g_lik, const float* __restrict__ g_yhat,
+                                                                  const float* __restrict__ packed, int B, int C, int64_t hw,
+                                                                  float* __restrict__ d_x, float* __restrict__ d_packed) {
+    constexpr int kPpc = EbStatic<NL, F>::kPpc;
+    __shared__ float sp[kPpc], sacc[kPpc];
+    const int c = blockIdx.y;
+    for (int i = threadIdx.x; i < kPpc; i += blockDim.x) { sp[i] = packed[(size_t)c * kPpc + i]; sacc[i] = 0.f; }
+    __syncthreads();
+    float acc[kPpc];
+#pragma unroll
+    for (int i = 0; i < kPpc; ++i) acc[i] = 0.f;
+    const int64_t n = (int64_t)B * hw;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const int64_t b = j / hw, i = j - b * hw;
+        const int64_t e = (b * C + c) * hw + i;
+        const float v = y_hat[e];
+        float ins_u[NL][F], ths_u[NL][F], ins_l[NL][F], ths_l[NL][F];
+        const float lower = eb_static_fwd<NL, F>(sp, v - 0.5f, ins_l, ths_l);
+        const float upper = eb_static_fwd<NL, F>(sp, v + 0.5f, ins_u, ths_u);
+        float g = g_lik ? g_lik[e] : 0.f;
+        float su, sl, lik;
+        if (m.form == LICOS_EB_FORM_PLAIN) {
+            const float a = sigmoidf_(upper), bq = sigmoidf_(lower);
+            lik = a - bq;
+            su = a * (1.f - a);
+            sl = -bq * (1.f - bq);
+        } else {
+            const float sum = lower + upper;
+            const float s = (sum > 0.f) ? -1.f : ((sum < 0.f) ? 1.f : 0.f);
+            const float a = sigmoidf_(s * upper), bq = sigmoidf_(s * lower);
+            const float d = a - bq;
+            lik = fabsf(d);
+            const float sg = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+            su = sg * s * a * (1.f - a);
+            sl = -sg * s * bq * (1.f - bq);
+        }
+        if (m.bound > 0.f && !(lik >= m.bound || g < 0.f)) g = 0.f;
+        float dv = eb_static_bwd<NL, F>(sp, g * su, ins_u, ths_u, acc);
+        dv += eb_static_bwd<NL, F>(sp, g * sl, ins_l, ths_l, acc);
+        d_x[e] = dv + (g_yhat ? g_yhat[e] : 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < kPpc; ++i) {
+        float a = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sacc[i], a);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kPpc; i += blockDim.x) atomicAdd(d_packed + (size_t)c * kPpc + i, sacc[i]);
+}
+
 __global__ void eb_symbols_kernel(const float* __restrict__ x, const float* __restrict__ med, int C, int64_t hw,
                                   int64_t n, int32_t* __restrict__ sym, int32_t* __restrict__ idx) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -691,7 +829,10 @@ int licos_eb_backward(const licos_eb_params* p, const float* y_hat, const float*
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     dim3 grid(gx, p->channels);
-    if (max_w <= 3) eb_train_bwd_kernel<3><<<grid, 128, sm, s>>>(m, y_hat, g_lik, g_yhat, p->packed, batch, p->channels, hw, d_x, d_packed);
+    bool stock = m.n_layers == 5 && m.ppc == EbStatic<5, 3>::kPpc;
+    for (int i = 1; i < 5 && stock; ++i) stock = m.widths[i] == 3;
+    if (stock) eb_train_bwd_static_kernel<5, 3><<<grid, 128, 0, s>>>(m, y_hat, g_lik, g_yhat, p->packed, batch, p->channels, hw, d_x, d_packed);
+    else if (max_w <= 3) eb_train_bwd_kernel<3><<<grid, 128, sm, s>>>(m, y_hat, g_lik, g_yhat, p->packed, batch, p->channels, hw, d_x, d_packed);
     else eb_train_bwd_kernel<16><<<grid, 128, sm, s>>>(m, y_hat, g_lik, g_yhat, p->packed, batch, p->channels, hw, d_x, d_packed);
     LICOS_CUDA_OK(cudaGetLastError());
     return LICOS_OK;

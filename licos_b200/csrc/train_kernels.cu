@@ -320,33 +320,40 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const uint4* __restric
 }
 
 // rows[(b, oh, ow)][k] = x[b][c][2*oh + kh - 2][2*ow + kw - 2], k = (c*5 + kh)*5 + kw, zero padded to k_pad: the patch
-// matrix of a 5x5 stride-2 window over a fp32 NCHW tensor (first-layer / last-layer weight gradients).
-__global__ void im2col5x5s2_kernel(const float* __restrict__ x, int B, int C, int H, int W, int OH, int OW, int k_pad,
-                                   __nv_bfloat16* __restrict__ rows) {
-    const int groups = k_pad / 8;
-    const int64_t total = (int64_t)B * OH * OW * groups;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+// matrix of a 5x5 stride-2 window over a fp32 NCHW tensor (first-layer / last-layer weight gradients).  A block owns
+// 32 consecutive output pixels of one row: the C x 5 x 67 input patch is read once, coalesced, into shared memory;
+// every thread then assembles 16-byte groups of 8 k's through a k -> patch-offset table and writes them coalesced.
+constexpr int kImPix = 32, kImPitch = 2 * kImPix + 4;
+__global__ void __launch_bounds__(256) im2col5x5s2_kernel(const float* __restrict__ x, int B, int C, int H, int W, int OH, int OW,
+                                                          int k_pad, int segs, __nv_bfloat16* __restrict__ rows) {
+    extern __shared__ float im_smem[];
+    float* patch = im_smem;                                              // [C][5][kImPitch]
+    int16_t* tab = reinterpret_cast<int16_t*>(patch + C * 5 * kImPitch);  // [k_pad]
     const int K = C * 25;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        const int gk = (int)(e % groups);
-        int64_t pix = e / groups;
-        const int ow = (int)(pix % OW);
-        pix /= OW;
-        const int oh = (int)(pix % OH);
-        const int b = (int)(pix / OH);
+    int blk = blockIdx.x;
+    const int seg = blk % segs;
+    blk /= segs;
+    const int oh = blk % OH, b = blk / OH;
+    const int ow0 = seg * kImPix;
+    for (int k = threadIdx.x; k < k_pad; k += blockDim.x)
+        tab[k] = (int16_t)(k < K ? ((k / 25) * 5 + (k % 25) / 5) * kImPitch + (k % 5) : -1);
+    for (int idx = threadIdx.x; idx < C * 5 * kImPitch; idx += blockDim.x) {
+        const int col = idx % kImPitch, r = (idx / kImPitch) % 5, c = idx / (5 * kImPitch);
+        const int ih = 2 * oh + r - 2, iw = 2 * ow0 + col - 2;
+        patch[idx] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(x + (((size_t)b * C + c) * H + ih) * W + iw) : 0.f;
+    }
+    __syncthreads();
+    const int groups = k_pad / 8;
+    for (int item = threadIdx.x; item < kImPix * groups; item += blockDim.x) {
+        const int pl = item / groups, gk = item % groups;
+        if (ow0 + pl >= OW) continue;
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int k = gk * 8 + j;
-            float val = 0.f;
-            if (k < K) {
-                const int c = k / 25, r = k % 25;
-                const int ih = 2 * oh + r / 5 - 2, iw = 2 * ow + r % 5 - 2;
-                if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = __ldg(x + (((size_t)b * C + c) * H + ih) * W + iw);
-            }
-            v[j] = val;
+            const int t = tab[gk * 8 + j];
+            v[j] = t < 0 ? 0.f : patch[t + 2 * pl];
         }
-        *reinterpret_cast<uint4*>(rows + (size_t)e * 8) = pack8(v);
+        *reinterpret_cast<uint4*>(rows + (((size_t)b * OH + oh) * OW + ow0 + pl) * k_pad + gk * 8) = pack8(v);
     }
 }
 
@@ -581,9 +588,12 @@ int licos_im2col5x5s2(const float* x, int batch, int channels, int h, int w, voi
     if (batch == 0) return LICOS_OK;
     const int oh = (h + 1) / 2, ow = (w + 1) / 2;
     const int kp = (int)licos_im2col5x5s2_kpad(channels);
-    const int64_t groups = (int64_t)batch * oh * ow * (kp / 8);
-    im2col5x5s2_kernel<<<wg_ew_grid(groups), 256, 0, (cudaStream_t)stream>>>(x, batch, channels, h, w, oh, ow, kp,
-                                                                             (__nv_bfloat16*)rows);
+    const int segs = (ow + kImPix - 1) / kImPix;
+    const int64_t blocks = (int64_t)batch * oh * segs;
+    if (blocks > 0x7fffffff) return LICOS_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)channels * 5 * kImPitch * sizeof(float) + (size_t)kp * sizeof(int16_t);
+    im2col5x5s2_kernel<<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(x, batch, channels, h, w, oh, ow, kp, segs,
+                                                                        (__nv_bfloat16*)rows);
     LICOS_CUDA_OK(cudaGetLastError());
     return LICOS_OK;
 }
