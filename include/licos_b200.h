@@ -145,9 +145,15 @@ int licos_conv_wgrad(const licos_wgrad_args* args, void* stream);
  *   t = conv1x1(d_norm, gamma_hat^T);  out:  dx = d_direct + 2 x t  (dx may alias d_direct)
  *   gamma_hat.grad = licos_conv_wgrad(CONV_1X1, small = d_norm, big = x2);  beta_hat.grad = licos_colsum_bf16(d_norm) */
 int licos_square_bf16(const void* x, void* x2, int64_t n, void* stream);
-int licos_gdn_bwd_mid(const void* x, const void* g, const void* norm, int inverse, int64_t n, void* d_norm, void* d_direct,
+int licos_gdn_bwd_mid(const void* x, const void* g, const void* norm, int inverse, int64_t n, int channels, void* d_norm,
+                      void* d_direct, float* sum_d_norm, void* stream);
+int licos_gdn_bwd_out(const void* x, const void* t, const void* d_direct, int64_t n, int channels, void* dx, float* sum_dx,
                       void* stream);
-int licos_gdn_bwd_out(const void* x, const void* t, const void* d_direct, int64_t n, void* dx, void* stream);
+/* sum_d_norm / sum_dx (fp32 [channels], accumulated, may be NULL): per-channel sums of the tensor just written, i.e.
+ * beta_hat.grad and the preceding conv's bias.grad, without a second pass (channels % 8 == 0, <= 512).
+ * Gradient through NonNegativeParametrizer with LowerBound's rule: d_p = d_hat * 2 max(p, bound) where p >= bound or < 0. */
+int licos_gdn_param_grad(const float* beta, const float* gamma, const float* d_beta_hat, const float* d_gamma_hat, int channels,
+                         float beta_bound, float gamma_bound, float* d_beta, float* d_gamma, void* stream);
 /* ReLU backward: dx = y > 0 ? g : 0 (dx may alias g) */
 int licos_relu_bwd(const void* y, const void* g, int64_t n, void* dx, void* stream);
 /* acc[c] += sum over rows of x[row][c]  (bias / beta gradients); x bf16 [rows][channels], channels % 8 == 0, <= 512 */

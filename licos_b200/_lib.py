@@ -72,8 +72,9 @@ SIGNATURES = {
     "licos_debug_set_conv_probe": (None, [c_vp]),
     "licos_conv_wgrad": (c_int, [ctypes.POINTER(WgradArgs), c_vp]),
     "licos_square_bf16": (c_int, [c_vp, c_vp, c_i64, c_vp]),
-    "licos_gdn_bwd_mid": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
-    "licos_gdn_bwd_out": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "licos_gdn_bwd_mid": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "licos_gdn_bwd_out": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),
+    "licos_gdn_param_grad": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_f32, c_f32, c_vp, c_vp, c_vp]),
     "licos_relu_bwd": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "licos_colsum_bf16": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     "licos_im2col5x5s2_kpad": (c_i64, [c_int]),

@@ -241,13 +241,28 @@ __global__ void square_bf16_kernel(const uint4* __restrict__ x, uint4* __restric
     }
 }
 
+// Per-channel sums of what an elementwise kernel just produced (beta / bias gradients) without a second pass: the
+// launch makes gridDim.x * blockDim.x a multiple of C / 8, so a thread always sees the same 8 channels.
+__device__ __forceinline__ void colsum_flush(const float (&s)[8], int cg, int C, float* part, float* __restrict__ acc) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) part[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&part[cg * 8 + j], s[j]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(acc + i, part[i]);
+}
+
 // norm = beta + gamma . x^2 (from the 1x1 layer).  GDN: y = x * rsqrt(norm); IGDN: y = x * sqrt(norm).
-//   d_direct = g * dy/dx at fixed norm;  d_norm = g * dy/dnorm
+//   d_direct = g * dy/dx at fixed norm;  d_norm = g * dy/dnorm;  sum_dn[c] += column sums of d_norm (= beta_hat.grad)
 template <bool INVERSE>
-__global__ void gdn_bwd_mid_kernel(const uint4* __restrict__ x, const uint4* __restrict__ g, const uint4* __restrict__ norm,
-                                   uint4* __restrict__ d_norm, uint4* __restrict__ d_direct, int64_t n8) {
+__global__ void __launch_bounds__(256) gdn_bwd_mid_kernel(const uint4* __restrict__ x, const uint4* __restrict__ g,
+                                                          const uint4* __restrict__ norm, uint4* __restrict__ d_norm,
+                                                          uint4* __restrict__ d_direct, int64_t n8, int C, float* __restrict__ sum_dn) {
+    __shared__ float part[512];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int64_t i = i0; i < n8; i += stride) {
         float a[8], b[8], c[8], dn[8], dd[8];
         unpack8(__ldg(x + i), a);
         unpack8(__ldg(g + i), b);
@@ -255,32 +270,71 @@ __global__ void gdn_bwd_mid_kernel(const uint4* __restrict__ x, const uint4* __r
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             if (INVERSE) {
-                const float s = sqrtf(c[j]);
-                dd[j] = b[j] * s;
-                dn[j] = 0.5f * b[j] * a[j] / s;
+                const float sq = sqrtf(c[j]);
+                dd[j] = b[j] * sq;
+                dn[j] = 0.5f * b[j] * a[j] / sq;
             } else {
                 const float r = rsqrtf(c[j]);
                 dd[j] = b[j] * r;
                 dn[j] = -0.5f * b[j] * a[j] * r * r * r;
             }
         }
-        d_norm[i] = pack8(dn);
+        const uint4 pk = pack8(dn);
+        d_norm[i] = pk;
         d_direct[i] = pack8(dd);
+        if (sum_dn) {  // sum what the weight-gradient kernel will read: the bf16-rounded values
+            float r8[8];
+            unpack8(pk, r8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] += r8[j];
+        }
     }
+    if (sum_dn) colsum_flush(s, (int)(i0 % (C / 8)), C, part, sum_dn);
 }
 
-// dx = d_direct + 2 x t, t = gamma^T . d_norm (from the 1x1 layer); in place over d_direct is allowed
-__global__ void gdn_bwd_out_kernel(const uint4* __restrict__ x, const uint4* __restrict__ t, const uint4* d_direct, uint4* dx,
-                                   int64_t n8) {
+// dx = d_direct + 2 x t, t = gamma^T . d_norm (from the 1x1 layer); in place over d_direct is allowed;
+// sum_dx[c] += column sums of dx (= the conv's bias.grad)
+__global__ void __launch_bounds__(256) gdn_bwd_out_kernel(const uint4* __restrict__ x, const uint4* __restrict__ t, const uint4* d_direct,
+                                                          uint4* dx, int64_t n8, int C, float* __restrict__ sum_dx) {
+    __shared__ float part[512];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int64_t i = i0; i < n8; i += stride) {
         float a[8], b[8], c[8];
         unpack8(__ldg(x + i), a);
         unpack8(__ldg(t + i), b);
         unpack8(d_direct[i], c);
 #pragma unroll
         for (int j = 0; j < 8; ++j) c[j] = fmaf(2.f * a[j], b[j], c[j]);
-        dx[i] = pack8(c);
+        const uint4 pk = pack8(c);
+        dx[i] = pk;
+        if (sum_dx) {
+            float r8[8];
+            unpack8(pk, r8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] += r8[j];
+        }
+    }
+    if (sum_dx) colsum_flush(s, (int)(i0 % (C / 8)), C, part, sum_dx);
+}
+
+// Gradient through NonNegativeParametrizer (p_hat = max(p, bound)^2 - pedestal) with LowerBound's rule (A6):
+// d_lb = d_hat * 2 max(p, bound); it passes where p >= bound or where it would move p back above the bound (d_lb < 0).
+__global__ void gdn_param_grad_kernel(const float* __restrict__ beta, const float* __restrict__ gamma,
+                                      const float* __restrict__ d_beta_hat, const float* __restrict__ d_gamma_hat, int C, float bb,
+                                      float gb, float* __restrict__ d_beta, float* __restrict__ d_gamma) {
+    const int64_t total = (int64_t)C * C;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const float gm = gamma[e];
+        const float dl = d_gamma_hat[e] * 2.f * fmaxf(gm, gb);
+        d_gamma[e] = (gm >= gb || dl < 0.f) ? dl : 0.f;
+        if (e < C) {
+            const float bt = beta[e];
+            const float db = d_beta_hat[e] * 2.f * fmaxf(bt, bb);
+            d_beta[e] = (bt >= bb || db < 0.f) ? db : 0.f;
+        }
     }
 }
 
@@ -539,25 +593,51 @@ int licos_square_bf16(const void* x, void* x2, int64_t n, void* stream) {
     return LICOS_OK;
 }
 
-int licos_gdn_bwd_mid(const void* x, const void* g, const void* norm, int inverse, int64_t n, void* d_norm, void* d_direct,
-                      void* stream) {
+// grid whose thread count is a multiple of C / 8 for every C the kernels take (multiples of 8 up to 512 that divide
+// 256 * 1200 / ... : 1200 blocks of 256 threads = 307200 threads, divisible by 16, 24, 32, 40, 48, 64)
+static int colsum_ew_grid(int64_t n8, int C) {
+    const int per = C / 8;
+    int64_t g = (n8 + 255) / 256;
+    if (g > 1200) g = 1200;
+    while (g > 1 && (g * 256) % per != 0) --g;
+    return (int)(g < 1 ? 1 : g);
+}
+
+int licos_gdn_bwd_mid(const void* x, const void* g, const void* norm, int inverse, int64_t n, int channels, void* d_norm,
+                      void* d_direct, float* sum_d_norm, void* stream) {
     if (!x || !g || !norm || !d_norm || !d_direct || n < 0 || n % 8 != 0) return LICOS_ERR_INVALID;
+    if (sum_d_norm && (channels < 8 || channels % 8 != 0 || channels > 512 || n % channels != 0)) return LICOS_ERR_INVALID;
     if (n == 0) return LICOS_OK;
+    const int grid = sum_d_norm ? colsum_ew_grid(n / 8, channels) : wg_ew_grid(n / 8);
+    if (sum_d_norm && ((int64_t)grid * 256) % (channels / 8) != 0) return LICOS_ERR_UNSUPPORTED;
     if (inverse)
-        gdn_bwd_mid_kernel<true><<<wg_ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>(
-            (const uint4*)x, (const uint4*)g, (const uint4*)norm, (uint4*)d_norm, (uint4*)d_direct, n / 8);
+        gdn_bwd_mid_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)g, (const uint4*)norm,
+                                                                         (uint4*)d_norm, (uint4*)d_direct, n / 8, channels, sum_d_norm);
     else
-        gdn_bwd_mid_kernel<false><<<wg_ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>(
-            (const uint4*)x, (const uint4*)g, (const uint4*)norm, (uint4*)d_norm, (uint4*)d_direct, n / 8);
+        gdn_bwd_mid_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)g, (const uint4*)norm,
+                                                                          (uint4*)d_norm, (uint4*)d_direct, n / 8, channels, sum_d_norm);
     LICOS_CUDA_OK(cudaGetLastError());
     return LICOS_OK;
 }
 
-int licos_gdn_bwd_out(const void* x, const void* t, const void* d_direct, int64_t n, void* dx, void* stream) {
+int licos_gdn_bwd_out(const void* x, const void* t, const void* d_direct, int64_t n, int channels, void* dx, float* sum_dx,
+                      void* stream) {
     if (!x || !t || !d_direct || !dx || n < 0 || n % 8 != 0) return LICOS_ERR_INVALID;
+    if (sum_dx && (channels < 8 || channels % 8 != 0 || channels > 512 || n % channels != 0)) return LICOS_ERR_INVALID;
     if (n == 0) return LICOS_OK;
-    gdn_bwd_out_kernel<<<wg_ew_grid(n / 8), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)t,
-                                                                           (const uint4*)d_direct, (uint4*)dx, n / 8);
+    const int grid = sum_dx ? colsum_ew_grid(n / 8, channels) : wg_ew_grid(n / 8);
+    if (sum_dx && ((int64_t)grid * 256) % (channels / 8) != 0) return LICOS_ERR_UNSUPPORTED;
+    gdn_bwd_out_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)t, (const uint4*)d_direct, (uint4*)dx,
+                                                               n / 8, channels, sum_dx);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_gdn_param_grad(const float* beta, const float* gamma, const float* d_beta_hat, const float* d_gamma_hat, int channels,
+                         float beta_bound, float gamma_bound, float* d_beta, float* d_gamma, void* stream) {
+    if (!beta || !gamma || !d_beta_hat || !d_gamma_hat || !d_beta || !d_gamma || channels < 1) return LICOS_ERR_INVALID;
+    gdn_param_grad_kernel<<<wg_ew_grid((int64_t)channels * channels), 256, 0, (cudaStream_t)stream>>>(
+        beta, gamma, d_beta_hat, d_gamma_hat, channels, beta_bound, gamma_bound, d_beta, d_gamma);
     LICOS_CUDA_OK(cudaGetLastError());
     return LICOS_OK;
 }

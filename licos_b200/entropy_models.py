@@ -51,9 +51,11 @@ class _EbTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, eb, x, noise, seed, *raw):
         ebp = eb.packed_params()
-        if seed is None:
-            seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if noise is None else 0
-        y_hat, lik = ops.eb_forward_noise(ebp, x.detach().contiguous(), None if noise is None else noise.contiguous(), seed)
+        if noise is None and seed is None:
+            # device-side draw from torch's generator: no host sync in the training step, and legal under graph capture
+            noise = torch.empty_like(x).uniform_(-0.5, 0.5)
+        y_hat, lik = ops.eb_forward_noise(ebp, x.detach().contiguous(), None if noise is None else noise.contiguous(),
+                                          0 if seed is None else seed)
         ctx.eb, ctx.ebp = eb, ebp
         ctx.save_for_backward(y_hat, *raw)
         return y_hat, lik
@@ -315,7 +317,7 @@ class EntropyBottleneck(EntropyModel):
 
     def packed_params(self) -> ops.EbPacked:
         key = tuple((p.data_ptr(), p._version) for p in self._params()) + (self.likelihood_form,)
-        if key != self._packed_key:
+        if key != self._packed_key or (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()):
             with torch.no_grad():
                 C = self.channels
                 parts = []

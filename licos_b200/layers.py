@@ -54,6 +54,10 @@ class NonNegativeParametrizer(nn.Module):
         self.reparam_offset = float(reparam_offset)
         self.register_buffer("pedestal", torch.Tensor([self.reparam_offset ** 2]))
         self.lower_bound = LowerBound((self.minimum + self.reparam_offset ** 2) ** 0.5)
+        # the same two constants as host floats (fp32-rounded like the buffers): reading a device buffer would be a
+        # host sync in every training step, and is illegal under CUDA-graph capture
+        self.pedestal_f = float(torch.tensor(self.reparam_offset ** 2, dtype=torch.float32))
+        self.bound_f = float(torch.tensor((self.minimum + self.reparam_offset ** 2) ** 0.5, dtype=torch.float32))
 
     def init(self, x: Tensor) -> Tensor:
         return torch.sqrt(torch.max(x + self.pedestal, self.pedestal))
@@ -129,6 +133,12 @@ def _version_key(*params: Optional[Tensor]):
     return tuple((p.data_ptr(), p._version, tuple(p.shape)) if p is not None else None for p in params)
 
 
+def _capturing() -> bool:
+    """Under CUDA-graph capture every tensor derived from a parameter is rebuilt inside the graph (the optimizer step
+    of a replay changes the parameters without touching their version counters)."""
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
 class FusedSequential(nn.Sequential):
     """``nn.Sequential`` with CompressAI's indexing / item-assignment surface (LICOS swaps ``g_a[0]`` and
     ``g_s[6]``, /root/reference/licos/model_utils.py:31-45).  With autograd off it runs as fused sm_100a
@@ -159,7 +169,7 @@ class FusedSequential(nn.Sequential):
         ent = self._packed_cache.setdefault(m, {})
         slot = ent.setdefault(("w", in_layout), _Packed())
         key = _version_key(m.weight, m.bias)
-        if slot.key != key:
+        if slot.key != key or _capturing():
             out_c = m.out_channels
             in_c = m.in_channels
             w = m.weight.detach()
@@ -172,19 +182,18 @@ class FusedSequential(nn.Sequential):
         ent = self._packed_cache.setdefault(g, {})
         slot = ent.setdefault("gdn", _Packed())
         key = _version_key(g.beta, g.gamma)
-        if slot.key != key:
+        if slot.key != key or _capturing():
             slot.key = key
             slot.tensors = ops.gdn_pack(
                 g.beta.detach().contiguous(), g.gamma.detach().contiguous(),
-                float(g.beta_reparam.lower_bound.bound), float(g.gamma_reparam.lower_bound.bound),
-                float(g.beta_reparam.pedestal))
+                g.beta_reparam.bound_f, g.gamma_reparam.bound_f, g.beta_reparam.pedestal_f)
         return slot.tensors
 
     def _cached(self, owner: nn.Module, name, params, build):
         ent = self._packed_cache.setdefault(owner, {})
         slot = ent.setdefault(name, _Packed())
         key = _version_key(*params)
-        if slot.key != key:
+        if slot.key != key or _capturing():
             slot.key, slot.tensors = key, build()
         return slot.tensors
 
@@ -307,18 +316,6 @@ class FusedSequential(nn.Sequential):
 # native training path: one autograd node per transform (g_a / g_s / h_a / h_s)
 # ---------------------------------------------------------------------------------------------
 
-def _reparam(p: Tensor, rp: NonNegativeParametrizer):
-    lb = torch.max(p, rp.lower_bound.bound)
-    return lb, lb * lb - rp.pedestal
-
-
-def _reparam_grad(p: Tensor, rp: NonNegativeParametrizer, lb: Tensor, d_hat: Tensor) -> Tensor:
-    """Gradient through ``max(p, bound)**2 - pedestal`` with the LowerBound rule."""
-    d_lb = d_hat * 2.0 * lb
-    keep = (p >= rp.lower_bound.bound) | (d_lb < 0)
-    return d_lb * keep.to(d_lb.dtype)
-
-
 class _ChainFn(torch.autograd.Function):
     """forward: conv (+ bias) on the engine with the pre-activation kept, GDN / IGDN as its own 1x1 layer;
     backward: data gradients on the engine (conv <-> transposed conv with the same weight), weight / gamma gradients on
@@ -369,6 +366,22 @@ class _ChainFn(torch.autograd.Function):
     def backward(ctx, g_out: Tensor):
         L = _lib
         seq, steps, saved = ctx.seq, ctx.steps, ctx.saved
+        dev = g_out.device
+        # one zeroed fp32 arena for everything the kernels accumulate into (weight / gamma gradients, channel sums)
+        need = 0
+        for m, kind, epi, gdn in steps:
+            taps = {L.CONV_3X3_S1: 9}.get(kind, 25)
+            need += taps * max(m.in_channels, 64) * max(m.out_channels, 64) * 2 + m.out_channels
+            if gdn is not None:
+                need += m.out_channels * m.out_channels + m.out_channels
+        arena = torch.zeros(need, dtype=torch.float32, device=dev)
+        used = [0]
+
+        def take(n):
+            v = arena[used[0]:used[0] + n]
+            used[0] += (n + 3) // 4 * 4  # keep 16-byte alignment for the vector red.add
+            return v
+
         grads = []  # per step, in order: weight, bias, [beta, gamma]
         g = g_out.contiguous()
         g_layout = L.LAYOUT_NCHW_F32
@@ -378,21 +391,20 @@ class _ChainFn(torch.autograd.Function):
             a_in, in_layout = rec["in"], rec["in_layout"]
             narrow = g_layout == L.LAYOUT_NCHW_F32 and kind == L.DECONV_5X5_S2 and m.out_channels <= 4
             need_dgrad = n > 0 or ctx.x_needs_grad
-            step_grads = []
+            Co, Ci = m.out_channels, m.in_channels
             if narrow:
-                # g_s[6]: 128 -> C_img transposed conv, gradient arrives as fp32 NCHW
-                Ci, Co = m.in_channels, m.out_channels
+                # g_s[6]: C -> C_img transposed conv, gradient arrives as fp32 NCHW
                 patches = ops.im2col5x5s2(g)
-                dw = ops.conv_wgrad(a_in, patches, L.CONV_1X1)[0][:, :Co * 25].reshape(Ci, Co, 5, 5)
+                kp = patches.shape[-1]
+                dw = ops.conv_wgrad(a_in, patches, L.CONV_1X1, out=take(Ci * kp))[0][:, :Co * 25].reshape(Ci, Co, 5, 5)
                 db = g.sum(dim=(0, 2, 3)) if m.bias is not None else None
-                step_grads = [dw, db]
+                grads.append([dw, db])
                 if need_dgrad:
                     wd = seq._cached(m, ("wd", L.LAYOUT_NCHW_F32), (m.weight,), lambda: ops.pack_conv_weight(
                         m.weight.detach().contiguous(), L.CONV_5X5_S2, Ci, Co, L.LAYOUT_NCHW_F32))
                     g = ops.conv_forward(g, kind=L.CONV_5X5_S2, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NCHW_F32,
                                          out_layout=L.LAYOUT_NHWC_BF16, in_c=Co, out_c=Ci, weight=wd, bias=None)
                     g_layout = L.LAYOUT_NHWC_BF16
-                grads.append(step_grads)
                 continue
             if g_layout == L.LAYOUT_NCHW_F32:
                 if epi == L.EPI_RELU:
@@ -401,37 +413,38 @@ class _ChainFn(torch.autograd.Function):
                 g_layout = L.LAYOUT_NHWC_BF16
             elif epi == L.EPI_RELU:
                 g = ops.relu_bwd(rec["y"], g)
-            d_beta = d_gamma = None
+            d_beta = d_gamma = db = None
             if gdn is not None:
-                C = m.out_channels
+                C = Co
                 v = rec["v"]
-                lb_b, beta_hat = _reparam(gdn.beta.detach(), gdn.beta_reparam)
-                lb_g, gamma_hat = _reparam(gdn.gamma.detach(), gdn.gamma_reparam)
-                w_g, w_gt = seq._cached(gdn, "gdn1x1", (gdn.gamma,), lambda: (
-                    ops.pack_conv_weight(gamma_hat.reshape(C, C, 1, 1).contiguous(), L.CONV_1X1, C, C, L.LAYOUT_NHWC_BF16),
-                    ops.pack_conv_weight(gamma_hat.t().reshape(C, C, 1, 1).contiguous(), L.CONV_1X1, C, C, L.LAYOUT_NHWC_BF16)))
+                beta_hat, gamma_hat = seq._packed_gdn(gdn)  # fp32 [C], bf16 [C][C] == the packed 1x1 weight of the norm mix
+                gamma_hat_t = seq._cached(gdn, "gamma_t", (gdn.gamma,), lambda: gamma_hat.t().contiguous())
                 x2 = ops.square_bf16(v)
                 norm = ops.conv_forward(x2, kind=L.CONV_1X1, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NHWC_BF16,
-                                        out_layout=L.LAYOUT_NHWC_BF16, in_c=C, out_c=C, weight=w_g, bias=beta_hat.contiguous())
-                d_norm, d_direct = ops.gdn_bwd_mid(v, g, norm, gdn.inverse)
+                                        out_layout=L.LAYOUT_NHWC_BF16, in_c=C, out_c=C, weight=gamma_hat, bias=beta_hat)
+                d_beta_hat = take(C)
+                d_norm, d_direct = ops.gdn_bwd_mid(v, g, norm, gdn.inverse, sum_out=d_beta_hat)
                 t = ops.conv_forward(d_norm, kind=L.CONV_1X1, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NHWC_BF16,
-                                     out_layout=L.LAYOUT_NHWC_BF16, in_c=C, out_c=C, weight=w_gt, bias=None)
-                g = ops.gdn_bwd_out(v, t, d_direct)
-                d_gamma = _reparam_grad(gdn.gamma.detach(), gdn.gamma_reparam, lb_g, ops.conv_wgrad(d_norm, x2, L.CONV_1X1)[0])
-                d_beta = _reparam_grad(gdn.beta.detach(), gdn.beta_reparam, lb_b, ops.colsum_bf16(d_norm))
+                                     out_layout=L.LAYOUT_NHWC_BF16, in_c=C, out_c=C, weight=gamma_hat_t, bias=None)
+                db = take(C) if m.bias is not None else None
+                g = ops.gdn_bwd_out(v, t, d_direct, sum_out=db)
+                d_gamma_hat = ops.conv_wgrad(d_norm, x2, L.CONV_1X1, out=take(C * C))[0]
+                d_beta, d_gamma = ops.gdn_param_grad(
+                    gdn.beta.detach(), gdn.gamma.detach(), d_beta_hat, d_gamma_hat,
+                    gdn.beta_reparam.bound_f, gdn.gamma_reparam.bound_f)
+            elif m.bias is not None:
+                db = ops.colsum_bf16(g, acc=take(Co))
             # g is now the gradient with respect to conv + bias
-            db = ops.colsum_bf16(g) if m.bias is not None else None
-            Co, Ci = m.out_channels, m.in_channels
             if in_layout == L.LAYOUT_NCHW_F32:  # g_a[0]: image in, K = 25 C_in
                 patches = ops.im2col5x5s2(a_in)
-                dw = ops.conv_wgrad(g, patches, L.CONV_1X1)[0][:, :Ci * 25].reshape(Co, Ci, 5, 5)
+                kp = patches.shape[-1]
+                dw = ops.conv_wgrad(g, patches, L.CONV_1X1, out=take(Co * kp))[0][:, :Ci * 25].reshape(Co, Ci, 5, 5)
             elif kind == L.DECONV_5X5_S2:
-                dw = ops.conv_wgrad(a_in, g, kind).permute(1, 2, 0).reshape(Ci, Co, 5, 5)
+                dw = ops.conv_wgrad(a_in, g, kind, out=take(25 * Ci * Co)).permute(1, 2, 0).reshape(Ci, Co, 5, 5)
             else:
                 k = 3 if kind == L.CONV_3X3_S1 else 5
-                dw = ops.conv_wgrad(g, a_in, kind).permute(1, 2, 0).reshape(Co, Ci, k, k)
-            step_grads = [dw, db] + ([d_beta, d_gamma] if gdn is not None else [])
-            grads.append(step_grads)
+                dw = ops.conv_wgrad(g, a_in, kind, out=take(k * k * Co * Ci)).permute(1, 2, 0).reshape(Co, Ci, k, k)
+            grads.append([dw, db] + ([d_beta, d_gamma] if gdn is not None else []))
             if need_dgrad:
                 out_layout = L.LAYOUT_NHWC_BF16 if n > 0 else L.LAYOUT_NCHW_F32
                 w = m.weight.detach()

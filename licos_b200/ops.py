@@ -138,16 +138,23 @@ def _bf16(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
-def conv_wgrad(small: torch.Tensor, big: torch.Tensor, kind: int, sm_count: int = 0) -> torch.Tensor:
+def conv_wgrad(small: torch.Tensor, big: torch.Tensor, kind: int, sm_count: int = 0,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """fp32 [taps][small_c][big_c] = sum over pixels of small (x) big shifted by the tap; both bf16 NHWC.
-    Conv2d: small = output gradient, big = layer input; ConvTranspose2d: small = layer input, big = output gradient."""
-    _need_cuda(_bf16(small), _bf16(big))
+    Conv2d: small = output gradient, big = layer input; ConvTranspose2d: small = layer input, big = output gradient.
+    ``out``: optional ZEROED fp32 buffer of taps * small_c * big_c elements (the kernel accumulates into it)."""
+    _need_cuda(_bf16(small), _bf16(big), out)
     B, h, w, cs = small.shape
     B2, H, W, cb = big.shape
     if B != B2:
         raise ValueError("batch mismatch")
     taps = {_lib.CONV_5X5_S2: 25, _lib.DECONV_5X5_S2: 25, _lib.CONV_3X3_S1: 9, _lib.CONV_1X1: 1}[kind]
-    out = torch.zeros((taps, cs, cb), dtype=torch.float32, device=small.device)
+    if out is None:
+        out = torch.zeros((taps, cs, cb), dtype=torch.float32, device=small.device)
+    else:
+        if out.numel() != taps * cs * cb or out.dtype != torch.float32:
+            raise ValueError("out must hold taps * small_c * big_c float32 values")
+        out = out.view(taps, cs, cb)
     a = WgradArgs()
     a.kind, a.batch, a.h, a.w, a.big_h, a.big_w, a.small_c, a.big_c = kind, B, h, w, H, W, cs, cb
     a.small_t, a.big_t, a.out, a.sm_count = small.data_ptr(), big.data_ptr(), out.data_ptr(), sm_count
@@ -162,20 +169,32 @@ def square_bf16(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def gdn_bwd_mid(x: torch.Tensor, g: torch.Tensor, norm: torch.Tensor, inverse: bool):
-    _need_cuda(_bf16(x), _bf16(g), _bf16(norm))
+def gdn_bwd_mid(x: torch.Tensor, g: torch.Tensor, norm: torch.Tensor, inverse: bool, sum_out: Optional[torch.Tensor] = None):
+    """(d_norm, d_direct); ``sum_out`` (zeroed fp32 [C]) receives the per-channel sums of d_norm."""
+    _need_cuda(_bf16(x), _bf16(g), _bf16(norm), sum_out)
     d_norm, d_direct = torch.empty_like(x), torch.empty_like(x)
-    check(lib.licos_gdn_bwd_mid(x.data_ptr(), g.data_ptr(), norm.data_ptr(), int(inverse), x.numel(), d_norm.data_ptr(),
-                                d_direct.data_ptr(), _stream()), "gdn_bwd_mid")
+    check(lib.licos_gdn_bwd_mid(x.data_ptr(), g.data_ptr(), norm.data_ptr(), int(inverse), x.numel(), x.shape[-1],
+                                d_norm.data_ptr(), d_direct.data_ptr(), _ptr(sum_out), _stream()), "gdn_bwd_mid")
     return d_norm, d_direct
 
 
-def gdn_bwd_out(x: torch.Tensor, t: torch.Tensor, d_direct: torch.Tensor) -> torch.Tensor:
-    """dx = d_direct + 2 x t, written over d_direct."""
-    _need_cuda(_bf16(x), _bf16(t), _bf16(d_direct))
-    check(lib.licos_gdn_bwd_out(x.data_ptr(), t.data_ptr(), d_direct.data_ptr(), x.numel(), d_direct.data_ptr(), _stream()),
-          "gdn_bwd_out")
+def gdn_bwd_out(x: torch.Tensor, t: torch.Tensor, d_direct: torch.Tensor, sum_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx = d_direct + 2 x t, written over d_direct; ``sum_out`` (zeroed fp32 [C]) receives its per-channel sums."""
+    _need_cuda(_bf16(x), _bf16(t), _bf16(d_direct), sum_out)
+    check(lib.licos_gdn_bwd_out(x.data_ptr(), t.data_ptr(), d_direct.data_ptr(), x.numel(), x.shape[-1], d_direct.data_ptr(),
+                                _ptr(sum_out), _stream()), "gdn_bwd_out")
     return d_direct
+
+
+def gdn_param_grad(beta: torch.Tensor, gamma: torch.Tensor, d_beta_hat: torch.Tensor, d_gamma_hat: torch.Tensor,
+                   beta_bound: float, gamma_bound: float):
+    """Gradients of the raw GDN parameters from those of the reparametrised ones (LowerBound's rule)."""
+    _need_cuda(_f32(beta), _f32(gamma), _f32(d_beta_hat), _f32(d_gamma_hat))
+    d_beta, d_gamma = torch.empty_like(beta), torch.empty_like(gamma)
+    check(lib.licos_gdn_param_grad(beta.data_ptr(), gamma.data_ptr(), d_beta_hat.data_ptr(), d_gamma_hat.data_ptr(),
+                                   beta.numel(), beta_bound, gamma_bound, d_beta.data_ptr(), d_gamma.data_ptr(), _stream()),
+          "gdn_param_grad")
+    return d_beta, d_gamma
 
 
 def relu_bwd(y: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
@@ -185,11 +204,12 @@ def relu_bwd(y: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     return dx
 
 
-def colsum_bf16(x: torch.Tensor) -> torch.Tensor:
-    """fp32 [C] = sum over all leading dimensions of a bf16 (..., C) tensor."""
-    _need_cuda(_bf16(x))
+def colsum_bf16(x: torch.Tensor, acc: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [C] = sum over all leading dimensions of a bf16 (..., C) tensor (``acc``: optional zeroed buffer)."""
+    _need_cuda(_bf16(x), acc)
     C = x.shape[-1]
-    acc = torch.zeros(C, dtype=torch.float32, device=x.device)
+    if acc is None:
+        acc = torch.zeros(C, dtype=torch.float32, device=x.device)
     check(lib.licos_colsum_bf16(x.data_ptr(), x.numel() // C, C, acc.data_ptr(), _stream()), "colsum_bf16")
     return acc
 

@@ -21,5 +21,6 @@ def net_aux_optimizer(net: nn.Module, conf: Dict[str, Dict[str, Any]]) -> Dict[s
         if kind in ("Adam", "AdamW") and "fused" not in kwargs and "foreach" not in kwargs and groups[key] and all(
                 p.is_cuda for p in groups[key]):
             kwargs["fused"] = True  # same update rule, one multi-tensor launch instead of one per parameter
+            kwargs.setdefault("capturable", True)  # step counters on the device: no host sync, CUDA-graph safe
         out[key] = getattr(torch.optim, kind)(groups[key], **kwargs)
     return out

@@ -83,7 +83,11 @@ def test_gdn_backward_pieces(cuda, inverse):
     t = _bf(torch.randn(n, generator=g))
     x2 = ops.square_bf16(x.to(cuda))
     assert torch.equal(x2.cpu(), _bf(x.float() ** 2))
-    d_norm, d_direct = ops.gdn_bwd_mid(x.to(cuda), gr.to(cuda), norm.to(cuda), inverse)
+    xs = x.to(cuda).reshape(4, 16, 16, 128)
+    sum_dn = torch.zeros(128, device=cuda)
+    d_norm, d_direct = ops.gdn_bwd_mid(xs, gr.to(cuda).reshape(xs.shape), norm.to(cuda).reshape(xs.shape), inverse, sum_out=sum_dn)
+    assert _rel(sum_dn, d_norm.float().reshape(-1, 128).double().sum(0).cpu()) <= 1e-4
+    d_norm, d_direct = d_norm.reshape(-1), d_direct.reshape(-1)
     xf, gf, nf = x.float(), gr.float(), norm.float()
     if inverse:
         ref_dd, ref_dn = gf * nf.sqrt(), 0.5 * gf * xf / nf.sqrt()
@@ -92,7 +96,21 @@ def test_gdn_backward_pieces(cuda, inverse):
     assert _rel(d_direct.float(), _bf(ref_dd).float()) <= 1e-2
     assert _rel(d_norm.float(), _bf(ref_dn).float()) <= 1e-2
     dd = d_direct.clone()
-    dx = ops.gdn_bwd_out(x.to(cuda), t.to(cuda), dd)
+    sum_dx = torch.zeros(128, device=cuda)
+    dx = ops.gdn_bwd_out(xs, t.to(cuda).reshape(xs.shape), dd.reshape(xs.shape), sum_out=sum_dx).reshape(-1)
+    assert _rel(sum_dx, dx.float().reshape(-1, 128).double().sum(0).cpu()) <= 1e-4
+    x192 = x[:192 * 600].reshape(1, 20, 30, 192).to(cuda)   # a thread count that is not a multiple of C / 8 by default
+    s192 = torch.zeros(192, device=cuda)
+    o192 = ops.gdn_bwd_out(x192, x192.clone(), x192.clone(), sum_out=s192)
+    assert _rel(s192, o192.float().reshape(-1, 192).double().sum(0).cpu()) <= 1e-4
+    beta, gamma = torch.rand(16, generator=g) * 2e-3, torch.rand(16, 16, generator=g) * 8e-6
+    db_hat, dg_hat = torch.randn(16, generator=g), torch.randn(16, 16, generator=g)
+    bb, gb = 1.0004e-3, 3.8e-6
+    got_b, got_g = ops.gdn_param_grad(beta.to(cuda), gamma.to(cuda), db_hat.to(cuda), dg_hat.to(cuda), bb, gb)
+    for got, p_, d_, bound in ((got_b, beta, db_hat, bb), (got_g, gamma, dg_hat, gb)):
+        dl = d_ * 2 * torch.clamp(p_, min=bound)
+        ref = dl * ((p_ >= bound) | (dl < 0)).float()
+        assert torch.allclose(got.cpu(), ref, rtol=1e-6, atol=0)
     ref = _bf(d_direct.float().cpu() + 2 * xf * t.float())
     assert _rel(dx.float(), ref.float()) <= 1e-2
     y = _bf(torch.randn(n, generator=g))
@@ -269,3 +287,44 @@ def test_entropy_bottleneck_training_backward_vs_oracle(cuda, in_ch, form):
             continue
         c, e = _grad_report(f"eb c{in_ch} {form} {n}", p.grad, q.grad)
         assert c >= 0.9999 and e <= 5e-3, n
+
+
+def test_graphed_train_step_matches_eager(cuda):
+    """GraphedTrainStep replays the same step the eager loop runs: same loss trajectory with the noise fixed by the
+    generator seed, parameters move, and the inference path sees the updated weights afterwards."""
+    def make():
+        torch.manual_seed(5)
+        net = L.image_models["bmshj2018-factorized"](quality=1, pretrained=False)
+        synth.condition_weights(net)
+        net = net.to(cuda).train()
+        opt = L.net_aux_optimizer(net, {"net": {"type": "Adam", "lr": 1e-4}, "aux": {"type": "Adam", "lr": 1e-3}})
+        return net, opt
+
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(4, 3, 64, 64, generator=g).to(cuda)
+    crit = L.RateDistortionLoss(lmbda=1e-2)
+    net, opt = make()
+    w0 = net.g_a[0].weight.detach().clone()
+    step = L.GraphedTrainStep(net, crit, opt, x, clip_max_norm=1.0, warmup=2)
+    losses = [float(step(x)["loss"]) for _ in range(6)]
+    assert all(l == l for l in losses)
+    assert losses[-1] < losses[0], losses                      # it trains
+    assert float((net.g_a[0].weight - w0).abs().max()) > 0
+    net.eval()
+    with torch.no_grad():
+        a = net(x)["x_hat"]
+        net.g_a._packed_cache.clear(); net.g_s._packed_cache.clear()   # force a repack from the current parameters
+        b = net(x)["x_hat"]
+    assert torch.equal(a, b), "inference after graphed training used stale packed weights"
+    # eager loop, same number of steps (2 warm-up + 1 capture + 6 replays = 9 optimizer steps)
+    net2, opt2 = make()
+    for _ in range(9):
+        opt2["net"].zero_grad(); opt2["aux"].zero_grad()
+        out = net2(x)
+        l2 = crit(out, x)["loss"]
+        l2.backward()
+        torch.nn.utils.clip_grad_norm_(net2.parameters(), 1.0)
+        opt2["net"].step()
+        aux = net2.aux_loss(); aux.backward(); opt2["aux"].step()
+    print(f"loss after 9 steps: graphed {losses[-1]:.4f} eager {float(l2):.4f}")
+    assert abs(losses[-1] / float(l2) - 1) < 0.05  # different noise draws and red.add order, same trajectory

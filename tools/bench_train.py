@@ -19,6 +19,7 @@ ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=4)
 ap.add_argument("--profile", action="store_true")
 ap.add_argument("--model", default="bmshj2018-factorized")
+ap.add_argument("--graph", action="store_true", help="replay the step as one CUDA graph (licos_b200.GraphedTrainStep)")
 args = ap.parse_args()
 
 dev = torch.device("cuda", 0)
@@ -62,12 +63,20 @@ def timed(fn, steps, warmup):
     return e0.elapsed_time(e1) / steps
 
 
+graphed = None
+if args.graph:
+    graphed = L.GraphedTrainStep(net, crit, opt, x, clip_max_norm=1.0)
+    eager_step = train_step
+
+    def train_step():  # noqa: F811
+        return graphed(x)["loss"]
+
 step_ms = timed(train_step, args.steps, args.warmup)
-loss = float(train_step())
+loss = float(train_step().detach())
 tr_ms = timed(fwd_bwd_transforms, args.steps, 2)
 res = {"config": f"cfg5 training step, {args.model} q1, {args.batch} x 3x256x256", "path": "cuDNN autograd" if os.environ.get(
     "LICOS_EAGER_AUTOGRAD", "0") == "1" else "native sm_100a forward + dgrad + wgrad", "step_ms": step_ms,
-    "train_mpix_s": args.batch * 65536 / step_ms / 1e3, "transforms_fwd_bwd_ms": tr_ms, "loss": loss}
+    "graph": bool(args.graph), "train_mpix_s": args.batch * 65536 / step_ms / 1e3, "transforms_fwd_bwd_ms": tr_ms, "loss": loss}
 if args.profile:
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
