@@ -50,7 +50,7 @@ class _EbTrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, eb, x, noise, seed, *raw):
-        ebp = eb.packed_params()
+        ebp = eb.packed_params(force=True)
         if noise is None and seed is None:
             # device-side draw from torch's generator: no host sync in the training step, and legal under graph capture
             noise = torch.empty_like(x).uniform_(-0.5, 0.5)
@@ -315,9 +315,13 @@ class EntropyBottleneck(EntropyModel):
             names += [f"_matrix{i:d}", f"_bias{i:d}"] + ([f"_factor{i:d}"] if i < len(self.filters) else [])
         return [getattr(self, n) for n in names] + [self.quantiles]
 
-    def packed_params(self) -> ops.EbPacked:
+    def train(self, mode: bool = True):
+        self._packed_key = None  # fused optimizers update parameters without bumping the versions the cache is keyed on
+        return super().train(mode)
+
+    def packed_params(self, force: bool = False) -> ops.EbPacked:
         key = tuple((p.data_ptr(), p._version) for p in self._params()) + (self.likelihood_form,)
-        if key != self._packed_key or (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()):
+        if key != self._packed_key or force or (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()):
             with torch.no_grad():
                 C = self.channels
                 parts = []

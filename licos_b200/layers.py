@@ -165,11 +165,17 @@ class FusedSequential(nn.Sequential):
         return self.fused_forward(x, take_abs=take_abs, nhwc=nhwc)
 
     # -- caches of kernel-layout parameters, rebuilt when a parameter's version or storage changes --
-    def _packed_weight(self, m: nn.Module, kind: int, in_layout: int):
+    def train(self, mode: bool = True):
+        # Entering or leaving training invalidates every kernel-layout copy of the parameters: fused / foreach
+        # optimizers update parameters in place WITHOUT bumping the version counters the caches are keyed on.
+        self._packed_cache.clear()
+        return super().train(mode)
+
+    def _packed_weight(self, m: nn.Module, kind: int, in_layout: int, force: bool = False):
         ent = self._packed_cache.setdefault(m, {})
         slot = ent.setdefault(("w", in_layout), _Packed())
         key = _version_key(m.weight, m.bias)
-        if slot.key != key or _capturing():
+        if slot.key != key or force or _capturing():
             out_c = m.out_channels
             in_c = m.in_channels
             w = m.weight.detach()
@@ -178,22 +184,22 @@ class FusedSequential(nn.Sequential):
             slot.key, slot.tensors = key, (packed, bias)
         return slot.tensors
 
-    def _packed_gdn(self, g: GDN):
+    def _packed_gdn(self, g: GDN, force: bool = False):
         ent = self._packed_cache.setdefault(g, {})
         slot = ent.setdefault("gdn", _Packed())
         key = _version_key(g.beta, g.gamma)
-        if slot.key != key or _capturing():
+        if slot.key != key or force or _capturing():
             slot.key = key
             slot.tensors = ops.gdn_pack(
                 g.beta.detach().contiguous(), g.gamma.detach().contiguous(),
                 g.beta_reparam.bound_f, g.gamma_reparam.bound_f, g.beta_reparam.pedestal_f)
         return slot.tensors
 
-    def _cached(self, owner: nn.Module, name, params, build):
+    def _cached(self, owner: nn.Module, name, params, build, force: bool = False):
         ent = self._packed_cache.setdefault(owner, {})
         slot = ent.setdefault(name, _Packed())
         key = _version_key(*params)
-        if slot.key != key or _capturing():
+        if slot.key != key or force or _capturing():
             slot.key, slot.tensors = key, build()
         return slot.tensors
 
@@ -337,7 +343,8 @@ class _ChainFn(torch.autograd.Function):
         for n, (m, kind, epi, gdn) in enumerate(steps):
             last = n == len(steps) - 1
             out_layout = L.LAYOUT_NCHW_F32 if last else L.LAYOUT_NHWC_BF16
-            packed, bias = seq._packed_weight(m, kind, layout)
+            # the training path never trusts the version-keyed caches (see FusedSequential.train)
+            packed, bias = seq._packed_weight(m, kind, layout, force=True)
             rec = {"in": cur, "in_layout": layout}
             if gdn is not None:
                 C = m.out_channels
@@ -345,7 +352,8 @@ class _ChainFn(torch.autograd.Function):
                     bias = torch.zeros(C, dtype=torch.float32, device=dev)
                 v = ops.conv_forward(cur, kind=kind, epilogue=L.EPI_NONE, in_layout=layout, out_layout=L.LAYOUT_NHWC_BF16,
                                      in_c=m.in_channels, out_c=C, weight=packed, bias=bias)
-                beta_hat, gamma_hat = seq._packed_gdn(gdn)
+                beta_hat, gamma_hat = seq._packed_gdn(gdn, force=True)
+                rec["gdn_packed"] = (beta_hat, gamma_hat)
                 eye = _identity_1x1(C, dev)
                 cur = ops.conv_forward(v, kind=L.CONV_1X1, epilogue=epi, in_layout=L.LAYOUT_NHWC_BF16, out_layout=out_layout,
                                        in_c=C, out_c=C, weight=eye, bias=_zeros(C, dev), beta=beta_hat, gamma=gamma_hat)
@@ -400,8 +408,7 @@ class _ChainFn(torch.autograd.Function):
                 db = g.sum(dim=(0, 2, 3)) if m.bias is not None else None
                 grads.append([dw, db])
                 if need_dgrad:
-                    wd = seq._cached(m, ("wd", L.LAYOUT_NCHW_F32), (m.weight,), lambda: ops.pack_conv_weight(
-                        m.weight.detach().contiguous(), L.CONV_5X5_S2, Ci, Co, L.LAYOUT_NCHW_F32))
+                    wd = ops.pack_conv_weight(m.weight.detach().contiguous(), L.CONV_5X5_S2, Ci, Co, L.LAYOUT_NCHW_F32)
                     g = ops.conv_forward(g, kind=L.CONV_5X5_S2, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NCHW_F32,
                                          out_layout=L.LAYOUT_NHWC_BF16, in_c=Co, out_c=Ci, weight=wd, bias=None)
                     g_layout = L.LAYOUT_NHWC_BF16
@@ -417,8 +424,8 @@ class _ChainFn(torch.autograd.Function):
             if gdn is not None:
                 C = Co
                 v = rec["v"]
-                beta_hat, gamma_hat = seq._packed_gdn(gdn)  # fp32 [C], bf16 [C][C] == the packed 1x1 weight of the norm mix
-                gamma_hat_t = seq._cached(gdn, "gamma_t", (gdn.gamma,), lambda: gamma_hat.t().contiguous())
+                beta_hat, gamma_hat = rec["gdn_packed"]  # fp32 [C], bf16 [C][C] == the packed 1x1 weight of the norm mix
+                gamma_hat_t = gamma_hat.t().contiguous()
                 x2 = ops.square_bf16(v)
                 norm = ops.conv_forward(x2, kind=L.CONV_1X1, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NHWC_BF16,
                                         out_layout=L.LAYOUT_NHWC_BF16, in_c=C, out_c=C, weight=gamma_hat, bias=beta_hat)
@@ -455,7 +462,7 @@ class _ChainFn(torch.autograd.Function):
                 else:
                     dk, build = L.CONV_3X3_S1, (lambda: ops.pack_conv_weight(w.flip(2, 3).transpose(0, 1).contiguous(), L.CONV_3X3_S1, Ci, Co,
                                                                               L.LAYOUT_NHWC_BF16))
-                wd = seq._cached(m, ("wd", L.LAYOUT_NHWC_BF16), (m.weight,), build)
+                wd = build()
                 g = ops.conv_forward(g, kind=dk, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NHWC_BF16, out_layout=out_layout,
                                      in_c=Co, out_c=Ci, weight=wd, bias=None)
                 g_layout = out_layout

@@ -8,6 +8,14 @@ import torch
 import torch.nn as nn
 
 
+def _bump_versions(optimizer, args, kwargs) -> None:
+    """Fused / foreach steps change parameters in place without bumping their version counters; the kernel-layout weight
+    caches of the inference path are keyed on those counters."""
+    for group in optimizer.param_groups:
+        for p in group["params"]:
+            torch.autograd.graph.increment_version(p)
+
+
 def net_aux_optimizer(net: nn.Module, conf: Dict[str, Dict[str, Any]]) -> Dict[str, torch.optim.Optimizer]:
     named = dict(net.named_parameters())
     groups = {"net": [], "aux": []}
@@ -23,4 +31,5 @@ def net_aux_optimizer(net: nn.Module, conf: Dict[str, Dict[str, Any]]) -> Dict[s
             kwargs["fused"] = True  # same update rule, one multi-tensor launch instead of one per parameter
             kwargs.setdefault("capturable", True)  # step counters on the device: no host sync, CUDA-graph safe
         out[key] = getattr(torch.optim, kind)(groups[key], **kwargs)
+        out[key].register_step_post_hook(_bump_versions)
     return out
