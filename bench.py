@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=32)
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE.json configs[4])")
     ap.add_argument("--min-warmup", type=int, default=5, help="the caching allocator needs ~5 steps to settle")
     return ap.parse_args()
 
@@ -388,10 +389,66 @@ def run_b200(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if not args.no_train:
+            torch.cuda.empty_cache()
+            line["train_step"] = run_train_step(torch, device)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_train_step(torch, device, steps: int = 20):
+    """BASELINE.json configs[4], the per-rank part: train.py's train_one_batch body (forward in train mode, RD loss,
+    backward, clip, Adam, aux step) on 32 synthetic 3x256x256 tiles, every kernel native (forward + dgrad on the conv
+    engine, wgrad / GDN / bottleneck backward kernels), replayed as one CUDA graph and, for comparison, as the eager
+    Python loop.  Reported beside the headline metric, not part of it."""
+    import licos_b200 as L
+    from licos_b200 import synth
+
+    torch.manual_seed(100)
+    net = L.image_models[MODEL](quality=QUALITY, pretrained=False).to(device).train()
+    crit = L.RateDistortionLoss(lmbda=1e-2)
+    opt = L.net_aux_optimizer(net, {"net": {"type": "Adam", "lr": 1e-4}, "aux": {"type": "Adam", "lr": 1e-3}})
+    tiles = 32
+    x = synth.make_input("rgb256", tiles, seed=1, device=device)
+
+    def eager():
+        opt["net"].zero_grad(); opt["aux"].zero_grad()
+        out = net(x)
+        loss = crit(out, x)["loss"]
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+        opt["net"].step()
+        aux = net.aux_loss()
+        aux.backward()
+        opt["aux"].step()
+        return loss.detach()
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            last = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n, last
+
+    loss0 = float(eager())
+    eager_ms, _ = timed(eager, steps)
+    graphed = L.GraphedTrainStep(net, crit, opt, x, clip_max_norm=1.0)
+    graph_ms, last = timed(lambda: graphed(x)["loss"], steps)
+    flop = tiles * 3 * (5.528e9 * 2)  # forward + dgrad + wgrad of the 11.056 GFLOP / tile transforms (SURVEY 8d)
+    pix = tiles * TILE[1] * TILE[2]
+    return {"workload": f"{MODEL} q{QUALITY} training step (forward + RD loss + backward + clip + Adam + aux step) on "
+                        f"{tiles} synthetic 3x256x256 tiles (BASELINE.json configs[4], one rank's share)",
+            "ms_per_step": graph_ms, "mpix_s": pix / (graph_ms * 1e-3) / 1e6, "how": "licos_b200.GraphedTrainStep (CUDA graph replay)",
+            "eager_loop_ms_per_step": eager_ms, "eager_loop_mpix_s": pix / (eager_ms * 1e-3) / 1e6,
+            "tflops": flop / (graph_ms * 1e-3) / 1e12, "loss_first": loss0, "loss_last": float(last),
+            "library_baseline": "same step through cuDNN autograd (LICOS_EAGER_AUTOGRAD=1 tools/bench_train.py): 15.2 ms"}
 
 
 def run_e2e(net, eb, x_dev, args, torch, device, world):
