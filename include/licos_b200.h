@@ -139,6 +139,14 @@ typedef struct licos_wgrad_args {
  * Conv2d.weight.grad[o][i][kh][kw] = out[..][o][i]; ConvTranspose2d.weight.grad[i][o][kh][kw] = out[..][i][o]. */
 int licos_conv_wgrad(const licos_wgrad_args* args, void* stream);
 
+/* The whole GDN / IGDN backward in ONE pass over x and g (channels == 128; other widths return LICOS_ERR_UNSUPPORTED and
+ * take the sequence below): x = the layer's pre-activation, g = the gradient of its output, both bf16 [n_pixels][channels];
+ * gamma_hat_bf16 / beta_hat from licos_gdn_pack.  Writes dx (bf16) and ACCUMULATES d_gamma_hat [C][C], d_beta_hat [C] and,
+ * when non-NULL, d_bias [C] (the column sums of dx = the preceding conv's bias.grad); the caller zeroes them. */
+int licos_gdn_backward(const void* x, const void* g, const void* gamma_hat_bf16, const float* beta_hat, int inverse,
+                       int64_t n_pixels, int channels, void* dx, float* d_gamma_hat, float* d_beta_hat, float* d_bias,
+                       int sm_count, void* stream);
+
 /* GDN backward, elementwise parts over n bf16 elements (n % 8 == 0); the two channel mixes between them are
  * LICOS_CONV_1X1 layers:  x2 = x^2;  norm = conv1x1(x2, gamma_hat, beta_hat);
  *   mid:  d_norm = g * dy/dnorm, d_direct = g * dy/dx|norm   (inverse != 0: IGDN)

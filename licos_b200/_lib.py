@@ -71,6 +71,7 @@ SIGNATURES = {
     "licos_conv_forward": (c_int, [ctypes.POINTER(ConvArgs), c_vp]),
     "licos_debug_set_conv_probe": (None, [c_vp]),
     "licos_conv_wgrad": (c_int, [ctypes.POINTER(WgradArgs), c_vp]),
+    "licos_gdn_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "licos_square_bf16": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "licos_gdn_bwd_mid": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     "licos_gdn_bwd_out": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_vp]),

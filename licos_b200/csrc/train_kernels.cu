@@ -15,6 +15,7 @@
 // The data gradients (dgrad) need no kernel of their own: dgrad of a stride-2 conv IS the transposed conv with the
 // same weight and vice versa, so they run on conv_engine.cu with re-packed weights.
 #include "common.cuh"
+#include "gdn_bwd.cuh"
 
 #include <string.h>
 #include <mutex>
@@ -478,6 +479,17 @@ static void wg_add_group(WgradParams& p, int view, const int* khs, int n_kh, con
     g.n_taps = (int8_t)n;
 }
 
+
+static bool gb_make_map2(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows) {
+    EncodeTiledFn fn = wg_encode_fn();
+    if (!fn || rows == 0) return false;
+    cuuint64_t gdims[2] = {cols, rows}, gstrides[1] = {cols * 2};
+    cuuint32_t gbox[2] = {64, 128}, estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdims, gstrides, gbox, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace licos
 
 using namespace licos;
@@ -581,6 +593,42 @@ int licos_conv_wgrad(const licos_wgrad_args* a, void* stream) {
     LICOS_CUDA_OK(ensure_max_dynamic_smem((const void*)wgrad_kernel, (int)smem));
     const int grid = p.n_units < sms ? p.n_units : sms;
     wgrad_kernel<<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(p);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_gdn_backward(const void* x, const void* g, const void* gamma_hat_bf16, const float* beta_hat, int inverse,
+                       int64_t n_pixels, int channels, void* dx, float* d_gamma_hat, float* d_beta_hat, float* d_bias,
+                       int sm_count, void* stream) {
+    if (!x || !g || !gamma_hat_bf16 || !beta_hat || !dx || !d_gamma_hat || !d_beta_hat || n_pixels < 0) return LICOS_ERR_INVALID;
+    if (channels != kGbC) return LICOS_ERR_UNSUPPORTED;  // other widths: the unfused sequence (see the header)
+    if (n_pixels == 0) return LICOS_OK;
+    const int64_t tiles = (n_pixels + 127) / 128;
+    if (tiles > 0x7fffffff) return LICOS_ERR_UNSUPPORTED;
+    GdnBwdParams p;
+    memset(&p, 0, sizeof(p));
+    if (!gb_make_map2(&p.x_map, x, kGbC, (uint64_t)n_pixels) || !gb_make_map2(&p.g_map, g, kGbC, (uint64_t)n_pixels) ||
+        !gb_make_map2(&p.dx_map, dx, kGbC, (uint64_t)n_pixels) || !gb_make_map2(&p.gamma_map, gamma_hat_bf16, kGbC, kGbC))
+        return LICOS_ERR_CUDA;
+    p.beta_hat = beta_hat;
+    p.d_gamma_hat = d_gamma_hat;
+    p.d_beta_hat = d_beta_hat;
+    p.d_bias = d_bias;
+    p.n_tiles = (int)tiles;
+    int sms = sm_count;
+    if (sms <= 0) {
+        int dev = 0;
+        LICOS_CUDA_OK(cudaGetDevice(&dev));
+        LICOS_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    if (inverse) {
+        LICOS_CUDA_OK(ensure_max_dynamic_smem((const void*)gdn_bwd_fused_kernel<true>, (int)kGbSmem));
+        gdn_bwd_fused_kernel<true><<<grid, kGbThreads, kGbSmem, (cudaStream_t)stream>>>(p);
+    } else {
+        LICOS_CUDA_OK(ensure_max_dynamic_smem((const void*)gdn_bwd_fused_kernel<false>, (int)kGbSmem));
+        gdn_bwd_fused_kernel<false><<<grid, kGbThreads, kGbSmem, (cudaStream_t)stream>>>(p);
+    }
     LICOS_CUDA_OK(cudaGetLastError());
     return LICOS_OK;
 }

@@ -120,6 +120,7 @@ def _conv_kind(m: nn.Module) -> int:
 
 
 _EAGER_AUTOGRAD = bool(int(os.environ.get("LICOS_EAGER_AUTOGRAD", "0")))  # development: compare against cuDNN autograd
+_UNFUSED_GDN_BWD = bool(int(os.environ.get("LICOS_UNFUSED_GDN_BWD", "0")))  # development: GDN backward as separate passes
 
 
 class _Packed:
@@ -425,19 +426,22 @@ class _ChainFn(torch.autograd.Function):
                 C = Co
                 v = rec["v"]
                 beta_hat, gamma_hat = rec["gdn_packed"]  # fp32 [C], bf16 [C][C] == the packed 1x1 weight of the norm mix
-                gamma_hat_t = gamma_hat.t().contiguous()
-                x2 = ops.square_bf16(v)
-                norm = ops.conv_forward(x2, kind=L.CONV_1X1, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NHWC_BF16,
-                                        out_layout=L.LAYOUT_NHWC_BF16, in_c=C, out_c=C, weight=gamma_hat, bias=beta_hat)
-                d_beta_hat = take(C)
-                d_norm, d_direct = ops.gdn_bwd_mid(v, g, norm, gdn.inverse, sum_out=d_beta_hat)
-                t = ops.conv_forward(d_norm, kind=L.CONV_1X1, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NHWC_BF16,
-                                     out_layout=L.LAYOUT_NHWC_BF16, in_c=C, out_c=C, weight=gamma_hat_t, bias=None)
+                d_beta_hat, d_gamma_hat = take(C), take(C * C)
                 db = take(C) if m.bias is not None else None
-                g = ops.gdn_bwd_out(v, t, d_direct, sum_out=db)
-                d_gamma_hat = ops.conv_wgrad(d_norm, x2, L.CONV_1X1, out=take(C * C))[0]
+                if C == 128 and not _UNFUSED_GDN_BWD:
+                    g = ops.gdn_backward(v, g, gamma_hat, beta_hat, gdn.inverse, d_gamma_hat, d_beta_hat, db)
+                else:
+                    gamma_hat_t = gamma_hat.t().contiguous()
+                    x2 = ops.square_bf16(v)
+                    norm = ops.conv_forward(x2, kind=L.CONV_1X1, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NHWC_BF16,
+                                            out_layout=L.LAYOUT_NHWC_BF16, in_c=C, out_c=C, weight=gamma_hat, bias=beta_hat)
+                    d_norm, d_direct = ops.gdn_bwd_mid(v, g, norm, gdn.inverse, sum_out=d_beta_hat)
+                    t = ops.conv_forward(d_norm, kind=L.CONV_1X1, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NHWC_BF16,
+                                         out_layout=L.LAYOUT_NHWC_BF16, in_c=C, out_c=C, weight=gamma_hat_t, bias=None)
+                    g = ops.gdn_bwd_out(v, t, d_direct, sum_out=db)
+                    ops.conv_wgrad(d_norm, x2, L.CONV_1X1, out=d_gamma_hat)
                 d_beta, d_gamma = ops.gdn_param_grad(
-                    gdn.beta.detach(), gdn.gamma.detach(), d_beta_hat, d_gamma_hat,
+                    gdn.beta.detach(), gdn.gamma.detach(), d_beta_hat, d_gamma_hat.view(C, C),
                     gdn.beta_reparam.bound_f, gdn.gamma_reparam.bound_f)
             elif m.bias is not None:
                 db = ops.colsum_bf16(g, acc=take(Co))

@@ -162,6 +162,19 @@ def conv_wgrad(small: torch.Tensor, big: torch.Tensor, kind: int, sm_count: int 
     return out
 
 
+def gdn_backward(x: torch.Tensor, g: torch.Tensor, gamma_hat: torch.Tensor, beta_hat: torch.Tensor, inverse: bool,
+                 d_gamma_hat: torch.Tensor, d_beta_hat: torch.Tensor, d_bias: Optional[torch.Tensor], sm_count: int = 0):
+    """Fused GDN / IGDN backward (128 channels): returns dx, accumulates into the zeroed fp32 d_gamma_hat [C][C],
+    d_beta_hat [C] and d_bias [C] (optional).  Raises NotImplementedError for other widths (use the unfused pieces)."""
+    _need_cuda(_bf16(x), _bf16(g), _bf16(gamma_hat), _f32(beta_hat), _f32(d_gamma_hat), _f32(d_beta_hat), d_bias)
+    C = x.shape[-1]
+    dx = torch.empty_like(x)
+    check(lib.licos_gdn_backward(x.data_ptr(), g.data_ptr(), gamma_hat.data_ptr(), beta_hat.data_ptr(), int(inverse),
+                                 x.numel() // C, C, dx.data_ptr(), d_gamma_hat.data_ptr(), d_beta_hat.data_ptr(), _ptr(d_bias),
+                                 sm_count, _stream()), "gdn_backward")
+    return dx
+
+
 def square_bf16(x: torch.Tensor) -> torch.Tensor:
     _need_cuda(_bf16(x))
     out = torch.empty_like(x)

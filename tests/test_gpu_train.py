@@ -328,3 +328,33 @@ def test_graphed_train_step_matches_eager(cuda):
         aux = net2.aux_loss(); aux.backward(); opt2["aux"].step()
     print(f"loss at step 8: graphed {losses[-1]:.4f} eager {float(l2):.4f}")
     assert abs(losses[-1] / float(l2) - 1) < 0.05  # different noise draws and red.add order, same trajectory
+
+
+@pytest.mark.parametrize("inverse,pixels", [(False, 3 * 37 * 29), (True, 3 * 37 * 29), (False, 50000), (True, 128 * 148 * 4)])
+def test_gdn_backward_fused_kernel(cuda, inverse, pixels):
+    """licos_gdn_backward (one pass, 128 channels) against the formulas in float64 on the same bf16 inputs; the kernel
+    rounds x^2, d_norm and dx to bf16 where the reference keeps float64, hence the 1e-2 scale-relative bar."""
+    g = torch.Generator().manual_seed(pixels % 1000 + int(inverse))
+    C = 128
+    x = _bf(torch.randn(pixels, C, generator=g) * 1.5)
+    gr = _bf(torch.randn(pixels, C, generator=g))
+    gamma = _bf(torch.rand(C, C, generator=g) * 0.02 + 0.1 * torch.eye(C))
+    beta = torch.rand(C, generator=g) + 0.5
+    d_gamma = torch.zeros(C, C, device=cuda)
+    d_beta = torch.zeros(C, device=cuda)
+    d_bias = torch.zeros(C, device=cuda)
+    dx = ops.gdn_backward(x.to(cuda), gr.to(cuda), gamma.to(cuda), beta.to(cuda), inverse, d_gamma, d_beta, d_bias)
+    torch.cuda.synchronize()
+    xd, gd, gm, bt = x.double(), gr.double(), gamma.double(), beta.double()
+    x2 = _bf((xd * xd).float()).double()
+    n = bt + x2 @ gm.t()
+    if inverse:
+        dd, dn = gd * n.sqrt(), 0.5 * gd * xd / n.sqrt()
+    else:
+        dd, dn = gd * n.rsqrt(), -0.5 * gd * xd * n.pow(-1.5)
+    dn_b = _bf(dn.float()).double()
+    ref_dx = dd + 2 * xd * (dn_b @ gm)
+    errs = {"dx": _rel(dx.float(), ref_dx), "d_gamma": _rel(d_gamma, dn_b.t() @ x2), "d_beta": _rel(d_beta, dn_b.sum(0)),
+            "d_bias": _rel(d_bias, _bf(ref_dx.float()).double().sum(0))}
+    print(f"gdn_backward fused inverse={inverse} P={pixels}: max|err|/max = " + ", ".join(f"{k} {v:.2e}" for k, v in errs.items()))
+    assert errs["dx"] <= 1e-2 and errs["d_gamma"] <= 1e-2 and errs["d_beta"] <= 1e-2 and errs["d_bias"] <= 2e-2
