@@ -1,5 +1,5 @@
 """cfg 5 on real GPUs (run under torchrun, one rank per GPU): a federated training step -- forward + backward +
-rate-distortion loss on 32 tiles per rank (autograd path), Adam step -- followed by the NCCL weight merge that
+rate-distortion loss on 32 tiles per rank (native backward kernels), Adam step -- followed by the NCCL weight merge that
 replaces the reference's checkpoint-file exchange (federation_utils.py:27-85).  Checks that every rank ends with the
 same weighted average and times the merge.  Prints one JSON line on rank 0."""
 import json
@@ -38,14 +38,25 @@ def train_step():
     opt["aux"].step()
     return float(loss["loss"])
 
-for _ in range(2):
-    loss = train_step()
-torch.cuda.synchronize()
-t0 = time.perf_counter()
 for _ in range(3):
     loss = train_step()
 torch.cuda.synchronize()
-step_ms = (time.perf_counter() - t0) / 3 * 1e3
+t0 = time.perf_counter()
+for _ in range(10):
+    loss = train_step()
+torch.cuda.synchronize()
+eager_ms = (time.perf_counter() - t0) / 10 * 1e3
+graphed = L.GraphedTrainStep(net, crit, opt, x, clip_max_norm=1.0)
+for _ in range(3):
+    graphed(x)
+torch.cuda.synchronize()
+dist.barrier()
+t0 = time.perf_counter()
+for _ in range(20):
+    out_terms = graphed(x)
+torch.cuda.synchronize()
+step_ms = (time.perf_counter() - t0) / 20 * 1e3
+loss = float(out_terms["loss"])
 
 before = state.flat.clone()
 gathered = [torch.empty_like(before) for _ in range(world)]
@@ -79,6 +90,8 @@ if rank == 0:
     print(json.dumps({"config": "cfg5 federated step", "world": world, "tiles_per_rank": 32, "train_step_ms": step_ms,
                       "train_mpix_s": 32 * 65536 * world / step_ms / 1e3, "loss": loss, "merge_bytes": state.numel * 4,
                       "merge_us": merge_us, "merge_max_abs_err_vs_weighted_mean": err, "ranks_identical": identical,
-                      "train_path": "torch autograd (cuDNN) -- not the native kernels"}))
+                      "eager_loop_step_ms": eager_ms,
+                      "train_path": "native sm_100a kernels (forward, dgrad, wgrad, GDN / bottleneck backward), "
+                                    "train_step_ms = CUDA-graph replay (GraphedTrainStep), eager_loop_step_ms = Python loop"}))
 dist.barrier()
 dist.destroy_process_group()
