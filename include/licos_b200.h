@@ -214,6 +214,29 @@ int licos_eb_forward_noise(const licos_eb_params* p, const float* x, const float
  *   tanh(_factor) as laid out in licos_eb_params.packed); the caller zeroes it and applies d softplus / d tanh. */
 int licos_eb_backward(const licos_eb_params* p, const float* y_hat, const float* g_lik, const float* g_yhat, int batch,
                       int64_t hw, float* d_x, float* d_packed, void* stream);
+/* The raw parameters of the density network (device pointers; entries >= n_layers, and factor[n_layers - 1], unused):
+ * _matrix_i (C, F[i+1], F[i]), _bias_i (C, F[i+1], 1), _factor_i (C, F[i+1], 1). */
+typedef struct licos_eb_raw_params {
+    const float* matrix[LICOS_EB_MAX_LAYERS];
+    const float* bias[LICOS_EB_MAX_LAYERS];
+    const float* factor[LICOS_EB_MAX_LAYERS];
+} licos_eb_raw_params;
+typedef struct licos_eb_raw_grads {
+    float* matrix[LICOS_EB_MAX_LAYERS];
+    float* bias[LICOS_EB_MAX_LAYERS];
+    float* factor[LICOS_EB_MAX_LAYERS];
+} licos_eb_raw_grads;
+/* packed[c][:] = (softplus(_matrix_i), _bias_i, tanh(_factor_i))_i, the block licos_eb_params.packed points to, in one launch. */
+int licos_eb_pack_params(const licos_eb_raw_params* raw, int channels, int n_layers, const int* widths, float* packed,
+                         void* stream);
+/* Raw-parameter gradients from licos_eb_backward's d_packed: d_matrix = d * sigmoid(_matrix), d_bias = d,
+ * d_factor = d * (1 - tanh(_factor)^2); written (not accumulated) into `grads`. */
+int licos_eb_param_grads(const licos_eb_raw_params* raw, const float* d_packed, int channels, int n_layers, const int* widths,
+                         const licos_eb_raw_grads* grads, void* stream);
+/* EntropyBottleneck.loss() (CompressionModel.aux_loss, train.py:198): loss[0] += sum |logits(quantiles) - target| with the
+ * parameters held constant (stop_gradient); d_quantiles[c][k] = its gradient.  quantiles: [C][3], target: [3]. */
+int licos_eb_aux_loss(const float* packed, int channels, int n_layers, const int* widths, const float* quantiles,
+                      const float* target, float* loss, float* d_quantiles, void* stream);
 /* EntropyModel.quantize(x, "symbols", medians) and EntropyBottleneck._build_indexes.
  * symbols / indexes: int32 [batch][channels][hw]; indexes may be NULL. */
 int licos_eb_symbols(const float* x, const float* medians, int batch, int channels, int64_t hw,

@@ -40,6 +40,11 @@ class ConvArgs(ctypes.Structure):
     ]
 
 
+class EbRawPtrs(ctypes.Structure):
+    """licos_eb_raw_params / licos_eb_raw_grads (same layout)."""
+    _fields_ = [("matrix", c_vp * EB_MAX_LAYERS), ("bias", c_vp * EB_MAX_LAYERS), ("factor", c_vp * EB_MAX_LAYERS)]
+
+
 class WgradArgs(ctypes.Structure):
     _fields_ = [
         ("kind", c_int), ("batch", c_int), ("h", c_int), ("w", c_int), ("big_h", c_int), ("big_w", c_int),
@@ -86,6 +91,10 @@ SIGNATURES = {
                                             c_vp]),
     "licos_eb_forward_noise": (c_int, [ctypes.POINTER(EbParams), c_vp, c_vp, c_u64, c_int, c_i64, c_vp, c_vp, c_vp]),
     "licos_eb_backward": (c_int, [ctypes.POINTER(EbParams), c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "licos_eb_pack_params": (c_int, [ctypes.POINTER(EbRawPtrs), c_int, c_int, ctypes.POINTER(c_int), c_vp, c_vp]),
+    "licos_eb_param_grads": (c_int, [ctypes.POINTER(EbRawPtrs), c_vp, c_int, c_int, ctypes.POINTER(c_int),
+                                     ctypes.POINTER(EbRawPtrs), c_vp]),
+    "licos_eb_aux_loss": (c_int, [c_vp, c_int, c_int, ctypes.POINTER(c_int), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "licos_eb_symbols": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp]),
     "licos_eb_dequantize": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_vp]),
     "licos_gc_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_u64, c_i64, c_int, c_f32, c_f32, c_vp, c_vp, c_vp]),

@@ -6,6 +6,8 @@
 // A13 the two reductions of RateDistortionLoss.
 #include "common.cuh"
 
+#include <string.h>
+
 namespace licos {
 
 // ----------------------------------------------------------------------------------------------
@@ -507,6 +509,99 @@ __global__ void __launch_bounds__(128) eb_train_bwd_static_kernel(EbMeta m, cons
     for (int i = threadIdx.x; i < kPpc; i += blockDim.x) atomicAdd(d_packed + (size_t)c * kPpc + i, sacc[i]);
 }
 
+// ----------------------------------------------------------------------------------------------
+// Parameter block <-> raw parameters of the density network, and the auxiliary (quantile) loss
+// ----------------------------------------------------------------------------------------------
+struct EbRaw {
+    const float* matrix[LICOS_EB_MAX_LAYERS];
+    const float* bias[LICOS_EB_MAX_LAYERS];
+    const float* factor[LICOS_EB_MAX_LAYERS];
+};
+struct EbRawOut {
+    float* matrix[LICOS_EB_MAX_LAYERS];
+    float* bias[LICOS_EB_MAX_LAYERS];
+    float* factor[LICOS_EB_MAX_LAYERS];
+};
+
+__device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }  // torch's threshold 20
+
+// MODE 0: packed[c][:] = (softplus(_matrix_i), _bias_i, tanh(_factor_i))_i
+// MODE 1: raw gradients from d_packed: d_matrix = d * sigmoid(_matrix), d_bias = d, d_factor = d * (1 - tanh(_factor)^2)
+template <int MODE>
+__global__ void eb_pack_kernel(EbMeta m, EbRaw raw, EbRawOut out, int C, float* __restrict__ packed) {
+    const int total = C * m.ppc;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int c = e / m.ppc;
+        int r = e - c * m.ppc;
+        for (int i = 0; i < m.n_layers; ++i) {
+            const int fi = m.widths[i], fo = m.widths[i + 1];
+            const bool last = (i == m.n_layers - 1);
+            if (r < fo * fi) {
+                const size_t j = (size_t)c * fo * fi + r;
+                if (MODE == 0) packed[e] = softplus_t(raw.matrix[i][j]);
+                else out.matrix[i][j] = packed[e] * sigmoidf_(raw.matrix[i][j]);
+                break;
+            }
+            r -= fo * fi;
+            if (r < fo) {
+                const size_t j = (size_t)c * fo + r;
+                if (MODE == 0) packed[e] = raw.bias[i][j];
+                else out.bias[i][j] = packed[e];
+                break;
+            }
+            r -= fo;
+            if (!last) {
+                if (r < fo) {
+                    const size_t j = (size_t)c * fo + r;
+                    const float th = tanhf(raw.factor[i][j]);
+                    if (MODE == 0) packed[e] = th;
+                    else out.factor[i][j] = packed[e] * (1.f - th * th);
+                    break;
+                }
+                r -= fo;
+            }
+        }
+    }
+}
+
+// EntropyBottleneck.loss(): sum |logits_cumulative(quantiles, stop_gradient=True) - target|; one thread per (channel, k).
+// loss[0] += the sum, d_quantiles[c][k] = sign(logit - target_k) * d logit / d quantile.
+template <int W>
+__global__ void eb_aux_loss_kernel(EbMeta m, const float* __restrict__ packed, const float* __restrict__ quantiles,
+                                   const float* __restrict__ target, int C, float* __restrict__ loss, float* __restrict__ d_quantiles) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    float part = 0.f;
+    if (e < C * 3) {
+        const int c = e / 3, k = e - 3 * c;
+        const float* p = packed + (size_t)c * m.ppc;
+        float ins[LICOS_EB_MAX_LAYERS][W], ths[LICOS_EB_MAX_LAYERS][W];
+        const float logit = eb_logits_fwd_keep<W>(p, m, quantiles[e], ins, ths);
+        const float diff = logit - target[k];
+        part = fabsf(diff);
+        // d logit / d input: reverse sweep through the layers without the parameter gradients
+        float d_out[W], d_in[W];
+        d_out[0] = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+        int off = m.ppc;
+        for (int i = m.n_layers - 1; i >= 0; --i) {
+            const int fi = m.widths[i], fo = m.widths[i + 1];
+            const bool last = (i == m.n_layers - 1);
+            off -= fo * fi + fo + (last ? 0 : fo);
+            const float* M = p + off;
+            const float* t = M + fo * fi + fo;
+            for (int q = 0; q < fi; ++q) d_in[q] = 0.f;
+            for (int o = 0; o < fo; ++o) {
+                const float da = last ? d_out[o] : d_out[o] * (1.f + t[o] * (1.f - ths[i][o] * ths[i][o]));
+                for (int q = 0; q < fi; ++q) d_in[q] += M[o * fi + q] * da;
+            }
+            for (int q = 0; q < fi; ++q) d_out[q] = d_in[q];
+        }
+        d_quantiles[e] = d_out[0];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0 && part != 0.f) atomicAdd(loss, part);
+}
+
 __global__ void eb_symbols_kernel(const float* __restrict__ x, const float* __restrict__ med, int C, int64_t hw,
                                   int64_t n, int32_t* __restrict__ sym, int32_t* __restrict__ idx) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -834,6 +929,74 @@ int licos_eb_backward(const licos_eb_params* p, const float* y_hat, const float*
     if (stock) eb_train_bwd_static_kernel<5, 3><<<grid, 128, 0, s>>>(m, y_hat, g_lik, g_yhat, p->packed, batch, p->channels, hw, d_x, d_packed);
     else if (max_w <= 3) eb_train_bwd_kernel<3><<<grid, 128, sm, s>>>(m, y_hat, g_lik, g_yhat, p->packed, batch, p->channels, hw, d_x, d_packed);
     else eb_train_bwd_kernel<16><<<grid, 128, sm, s>>>(m, y_hat, g_lik, g_yhat, p->packed, batch, p->channels, hw, d_x, d_packed);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+static bool make_meta_shape(int channels, int n_layers, const int* widths, EbMeta& m, int& max_w) {
+    if (channels < 1 || n_layers < 1 || n_layers > LICOS_EB_MAX_LAYERS || !widths) return false;
+    m.n_layers = n_layers;
+    max_w = 1;
+    int ppc = 0;
+    for (int i = 0; i <= n_layers; ++i) {
+        m.widths[i] = widths[i];
+        if (widths[i] < 1 || widths[i] > 16) return false;
+        if (widths[i] > max_w) max_w = widths[i];
+    }
+    for (int i = n_layers + 1; i <= LICOS_EB_MAX_LAYERS; ++i) m.widths[i] = 0;
+    if (widths[0] != 1 || widths[n_layers] != 1) return false;
+    for (int i = 0; i < n_layers; ++i) ppc += widths[i + 1] * widths[i] + widths[i + 1] + (i < n_layers - 1 ? widths[i + 1] : 0);
+    m.ppc = ppc;
+    m.form = 0;
+    m.bound = 0.f;
+    return true;
+}
+
+int licos_eb_pack_params(const licos_eb_raw_params* raw, int channels, int n_layers, const int* widths, float* packed,
+                         void* stream) {
+    EbMeta m;
+    int max_w;
+    if (!raw || !packed || !make_meta_shape(channels, n_layers, widths, m, max_w)) return LICOS_ERR_INVALID;
+    EbRaw r;
+    EbRawOut o;
+    memset(&o, 0, sizeof(o));
+    for (int i = 0; i < LICOS_EB_MAX_LAYERS; ++i) { r.matrix[i] = raw->matrix[i]; r.bias[i] = raw->bias[i]; r.factor[i] = raw->factor[i]; }
+    for (int i = 0; i < n_layers; ++i)
+        if (!r.matrix[i] || !r.bias[i] || (i < n_layers - 1 && !r.factor[i])) return LICOS_ERR_INVALID;
+    eb_pack_kernel<0><<<grid_for((int64_t)channels * m.ppc, 256), 256, 0, (cudaStream_t)stream>>>(m, r, o, channels, packed);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_eb_param_grads(const licos_eb_raw_params* raw, const float* d_packed, int channels, int n_layers, const int* widths,
+                         const licos_eb_raw_grads* grads, void* stream) {
+    EbMeta m;
+    int max_w;
+    if (!raw || !d_packed || !grads || !make_meta_shape(channels, n_layers, widths, m, max_w)) return LICOS_ERR_INVALID;
+    EbRaw r;
+    EbRawOut o;
+    for (int i = 0; i < LICOS_EB_MAX_LAYERS; ++i) {
+        r.matrix[i] = raw->matrix[i]; r.bias[i] = raw->bias[i]; r.factor[i] = raw->factor[i];
+        o.matrix[i] = grads->matrix[i]; o.bias[i] = grads->bias[i]; o.factor[i] = grads->factor[i];
+    }
+    for (int i = 0; i < n_layers; ++i)
+        if (!r.matrix[i] || !r.bias[i] || !o.matrix[i] || !o.bias[i] || (i < n_layers - 1 && (!r.factor[i] || !o.factor[i])))
+            return LICOS_ERR_INVALID;
+    eb_pack_kernel<1><<<grid_for((int64_t)channels * m.ppc, 256), 256, 0, (cudaStream_t)stream>>>(m, r, o, channels,
+                                                                                                const_cast<float*>(d_packed));
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_eb_aux_loss(const float* packed, int channels, int n_layers, const int* widths, const float* quantiles,
+                      const float* target, float* loss, float* d_quantiles, void* stream) {
+    EbMeta m;
+    int max_w;
+    if (!packed || !quantiles || !target || !loss || !d_quantiles || !make_meta_shape(channels, n_layers, widths, m, max_w))
+        return LICOS_ERR_INVALID;
+    const int n = channels * 3;
+    if (max_w <= 3) eb_aux_loss_kernel<3><<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(m, packed, quantiles, target, channels, loss, d_quantiles);
+    else eb_aux_loss_kernel<16><<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(m, packed, quantiles, target, channels, loss, d_quantiles);
     LICOS_CUDA_OK(cudaGetLastError());
     return LICOS_OK;
 }

@@ -43,14 +43,36 @@ def _wants_grad(module: nn.Module, *tensors: Optional[Tensor]) -> bool:
 _EAGER_AUTOGRAD = bool(int(os.environ.get("LICOS_EAGER_AUTOGRAD", "0")))  # development: torch-expression autograd
 
 
+def _split_raw(eb, raw):
+    """raw = (_matrix0, _bias0, _factor0, _matrix1, ...) -> (matrices, biases, factors)"""
+    n_layers = len(eb.filters) + 1
+    ms, bs, fs, k = [], [], [], 0
+    for i in range(n_layers):
+        ms.append(raw[k]); bs.append(raw[k + 1])
+        k += 2
+        if i < n_layers - 1:
+            fs.append(raw[k])
+            k += 1
+    return ms, bs, fs
+
+
+def _native_packed(eb, raw) -> ops.EbPacked:
+    ms, bs, fs = _split_raw(eb, [t.detach().contiguous() for t in raw])
+    widths = (1,) + tuple(eb.filters) + (1,)
+    packed = ops.eb_pack_params(ms, bs, fs, widths)
+    form = _lib.EB_FORM_PLAIN if eb.likelihood_form == "plain" else _lib.EB_FORM_STABLE
+    return ops.EbPacked(packed, eb.quantiles.detach()[:, 0, 1].contiguous(), widths, form,
+                        eb.likelihood_bound if eb.use_likelihood_bound else 0.0)
+
+
 class _EbTrainFn(torch.autograd.Function):
-    """EntropyBottleneck.forward(x, training=True) with its backward on the device: the forward is the noise kernel, the
-    backward one kernel that re-evaluates the density network per element and sweeps it in reverse (d x, and the
-    per-channel parameter gradients reduced in the block)."""
+    """EntropyBottleneck.forward(x, training=True) with its backward on the device: parameter block in one launch, the
+    noise kernel, and a backward kernel that re-evaluates the density network per element and sweeps it in reverse
+    (d x, per-channel parameter gradients reduced in the block), then one launch back to the raw parameters."""
 
     @staticmethod
     def forward(ctx, eb, x, noise, seed, *raw):
-        ebp = eb.packed_params(force=True)
+        ebp = _native_packed(eb, raw)
         if noise is None and seed is None:
             # device-side draw from torch's generator: no host sync in the training step, and legal under graph capture
             noise = torch.empty_like(x).uniform_(-0.5, 0.5)
@@ -67,24 +89,31 @@ class _EbTrainFn(torch.autograd.Function):
         g_yhat = None if g_yhat is None else g_yhat.contiguous()
         g_lik = None if g_lik is None else g_lik.contiguous()
         d_x, d_packed = ops.eb_backward(ctx.ebp, y_hat, g_lik, g_yhat)
-        grads, off, C = [], 0, eb.channels
-        n_layers = len(eb.filters) + 1
-        k = 0
-        for i in range(n_layers):
-            matrix, bias = raw[k], raw[k + 1]
-            k += 2
-            nm, nb = matrix[0].numel(), bias[0].numel()
-            grads.append(d_packed[:, off:off + nm].reshape(matrix.shape) * torch.sigmoid(matrix))  # d softplus
-            off += nm
-            grads.append(d_packed[:, off:off + nb].reshape(bias.shape))
-            off += nb
-            if i < n_layers - 1:
-                factor = raw[k]
-                k += 1
-                th = torch.tanh(factor)
-                grads.append(d_packed[:, off:off + nb].reshape(factor.shape) * (1 - th * th))
-                off += nb
+        ms, bs, fs = _split_raw(eb, [t.detach().contiguous() for t in raw])
+        gm, gb, gf = ops.eb_param_grads(ms, bs, fs, d_packed, (1,) + tuple(eb.filters) + (1,))
+        grads = []
+        for i in range(len(ms)):
+            grads += [gm[i], gb[i]] + ([gf[i]] if i < len(fs) else [])
         return (None, d_x, None, None, *grads)
+
+
+class _EbAuxLossFn(torch.autograd.Function):
+    """EntropyBottleneck.loss(): sum |logits_cumulative(quantiles, stop_gradient=True) - target| and its gradient with
+    respect to the quantiles, two launches (parameter block, loss kernel)."""
+
+    @staticmethod
+    def forward(ctx, eb, quantiles, *raw):
+        ebp = _native_packed(eb, raw)
+        loss, d_q = ops.eb_aux_loss(ebp.packed, (1,) + tuple(eb.filters) + (1,), quantiles.detach().contiguous(),
+                                    eb.target.detach().float().contiguous())
+        ctx.save_for_backward(d_q)
+        ctx.n_raw = len(raw)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_q,) = ctx.saved_tensors
+        return (None, d_q * g) + (None,) * ctx.n_raw
 
 
 class EntropyModel(nn.Module):
@@ -282,6 +311,9 @@ class EntropyBottleneck(EntropyModel):
         return likelihood, lower, upper
 
     def loss(self) -> Tensor:
+        if (self.quantiles.is_cuda and torch.is_grad_enabled() and self.quantiles.requires_grad and not _EAGER_AUTOGRAD
+                and self.quantiles.dtype == torch.float32):
+            return _EbAuxLossFn.apply(self, self.quantiles, *self._params()[:-1])
         logits = self._logits_cumulative(self.quantiles, stop_gradient=True)
         return torch.abs(logits - self.target).sum()
 

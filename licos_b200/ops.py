@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ConvArgs, EbParams, WgradArgs, check, lib
+from ._lib import ConvArgs, EbParams, EbRawPtrs, WgradArgs, check, lib
 
 
 def _stream() -> int:
@@ -320,6 +320,55 @@ def eb_backward(ebp: EbPacked, y_hat: torch.Tensor, g_lik: Optional[torch.Tensor
     check(lib.licos_eb_backward(ctypes.byref(ebp.p), y_hat.data_ptr(), _ptr(g_lik), _ptr(g_yhat), B, hw, d_x.data_ptr(),
                                 d_packed.data_ptr(), _stream()), "eb_backward")
     return d_x, d_packed
+
+
+def _eb_raw_ptrs(matrices, biases, factors) -> EbRawPtrs:
+    r = EbRawPtrs()
+    for i, t in enumerate(matrices):
+        r.matrix[i] = t.data_ptr()
+    for i, t in enumerate(biases):
+        r.bias[i] = t.data_ptr()
+    for i, t in enumerate(factors):
+        r.factor[i] = t.data_ptr()
+    return r
+
+
+def _eb_widths(widths: Sequence[int]):
+    return (ctypes.c_int * len(widths))(*[int(w) for w in widths])
+
+
+def eb_pack_params(matrices, biases, factors, widths: Sequence[int]) -> torch.Tensor:
+    """[C][params_per_channel] block (softplus(_matrix_i), _bias_i, tanh(_factor_i))_i in one launch."""
+    _need_cuda(*[_f32(t) for t in (*matrices, *biases, *factors)])
+    C = matrices[0].shape[0]
+    ppc = sum(t[0].numel() for t in (*matrices, *biases, *factors))
+    packed = torch.empty((C, ppc), dtype=torch.float32, device=matrices[0].device)
+    raw = _eb_raw_ptrs(matrices, biases, factors)
+    check(lib.licos_eb_pack_params(ctypes.byref(raw), C, len(widths) - 1, _eb_widths(widths), packed.data_ptr(), _stream()),
+          "eb_pack_params")
+    return packed
+
+
+def eb_param_grads(matrices, biases, factors, d_packed: torch.Tensor, widths: Sequence[int]):
+    """Raw-parameter gradients from licos_eb_backward's d_packed: (d_matrices, d_biases, d_factors)."""
+    _need_cuda(_f32(d_packed), *[_f32(t) for t in (*matrices, *biases, *factors)])
+    C = matrices[0].shape[0]
+    gm, gb, gf = [torch.empty_like(t) for t in matrices], [torch.empty_like(t) for t in biases], [torch.empty_like(t) for t in factors]
+    raw, out = _eb_raw_ptrs(matrices, biases, factors), _eb_raw_ptrs(gm, gb, gf)
+    check(lib.licos_eb_param_grads(ctypes.byref(raw), d_packed.data_ptr(), C, len(widths) - 1, _eb_widths(widths),
+                                   ctypes.byref(out), _stream()), "eb_param_grads")
+    return gm, gb, gf
+
+
+def eb_aux_loss(packed: torch.Tensor, widths: Sequence[int], quantiles: torch.Tensor, target: torch.Tensor):
+    """(loss [1], d_quantiles like quantiles) of EntropyBottleneck.loss() with the density parameters held constant."""
+    _need_cuda(_f32(packed), _f32(quantiles), _f32(target))
+    C = packed.shape[0]
+    loss = torch.zeros(1, dtype=torch.float32, device=packed.device)
+    d_q = torch.empty_like(quantiles)
+    check(lib.licos_eb_aux_loss(packed.data_ptr(), C, len(widths) - 1, _eb_widths(widths), quantiles.data_ptr(), target.data_ptr(),
+                                loss.data_ptr(), d_q.data_ptr(), _stream()), "eb_aux_loss")
+    return loss, d_q
 
 
 def eb_symbols(x: torch.Tensor, medians: torch.Tensor, want_indexes: bool = False):

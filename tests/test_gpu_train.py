@@ -358,3 +358,24 @@ def test_gdn_backward_fused_kernel(cuda, inverse, pixels):
             "d_bias": _rel(d_bias, _bf(ref_dx.float()).double().sum(0))}
     print(f"gdn_backward fused inverse={inverse} P={pixels}: max|err|/max = " + ", ".join(f"{k} {v:.2e}" for k, v in errs.items()))
     assert errs["dx"] <= 1e-2 and errs["d_gamma"] <= 1e-2 and errs["d_beta"] <= 1e-2 and errs["d_bias"] <= 2e-2
+
+
+@pytest.mark.parametrize("in_ch", [3, 13])
+def test_entropy_bottleneck_native_pack_and_aux_loss(cuda, in_ch):
+    """licos_eb_pack_params against the torch packing, and EntropyBottleneck.loss() (aux loss) + its quantile gradient
+    against the oracle."""
+    from licos_b200.entropy_models import _native_packed
+    net, ref = _pair("bmshj2018-factorized", in_ch)
+    eb, reb = net.entropy_bottleneck.to(cuda).train(), ref.entropy_bottleneck.train()
+    a = eb.packed_params(force=True).packed
+    b = _native_packed(eb, eb._params()[:-1]).packed
+    assert _rel(b, a.cpu()) <= 1e-6
+    la, lr = eb.loss(), reb.loss()
+    assert "EbAuxLossFn" in type(la.grad_fn).__name__
+    la.backward(); lr.backward()
+    print(f"aux loss {float(la):.4f} vs oracle {float(lr):.4f}")
+    assert abs(float(la) / float(lr) - 1) <= 1e-5
+    assert _rel(eb.quantiles.grad, reb.quantiles.grad) <= 1e-4
+    for n, p in eb.named_parameters():
+        if not n.endswith("quantiles"):
+            assert p.grad is None, n
