@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "gdn_bwd.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 
@@ -549,11 +550,17 @@ int licos_conv_wgrad(const licos_wgrad_args* a, void* stream) {
     {
         int64_t total = 0;
         for (int g = 0; g < p.n_groups; ++g) total += (int64_t)p.groups[g].n_taps * p.m_blocks * p.n_blocks;
-        const int64_t target = 2 * (int64_t)sms;
+        // Every unit ends with a flush of its accumulators (up to 256 KB of red.add traffic, the tensor pipe idle
+        // meanwhile), so a unit must be long enough to amortise it: at most `per_sm` units per SM, at least
+        // `min_tiles` pixel tiles each (development knobs LICOS_WGRAD_UNITS_PER_SM / LICOS_WGRAD_MIN_TILES).
+        static const int per_sm = [] { const char* e = getenv("LICOS_WGRAD_UNITS_PER_SM"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 2; }();
+        static const int min_tiles = [] { const char* e = getenv("LICOS_WGRAD_MIN_TILES"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
+        const int64_t target = (int64_t)per_sm * sms;
         int n = 0;
         for (int c = 0; c < p.n_combos; ++c) {
             const int g = c / (p.m_blocks * p.n_blocks);
             int64_t s = ((int64_t)p.groups[g].n_taps * target + total / 2) / total;
+            if (s > n_tiles / min_tiles) s = n_tiles / min_tiles;
             if (s < 1) s = 1;
             if (s > n_tiles) s = n_tiles;
             p.unit_begin[c] = n;
@@ -622,12 +629,13 @@ int licos_gdn_backward(const void* x, const void* g, const void* gamma_hat_bf16,
         LICOS_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
     const int grid = (int)(tiles < sms ? tiles : sms);
+    cudaStream_t st = (cudaStream_t)stream;
     if (inverse) {
         LICOS_CUDA_OK(ensure_max_dynamic_smem((const void*)gdn_bwd_fused_kernel<true>, (int)kGbSmem));
-        gdn_bwd_fused_kernel<true><<<grid, kGbThreads, kGbSmem, (cudaStream_t)stream>>>(p);
+        gdn_bwd_fused_kernel<true><<<grid, kGbThreads, kGbSmem, st>>>(p);
     } else {
         LICOS_CUDA_OK(ensure_max_dynamic_smem((const void*)gdn_bwd_fused_kernel<false>, (int)kGbSmem));
-        gdn_bwd_fused_kernel<false><<<grid, kGbThreads, kGbSmem, (cudaStream_t)stream>>>(p);
+        gdn_bwd_fused_kernel<false><<<grid, kGbThreads, kGbSmem, st>>>(p);
     }
     LICOS_CUDA_OK(cudaGetLastError());
     return LICOS_OK;

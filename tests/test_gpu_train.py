@@ -379,3 +379,34 @@ def test_entropy_bottleneck_native_pack_and_aux_loss(cuda, in_ch):
     for n, p in eb.named_parameters():
         if not n.endswith("quantiles"):
             assert p.grad is None, n
+
+
+@pytest.mark.parametrize("name", ["bmshj2018-hyperprior", "bmshj2018-factorized-relu"])
+def test_other_models_train_step_runs_native(cuda, name):
+    """train.py's step on the other two architectures get_model accepts (model_utils.py:20-24): the four transforms take
+    the native path, every parameter receives a finite gradient, and a few Adam steps lower the loss."""
+    torch.manual_seed(3)
+    net = L.image_models[name](quality=1, pretrained=False)
+    synth.condition_weights(net)
+    net = net.to(cuda).train()
+    opt = L.net_aux_optimizer(net, {"net": {"type": "Adam", "lr": 1e-4}, "aux": {"type": "Adam", "lr": 1e-3}})
+    crit = L.RateDistortionLoss(lmbda=1e-2)
+    x = torch.rand(4, 3, 128, 128, generator=torch.Generator().manual_seed(12)).to(cuda)
+    losses = []
+    for it in range(6):
+        opt["net"].zero_grad(); opt["aux"].zero_grad()
+        out = net(x)
+        assert "ChainFn" in type(out["x_hat"].grad_fn).__name__
+        loss = crit(out, x)["loss"]
+        loss.backward()
+        if it == 0:
+            for n, p in net.named_parameters():
+                if n.endswith("quantiles"):
+                    continue
+                assert p.grad is not None and bool(torch.isfinite(p.grad).all()), n
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)
+        opt["net"].step()
+        aux = net.aux_loss(); aux.backward(); opt["aux"].step()
+        losses.append(float(loss))
+    print(f"{name}: loss {losses[0]:.3f} -> {losses[-1]:.3f}")
+    assert losses[-1] < losses[0]
