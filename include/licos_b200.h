@@ -252,6 +252,12 @@ int licos_eb_dequantize(const int32_t* symbols, const float* medians, int batch,
 int licos_gc_forward(const float* y, const float* scales, const float* means, const float* noise,
                      uint64_t seed, int64_t n, int training, float scale_bound, float likelihood_bound,
                      float* y_hat, float* lik, void* stream);
+/* Backward of the training-mode forward (y_hat = y + noise is the forward's output): d_y = g_yhat + g_lik * d lik / d y_hat,
+ * d_scales = g_lik * d lik / d scale, d_means (may be NULL) = -(the likelihood part of d_y); either incoming gradient may be
+ * NULL; LowerBound's gradient rule is applied to the likelihood bound and to the scale bound. */
+int licos_gc_backward(const float* y_hat, const float* scales, const float* means, const float* g_lik, const float* g_yhat,
+                      int64_t n, float scale_bound, float likelihood_bound, float* d_y, float* d_scales, float* d_means,
+                      void* stream);
 /* build_indexes(scales): idx = n_table-1 - #{k < n_table-1 : max(scale, bound) <= table[k]} */
 int licos_gc_build_indexes(const float* scales, int64_t n, const float* table, int n_table,
                            float scale_bound, int32_t* indexes, void* stream);

@@ -98,6 +98,7 @@ SIGNATURES = {
     "licos_eb_symbols": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp]),
     "licos_eb_dequantize": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_vp]),
     "licos_gc_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_u64, c_i64, c_int, c_f32, c_f32, c_vp, c_vp, c_vp]),
+    "licos_gc_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp]),
     "licos_gc_build_indexes": (c_int, [c_vp, c_i64, c_vp, c_int, c_f32, c_vp, c_vp]),
     "licos_gc_symbols": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "licos_sum_log": (c_int, [c_vp, c_i64, c_vp, c_vp]),

@@ -116,6 +116,33 @@ class _EbAuxLossFn(torch.autograd.Function):
         return (None, d_q * g) + (None,) * ctx.n_raw
 
 
+class _GcTrainFn(torch.autograd.Function):
+    """GaussianConditional.forward(y, scales, means, training=True): the noise kernel forward, one elementwise kernel back
+    (gradients of y, the scales and, when given, the means; LowerBound's rule on both bounds)."""
+
+    @staticmethod
+    def forward(ctx, gc, y, scales, means, noise):
+        if noise is None:
+            noise = torch.empty_like(y).uniform_(-0.5, 0.5)  # device-side draw: no host sync, graph-capture safe
+        y, scales = y.detach().contiguous(), scales.detach().contiguous()
+        means = None if means is None else means.detach().contiguous()
+        bound = gc.likelihood_bound if gc.use_likelihood_bound else 0.0
+        y_hat, lik = ops.gc_forward(y, scales, means, noise.contiguous(), training=True, scale_bound=gc._scale_bound_f,
+                                    likelihood_bound=bound)
+        ctx.gc, ctx.bound, ctx.has_means = gc, bound, means is not None
+        ctx.save_for_backward(y_hat, scales, *([means] if means is not None else []))
+        return y_hat, lik
+
+    @staticmethod
+    def backward(ctx, g_yhat, g_lik):
+        y_hat, scales, *rest = ctx.saved_tensors
+        means = rest[0] if ctx.has_means else None
+        d_y, d_s, d_m = ops.gc_backward(y_hat, scales, means, None if g_lik is None else g_lik.contiguous(),
+                                        None if g_yhat is None else g_yhat.contiguous(), ctx.gc._scale_bound_f, ctx.bound,
+                                        want_means=ctx.has_means and ctx.needs_input_grad[3])
+        return None, d_y, d_s, d_m, None
+
+
 class EntropyModel(nn.Module):
     def __init__(self, likelihood_bound: float = 1e-9, entropy_coder: Optional[str] = None,
                  entropy_coder_precision: int = 16):
@@ -559,6 +586,9 @@ class GaussianConditional(EntropyModel):
             training = self.training
         _require_cuda(inputs, "GaussianConditional.forward")
         if _wants_grad(self, inputs, scales, means):
+            if (training and not _EAGER_AUTOGRAD and inputs.dtype == torch.float32 and scales.shape == inputs.shape
+                    and (means is None or means.shape == inputs.shape)):
+                return _GcTrainFn.apply(self, inputs, scales, means, noise)
             if training:
                 nz = torch.empty_like(inputs).uniform_(-0.5, 0.5) if noise is None else noise
                 outputs = inputs + nz

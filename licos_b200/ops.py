@@ -416,6 +416,17 @@ def gc_forward(y, scales, means=None, noise=None, *, training=False, scale_bound
     return y_hat, lik
 
 
+def gc_backward(y_hat: torch.Tensor, scales: torch.Tensor, means: Optional[torch.Tensor], g_lik: Optional[torch.Tensor],
+                g_yhat: Optional[torch.Tensor], scale_bound: float, likelihood_bound: float, want_means: bool = False):
+    """Backward of the training-mode GaussianConditional: (d_y, d_scales, d_means | None)."""
+    _need_cuda(_f32(y_hat), _f32(scales), means, g_lik, g_yhat)
+    d_y, d_s = torch.empty_like(y_hat), torch.empty_like(y_hat)
+    d_m = torch.empty_like(y_hat) if (want_means and means is not None) else None
+    check(lib.licos_gc_backward(y_hat.data_ptr(), scales.data_ptr(), _ptr(means), _ptr(g_lik), _ptr(g_yhat), y_hat.numel(),
+                                scale_bound, likelihood_bound, d_y.data_ptr(), d_s.data_ptr(), _ptr(d_m), _stream()), "gc_backward")
+    return d_y, d_s, d_m
+
+
 def gc_build_indexes(scales: torch.Tensor, table: torch.Tensor, scale_bound: float) -> torch.Tensor:
     _need_cuda(_f32(scales), _f32(table))
     idx = torch.empty(scales.shape, dtype=torch.int32, device=scales.device)

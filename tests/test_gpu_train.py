@@ -410,3 +410,34 @@ def test_other_models_train_step_runs_native(cuda, name):
         losses.append(float(loss))
     print(f"{name}: loss {losses[0]:.3f} -> {losses[-1]:.3f}")
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("with_means", [False, True])
+def test_gaussian_conditional_training_backward_vs_oracle(cuda, with_means):
+    """GaussianConditional.forward(training=True) with a given noise tensor: outputs and the gradients with respect to y,
+    the scales (both sides of the 0.11 bound) and the means, against the oracle's autograd (fp32 on both sides)."""
+    gc, rgc = L.GaussianConditional(None).to(cuda).train(), R.GaussianConditional(None).train()
+    g = torch.Generator().manual_seed(31 + int(with_means))
+    shape = (2, 8, 12, 10)
+    y = torch.randn(shape, generator=g) * 3
+    scales = torch.exp(torch.randn(shape, generator=g) * 1.5 - 1.0)      # 0.02 .. 20: both sides of the scale bound
+    y[0, 0, 0, :3] = torch.tensor([90.0, -80.0, 70.0]); scales[0, 0, 0, :3] = 0.5   # likelihood below 1e-9
+    means = torch.randn(shape, generator=g) if with_means else None
+    noise = torch.rand(shape, generator=g) - 0.5
+    r = torch.randn(shape, generator=g)
+
+    def run(m, dev):
+        yi, si = y.to(dev).requires_grad_(True), scales.to(dev).requires_grad_(True)
+        mi = means.to(dev).requires_grad_(True) if with_means else None
+        y_hat, lik = m(yi, si, mi, training=True, noise=noise.to(dev))
+        (-torch.log(lik).sum() / 5.0 + (y_hat * r.to(dev)).sum()).backward()
+        return (y_hat.detach().cpu(), lik.detach().cpu(), yi.grad.cpu(), si.grad.cpu(), mi.grad.cpu() if with_means else None,
+                type(y_hat.grad_fn).__name__)
+
+    yh, lk, gy, gs, gm, fn = run(gc, cuda)
+    ryh, rlk, rgy, rgs, rgm, _ = run(rgc, "cpu")
+    assert fn.startswith("_GcTrainFn")
+    assert torch.allclose(yh, ryh, atol=1e-6) and _rel(lk, rlk) <= 1e-5
+    for what, a, b in (("y", gy, rgy), ("scales", gs, rgs)) + ((("means", gm, rgm),) if with_means else ()):
+        c, e = _grad_report(f"gc {what}", a, b)
+        assert c >= 0.99999 and e <= 2e-3, what
