@@ -441,3 +441,18 @@ def test_gaussian_conditional_training_backward_vs_oracle(cuda, with_means):
     for what, a, b in (("y", gy, rgy), ("scales", gs, rgs)) + ((("means", gm, rgm),) if with_means else ()):
         c, e = _grad_report(f"gc {what}", a, b)
         assert c >= 0.99999 and e <= 2e-3, what
+
+
+def test_wide_model_gradients_vs_oracle(cuda):
+    """Quality 6 (N = 192, M = 320): the 192-channel GDN backward takes the unfused sequence (square, 1x1 layers, mid / out
+    kernels, 1x1 weight gradient), the weight-gradient kernel runs three channel blocks (320 = 128 + 128 + 64)."""
+    torch.manual_seed(42)
+    net = L.image_models["bmshj2018-factorized"](quality=6, pretrained=False)
+    ref = R.image_models["bmshj2018-factorized"](quality=6)
+    synth.condition_weights(net)
+    ref.load_state_dict(net.state_dict())
+    g = torch.Generator().manual_seed(13)
+    x = torch.rand(2, 3, 64, 96, generator=g)
+    _check_chain(cuda, net.g_a, ref.g_a, x, "g_a q6")
+    y = torch.round(torch.randn(2, 320, 4, 6, generator=g) * 3)
+    _check_chain(cuda, net.g_s, ref.g_s, y, "g_s q6", x_grad=True)
