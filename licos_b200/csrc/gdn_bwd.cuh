@@ -17,7 +17,7 @@
 // Measured (ncu source page): ~5.9 k warp instructions per tile and warp, i.e. the kernel is bound by the issue rate of the
 // pixel-row code (bf16 unpack / pack, scalar fp32 math), not by latency: a two-team variant with a dedicated issuer warp
 // (two warps per scheduler) was built and measured at the same 165-170 us for 32 x 128 x 128 pixels, so it was dropped.
-// The next step is the packed fp32x2 arithmetic of epilogue.cuh in steps 2 and 3.
+// Steps 2 and 3 use the packed fp32x2 arithmetic of epilogue.cuh (FMUL2 / FADD2 / FFMA2).
 #pragma once
 
 #include "common.cuh"
@@ -190,22 +190,31 @@ __global__ void __launch_bounds__(kGbThreads, 1) gdn_bwd_fused_kernel(const __gr
                 uint32_t gp[16], dn[16];
                 load_row32(gt, et, cc, gp);
                 tmem_ld_wait();
+                const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(beta_s + cc * 32);
+                const uint64_t half = INVERSE ? f2_pack(0.5f, 0.5f) : f2_pack(-0.5f, -0.5f);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float d0 = v[2 * j] + beta_s[cc * 32 + 2 * j], d1 = v[2 * j + 1] + beta_s[cc * 32 + 2 * j + 1];
-                    const float r0 = fast_rsqrt(d0), r1 = fast_rsqrt(d1);
-                    const float g0 = __uint_as_float(gp[j] << 16), g1 = __uint_as_float(gp[j] & 0xffff0000u);
-                    const float x0 = __uint_as_float(xs[cc * 16 + j] << 16), x1 = __uint_as_float(xs[cc * 16 + j] & 0xffff0000u);
-                    float dd0, dd1, dn0, dn1;
-                    if (INVERSE) {  // y = x sqrt(d): dy/dx = sqrt(d) = d r, dy/dd = x r / 2
-                        dd0 = g0 * d0 * r0; dd1 = g1 * d1 * r1;
-                        dn0 = 0.5f * g0 * x0 * r0; dn1 = 0.5f * g1 * x1 * r1;
-                    } else {        // y = x rsqrt(d): dy/dx = r, dy/dd = -x r^3 / 2
-                        dd0 = g0 * r0; dd1 = g1 * r1;
-                        dn0 = -0.5f * g0 * x0 * r0 * r0 * r0; dn1 = -0.5f * g1 * x1 * r1 * r1 * r1;
+                for (int q = 0; q < 8; ++q) {
+                    const ulonglong2 bq = b2[q];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int j = 2 * q + h;
+                        const uint64_t d = f2_add(f2_pack(v[2 * j], v[2 * j + 1]), h ? bq.y : bq.x);
+                        float d0, d1;
+                        f2_unpack(d, d0, d1);
+                        const uint64_t r = f2_pack(fast_rsqrt(d0), fast_rsqrt(d1));
+                        const uint64_t g2 = bf16x2_to_f2(gp[j]);
+                        const uint64_t gx = f2_mul(g2, bf16x2_to_f2(xs[cc * 16 + j]));
+                        uint64_t ddv, dnv;
+                        if (INVERSE) {  // y = x sqrt(d): dy/dx = sqrt(d) = d r, dy/dd = x r / 2
+                            ddv = f2_mul(g2, f2_mul(d, r));
+                            dnv = f2_mul(gx, f2_mul(r, half));
+                        } else {        // y = x rsqrt(d): dy/dx = r, dy/dd = -x r^3 / 2
+                            ddv = f2_mul(g2, r);
+                            dnv = f2_mul(gx, f2_mul(f2_mul(r, r), f2_mul(r, half)));
+                        }
+                        dd[cc * 16 + j] = f2_to_bf16x2(ddv);
+                        dn[j] = f2_to_bf16x2(dnv);
                     }
-                    dd[cc * 16 + j] = pack_bf16x2(dd0, dd1);
-                    dn[j] = pack_bf16x2(dn0, dn1);
                 }
                 store_row32(dn_s, et, cc, dn);
             }
@@ -248,9 +257,8 @@ __global__ void __launch_bounds__(kGbThreads, 1) gdn_bwd_fused_kernel(const __gr
                 uint32_t out[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const float x0 = __uint_as_float(xs[cc * 16 + j] << 16), x1 = __uint_as_float(xs[cc * 16 + j] & 0xffff0000u);
-                    const float e0 = __uint_as_float(dd[cc * 16 + j] << 16), e1 = __uint_as_float(dd[cc * 16 + j] & 0xffff0000u);
-                    out[j] = pack_bf16x2(fmaf(2.f * x0, v[2 * j], e0), fmaf(2.f * x1, v[2 * j + 1], e1));
+                    const uint64_t x2 = bf16x2_to_f2(xs[cc * 16 + j]);
+                    out[j] = f2_to_bf16x2(f2_fma(f2_add(x2, x2), f2_pack(v[2 * j], v[2 * j + 1]), bf16x2_to_f2(dd[cc * 16 + j])));
                 }
                 store_row32(gt, et, cc, out);
             }

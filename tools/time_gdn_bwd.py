@@ -29,4 +29,4 @@ for hw in (128, 64, 32):
         us = e0.elapsed_time(e1) / 20 * 1e3
         tot += us
         print(f"{'IGDN' if inverse else 'GDN '} backward 32 x {hw}x{hw} x 128: {us:7.1f} us  {3 * P * C * 2 / us / 1e6:6.2f} TB/s (x, g in; dx out)")
-print(f"sum {tot:.1f} us ({'single team' if os.environ.get('LICOS_GDN_BWD_V1') else 'two teams'})")
+print(f"sum {tot:.1f} us")
