@@ -205,6 +205,8 @@ class FusedSequential(nn.Sequential):
         return slot.tensors
 
     def _steps(self):
+        """The chain as (conv module, kernel kind, fused epilogue, GDN module | None) launches: a GDN / IGDN / ReLU that
+        follows a conv becomes that conv's epilogue."""
         mods = list(self)
         steps = []
         i = 0
@@ -269,23 +271,7 @@ class FusedSequential(nn.Sequential):
         """x: fp32 (B, C, H, W) on a B200.  Returns fp32 NCHW like the module chain would."""
         if not x.is_cuda:
             raise RuntimeError("licos_b200: the fused path needs CUDA tensors (no CPU fallback exists)")
-        mods = list(self)
-        steps = []
-        i = 0
-        while i < len(mods):
-            m = mods[i]
-            kind = _conv_kind(m)
-            epi, gdn = _lib.EPI_NONE, None
-            if i + 1 < len(mods):
-                nxt = mods[i + 1]
-                if isinstance(nxt, GDN):
-                    epi, gdn = (_lib.EPI_IGDN if nxt.inverse else _lib.EPI_GDN), nxt
-                    i += 1
-                elif isinstance(nxt, nn.ReLU):
-                    epi = _lib.EPI_RELU
-                    i += 1
-            steps.append((m, kind, epi, gdn))
-            i += 1
+        steps = self._steps()
         if not steps:
             return x
 
