@@ -127,7 +127,7 @@ typedef struct licos_wgrad_args {
     int batch;
     int h, w;         /* spatial size of `small_t`                                                  */
     int big_h, big_w; /* spatial size of `big_t`: h == ceil(big_h / 2) for the stride-2 kinds       */
-    int small_c, big_c; /* channels, multiples of 64                                                */
+    int small_c, big_c; /* channels, multiples of 64 (CONV_1X1: big_c any multiple of 16)           */
     const void* small_t; /* bf16 NHWC: Conv2d -> the OUTPUT gradient; ConvTranspose2d -> the layer INPUT */
     const void* big_t;   /* bf16 NHWC: Conv2d -> the layer INPUT; ConvTranspose2d -> the OUTPUT gradient */
     float* out;       /* fp32 [KH*KW][small_c][big_c], ACCUMULATED into with red.add: the caller zeroes it */
@@ -168,7 +168,7 @@ int licos_relu_bwd(const void* y, const void* g, int64_t n, void* dx, void* stre
 int licos_colsum_bf16(const void* x, int64_t rows, int channels, float* acc, void* stream);
 /* Patch matrix of a 5x5 stride-2 window over a fp32 NCHW tensor (weight gradients of g_a[0] and g_s[6]):
  * rows[(b, oh, ow)][k] = x[b][c][2 oh + kh - 2][2 ow + kw - 2], k = (c*5 + kh)*5 + kw, zero padded to
- * licos_im2col5x5s2_kpad(channels) bf16 columns. */
+ * licos_im2col5x5s2_kpad(channels) bf16 columns (the next multiple of 16). */
 int64_t licos_im2col5x5s2_kpad(int channels);
 int licos_im2col5x5s2(const float* x, int batch, int channels, int h, int w, void* rows, void* stream);
 

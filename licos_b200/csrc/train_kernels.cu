@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
             const WgUnit w = wg_decode(p, u);
             const WgGroup& g = p.groups[w.g];
             const int nt = (p.Cb - w.nb * 128) > 64 ? 128 : 64;
+            const int n_valid = p.Cb - w.nb * 128;  // columns of this block that exist in `out` (a multiple of 16)
             const int cs = w.mb * 128 + row;
             mbar_wait(&acc_full, n_unit & 1u);
             tc_fence_after();
@@ -200,7 +201,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
                     tmem_ld_wait();
                     if (cs < p.Cs) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) red_add_v4(o + cc * 32 + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        for (int j = 0; j < 8; ++j)
+                            if (cc * 32 + 4 * j < n_valid) red_add_v4(o + cc * 32 + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     }
                 }
             }
@@ -501,8 +503,10 @@ int licos_conv_wgrad(const licos_wgrad_args* a, void* stream) {
     if (!a || !a->small_t || !a->big_t || !a->out) return LICOS_ERR_INVALID;
     if (a->batch < 0 || a->h < 1 || a->w < 1 || a->small_c < 1 || a->big_c < 1) return LICOS_ERR_INVALID;
     if (a->batch == 0) return LICOS_OK;
-    if (a->small_c % 64 != 0 || a->big_c % 64 != 0) return LICOS_ERR_UNSUPPORTED;
     const bool strided = a->kind == LICOS_CONV_5X5_S2 || a->kind == LICOS_DECONV_5X5_S2;
+    // channel counts: multiples of 64; the 1x1 kind also takes any multiple of 16 for `big` (patch matrices): the columns
+    // beyond big_c are TMA zero fill and are not flushed
+    if (a->small_c % 64 != 0 || a->big_c % (a->kind == LICOS_CONV_1X1 ? 16 : 64) != 0) return LICOS_ERR_UNSUPPORTED;
     if (!strided && a->kind != LICOS_CONV_3X3_S1 && a->kind != LICOS_CONV_1X1) return LICOS_ERR_INVALID;
     if (strided ? (a->h != (a->big_h + 1) / 2 || a->w != (a->big_w + 1) / 2) : (a->h != a->big_h || a->w != a->big_w))
         return LICOS_ERR_INVALID;
@@ -717,7 +721,9 @@ int licos_colsum_bf16(const void* x, int64_t rows, int channels, float* acc, voi
     return LICOS_OK;
 }
 
-int64_t licos_im2col5x5s2_kpad(int channels) { return channels < 1 ? LICOS_ERR_INVALID : (int64_t)(channels * 25 + 63) / 64 * 64; }
+// patch rows are padded to a multiple of 16 columns only (75 -> 80 for three bands): the weight-gradient kernel reads them
+// through a 64-channel TMA box whose out-of-range columns are zero fill, so narrower rows are simply less HBM traffic
+int64_t licos_im2col5x5s2_kpad(int channels) { return channels < 1 ? LICOS_ERR_INVALID : (int64_t)(channels * 25 + 15) / 16 * 16; }
 
 int licos_im2col5x5s2(const float* x, int batch, int channels, int h, int w, void* rows, void* stream) {
     if (!x || !rows || batch < 0 || channels < 1 || channels > 16 || h < 1 || w < 1) return LICOS_ERR_INVALID;

@@ -48,6 +48,9 @@ def _wgrad_ref(small, big, kind):
     (_lib.CONV_3X3_S1, 128, 320, (16, 16), (16, 16), 2),
     (_lib.CONV_1X1, 128, 128, (32, 32), (32, 32), 2),
     (_lib.CONV_1X1, 192, 64, (10, 7), (10, 7), 5),
+    (_lib.CONV_1X1, 128, 80, (24, 20), (24, 20), 3),     # 3-band patch matrix: 75 columns padded to 80
+    (_lib.CONV_1X1, 128, 32, (9, 33), (9, 33), 2),       # 1 band: 25 -> 32
+    (_lib.CONV_1X1, 128, 336, (8, 16), (8, 16), 2),      # 13 bands: 325 -> 336 = 128 + 128 + 80
     (_lib.CONV_5X5_S2, 128, 128, (64, 64), (128, 128), 8),
 ])
 def test_wgrad_vs_cpu(cuda, kind, cs, cb, hw, big_hw, batch):
@@ -137,7 +140,7 @@ def test_conv1x1_engine_and_im2col(cuda):
     img = torch.rand(2, 3, 20, 28, generator=g)
     rows = ops.im2col5x5s2(img.to(cuda))
     ref = F.unfold(img, 5, padding=2, stride=2).transpose(1, 2).reshape(2, 10, 14, 75)
-    assert rows.shape == (2, 10, 14, 128)
+    assert rows.shape == (2, 10, 14, 80)
     assert torch.equal(rows[..., :75].cpu(), _bf(ref))
     assert float(rows[..., 75:].abs().max()) == 0.0
 
