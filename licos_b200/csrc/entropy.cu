@@ -454,6 +454,69 @@ __device__ __forceinline__ float eb_static_bwd(const float* __restrict__ p, floa
     return d_out[0];
 }
 
+// Training-mode forward for the stock density network: the same arithmetic, in the same order, as eb_logits<3>, with
+// compile-time layer shapes (no per-layer offset arithmetic or width predicates).
+template <int NL, int F>
+__device__ __forceinline__ float eb_static_logits(const float* __restrict__ p, float x) {
+    float cur[F];
+#pragma unroll
+    for (int k = 0; k < F; ++k) cur[k] = 0.f;
+    cur[0] = x;
+    int off = 0;
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+        const int fi = (i == 0) ? 1 : F, fo = (i == NL - 1) ? 1 : F;
+        float nxt[F];
+#pragma unroll
+        for (int o = 0; o < F; ++o) {
+            float acc = 0.f;
+            if (o < fo) {
+#pragma unroll
+                for (int k = 0; k < F; ++k)
+                    if (k < fi) acc += p[off + o * fi + k] * cur[k];
+                acc += p[off + fo * fi + o];
+                if (i < NL - 1) acc += p[off + fo * fi + fo + o] * tanhf(acc);
+            }
+            nxt[o] = acc;
+        }
+#pragma unroll
+        for (int k = 0; k < F; ++k) cur[k] = nxt[k];
+        off += fo * fi + fo + (i < NL - 1 ? fo : 0);
+    }
+    return cur[0];
+}
+
+template <int NL, int F>
+__global__ void __launch_bounds__(256) eb_noise_static_kernel(EbMeta m, const float* __restrict__ x, const float* __restrict__ noise,
+                                                              uint64_t seed, const float* __restrict__ packed, int B, int C, int64_t hw,
+                                                              float* __restrict__ y_hat, float* __restrict__ lik) {
+    constexpr int kPpc = EbStatic<NL, F>::kPpc;
+    __shared__ float sp[kPpc];
+    const int c = blockIdx.y;
+    for (int i = threadIdx.x; i < kPpc; i += blockDim.x) sp[i] = packed[(size_t)c * kPpc + i];
+    __syncthreads();
+    const int64_t n = (int64_t)B * hw;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const int64_t b = j / hw, i = j - b * hw;
+        const int64_t e = (b * C + c) * hw + i;
+        const float nz = noise ? __ldcs(noise + e) : uniform_pm_half(seed, (uint64_t)e);
+        const float v = __ldcs(x + e) + nz;
+        const float lower = eb_static_logits<NL, F>(sp, v - 0.5f), upper = eb_static_logits<NL, F>(sp, v + 0.5f);
+        float l;
+        if (m.form == LICOS_EB_FORM_PLAIN) {
+            l = sigmoidf_(upper) - sigmoidf_(lower);
+        } else {
+            const float su = lower + upper;
+            const float s = (su > 0.f) ? -1.f : ((su < 0.f) ? 1.f : 0.f);
+            l = fabsf(sigmoidf_(s * upper) - sigmoidf_(s * lower));
+        }
+        if (m.bound > 0.f) l = fmaxf(l, m.bound);
+        __stcs(y_hat + e, v);
+        __stcs(lik + e, l);
+    }
+}
+
 template <int NL, int F>
 __global__ void __launch_bounds__(128) eb_train_bwd_static_kernel(EbMeta m, const float* __restrict__ y_hat,
                                                                   const float* __restrict__ g_lik, const float* __restrict__ g_yhat,
@@ -932,7 +995,10 @@ int licos_eb_forward_noise(const licos_eb_params* p, const float* x, const float
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     dim3 grid(gx, p->channels);
-    if (max_w <= 3) eb_noise_kernel<3><<<grid, 256, sm, s>>>(m, x, noise, seed, p->packed, batch, p->channels, hw, y_hat, lik);
+    bool stock = m.n_layers == 5 && m.ppc == EbStatic<5, 3>::kPpc;
+    for (int i = 1; i < 5 && stock; ++i) stock = m.widths[i] == 3;
+    if (stock) eb_noise_static_kernel<5, 3><<<grid, 256, 0, s>>>(m, x, noise, seed, p->packed, batch, p->channels, hw, y_hat, lik);
+    else if (max_w <= 3) eb_noise_kernel<3><<<grid, 256, sm, s>>>(m, x, noise, seed, p->packed, batch, p->channels, hw, y_hat, lik);
     else eb_noise_kernel<16><<<grid, 256, sm, s>>>(m, x, noise, seed, p->packed, batch, p->channels, hw, y_hat, lik);
     LICOS_CUDA_OK(cudaGetLastError());
     return LICOS_OK;

@@ -379,9 +379,9 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const uint4* __restric
 
 // rows[(b, oh, ow)][k] = x[b][c][2*oh + kh - 2][2*ow + kw - 2], k = (c*5 + kh)*5 + kw, zero padded to k_pad: the patch
 // matrix of a 5x5 stride-2 window over a fp32 NCHW tensor (first-layer / last-layer weight gradients).  A block owns
-// 32 consecutive output pixels of one row: the C x 5 x 67 input patch is read once, coalesced, into shared memory;
+// 64 consecutive output pixels of one row: the C x 5 x 131 input patch is read once, coalesced, into shared memory;
 // every thread then assembles 16-byte groups of 8 k's through a k -> patch-offset table and writes them coalesced.
-constexpr int kImPix = 32, kImPitch = 2 * kImPix + 4;
+constexpr int kImPix = 64, kImPitch = 2 * kImPix + 4;
 __global__ void __launch_bounds__(256) im2col5x5s2_kernel(const float* __restrict__ x, int B, int C, int H, int W, int OH, int OW,
                                                           int k_pad, int segs, __nv_bfloat16* __restrict__ rows) {
     extern __shared__ float im_smem[];
