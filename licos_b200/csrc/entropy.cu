@@ -371,11 +371,6 @@ __global__ void __launch_bounds__(128) eb_train_bwd_kernel(EbMeta m, const float
     for (int i = threadIdx.x; i < m.ppc; i += blockDim.x) atomicAdd(d_packed + (size_t)c * m.ppc + i, sacc[i]);
 }
 
-// tanh through one MUFU exponential and one fast division: absolute error ~1e-7 (tanhf's polynomial / exact-division path
-// costs ~25 instructions, and the backward sweep evaluates 24 of them per latent element).  Used by the BACKWARD kernel
-// only; the likelihoods the forward returns keep tanhf.
-__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
-
 // Fast path for the stock density network (filters (3,3,3,3): widths 1,3,3,3,3,1): every loop bound is a compile-time
 // constant, so activations and the 58 parameter-gradient accumulators live in registers.
 template <int NL, int F>
@@ -407,7 +402,7 @@ __device__ __forceinline__ float eb_static_fwd(const float* __restrict__ p, floa
                 for (int k = 0; k < F; ++k)
                     if (k < fi) acc += p[off + o * fi + k] * cur[k];
                 acc += p[off + fo * fi + o];
-                if (i < NL - 1) { th = tanh_fast(acc); acc += p[off + fo * fi + fo + o] * th; }
+                if (i < NL - 1) { th = tanhf(acc); acc += p[off + fo * fi + fo + o] * th; }
             }
             ths[i][o] = th;
             nxt[o] = acc;
