@@ -459,3 +459,12 @@ def test_wide_model_gradients_vs_oracle(cuda):
     _check_chain(cuda, net.g_a, ref.g_a, x, "g_a q6")
     y = torch.round(torch.randn(2, 320, 4, 6, generator=g) * 3)
     _check_chain(cuda, net.g_s, ref.g_s, y, "g_s q6", x_grad=True)
+
+
+@pytest.mark.parametrize("in_ch", [3, 13])
+def test_g_a_input_gradient_vs_oracle(cuda, in_ch):
+    """d loss / d image through g_a (the data gradient of the first layer: a 128 -> C_img transposed conv, fp32 NCHW out)."""
+    net, ref = _pair("bmshj2018-factorized", in_ch)
+    g = torch.Generator().manual_seed(17)
+    x = torch.rand(2, in_ch, 64, 64, generator=g)
+    _check_chain(cuda, net.g_a, ref.g_a, x, f"g_a c{in_ch} with input gradient", x_grad=True)
