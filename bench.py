@@ -185,6 +185,31 @@ class ClockSampler:
 # B200 arm
 # ---------------------------------------------------------------------------------------------
 
+def bind_to_gpu_numa_node(torch, local: int):
+    """Multi-GPU runs: pin this rank (and therefore the pinned host buffers it first-touches) to the NUMA node its GPU
+    hangs off, when the host exposes one.  Without it the host-buffer leg of ranks on the far socket crosses the
+    inter-socket link in both directions.  Returns the node or None; never raises."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:  # noqa: BLE001  (no sysfs, no such attribute, containerised cpuset: run unbound)
+        return None
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -196,6 +221,7 @@ def run_b200(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa_node = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
@@ -368,7 +394,8 @@ def run_b200(args):
             "clocks": clocks,
             "e2e": {"value": pix_per_step / (e2e_ms * 1e-3) / 1e6, "unit": "MPix/s",
                     "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                    "path": "pinned host x -> model.g_a / entropy_bottleneck / g_s -> x_hat, symbols, bpp on host"},
+                    "path": "pinned host x -> model.g_a / entropy_bottleneck / g_s -> x_hat, symbols, bpp on host",
+                    "rank0_numa_node": numa_node},
             "gpu_launches": n_launch,
             "roofline": {"bound": "tensor",
                          "kernel": "conv_igemm_kernel (6 launches per step: g_a[2,4,6], g_s[0,2,4], GDN/IGDN fused)",
