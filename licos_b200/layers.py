@@ -8,6 +8,7 @@ does arithmetic on every key, eval_script.py:70-71 loads them).
 from __future__ import annotations
 
 import os
+import warnings
 import weakref
 from typing import Optional
 
@@ -160,8 +161,14 @@ class FusedSequential(nn.Sequential):
             raise RuntimeError("licos_b200: g_a / g_s / h_a / h_s need CUDA tensors on a B200 (no CPU path exists)")
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             xin = torch.abs(x) if take_abs else x
-            if _EAGER_AUTOGRAD or not self._native_backward_ok(xin):
-                return self._eager_forward(xin)  # library (cuDNN) autograd: development comparison / odd shapes only
+            if _EAGER_AUTOGRAD:
+                return self._eager_forward(xin)  # development comparison against cuDNN autograd
+            if not self._native_backward_ok(xin):
+                # loud, not silent: this shape trains through torch's own kernels, not through this package's
+                warnings.warn(f"licos_b200: no native backward for input shape {tuple(xin.shape)} through {self.__class__.__name__} "
+                              "(stride-2 layers need even sizes, channel counts multiples of 64): using torch autograd",
+                              RuntimeWarning, stacklevel=2)
+                return self._eager_forward(xin)
             return self.train_forward(xin)
         return self.fused_forward(x, take_abs=take_abs, nhwc=nhwc)
 
