@@ -704,10 +704,11 @@ static unsigned long long* g_conv_probe = nullptr;
 // Development knobs, read once (tools/probe_conv.py experiments; none is needed in production):
 //   LICOS_FIRST_V1=1       route the first layer to the non-pipelined kernel
 //   LICOS_PREFER_NACC2=1   two single-buffered accumulators instead of one double-buffered one when both do not fit
+//   LICOS_NO_SMALL_TILES=1 keep 16-row tiles even when there are fewer of them than SMs
 //   LICOS_SA / LICOS_SB    force the slab / weight ring depths
 //   LICOS_DBG_FLAGS        bit 0 / 1: load every slab / weight ring slot only once (isolates the mainloop from data movement)
 struct DevKnobs {
-    bool first_v1, prefer_nacc2;
+    bool first_v1, prefer_nacc2, no_small_tiles;
     int sa, sb, dbg_flags;
 };
 static const DevKnobs& knobs() {
@@ -715,6 +716,7 @@ static const DevKnobs& knobs() {
         DevKnobs v{};
         v.first_v1 = getenv("LICOS_FIRST_V1") != nullptr;
         v.prefer_nacc2 = getenv("LICOS_PREFER_NACC2") != nullptr;
+        v.no_small_tiles = getenv("LICOS_NO_SMALL_TILES") != nullptr;
         if (const char* e = getenv("LICOS_SA")) v.sa = atoi(e);
         if (const char* e = getenv("LICOS_SB")) v.sb = atoi(e);
         if (const char* e = getenv("LICOS_DBG_FLAGS")) v.dbg_flags = atoi(e);
@@ -1113,6 +1115,16 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     if (n_acc == 2 && 2 * groups * 2 * pl.N > (int)kTmemCols && 2 * groups * pl.N <= (int)kTmemCols &&
         !knobs().prefer_nacc2)
         n_acc = 1;  // one double-buffered accumulator beats two single-buffered ones that share weight tiles
+    if (n_acc == 2 && !knobs().no_small_tiles) {
+        // Small batches (a 32-tile training step, the 16 x 16 latent end of the transforms): 16-row tiles would leave SMs
+        // without a tile, so take 8-row tiles (twice as many) while those still fit one wave.  Never true at the inference batch.
+        int sms_q = 0;
+        if (sm_count_of(a, &sms_q) == LICOS_OK) {
+            const int64_t tiles16 = (int64_t)a->batch * ((p.grid_h + 2 * kAccRows - 1) / (2 * kAccRows)) *
+                                    ((p.grid_w + kTileW - 1) / kTileW) * pl.n_split;
+            if (2 * tiles16 <= sms_q) n_acc = 1;  // (measured: with 128 tiles of 148, halving them costs more than it fills)
+        }
+    }
     if (groups * n_acc * pl.N > (int)kTmemCols) return LICOS_ERR_UNSUPPORTED;
     p.n_acc = n_acc;
     p.n_buf = (2 * groups * n_acc * pl.N <= (int)kTmemCols) ? 2 : 1;
