@@ -555,20 +555,42 @@ int licos_conv_wgrad(const licos_wgrad_args* a, void* stream) {
         int64_t total = 0;
         for (int g = 0; g < p.n_groups; ++g) total += (int64_t)p.groups[g].n_taps * p.m_blocks * p.n_blocks;
         // Every unit ends with a flush of its accumulators (up to 256 KB of red.add traffic, the tensor pipe idle
-        // meanwhile), so a unit must be long enough to amortise it: at most `per_sm` units per SM, at least
-        // `min_tiles` pixel tiles each (development knobs LICOS_WGRAD_UNITS_PER_SM / LICOS_WGRAD_MIN_TILES).
-        static const int per_sm = [] { const char* e = getenv("LICOS_WGRAD_UNITS_PER_SM"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 2; }();
+        // meanwhile), so the default is ONE unit per SM, all of equal cost (measured: 96.7 us against 101.3 us with two per SM
+        // for 128->128 @ 64^2 x 32 tiles, 35 against 47 us one level down), and at least `min_tiles` pixel tiles per unit
+        // (development knobs LICOS_WGRAD_UNITS_PER_SM / LICOS_WGRAD_MIN_TILES).
+        static const int per_sm = [] { const char* e = getenv("LICOS_WGRAD_UNITS_PER_SM"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 1; }();
         static const int min_tiles = [] { const char* e = getenv("LICOS_WGRAD_MIN_TILES"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
         const int64_t target = (int64_t)per_sm * sms;
-        int n = 0;
+        // largest-remainder allocation: exactly `target` units in all (when the caps allow), each combo's share proportional
+        // to its tap count, so that every unit costs the same and no CTA ends up with one unit more than the others
+        int share[kWgMaxCombos];
+        int64_t rem[kWgMaxCombos];
+        int64_t cap = n_tiles / min_tiles;
+        if (cap < 1) cap = 1;
+        int64_t given = 0;
         for (int c = 0; c < p.n_combos; ++c) {
             const int g = c / (p.m_blocks * p.n_blocks);
-            int64_t s = ((int64_t)p.groups[g].n_taps * target + total / 2) / total;
-            if (s > n_tiles / min_tiles) s = n_tiles / min_tiles;
-            if (s < 1) s = 1;
-            if (s > n_tiles) s = n_tiles;
+            const int64_t num = (int64_t)p.groups[g].n_taps * target;
+            int64_t sh = num / total;
+            rem[c] = num % total;
+            if (sh < 1) { sh = 1; rem[c] = -1; }
+            if (sh >= cap) { sh = cap; rem[c] = -1; }
+            share[c] = (int)sh;
+            given += sh;
+        }
+        while (given < target) {
+            int best = -1;
+            for (int c = 0; c < p.n_combos; ++c)
+                if (rem[c] >= 0 && (best < 0 || rem[c] > rem[best])) best = c;
+            if (best < 0) break;
+            ++share[best];
+            rem[best] = -1;
+            ++given;
+        }
+        int n = 0;
+        for (int c = 0; c < p.n_combos; ++c) {
             p.unit_begin[c] = n;
-            n += (int)s;
+            n += share[c];
         }
         p.unit_begin[p.n_combos] = n;
         p.n_units = n;

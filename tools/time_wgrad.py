@@ -32,5 +32,5 @@ for name, kind, s, b in shapes:
     flop = 2.0 * taps * s[2] * b[2] * B * s[0] * s[1]
     tot += us
     print(f"{name:36s} {us:8.1f} us  {flop / us / 1e6:7.1f} TFLOP/s")
-print(f"sum {tot:.1f} us  (LICOS_WGRAD_UNITS_PER_SM={os.environ.get('LICOS_WGRAD_UNITS_PER_SM', '2')}, "
-      f"LICOS_WGRAD_MIN_TILES={os.environ.get('LICOS_WGRAD_MIN_TILES', '1')})")
+print(f"sum {tot:.1f} us  (LICOS_WGRAD_UNITS_PER_SM={os.environ.get('LICOS_WGRAD_UNITS_PER_SM', '1')}, "
+      f"LICOS_WGRAD_MIN_TILES={os.environ.get('LICOS_WGRAD_MIN_TILES', '8')})")
