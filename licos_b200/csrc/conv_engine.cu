@@ -705,10 +705,11 @@ static unsigned long long* g_conv_probe = nullptr;
 //   LICOS_FIRST_V1=1       route the first layer to the non-pipelined kernel
 //   LICOS_PREFER_NACC2=1   two single-buffered accumulators instead of one double-buffered one when both do not fit
 //   LICOS_NO_SMALL_TILES=1 keep 16-row tiles even when there are fewer of them than SMs
+//   LICOS_FORCE_NACC1=1    8-row tiles everywhere (tile-quantisation experiments at small batches)
 //   LICOS_SA / LICOS_SB    force the slab / weight ring depths
 //   LICOS_DBG_FLAGS        bit 0 / 1: load every slab / weight ring slot only once (isolates the mainloop from data movement)
 struct DevKnobs {
-    bool first_v1, prefer_nacc2, no_small_tiles;
+    bool first_v1, prefer_nacc2, no_small_tiles, force_nacc1;
     int sa, sb, dbg_flags;
 };
 static const DevKnobs& knobs() {
@@ -717,6 +718,7 @@ static const DevKnobs& knobs() {
         v.first_v1 = getenv("LICOS_FIRST_V1") != nullptr;
         v.prefer_nacc2 = getenv("LICOS_PREFER_NACC2") != nullptr;
         v.no_small_tiles = getenv("LICOS_NO_SMALL_TILES") != nullptr;
+        v.force_nacc1 = getenv("LICOS_FORCE_NACC1") != nullptr;
         if (const char* e = getenv("LICOS_SA")) v.sa = atoi(e);
         if (const char* e = getenv("LICOS_SB")) v.sb = atoi(e);
         if (const char* e = getenv("LICOS_DBG_FLAGS")) v.dbg_flags = atoi(e);
@@ -1125,6 +1127,7 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
             if (2 * tiles16 <= sms_q) n_acc = 1;  // (measured: with 128 tiles of 148, halving them costs more than it fills)
         }
     }
+    if (knobs().force_nacc1) n_acc = 1;  // experiment: 8-row tiles everywhere
     if (groups * n_acc * pl.N > (int)kTmemCols) return LICOS_ERR_UNSUPPORTED;
     p.n_acc = n_acc;
     p.n_buf = (2 * groups * n_acc * pl.N <= (int)kTmemCols) ? 2 : 1;

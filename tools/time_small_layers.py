@@ -9,7 +9,8 @@ from licos_b200 import _lib as L, ops  # noqa: E402
 
 dev = torch.device("cuda", 0)
 B = 32
-cases = [("conv 128->128 in 64 (g_a[4])", L.CONV_5X5_S2, 128, 128, 64, L.LAYOUT_NHWC_BF16),
+cases = [("conv 128->128 in 128 (g_a[2])", L.CONV_5X5_S2, 128, 128, 128, L.LAYOUT_NHWC_BF16),
+         ("conv 128->128 in 64 (g_a[4])", L.CONV_5X5_S2, 128, 128, 64, L.LAYOUT_NHWC_BF16),
          ("conv 128->192 in 32 (g_a[6], NCHW out)", L.CONV_5X5_S2, 128, 192, 32, L.LAYOUT_NCHW_F32),
          ("deconv 192->128 in 16 (g_s[0])", L.DECONV_5X5_S2, 192, 128, 16, L.LAYOUT_NHWC_BF16),
          ("deconv 128->128 in 32 (g_s[2])", L.DECONV_5X5_S2, 128, 128, 32, L.LAYOUT_NHWC_BF16),
@@ -32,4 +33,5 @@ for name, kind, ci, co, hw, ol in cases:
     us = e0.elapsed_time(e1) / 20 * 1e3
     tot += us
     print(f"{name:42s} {us:7.1f} us")
-print(f"sum {tot:.1f} us (LICOS_NO_SMALL_TILES={os.environ.get('LICOS_NO_SMALL_TILES', '')})")
+print(f"sum {tot:.1f} us (LICOS_NO_SMALL_TILES={os.environ.get('LICOS_NO_SMALL_TILES', '')}, "
+      f"LICOS_FORCE_NACC1={os.environ.get('LICOS_FORCE_NACC1', '')})")
