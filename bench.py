@@ -376,6 +376,13 @@ def run_b200(args):
             traffic = json.load(f).get("conv_igemm_dram_bytes_per_launch")
 
     if rank == 0:
+        train = None
+        if not args.no_train:  # before the CPU baseline: its idle worker threads would slow the eager Python loop
+            torch.cuda.empty_cache()
+            try:  # an extra leg: it must never cost the headline line
+                train = run_train_step(torch, device)
+            except Exception as e:  # noqa: BLE001
+                train = {"error": f"{type(e).__name__}: {e}"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             sd = {k: v.cpu() for k, v in net.state_dict().items()}
@@ -416,12 +423,8 @@ def run_b200(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        if not args.no_train:
-            torch.cuda.empty_cache()
-            try:  # an extra leg: it must never cost the headline line
-                line["train_step"] = run_train_step(torch, device)
-            except Exception as e:  # noqa: BLE001
-                line["train_step"] = {"error": f"{type(e).__name__}: {e}"}
+        if train is not None:
+            line["train_step"] = train
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -456,7 +459,7 @@ def run_train_step(torch, device, steps: int = 20):
         return loss.detach()
 
     def timed(fn, n):
-        for _ in range(3):
+        for _ in range(5):
             fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
