@@ -130,7 +130,7 @@ typedef struct licos_wgrad_args {
     int small_c, big_c; /* channels, multiples of 64 (CONV_1X1: big_c any multiple of 16)           */
     const void* small_t; /* bf16 NHWC: Conv2d -> the OUTPUT gradient; ConvTranspose2d -> the layer INPUT */
     const void* big_t;   /* bf16 NHWC: Conv2d -> the layer INPUT; ConvTranspose2d -> the OUTPUT gradient */
-    float* out;       /* fp32 [KH*KW][small_c][big_c], ACCUMULATED into with red.add: the caller zeroes it */
+    float* out;       /* fp32 [KH*KW][small_c][big_c], 16-byte aligned, ACCUMULATED into with red.add: the caller zeroes it */
     int sm_count;     /* 0 = query the device                                                      */
     int reserved;
 } licos_wgrad_args;
@@ -142,7 +142,8 @@ int licos_conv_wgrad(const licos_wgrad_args* args, void* stream);
 /* The whole GDN / IGDN backward in ONE pass over x and g (channels == 128; other widths return LICOS_ERR_UNSUPPORTED and
  * take the sequence below): x = the layer's pre-activation, g = the gradient of its output, both bf16 [n_pixels][channels];
  * gamma_hat_bf16 / beta_hat from licos_gdn_pack.  Writes dx (bf16) and ACCUMULATES d_gamma_hat [C][C], d_beta_hat [C] and,
- * when non-NULL, d_bias [C] (the column sums of dx = the preceding conv's bias.grad); the caller zeroes them. */
+ * when non-NULL, d_bias [C] (the column sums of dx = the preceding conv's bias.grad); the caller zeroes them
+ * (d_gamma_hat 16-byte aligned: vector red.add). */
 int licos_gdn_backward(const void* x, const void* g, const void* gamma_hat_bf16, const float* beta_hat, int inverse,
                        int64_t n_pixels, int channels, void* dx, float* d_gamma_hat, float* d_beta_hat, float* d_bias,
                        int sm_count, void* stream);
