@@ -501,6 +501,7 @@ extern "C" {
 
 int licos_conv_wgrad(const licos_wgrad_args* a, void* stream) {
     if (!a || !a->small_t || !a->big_t || !a->out) return LICOS_ERR_INVALID;
+    if (((uintptr_t)a->out & 15) != 0) return LICOS_ERR_INVALID;  // the flush is a 16-byte vector red.add
     if (a->batch < 0 || a->h < 1 || a->w < 1 || a->small_c < 1 || a->big_c < 1) return LICOS_ERR_INVALID;
     if (a->batch == 0) return LICOS_OK;
     const bool strided = a->kind == LICOS_CONV_5X5_S2 || a->kind == LICOS_DECONV_5X5_S2;
@@ -634,6 +635,7 @@ int licos_gdn_backward(const void* x, const void* g, const void* gamma_hat_bf16,
                        int64_t n_pixels, int channels, void* dx, float* d_gamma_hat, float* d_beta_hat, float* d_bias,
                        int sm_count, void* stream) {
     if (!x || !g || !gamma_hat_bf16 || !beta_hat || !dx || !d_gamma_hat || !d_beta_hat || n_pixels < 0) return LICOS_ERR_INVALID;
+    if (((uintptr_t)d_gamma_hat & 15) != 0) return LICOS_ERR_INVALID;
     if (channels != kGbC) return LICOS_ERR_UNSUPPORTED;  // other widths: the unfused sequence (see the header)
     if (n_pixels == 0) return LICOS_OK;
     const int64_t tiles = (n_pixels + 127) / 128;
