@@ -8,6 +8,7 @@ thing no matter how well they match their own formulas.
   * weight gradients == sum over pixels of (small tensor) x (big tensor shifted by the tap)        [licos_conv_wgrad]
   * GDN / IGDN backward == the norm / d_norm / t / dx sequence of licos_gdn_backward, incl. gamma, beta gradients
   * GaussianConditional backward == phi at the two bin edges                                       [licos_gc_backward]
+  * EntropyBottleneck backward == per-element reverse sweep through the packed parameters   [licos_eb_backward + param_grads]
 """
 import math
 
@@ -161,3 +162,92 @@ def test_gaussian_conditional_backward_formula(with_means):
     assert _close(d_y, y.grad) and _close(d_s, scales.grad)
     if with_means:
         assert _close(-d_y, means.grad)
+
+
+@pytest.mark.parametrize("form", ["plain", "stable"])
+def test_entropy_bottleneck_backward_sweep(form):
+    """licos_eb_backward + licos_eb_param_grads restated per element in float64: forward through the packed parameters
+    (softplus / tanh applied), reverse sweep with the activations kept, LowerBound gating on the likelihood, then the chain
+    back to the raw parameters -- against autograd through the oracle's EntropyBottleneck."""
+    torch.manual_seed(9)
+    C = 3
+    eb = R.EntropyBottleneck(C).double()
+    eb.likelihood_form = form
+    with torch.no_grad():
+        for n, p in eb.named_parameters():
+            if "factor" in n:
+                p.normal_(0, 0.5)
+            elif "matrix" in n:
+                p.add_(torch.randn_like(p) * 0.3)
+    x = (torch.randn(2, C, 3, 4, dtype=torch.float64) * 4)
+    x[0, 0, 0, :2] = torch.tensor([60.0, -70.0])     # likelihood under the 1e-9 bound
+    x.requires_grad_(True)
+    noise = torch.rand(x.shape, dtype=torch.float64) - 0.5
+    y_hat, lik = eb(x, training=True, noise=noise)
+    g_lik = torch.randn(x.shape, dtype=torch.float64)
+    g_lik[0, 0, 0, 0] = -1.0                          # negative gradient passes the bound, positive does not
+    g_lik[0, 0, 0, 1] = 1.0
+    g_yhat = torch.randn(x.shape, dtype=torch.float64)
+    ((lik * g_lik).sum() + (y_hat * g_yhat).sum()).backward()
+
+    n_layers = len(eb.filters) + 1
+    mats = [F.softplus(getattr(eb, f"_matrix{i}").detach()) for i in range(n_layers)]
+    bias = [getattr(eb, f"_bias{i}").detach() for i in range(n_layers)]
+    facs = [torch.tanh(getattr(eb, f"_factor{i}").detach()) for i in range(n_layers - 1)]
+    d_m = [torch.zeros_like(m) for m in mats]
+    d_b = [torch.zeros_like(b) for b in bias]
+    d_f = [torch.zeros_like(f) for f in facs]
+    d_x = torch.zeros_like(x)
+    sig = torch.sigmoid
+    for b_ in range(x.shape[0]):
+        for c in range(C):
+            for i_ in range(x.shape[2]):
+                for j_ in range(x.shape[3]):
+                    v = y_hat[b_, c, i_, j_].detach()
+
+                    def fwd(inp):
+                        cur, ins, ths = inp.reshape(1, 1), [], []
+                        for L in range(n_layers):
+                            ins.append(cur)
+                            a = mats[L][c] @ cur + bias[L][c]
+                            th = torch.tanh(a) if L < n_layers - 1 else torch.zeros_like(a)
+                            ths.append(th)
+                            cur = a + facs[L][c] * th if L < n_layers - 1 else a
+                        return cur.reshape(()), ins, ths
+
+                    def bwd(seed, ins, ths):
+                        d_out = seed.reshape(1, 1)
+                        for L in range(n_layers - 1, -1, -1):
+                            if L < n_layers - 1:
+                                d_f[L][c] += d_out * ths[L]
+                                da = d_out * (1 + facs[L][c] * (1 - ths[L] ** 2))
+                            else:
+                                da = d_out
+                            d_b[L][c] += da
+                            d_m[L][c] += da @ ins[L].t()
+                            d_out = mats[L][c].t() @ da
+                        return d_out.reshape(())
+
+                    lower, ins_l, ths_l = fwd(v - 0.5)
+                    upper, ins_u, ths_u = fwd(v + 0.5)
+                    if form == "plain":
+                        a, bq = sig(upper), sig(lower)
+                        likv, su, sl = a - bq, a * (1 - a), -bq * (1 - bq)
+                    else:
+                        s = -torch.sign(lower + upper)
+                        a, bq = sig(s * upper), sig(s * lower)
+                        likv = (a - bq).abs()
+                        sg = torch.sign(a - bq)
+                        su, sl = sg * s * a * (1 - a), -sg * s * bq * (1 - bq)
+                    gl = g_lik[b_, c, i_, j_]
+                    if not (likv >= 1e-9 or gl < 0):
+                        gl = gl * 0
+                    d_x[b_, c, i_, j_] = bwd(gl * su, ins_u, ths_u) + bwd(gl * sl, ins_l, ths_l) + g_yhat[b_, c, i_, j_]
+    assert _close(d_x, x.grad, 1e-9)
+    for L in range(n_layers):
+        raw_m = getattr(eb, f"_matrix{L}")
+        assert _close(d_m[L] * torch.sigmoid(raw_m.detach()), raw_m.grad, 1e-9)          # d softplus = sigmoid
+        assert _close(d_b[L], getattr(eb, f"_bias{L}").grad, 1e-9)
+        if L < n_layers - 1:
+            raw_f = getattr(eb, f"_factor{L}")
+            assert _close(d_f[L] * (1 - torch.tanh(raw_f.detach()) ** 2), raw_f.grad, 1e-9)
