@@ -106,10 +106,6 @@ typedef struct licos_conv_args {
 /* Scratch bytes licos_conv_forward needs for these args (0 unless in_layout == NCHW_F32). */
 int64_t licos_conv_workspace_bytes(const licos_conv_args* args);
 
-/* Development aid: when non-NULL, every conv launch writes 16 uint64 cycle counters per CTA (waits of each
- * warp role, epilogue stages) to this device buffer (>= 16 * SM count entries).  NULL disables it. */
-void licos_debug_set_conv_probe(unsigned long long* device_buf);
-
 /* One conv / deconv layer with its fused epilogue.  Output spatial size:
  * CONV_5X5_S2 -> ceil(in/2), DECONV_5X5_S2 -> 2*in, CONV_3X3_S1 -> in. */
 int licos_conv_forward(const licos_conv_args* args, void* stream);

@@ -74,7 +74,6 @@ SIGNATURES = {
     "licos_gdn_pack": (c_int, [c_vp, c_vp, c_int, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp]),
     "licos_conv_workspace_bytes": (c_i64, [ctypes.POINTER(ConvArgs)]),
     "licos_conv_forward": (c_int, [ctypes.POINTER(ConvArgs), c_vp]),
-    "licos_debug_set_conv_probe": (None, [c_vp]),
     "licos_conv_wgrad": (c_int, [ctypes.POINTER(WgradArgs), c_vp]),
     "licos_gdn_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "licos_square_bf16": (c_int, [c_vp, c_vp, c_i64, c_vp]),

@@ -97,7 +97,7 @@ struct ConvParams {
     int jobs_per_pass;  // accumulators per pass (n_groups * n_acc): each is one epilogue job
     int n_buf;  // TMEM accumulator sets (2 = the epilogue of pass p overlaps the mainloop of pass p+1)
     int total_tiles;
-    unsigned long long* dbg;  // optional per-CTA cycle probes (licos_debug_set_conv_probe)
+    unsigned long long* dbg;  // optional per-CTA cycle probes (licos_internal_set_conv_probe, development only)
     int dbg_flags;            // LICOS_DBG_FLAGS experiments: 1 = A slabs loaded only once per ring slot, 2 = same for weights
 };
 
@@ -1015,7 +1015,10 @@ int licos_gdn_pack(const float* beta, const float* gamma, int channels, float be
     return LICOS_OK;
 }
 
-void licos_debug_set_conv_probe(unsigned long long* device_buf) { g_conv_probe = device_buf; }
+// Development aid, deliberately NOT part of include/licos_b200.h: when non-NULL, every conv launch writes 16 uint64 cycle
+// counters per CTA (waits of each warp role, epilogue stages) to this device buffer (>= 16 * SM count entries).
+// tools/probe_conv.py binds it ad hoc.
+void licos_internal_set_conv_probe(unsigned long long* device_buf) { g_conv_probe = device_buf; }
 
 int64_t licos_conv_workspace_bytes(const licos_conv_args* a) {
     if (!a) return LICOS_ERR_INVALID;

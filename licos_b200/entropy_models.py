@@ -6,9 +6,11 @@ Division of labour:
   * quantize("symbols") / build_indexes / dequantize -> bit-exact integer kernels;
   * update() -> host logic exactly as upstream (torch CPU ops for the tiny PMF tables) + the C++
     licos_pmf_to_quantized_cdf; run once per model (eval_script.py:72,88);
-  * compress()/decompress() -> symbols on the GPU, one D2H per batch, C++ rANS on host threads;
-  * forward(training=True) with autograd on -> the noise kernel + licos_eb_backward (training step, train.py:190-193);
-    the eval-mode-with-autograd corner and GaussianConditional keep the differentiable torch expression.
+  * compress()/decompress() -> symbols, indexes and the rANS coder stay on the GPU (csrc/rans_device.cu, bitstream-identical
+    to the host coder in csrc/host_codec.cpp, which remains the fallback for streams that overflow the scratch row);
+  * forward() with autograd on -> the noise (training) or rounding (eval) kernel forward, licos_eb_backward /
+    licos_gc_backward back (training step, train.py:190-193).  There is no torch-expression path on the device:
+    inputs the kernels do not take (non-fp32, fewer than 2 dims) raise.
 """
 from __future__ import annotations
 
@@ -40,7 +42,7 @@ def _wants_grad(module: nn.Module, *tensors: Optional[Tensor]) -> bool:
     return any(p.requires_grad for p in module.parameters())
 
 
-_EAGER_AUTOGRAD = bool(int(os.environ.get("LICOS_EAGER_AUTOGRAD", "0")))  # development: torch-expression autograd
+EB_NATIVE_BACKWARD_MAX_PPC = 320  # kEbMaxPpc in csrc/entropy.cu: filters up to (13, 13, 3, 3) (298 parameters per channel)
 
 
 def _split_raw(eb, raw):
@@ -71,14 +73,19 @@ class _EbTrainFn(torch.autograd.Function):
     (d x, per-channel parameter gradients reduced in the block), then one launch back to the raw parameters."""
 
     @staticmethod
-    def forward(ctx, eb, x, noise, seed, *raw):
+    def forward(ctx, eb, x, noise, seed, training, *raw):
         ebp = _native_packed(eb, raw)
-        if noise is None and seed is None:
-            # device-side draw from torch's generator: no host sync in the training step, and legal under graph capture
-            noise = torch.empty_like(x).uniform_(-0.5, 0.5)
-        y_hat, lik = ops.eb_forward_noise(ebp, x.detach().contiguous(), None if noise is None else noise.contiguous(),
-                                          0 if seed is None else seed)
-        ctx.eb, ctx.ebp = eb, ebp
+        if not training:
+            # eval mode under autograd (e.g. a validation loss that is differentiated): rounding has zero gradient with
+            # respect to x, the density parameters get theirs from the same backward kernel evaluated at y_hat
+            y_hat, lik = ops.eb_forward_eval(ebp, x.detach().contiguous())
+        else:
+            if noise is None and seed is None:
+                # device-side draw from torch's generator: no host sync in the training step, legal under graph capture
+                noise = torch.empty_like(x).uniform_(-0.5, 0.5)
+            y_hat, lik = ops.eb_forward_noise(ebp, x.detach().contiguous(), None if noise is None else noise.contiguous(),
+                                              0 if seed is None else seed)
+        ctx.eb, ctx.ebp, ctx.training = eb, ebp, bool(training)
         ctx.save_for_backward(y_hat, *raw)
         return y_hat, lik
 
@@ -89,12 +96,14 @@ class _EbTrainFn(torch.autograd.Function):
         g_yhat = None if g_yhat is None else g_yhat.contiguous()
         g_lik = None if g_lik is None else g_lik.contiguous()
         d_x, d_packed = ops.eb_backward(ctx.ebp, y_hat, g_lik, g_yhat)
+        if not ctx.training:
+            d_x = torch.zeros_like(d_x)  # y_hat = round(x - median) + median
         ms, bs, fs = _split_raw(eb, [t.detach().contiguous() for t in raw])
         gm, gb, gf = ops.eb_param_grads(ms, bs, fs, d_packed, (1,) + tuple(eb.filters) + (1,))
         grads = []
         for i in range(len(ms)):
             grads += [gm[i], gb[i]] + ([gf[i]] if i < len(fs) else [])
-        return (None, d_x, None, None, *grads)
+        return (None, d_x, None, None, None, *grads)
 
 
 class _EbAuxLossFn(torch.autograd.Function):
@@ -121,15 +130,15 @@ class _GcTrainFn(torch.autograd.Function):
     (gradients of y, the scales and, when given, the means; LowerBound's rule on both bounds)."""
 
     @staticmethod
-    def forward(ctx, gc, y, scales, means, noise):
-        if noise is None:
+    def forward(ctx, gc, y, scales, means, noise, training):
+        if noise is None and training:
             noise = torch.empty_like(y).uniform_(-0.5, 0.5)  # device-side draw: no host sync, graph-capture safe
         y, scales = y.detach().contiguous(), scales.detach().contiguous()
         means = None if means is None else means.detach().contiguous()
         bound = gc.likelihood_bound if gc.use_likelihood_bound else 0.0
-        y_hat, lik = ops.gc_forward(y, scales, means, noise.contiguous(), training=True, scale_bound=gc._scale_bound_f,
-                                    likelihood_bound=bound)
-        ctx.gc, ctx.bound, ctx.has_means = gc, bound, means is not None
+        y_hat, lik = ops.gc_forward(y, scales, means, noise.contiguous() if training else None, training=bool(training),
+                                    scale_bound=gc._scale_bound_f, likelihood_bound=bound)
+        ctx.gc, ctx.bound, ctx.has_means, ctx.training = gc, bound, means is not None, bool(training)
         ctx.save_for_backward(y_hat, scales, *([means] if means is not None else []))
         return y_hat, lik
 
@@ -140,7 +149,12 @@ class _GcTrainFn(torch.autograd.Function):
         d_y, d_s, d_m = ops.gc_backward(y_hat, scales, means, None if g_lik is None else g_lik.contiguous(),
                                         None if g_yhat is None else g_yhat.contiguous(), ctx.gc._scale_bound_f, ctx.bound,
                                         want_means=ctx.has_means and ctx.needs_input_grad[3])
-        return None, d_y, d_s, d_m, None
+        if not ctx.training:
+            # y_hat = round(y - means) + means: no gradient reaches y, the means only see the pass-through of y_hat
+            d_y = torch.zeros_like(d_y)
+            if d_m is not None:
+                d_m = g_yhat.contiguous() if g_yhat is not None else torch.zeros_like(d_m)
+        return None, d_y, d_s, d_m, None, None
 
 
 class EntropyModel(nn.Module):
@@ -273,7 +287,10 @@ class EntropyBottleneck(EntropyModel):
     """Fully-factorized density (Balle et al. 2018).  ``filters`` may be any widths <= 16: LICOS uses
     ``(in_channels, in_channels, 3, 3)`` (/root/reference/licos/model_utils.py:25-29)."""
 
-    # "plain" = CompressAI >= 1.2 forward; "stable" = the sign-stabilised form (<= 1.1, still used in update()).
+    # "plain" = CompressAI >= 1.2 (forward and update() both call the tuple-returning _likelihood: sigmoid difference);
+    # "stable" = the sign-stabilised form of <= 1.1.x (forward and update() alike).  One switch drives both, as upstream:
+    # the integer tables update() writes must describe the same density forward() evaluates, or strings coded by one
+    # release are not decodable by the other on the channels where the two forms round differently.
     likelihood_form = "plain"
 
     def __init__(self, channels: int, *args, tail_mass: float = 1e-9, init_scale: float = 10,
@@ -311,7 +328,14 @@ class EntropyBottleneck(EntropyModel):
     def _get_medians(self) -> Tensor:
         return self.quantiles[:, :, 1:2]
 
-    # ------------------------------------------------------------------ differentiable / host expressions
+    def __getstate__(self):
+        # the kernel parameter block holds a ctypes struct with raw device pointers: a cache, never part of a copy / pickle
+        # (copy.deepcopy(net) for EMA / best-model snapshots, torch.save(net), DataParallel replicas)
+        state = self.__dict__.copy()
+        state["_packed"] = state["_packed_key"] = None
+        return state
+
+    # ------------------------------------------------------------------ host expressions (update(), CPU-side loss value)
     def _logits_cumulative(self, inputs: Tensor, stop_gradient: bool) -> Tensor:
         logits = inputs
         for i in range(len(self.filters) + 1):
@@ -338,7 +362,7 @@ class EntropyBottleneck(EntropyModel):
         return likelihood, lower, upper
 
     def loss(self) -> Tensor:
-        if (self.quantiles.is_cuda and torch.is_grad_enabled() and self.quantiles.requires_grad and not _EAGER_AUTOGRAD
+        if (self.quantiles.is_cuda and torch.is_grad_enabled() and self.quantiles.requires_grad
                 and self.quantiles.dtype == torch.float32):
             return _EbAuxLossFn.apply(self, self.quantiles, *self._params()[:-1])
         logits = self._logits_cumulative(self.quantiles, stop_gradient=True)
@@ -358,7 +382,7 @@ class EntropyBottleneck(EntropyModel):
             pmf_length = maxima + minima + 1
             max_length = int(pmf_length.max().item())
             samples = torch.arange(max_length)[None, :] + pmf_start[:, None, None]
-            pmf, lower, upper = host._likelihood(samples, stop_gradient=True, form="stable")
+            pmf, lower, upper = host._likelihood(samples, stop_gradient=True, form=self.likelihood_form)
             pmf = pmf[:, 0, :]
             tail_mass = torch.sigmoid(lower[:, 0, :1]) + torch.sigmoid(-upper[:, 0, -1:])
             quantized_cdf = self._pmf_to_cdf(pmf, tail_mass, pmf_length, max_length)
@@ -404,9 +428,15 @@ class EntropyBottleneck(EntropyModel):
             training = self.training
         _require_cuda(x, "EntropyBottleneck.forward")
         if _wants_grad(self, x):
-            if training and x.dim() >= 2 and x.dtype == torch.float32 and not _EAGER_AUTOGRAD:
-                return _EbTrainFn.apply(self, x, noise, seed, *self._params()[:-1])
-            return self._forward_autograd(x, training, noise)
+            if x.dim() < 2 or x.dtype != torch.float32:
+                raise NotImplementedError("licos_b200: EntropyBottleneck under autograd takes float32 (B, C, ...) tensors")
+            ppc = sum(p[0].numel() for p in self._params()[:-1])
+            if ppc > EB_NATIVE_BACKWARD_MAX_PPC:
+                # said here, at forward time, not from inside autograd's backward in the middle of a training step
+                raise NotImplementedError(
+                    f"licos_b200: the backward kernel holds at most {EB_NATIVE_BACKWARD_MAX_PPC} density parameters per "
+                    f"channel; filters={self.filters} need {ppc} (LICOS uses (c, c, 3, 3) with c in 1, 3, 13)")
+            return _EbTrainFn.apply(self, x, noise, seed, training, *self._params()[:-1])
         x = x.contiguous()
         ebp = self.packed_params()
         if not training:
@@ -424,25 +454,6 @@ class EntropyBottleneck(EntropyModel):
             raise RuntimeError("forward_fused is an inference path: call it under torch.no_grad()")
         return ops.eb_forward_eval_fused(self.packed_params(), x.contiguous(), want_symbols=want_symbols,
                                          want_nhwc=want_nhwc)
-
-    def _forward_autograd(self, x: Tensor, training: bool, noise: Optional[Tensor]):
-        perm = [1, 0] + list(range(2, x.dim()))
-        xp = x.permute(*perm).contiguous()
-        shape = xp.size()
-        values = xp.reshape(xp.size(0), 1, -1)
-        if training:
-            nz = (torch.empty_like(values).uniform_(-0.5, 0.5) if noise is None
-                  else noise.permute(*perm).contiguous().reshape(values.shape))
-            outputs = values + nz
-        else:
-            med = self._get_medians().detach()
-            outputs = torch.round(values - med) + med
-        likelihood, _, _ = self._likelihood(outputs)
-        if self.use_likelihood_bound:
-            likelihood = self.likelihood_lower_bound(likelihood)
-        outputs = outputs.reshape(shape).permute(*perm).contiguous()
-        likelihood = likelihood.reshape(shape).permute(*perm).contiguous()
-        return outputs, likelihood
 
     # ------------------------------------------------------------------ integer path
     @staticmethod
@@ -586,18 +597,10 @@ class GaussianConditional(EntropyModel):
             training = self.training
         _require_cuda(inputs, "GaussianConditional.forward")
         if _wants_grad(self, inputs, scales, means):
-            if (training and not _EAGER_AUTOGRAD and inputs.dtype == torch.float32 and scales.shape == inputs.shape
-                    and (means is None or means.shape == inputs.shape)):
-                return _GcTrainFn.apply(self, inputs, scales, means, noise)
-            if training:
-                nz = torch.empty_like(inputs).uniform_(-0.5, 0.5) if noise is None else noise
-                outputs = inputs + nz
-            else:
-                outputs = self.quantize(inputs, "dequantize", means)
-            likelihood = self._likelihood(outputs, scales, means)
-            if self.use_likelihood_bound:
-                likelihood = self.likelihood_lower_bound(likelihood)
-            return outputs, likelihood
+            if inputs.dtype != torch.float32 or scales.shape != inputs.shape or (means is not None and means.shape != inputs.shape):
+                raise NotImplementedError("licos_b200: GaussianConditional under autograd takes float32 inputs with scales "
+                                          "(and means) of the same shape")
+            return _GcTrainFn.apply(self, inputs, scales, means, noise, training)
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (training and noise is None) else 0
         m = None if means is None else means.expand_as(inputs).contiguous()

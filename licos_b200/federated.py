@@ -29,9 +29,7 @@ def merge_pair(local_sd: Dict[str, torch.Tensor], central_sd: Dict[str, torch.Te
         b = central_sd[key].to(a.device)
         if a.is_cuda and a.dtype == torch.float32 and a.numel() > 0:
             out[key] = ops.weighted_sum2(a.contiguous(), b.contiguous(), w_local, w_central)
-        elif a.numel() == 0:
-            out[key] = a.clone()
-        else:  # integer tables (empty at train time in the reference) follow torch type promotion
+        else:  # integer tables (empty at train time in the reference) follow torch type promotion, as in the reference
             v = w_local * a
             v += w_central * b
             out[key] = v

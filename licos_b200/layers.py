@@ -8,7 +8,6 @@ does arithmetic on every key, eval_script.py:70-71 loads them).
 from __future__ import annotations
 
 import os
-import warnings
 import weakref
 from typing import Optional
 
@@ -120,7 +119,6 @@ def _conv_kind(m: nn.Module) -> int:
     raise NotImplementedError(f"licos_b200 has no kernel for layer {m!r}")
 
 
-_EAGER_AUTOGRAD = bool(int(os.environ.get("LICOS_EAGER_AUTOGRAD", "0")))  # development: compare against cuDNN autograd
 _UNFUSED_GDN_BWD = bool(int(os.environ.get("LICOS_UNFUSED_GDN_BWD", "0")))  # development: GDN backward as separate passes
 
 
@@ -151,9 +149,6 @@ class FusedSequential(nn.Sequential):
         super().__init__(*args)
         self._packed_cache = weakref.WeakKeyDictionary()
 
-    def _eager_forward(self, x: Tensor) -> Tensor:
-        return super().forward(x)
-
     def forward(self, x: Tensor, take_abs: bool = False, nhwc: Optional[Tensor] = None) -> Tensor:
         """``nhwc``: optional bf16 (B, H, W, C) copy of ``x`` that a fused producer already wrote
         (``EntropyBottleneck.forward_fused``); saves the layout-conversion launch on the fused path."""
@@ -161,14 +156,12 @@ class FusedSequential(nn.Sequential):
             raise RuntimeError("licos_b200: g_a / g_s / h_a / h_s need CUDA tensors on a B200 (no CPU path exists)")
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             xin = torch.abs(x) if take_abs else x
-            if _EAGER_AUTOGRAD:
-                return self._eager_forward(xin)  # development comparison against cuDNN autograd
             if not self._native_backward_ok(xin):
-                # loud, not silent: this shape trains through torch's own kernels, not through this package's
-                warnings.warn(f"licos_b200: no native backward for input shape {tuple(xin.shape)} through {self.__class__.__name__} "
-                              "(stride-2 layers need even sizes, channel counts multiples of 64): using torch autograd",
-                              RuntimeWarning, stacklevel=2)
-                return self._eager_forward(xin)
+                # no second backend: a shape the backward kernels do not take is an error, not a detour through cuDNN
+                raise NotImplementedError(
+                    f"licos_b200: no native backward for input shape {tuple(xin.shape)} through {self.__class__.__name__}: "
+                    "every stride-2 layer needs even sizes (the reference trains on 256x256 patches, "
+                    "cfg/default_cfg.toml:29) and hidden channel counts that are multiples of 64")
             return self.train_forward(xin)
         return self.fused_forward(x, take_abs=take_abs, nhwc=nhwc)
 
@@ -360,6 +353,12 @@ class _ChainFn(torch.autograd.Function):
             layout = out_layout
             saved.append(rec)
         ctx.seq, ctx.steps, ctx.saved = seq, steps, saved
+        # The chain's OUTPUT doubles as the ReLU mask of its last layer (h_s): keep it through save_for_backward so that an
+        # in-place edit by the caller (clamp_, mul_) trips autograd's version check instead of silently corrupting the mask.
+        # Inner activations never leave this function, so they stay plain references.
+        ctx.out_is_mask = bool(saved) and "y" in saved[-1] and saved[-1]["y"] is cur
+        if ctx.out_is_mask:
+            ctx.save_for_backward(cur)
         ctx.x_needs_grad = x.requires_grad
         ctx.param_needs = [p is not None and p.requires_grad for p in params]
         return cur
@@ -368,6 +367,8 @@ class _ChainFn(torch.autograd.Function):
     def backward(ctx, g_out: Tensor):
         L = _lib
         seq, steps, saved = ctx.seq, ctx.steps, ctx.saved
+        if ctx.out_is_mask:
+            saved[-1]["y"] = ctx.saved_tensors[0]  # raises if the caller modified the output in place
         dev = g_out.device
         # one zeroed fp32 arena for everything the kernels accumulate into (weight / gamma gradients, channel sums)
         need = 0

@@ -284,9 +284,12 @@ class EntropyBottleneck(EntropyModel):
 
     _offset: Tensor
 
-    # "plain": sigmoid(upper) - sigmoid(lower)           (CompressAI >= 1.2.0 forward)
+    # "plain": sigmoid(upper) - sigmoid(lower)           (CompressAI >= 1.2: forward AND update() both call
+    #           the tuple-returning _likelihood)
     # "stable": |sigmoid(s*upper) - sigmoid(s*lower)|, s = -sign(lower + upper)
-    #           (CompressAI <= 1.1.x forward; still what update() uses)
+    #           (CompressAI <= 1.1.x: forward's _likelihood and the inline expression in update())
+    # No upstream release mixes the two, so ONE switch drives forward and update(): the tables a release writes
+    # are the tables its forward's likelihoods describe.
     likelihood_form = "plain"
 
     def __init__(self, channels: int, *args, tail_mass: float = 1e-9,
@@ -355,8 +358,11 @@ class EntropyBottleneck(EntropyModel):
         half = float(0.5)
         lower = self._logits_cumulative(samples - half, stop_gradient=True)
         upper = self._logits_cumulative(samples + half, stop_gradient=True)
-        sign = -torch.sign(lower + upper)
-        pmf = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))
+        if self.likelihood_form == "plain":
+            pmf = torch.sigmoid(upper) - torch.sigmoid(lower)
+        else:
+            sign = -torch.sign(lower + upper)
+            pmf = torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))
 
         pmf = pmf[:, 0, :]
         tail_mass = torch.sigmoid(lower[:, 0, :1]) + torch.sigmoid(-upper[:, 0, -1:])

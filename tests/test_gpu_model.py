@@ -94,7 +94,7 @@ def test_factorized_integer_path_bit_exact_and_strings(cuda):
     agree = (sym == ref.entropy_bottleneck.quantize(ry, "symbols", med)).float().mean().item()
     print(f"end-to-end symbol agreement from x (bf16 operands): {agree:.5f}; |y - y_ref| max "
           f"{(y.cpu() - ry).abs().max().item():.4f} at |y| max {ry.abs().max().item():.2f}")
-    assert agree > 0.95
+    assert agree >= 0.98  # ~1 - 1.4e-2 expected with bf16 operands
     assert abs(_psnr(x, dec["x_hat"].cpu()) - _psnr(x, rdec["x_hat"])) <= PSNR_TOL_DB
     nbytes = sum(len(s) for s in comp["strings"][0])
     assert abs(nbytes * 8 / (3 * 128 * 128) / _bpp(net(x.to(cuda)), x) - 1) < 0.05  # coder within 5 % of entropy
@@ -111,10 +111,23 @@ def test_hyperprior_forward_compress_vs_oracle(cuda):
             dec = net.decompress(comp["strings"], comp["shape"])
             rdec = ref.decompress(comp["strings"], comp["shape"])
         assert len(comp["strings"]) == 2 and len(comp["strings"][0]) == 2
-        # the oracle, running its own h_s in fp32, derives slightly different scales from our z string, so
-        # only the product's own round trip is exact; the cross-decode must still be a valid image
         assert dec["x_hat"].shape == x.shape and rdec["x_hat"].shape == x.shape
-        assert torch.isfinite(dec["x_hat"]).all()
+        # Cross-decode, stage by stage.  The oracle runs its own h_s in fp32 and so derives slightly different scales from
+        # the same z string; one differing index desynchronises a range decoder, so the END-TO-END cross-decode is not a
+        # meaningful bound.  What must hold exactly: (1) the oracle decodes our z string to our z_hat; (2) given the same
+        # scales both sides build the same indexes; (3) given the same indexes the oracle decodes our y string to our y_hat.
+        with torch.no_grad():
+            eb, gc = net.entropy_bottleneck, net.gaussian_conditional
+            z_hat = eb.decompress(comp["strings"][1], comp["shape"])
+            assert torch.equal(z_hat.cpu(), ref.entropy_bottleneck.decompress(comp["strings"][1], comp["shape"]))
+            scales = net.h_s(z_hat)
+            idx = gc.build_indexes(scales)
+            assert torch.equal(idx.cpu(), ref.gaussian_conditional.build_indexes(scales.cpu()))
+            y_hat = gc.decompress(comp["strings"][0], idx, z_hat.dtype)
+            assert torch.equal(y_hat.cpu(), ref.gaussian_conditional.decompress(comp["strings"][0], idx.cpu(), torch.float32))
+            assert torch.equal(dec["x_hat"], net.g_s(y_hat).clamp_(0, 1))
+            # and the oracle's synthesis of that y_hat is our image within the float tolerance
+            assert abs(_psnr(x, dec["x_hat"].cpu()) - _psnr(x, ref.g_s(y_hat.cpu()).clamp_(0, 1))) <= PSNR_TOL_DB
 
 
 def test_hyperprior_integer_path_on_golden(cuda):
@@ -128,6 +141,17 @@ def test_hyperprior_integer_path_on_golden(cuda):
     import hashlib
     assert [hashlib.sha256(b).hexdigest() for b in ys] == z["y_string_sha"].tolist()
     assert torch.equal(back.cpu(), torch.round(torch.from_numpy(z["y"])))
+
+
+def test_baseline_config_shapes_vs_oracle(cuda):
+    """BASELINE.json configs[2] and [3] at their TRUE tile shapes against the oracle (reduced batch: the CPU side costs
+    42.5 GFLOP per 1x512x512 tile and 407 GFLOP per 3x1024x1024 crop): PSNR within 0.01 dB, bpp within 0.1 %."""
+    net, ref = _models("bmshj2018-factorized", 1, 1, cuda)                      # cfg 3: raw split, 12-bit single band
+    x = synth.make_input("raw512", 2, seed=43)
+    _compare_forward(net, ref, x, cuda, "cfg 3: factorized c1 2 x 1x512x512")
+    net, ref = _models("bmshj2018-hyperprior", 3, 6, cuda)                      # cfg 4: N = 192, M = 320
+    x = synth.make_input("rgb1024", 1, seed=44)
+    _compare_forward(net, ref, x, cuda, "cfg 4: hyperprior q6 1 x 3x1024x1024")
 
 
 def test_state_swaps_invalidate_weight_caches(cuda):

@@ -1,5 +1,5 @@
 """Per-layer timing of the conv engine at benchmark shapes plus the in-kernel cycle probes
-(licos_debug_set_conv_probe).  Usage: python tools/probe_conv.py [batch]"""
+(licos_internal_set_conv_probe, a development symbol outside the public header).  Usage: python tools/probe_conv.py [batch]"""
 import os
 import sys
 
@@ -7,6 +7,16 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from licos_b200 import _lib, ops  # noqa: E402
+
+import ctypes  # noqa: E402
+
+_probe_fn = _lib.lib.licos_internal_set_conv_probe
+_probe_fn.restype, _probe_fn.argtypes = None, [ctypes.c_void_p]
+
+
+def _set_probe(ptr):
+    _probe_fn(ptr)
+
 
 NAMES = ["pA_wait", "pB_wait", "mma_waitA", "mma_waitB", "mma_waitAcc", "mma_waitX2", "mma_total", "epi_waitAcc",
          "epi_s1", "epi_waitNorm", "epi_s2", "epi_store", "epi_total", "tiles", "pA_total", "pB_total"]
@@ -55,10 +65,10 @@ for name, kind, cin, cout, H, W, epi, first, nchw in LAYERS:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
     probe.zero_()
-    _lib.lib.licos_debug_set_conv_probe(probe.data_ptr())
+    _set_probe(probe.data_ptr())
     ops.conv_forward(xd, **kw)
     torch.cuda.synchronize()
-    _lib.lib.licos_debug_set_conv_probe(None)
+    _set_probe(None)
     p = probe.view(-1, 16).cpu()
     p = p[p[:, 13] > 0].double()
     tiles = p[:, 13].mean().item()
