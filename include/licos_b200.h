@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define LICOS_ABI_VERSION 1
+#define LICOS_ABI_VERSION 2
 
 enum {
     LICOS_OK = 0,
@@ -45,6 +45,19 @@ int licos_device_ok(int device);
 /* ------------------------------------------------------------------------------------------ */
 #define LICOS_LAYOUT_NCHW_F32 0  /* the CompressAI-facing layout (x, y, x_hat, likelihoods)     */
 #define LICOS_LAYOUT_NHWC_BF16 1 /* inter-layer activations; C must be a multiple of 64         */
+/* Integer pixel tiles (N4; /root/reference/licos/raw_image_folder.py:192-196 scales DN / DN_MAX on the host and ships
+ * fp32): the first layer reads them directly and scales in its patch builders, the last layer can write them.
+ *   input : x = v / int_max, bit-identical (after the bf16 operand rounding) to feeding float32(float64(v) / int_max);
+ *           U16_Q8 adds the reference's default 8-bit step, x = rint(v / int_max * 255) / 255 (img_as_ubyte, :195).
+ *   output: v = rint(clamp(x_hat, 0, 1) * int_max).
+ * int_max = licos_conv_args.int_max, 0 = 255 (U8) / 4095 (U16: the 12-bit DN_MAX of raw_utils.py:128). */
+#define LICOS_LAYOUT_NCHW_U8 2
+#define LICOS_LAYOUT_NCHW_U16 3
+#define LICOS_LAYOUT_NCHW_U16_Q8 4 /* input only */
+/* Host-only: 1 when the single-multiply scaling the first layer applies to integer pixels reproduces
+ * float32(float64(v) / int_max) (requant8: float32(rint(v / int_max * 255) / 255)) after the bf16 operand rounding for
+ * EVERY v in [0, int_max] (checked exhaustively); licos_conv_forward refuses any other int_max. */
+int licos_pixel_scale_exact(int int_max, int requant8);
 
 /* fp32 NCHW -> bf16 NHWC (optionally |x|: ScaleHyperprior.forward's `h_a(torch.abs(y))`). */
 int licos_nchw_f32_to_nhwc_bf16(const float* in, void* out, int batch, int channels, int64_t hw,
@@ -100,7 +113,7 @@ typedef struct licos_conv_args {
     void* workspace;    /* scratch for in_layout == NCHW_F32 (licos_conv_workspace_bytes)        */
     int64_t workspace_bytes;
     int sm_count;       /* 0 = query the device                                                */
-    int reserved;
+    int int_max;        /* integer pixel layouts: full-scale value (0 = the layout's default)   */
 } licos_conv_args;
 
 /* Scratch bytes licos_conv_forward needs for these args (0 unless in_layout == NCHW_F32). */
@@ -196,11 +209,32 @@ int64_t licos_eb_lut_floats(int channels); /* size of the eval-mode workspace, i
  * x, y_hat, lik: fp32 [batch][channels][hw].  lut_ws: licos_eb_lut_floats(channels) floats. */
 int licos_eb_forward_eval(const licos_eb_params* p, const float* x, int batch, int64_t hw, float* lut_ws,
                           float* y_hat, float* lik, void* stream);
-/* The same, in ONE pass over x, optionally also producing what the callers of forward() ask for next:
- * symbols (EntropyModel.quantize(x, "symbols", medians), int32 [batch][channels][hw], may be NULL) and a bf16 NHWC
- * copy of y_hat (the layout licos_conv_forward reads, may be NULL).  hw % 4 == 0, channels even. */
-int licos_eb_forward_eval_fused(const licos_eb_params* p, const float* x, int batch, int64_t hw, float* lut_ws,
-                                float* y_hat, float* lik, int32_t* symbols, void* y_hat_nhwc_bf16, void* stream);
+/* The [channels][257] likelihood table of the eval-mode passes: a function of the parameters only, so an inference
+ * loop builds it once per parameter version (licos_eb_lut_floats(channels) floats). */
+int licos_eb_build_lut(const licos_eb_params* p, float* lut, void* stream);
+
+/* Eval-mode bottleneck in ONE pass over x, producing whichever of the outputs are non-NULL:
+ *   y_hat, lik            EntropyBottleneck.forward(x, training=False)
+ *   symbols               EntropyModel.quantize(x, "symbols", medians), int32 [batch][channels][hw]
+ *   symbols_i16           the same saturated to int16 (what leaves the device in the codec loop: half the bytes)
+ *   y_hat_nhwc_bf16       y_hat in the layout licos_conv_forward reads
+ *   sum_ln                *sum_ln += sum(ln(lik)) in float64 -- the rate term of compute_bpp (eval_utils.py:172-186)
+ *                         and of RateDistortionLoss, without a second pass over the likelihoods
+ * hw % 4 == 0, channels even. */
+typedef struct licos_eb_fused_args {
+    const float* x;
+    int batch;
+    int lut_ready; /* 1: `lut` already holds licos_eb_build_lut's output for these parameters; 0: build it first */
+    int64_t hw;
+    float* lut;
+    float* y_hat;
+    float* lik;
+    int32_t* symbols;
+    int16_t* symbols_i16;
+    void* y_hat_nhwc_bf16;
+    double* sum_ln;
+} licos_eb_fused_args;
+int licos_eb_eval_fused(const licos_eb_params* p, const licos_eb_fused_args* args, void* stream);
 /* EntropyBottleneck.forward(x, training=True): y_hat = x + noise.  noise == NULL draws U(-0.5, 0.5)
  * from an in-kernel Philox stream keyed by (seed, element index). */
 int licos_eb_forward_noise(const licos_eb_params* p, const float* x, const float* noise, uint64_t seed,
@@ -341,8 +375,26 @@ int licos_rans_pack_device(const uint32_t* work, int64_t cap_words, const int32_
 /* dst[i] = w_a * a[i] + w_b * b[i] over a flat fp32 parameter buffer. */
 int licos_weighted_sum2(const float* a, const float* b, float w_a, float w_b, int64_t n, float* dst,
                         void* stream);
-/* buf[i] *= w   (the per-rank pre-multiply in front of the NCCL all-reduce) */
+/* buf[i] *= w */
 int licos_scale_inplace(float* buf, float w, int64_t n, void* stream);
+
+/* N-way merge over NCCL / NVLink (BASELINE.json configs[4]: one rank per GPU replaces the reference's file + lock-file
+ * merge, federation_utils.py:27-85).  NCCL is bound at run time from the libnccl.so.2 the process already carries.
+ *   licos_nccl_unique_id     rank 0 fills 128 host bytes; the caller ships them to the other ranks (any transport)
+ *   licos_nccl_comm_create   collective over all ranks (ncclCommInitRank) on the current CUDA device
+ *   licos_nccl_weighted_allreduce
+ *       flat[0..n) <- sum_r w_r flat_r[0..n) / sum_r w_r,   w_r = *weight_dev if given, else 1 / *loss_dev (a loss that is
+ *       not a positive finite number gets a vanishing weight) -- both DEVICE scalars, nothing is read back by the host.
+ *       One prep kernel, ONE ncclAllReduce with an ncclRedOpCreatePreMulSum operator (scalar dereferenced on the device
+ *       while the collective runs) over n + 1 elements, one normalising kernel.  `flat` must have room for n + 1 floats
+ *       (the spare element carries sum_r w_r) and be 16-byte aligned; scalar_dev is one float of scratch.
+ * With two ranks and weights (w, 1 - w) this is federation_utils.py:47-53 exactly. */
+int licos_nccl_version(void); /* e.g. 22809, or LICOS_ERR_UNSUPPORTED when no libnccl can be loaded */
+int licos_nccl_unique_id(void* id128_host);
+int licos_nccl_comm_create(const void* id128_host, int world, int rank, void** comm_out);
+int licos_nccl_comm_destroy(void* comm);
+int licos_nccl_weighted_allreduce(void* comm, float* flat, int64_t n, const float* loss_dev, const float* weight_dev,
+                                  float* scalar_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "liblicos_b200.so")
 
 LICOS_OK = 0
+ABI_VERSION = 2
 ERR_NAMES = {
     -1: "LICOS_ERR_INVALID", -2: "LICOS_ERR_CUDA", -3: "LICOS_ERR_UNSUPPORTED", -4: "LICOS_ERR_NO_DEVICE",
     -5: "LICOS_ERR_DOMAIN", -6: "LICOS_ERR_NOMEM", -7: "LICOS_ERR_BUFFER",
@@ -19,6 +20,7 @@ ERR_NAMES = {
 
 LAYOUT_NCHW_F32 = 0
 LAYOUT_NHWC_BF16 = 1
+LAYOUT_NCHW_U8, LAYOUT_NCHW_U16, LAYOUT_NCHW_U16_Q8 = 2, 3, 4
 CONV_5X5_S2 = 0
 DECONV_5X5_S2 = 1
 CONV_3X3_S1 = 2
@@ -36,7 +38,7 @@ class ConvArgs(ctypes.Structure):
         ("kind", c_int), ("epilogue", c_int), ("batch", c_int), ("in_h", c_int), ("in_w", c_int),
         ("in_c", c_int), ("out_c", c_int), ("in_layout", c_int), ("out_layout", c_int),
         ("in_", c_vp), ("out", c_vp), ("weight", c_vp), ("bias", c_vp), ("beta", c_vp), ("gamma", c_vp),
-        ("workspace", c_vp), ("workspace_bytes", c_i64), ("sm_count", c_int), ("reserved", c_int),
+        ("workspace", c_vp), ("workspace_bytes", c_i64), ("sm_count", c_int), ("int_max", c_int),
     ]
 
 
@@ -61,12 +63,20 @@ class EbParams(ctypes.Structure):
     ]
 
 
+class EbFusedArgs(ctypes.Structure):
+    _fields_ = [
+        ("x", c_vp), ("batch", c_int), ("lut_ready", c_int), ("hw", c_i64), ("lut", c_vp), ("y_hat", c_vp), ("lik", c_vp),
+        ("symbols", c_vp), ("symbols_i16", c_vp), ("y_hat_nhwc_bf16", c_vp), ("sum_ln", c_vp),
+    ]
+
+
 # name -> (restype, argtypes); this table is also what tests/test_abi.py checks against the header
 SIGNATURES = {
     "licos_abi_version": (c_int, []),
     "licos_strerror": (ctypes.c_char_p, [c_int]),
     "licos_last_cuda_error": (c_int, []),
     "licos_device_ok": (c_int, [c_int]),
+    "licos_pixel_scale_exact": (c_int, [c_int, c_int]),
     "licos_nchw_f32_to_nhwc_bf16": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_int, c_vp]),
     "licos_nhwc_bf16_to_nchw_f32": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
     "licos_packed_weight_bytes": (c_i64, [c_int, c_int, c_int, c_int]),
@@ -86,8 +96,8 @@ SIGNATURES = {
     "licos_im2col5x5s2": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "licos_eb_lut_floats": (c_i64, [c_int]),
     "licos_eb_forward_eval": (c_int, [ctypes.POINTER(EbParams), c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp]),
-    "licos_eb_forward_eval_fused": (c_int, [ctypes.POINTER(EbParams), c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp,
-                                            c_vp]),
+    "licos_eb_build_lut": (c_int, [ctypes.POINTER(EbParams), c_vp, c_vp]),
+    "licos_eb_eval_fused": (c_int, [ctypes.POINTER(EbParams), ctypes.POINTER(EbFusedArgs), c_vp]),
     "licos_eb_forward_noise": (c_int, [ctypes.POINTER(EbParams), c_vp, c_vp, c_u64, c_int, c_i64, c_vp, c_vp, c_vp]),
     "licos_eb_backward": (c_int, [ctypes.POINTER(EbParams), c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
     "licos_eb_pack_params": (c_int, [ctypes.POINTER(EbRawPtrs), c_int, c_int, ctypes.POINTER(c_int), c_vp, c_vp]),
@@ -122,6 +132,11 @@ SIGNATURES = {
                                          c_vp, c_vp]),
     "licos_weighted_sum2": (c_int, [c_vp, c_vp, c_f32, c_f32, c_i64, c_vp, c_vp]),
     "licos_scale_inplace": (c_int, [c_vp, c_f32, c_i64, c_vp]),
+    "licos_nccl_version": (c_int, []),
+    "licos_nccl_unique_id": (c_int, [c_vp]),
+    "licos_nccl_comm_create": (c_int, [c_vp, c_int, c_int, ctypes.POINTER(c_vp)]),
+    "licos_nccl_comm_destroy": (c_int, [c_vp]),
+    "licos_nccl_weighted_allreduce": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
 }
 
 
@@ -135,8 +150,8 @@ def _load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here == header / library mismatch: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.licos_abi_version() != 1:
-        raise ImportError(f"liblicos_b200.so ABI version {lib.licos_abi_version()} != 1")
+    if lib.licos_abi_version() != ABI_VERSION:
+        raise ImportError(f"liblicos_b200.so ABI version {lib.licos_abi_version()} != {ABI_VERSION}")
     return lib
 
 

@@ -9,7 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "lib", "liblicos_b200.so")
-SOURCES = ["entropy.cu", "conv_engine.cu", "rans_device.cu", "metrics.cu", "train_kernels.cu", "host_codec.cpp"]
+SOURCES = ["entropy.cu", "conv_engine.cu", "rans_device.cu", "metrics.cu", "train_kernels.cu", "federated_nccl.cu",
+           "host_codec.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -47,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= pr.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed building liblicos_b200.so")
-    link = [NVCC, "-shared", "-o", OUT, *objs, "-lcudart", "-Xcompiler", "-pthread"]
+    link = [NVCC, "-shared", "-o", OUT, *objs, "-lcudart", "-ldl", "-Xcompiler", "-pthread"]
     subprocess.check_call(link)
     return OUT
 

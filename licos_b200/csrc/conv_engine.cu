@@ -810,25 +810,82 @@ static int launch_first(const licos_conv_args* a, cudaStream_t s) {
     return LICOS_OK;
 }
 
-// fp32 tensor, 4 dims, innermost contiguous, no swizzle (input patches of the fused first layer)
-static bool make_map_f32(CUtensorMap* m, const void* base, const uint64_t* dims, const uint64_t* strides_elems,
-                         const uint32_t* box) {
+// fp32 / u8 / u16 tensor, 4 dims, innermost contiguous, no swizzle (input patches of the fused first layer)
+static bool make_map_plain(CUtensorMap* m, const void* base, int elem_bytes, const uint64_t* dims,
+                           const uint64_t* strides_elems, const uint32_t* box) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return false;
     cuuint64_t gdims[4], gstrides[3];
     cuuint32_t gbox[4], estr[4];
     for (int i = 0; i < 4; ++i) { gdims[i] = dims[i]; gbox[i] = box[i]; estr[i] = 1; }
-    for (int i = 0; i < 3; ++i) gstrides[i] = strides_elems[i] * 4;
-    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdims, gstrides, gbox, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    for (int i = 0; i < 3; ++i) gstrides[i] = strides_elems[i] * (uint64_t)elem_bytes;
+    const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                                   : (elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
+    const CUresult r = fn(m, dt, 4, const_cast<void*>(base), gdims, gstrides, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
-// pipelined first layer (conv_first2.cuh): 1 or 3 bands, N in {64, 128}, rows of x 16-byte aligned (TMA)
+static bool is_pixel_layout(int layout) {
+    return layout == LICOS_LAYOUT_NCHW_F32 || layout == LICOS_LAYOUT_NCHW_U8 || layout == LICOS_LAYOUT_NCHW_U16 ||
+           layout == LICOS_LAYOUT_NCHW_U16_Q8;
+}
+static int first2_mode_of(int layout) {
+    return layout == LICOS_LAYOUT_NCHW_U8 ? kF2InU8
+                                          : (layout == LICOS_LAYOUT_NCHW_U16 ? kF2InU16 : (layout == LICOS_LAYOUT_NCHW_U16_Q8 ? kF2InU16Q8 : kF2InF32));
+}
+static int default_int_max(int layout) { return layout == LICOS_LAYOUT_NCHW_U8 ? 255 : 4095; }
+
+// bf16 bits of an fp32 value, round to nearest even (finite inputs)
+static uint16_t host_bf16(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+// The builders turn an integer pixel v into bf16(float(v) * fl(1 / int_max)) (one FMUL).  The fp32 path feeds
+// bf16(float32(float64(v) / int_max)) (raw_image_folder.py:192 followed by the tensor conversion at :196).  The two agree
+// for every v of every int_max tried (255, 1023, 4095, 16383, 65535), but that is a property of the constant, so it is
+// CHECKED here, exhaustively, the first time an int_max is used; the same for the exact integer form of the 8-bit
+// re-quantisation.  A failing int_max is refused (LICOS_ERR_UNSUPPORTED), never approximated.
+static bool int_input_exact(int int_max, bool q8, uint32_t* magic_out) {
+    static std::mutex mu;
+    static int ok_plain[8], ok_q8[8], n_plain = 0, n_q8 = 0;
+    if (int_max < 1 || int_max > 65535) return false;
+    const uint32_t magic = (uint32_t)((((uint64_t)1 << 43) + 2ull * int_max - 1) / (2ull * int_max));
+    if (magic_out) *magic_out = magic;
+    std::lock_guard<std::mutex> lock(mu);
+    int* list = q8 ? ok_q8 : ok_plain;
+    int& n = q8 ? n_q8 : n_plain;
+    for (int i = 0; i < n; ++i)
+        if (list[i] == int_max) return true;
+    if (q8) {
+        if (int_max % 2 == 0) return false;  // an even int_max has exact ties in v / int_max * 255
+        const float s255 = (float)(1.0 / 255.0);
+        for (int v = 0; v <= int_max; ++v) {
+            const double t = (double)v / int_max * 255.0;
+            double r = nearbyint(t);
+            if (r < 0) r = 0;
+            if (r > 255) r = 255;
+            const uint32_t q = (uint32_t)((((uint64_t)((uint32_t)v * 510u + (uint32_t)int_max)) * magic) >> 43);
+            if (q != (uint32_t)r) return false;
+            if (host_bf16((float)q * s255) != host_bf16((float)((double)q / 255.0))) return false;
+        }
+    } else {
+        const float sc = (float)(1.0 / (double)int_max);
+        for (int v = 0; v <= int_max; ++v)
+            if (host_bf16((float)v * sc) != host_bf16((float)((double)v / (double)int_max))) return false;
+    }
+    if (n < 8) list[n++] = int_max;
+    return true;
+}
+
+// pipelined first layer (conv_first2.cuh): 1 or 3 bands, N in {64, 128, 192}, rows of x 16-byte aligned (TMA)
 static bool use_first2(const licos_conv_args* a) {
-    return (a->in_c == 1 || a->in_c == 3) && (a->out_c == 64 || a->out_c == 128 || a->out_c == 192) && a->in_w % 4 == 0 &&
-           ((uintptr_t)a->in & 15) == 0 && !knobs().first_v1;
+    const int eb = first2_elem_bytes(first2_mode_of(a->in_layout));
+    return (a->in_c == 1 || a->in_c == 3) && (a->out_c == 64 || a->out_c == 128 || a->out_c == 192) &&
+           ((int64_t)a->in_w * eb) % 16 == 0 && ((uintptr_t)a->in & 15) == 0 &&
+           (!knobs().first_v1 || a->in_layout != LICOS_LAYOUT_NCHW_F32);
 }
 
 static int launch_first2(const licos_conv_args* a, cudaStream_t s) {
@@ -848,12 +905,24 @@ static int launch_first2(const licos_conv_args* a, cudaStream_t s) {
     const int teams = p.N <= 128 ? 2 : 1;
     p.tmem_cols = 512u;
     if (p.N == 64) p.tmem_cols = 256u;
+    p.in_mode = first2_mode_of(a->in_layout);
+    if (p.in_mode != kF2InF32) {
+        const int int_max = a->int_max > 0 ? a->int_max : default_int_max(a->in_layout);
+        if (p.in_mode == kF2InU8 && int_max > 255) return LICOS_ERR_INVALID;
+        if (!int_input_exact(int_max, false, &p.q8_magic)) return LICOS_ERR_UNSUPPORTED;
+        p.in_scale = (float)(1.0 / (double)int_max);
+        p.q8_add = (uint32_t)int_max;
+        if (p.in_mode == kF2InU16Q8) {
+            if (!int_input_exact(int_max, true, &p.q8_magic)) return LICOS_ERR_UNSUPPORTED;
+            p.in_scale = (float)(1.0 / 255.0);
+        }
+    }
     {
         const uint64_t W = (uint64_t)a->in_w, H = (uint64_t)a->in_h, C = (uint64_t)a->in_c;
         const uint64_t dims[4] = {W, H, C, (uint64_t)a->batch};
         const uint64_t strides[3] = {W, H * W, C * H * W};
-        const uint32_t box[4] = {(uint32_t)kF2PatchPitch, (uint32_t)kF2PatchRows, (uint32_t)a->in_c, 1};
-        if (!make_map_f32(&p.x_map, a->in, dims, strides, box)) return LICOS_ERR_CUDA;
+        const uint32_t box[4] = {(uint32_t)first2_pitch(p.in_mode), (uint32_t)kF2PatchRows, (uint32_t)a->in_c, 1};
+        if (!make_map_plain(&p.x_map, a->in, first2_elem_bytes(p.in_mode), dims, strides, box)) return LICOS_ERR_CUDA;
     }
     {
         const uint64_t dims[2] = {(uint64_t)p.k_pad, (uint64_t)p.N};
@@ -921,6 +990,12 @@ static int launch_narrow(const licos_conv_args* a, cudaStream_t s) {
     p.OH = 2 * a->in_h; p.OW = 2 * a->in_w;
     p.chunks = a->in_c / 64;
     p.relu = a->epilogue == LICOS_EPI_RELU;
+    p.out_mode = a->out_layout == LICOS_LAYOUT_NCHW_U8 ? 1 : (a->out_layout == LICOS_LAYOUT_NCHW_U16 ? 2 : 0);
+    if (p.out_mode) {
+        const int int_max = a->int_max > 0 ? a->int_max : default_int_max(a->out_layout);
+        if (int_max > (p.out_mode == 1 ? 255 : 65535)) return LICOS_ERR_INVALID;
+        p.out_scale = (float)int_max;
+    }
     p.strip_rows = a->in_h < 32 ? a->in_h : 32;
     p.strips = (a->in_h + p.strip_rows - 1) / p.strip_rows;
     p.segs = (a->in_w + kN2SegPx - 1) / kN2SegPx;
@@ -969,10 +1044,14 @@ int licos_device_ok(int device) {
     return prop.major == 10 ? LICOS_OK : LICOS_ERR_NO_DEVICE;
 }
 
+int licos_pixel_scale_exact(int int_max, int requant8) {
+    return int_input_exact(int_max, requant8 != 0, nullptr) ? 1 : 0;
+}
+
 int64_t licos_packed_weight_bytes(int kind, int out_c, int in_c, int in_layout) {
     if (out_c < 1 || in_c < 1) return LICOS_ERR_INVALID;
     const NPlan pl = plan_n(out_c);
-    if (in_layout == LICOS_LAYOUT_NCHW_F32) {
+    if (is_pixel_layout(in_layout)) {
         if (kind != LICOS_CONV_5X5_S2 || in_c > 16) return LICOS_ERR_UNSUPPORTED;
         return (int64_t)pl.rows * first_kpad(in_c) * 2;
     }
@@ -987,7 +1066,7 @@ int licos_pack_conv_weight(const float* w, int kind, int out_c, int in_c, int in
         return LICOS_ERR_INVALID;
     const NPlan pl = plan_n(out_c);
     cudaStream_t s = (cudaStream_t)stream;
-    if (in_layout == LICOS_LAYOUT_NCHW_F32) {
+    if (is_pixel_layout(in_layout)) {
         if (kind != LICOS_CONV_5X5_S2 || in_c > 16) return LICOS_ERR_UNSUPPORTED;
         const int kp = first_kpad(in_c);
         pack_weight_first_kernel<<<ew_grid((int64_t)pl.rows * kp), 256, 0, s>>>(w, out_c, in_c * 25, pl.rows, kp,
@@ -1035,15 +1114,22 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     const bool gdn = (a->epilogue == LICOS_EPI_GDN || a->epilogue == LICOS_EPI_IGDN);
     if (a->epilogue < LICOS_EPI_NONE || a->epilogue > LICOS_EPI_RELU) return LICOS_ERR_INVALID;
     if (gdn && (!a->beta || !a->gamma || !a->bias)) return LICOS_ERR_INVALID;
-    if (a->out_layout != LICOS_LAYOUT_NCHW_F32 && a->out_layout != LICOS_LAYOUT_NHWC_BF16) return LICOS_ERR_INVALID;
+    const bool int_out = a->out_layout == LICOS_LAYOUT_NCHW_U8 || a->out_layout == LICOS_LAYOUT_NCHW_U16;
+    if (a->out_layout != LICOS_LAYOUT_NCHW_F32 && a->out_layout != LICOS_LAYOUT_NHWC_BF16 && !int_out) return LICOS_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
 
+    if (is_pixel_layout(a->in_layout) && a->in_layout != LICOS_LAYOUT_NCHW_F32) {
+        // integer tiles: only the pipelined first-layer kernel scales them on the fly
+        if (!use_first_direct(a->kind, a->in_c, a->out_c, a->out_layout) || !use_first2(a)) return LICOS_ERR_UNSUPPORTED;
+        return launch_first2(a, s);
+    }
     if (a->in_layout == LICOS_LAYOUT_NCHW_F32 && use_first_direct(a->kind, a->in_c, a->out_c, a->out_layout))
         return use_first2(a) ? launch_first2(a, s) : launch_first(a, s);
     if (a->in_layout == LICOS_LAYOUT_NHWC_BF16 && use_narrow(a->kind, a->out_c, a->in_c)) {
-        if (a->out_layout != LICOS_LAYOUT_NCHW_F32 || gdn) return LICOS_ERR_UNSUPPORTED;
+        if ((a->out_layout != LICOS_LAYOUT_NCHW_F32 && !int_out) || gdn) return LICOS_ERR_UNSUPPORTED;
         return launch_narrow(a, s);
     }
+    if (int_out) return LICOS_ERR_UNSUPPORTED;  // integer pixels come out of the model's last layer only
 
     ConvParams p;  // ~3.3 KB of plain data, passed by value as a __grid_constant__ kernel parameter
     memset(&p, 0, sizeof(p));

@@ -30,8 +30,68 @@ __host__ __device__ constexpr int first2_bufs(int teams) { return teams == 2 ? 4
 // innermost dimension (measured: an unaligned start coordinate raises an illegal-instruction fault)
 constexpr int kF2PatchRows = 19, kF2PatchPitch = 40;
 
+// Input element types (N4, /root/reference/licos/raw_image_folder.py:192-196: integer tiles go straight into the first
+// layer, the DN -> [0, 1] scaling happens in the im2col builders).  The patch of an integer tile starts further left so
+// that the TMA box still starts on a 16-byte boundary: 8 columns for 16-bit, 16 columns for 8-bit elements.
+enum { kF2InF32 = 0, kF2InU8 = 1, kF2InU16 = 2, kF2InU16Q8 = 3 };
+__host__ __device__ constexpr int first2_elem_bytes(int mode) { return mode == kF2InF32 ? 4 : (mode == kF2InU8 ? 1 : 2); }
+__host__ __device__ constexpr int first2_col_off(int mode) { return mode == kF2InF32 ? 4 : (mode == kF2InU8 ? 16 : 8); }
+__host__ __device__ constexpr int first2_pitch(int mode) { return mode == kF2InF32 ? 40 : (mode == kF2InU8 ? 64 : 48); }
+
+// Seven (C_in = 3) or five (C_in = 1) consecutive pixels of one patch row, starting at an EVEN element index e0 with
+// e0 + 2 a multiple of four: three loads ([2][4][1] / [2][2][1] elements) whatever the element type.
+template <int MODE>
+struct F2Px {
+    float scale;        // fl(1 / int_max) (integer modes), or fl(1 / 255) after the 8-bit re-quantisation
+    uint32_t q8_magic;  // ceil(2^43 / (2 int_max)): exact (v * 510 + int_max) / (2 int_max) for v < 65536 (host-verified)
+    uint32_t q8_add;    // int_max
+    __device__ __forceinline__ float cvt(uint32_t v) const {
+        if (MODE == kF2InU16Q8) {  // img_as_ubyte(v / int_max) / 255: rint(v / int_max * 255) by exact integer arithmetic
+            const uint64_t n = (uint64_t)(v * 510u + q8_add) * q8_magic;
+            v = (uint32_t)(n >> 43);
+        }
+        return (float)v * scale;  // host-verified per int_max: bf16(this) == bf16(float32(float64(v) / int_max)) for all v
+    }
+    __device__ __forceinline__ void load7(const uint8_t* patch, int e0, float (&f)[7]) const {
+        if (MODE == kF2InF32) {
+            const float* pr = reinterpret_cast<const float*>(patch) + e0;
+            const float2 a = *reinterpret_cast<const float2*>(pr);
+            const float4 b = *reinterpret_cast<const float4*>(pr + 2);
+            f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = b.z; f[5] = b.w; f[6] = pr[6];
+        } else if (MODE == kF2InU8) {
+            const uint8_t* pr = patch + e0;
+            const uint32_t a = *reinterpret_cast<const uint16_t*>(pr), b = *reinterpret_cast<const uint32_t*>(pr + 2);
+            f[0] = cvt(a & 0xffu); f[1] = cvt(a >> 8);
+            f[2] = cvt(b & 0xffu); f[3] = cvt((b >> 8) & 0xffu); f[4] = cvt((b >> 16) & 0xffu); f[5] = cvt(b >> 24);
+            f[6] = cvt(pr[6]);
+        } else {
+            const uint16_t* pr = reinterpret_cast<const uint16_t*>(patch) + e0;
+            const uint32_t a = *reinterpret_cast<const uint32_t*>(pr);
+            const uint2 b = *reinterpret_cast<const uint2*>(pr + 2);
+            f[0] = cvt(a & 0xffffu); f[1] = cvt(a >> 16);
+            f[2] = cvt(b.x & 0xffffu); f[3] = cvt(b.x >> 16); f[4] = cvt(b.y & 0xffffu); f[5] = cvt(b.y >> 16);
+            f[6] = cvt(pr[6]);
+        }
+    }
+    __device__ __forceinline__ void load5(const uint8_t* patch, int e0, float (&f)[5]) const {
+        if (MODE == kF2InF32) {
+            const float* pr = reinterpret_cast<const float*>(patch) + e0;
+            const float2 a = *reinterpret_cast<const float2*>(pr), b = *reinterpret_cast<const float2*>(pr + 2);
+            f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = pr[4];
+        } else if (MODE == kF2InU8) {
+            const uint8_t* pr = patch + e0;
+            const uint32_t a = *reinterpret_cast<const uint16_t*>(pr), b = *reinterpret_cast<const uint16_t*>(pr + 2);
+            f[0] = cvt(a & 0xffu); f[1] = cvt(a >> 8); f[2] = cvt(b & 0xffu); f[3] = cvt(b >> 8); f[4] = cvt(pr[4]);
+        } else {
+            const uint16_t* pr = reinterpret_cast<const uint16_t*>(patch) + e0;
+            const uint32_t a = *reinterpret_cast<const uint32_t*>(pr), b = *reinterpret_cast<const uint32_t*>(pr + 2);
+            f[0] = cvt(a & 0xffffu); f[1] = cvt(a >> 16); f[2] = cvt(b & 0xffffu); f[3] = cvt(b >> 16); f[4] = cvt(pr[4]);
+        }
+    }
+};
+
 struct First2Params {
-    CUtensorMap x_map;    // fp32 (W, H, C, B), box (40, 19, C, 1), no swizzle
+    CUtensorMap x_map;    // fp32 / u8 / u16 (W, H, C, B), box (pitch, 19, C, 1), no swizzle
     CUtensorMap w_map;    // [N][k_pad] bf16, box (64, N): K columns 0..63
     CUtensorMap g_map;    // gamma [N][N] bf16, box (64, N)
     CUtensorMap out_map;  // NHWC bf16 (N, OW, OH, B), box (64, 16, 8, 1)
@@ -42,6 +102,9 @@ struct First2Params {
     int N;
     int tiles_h, tiles_w, total_tiles;
     uint32_t tmem_cols;
+    int in_mode;          // kF2In*
+    float in_scale;       // see F2Px
+    uint32_t q8_magic, q8_add;
 };
 
 template <int CIN>
@@ -150,6 +213,8 @@ __global__ void __launch_bounds__(first2_threads(TEAMS), 1) conv_first2_kernel(c
         // ===================== patch loader =====================
         if (lane == 0) {
             tma_prefetch_desc(&p.x_map);
+            const int col_off = first2_col_off(p.in_mode);
+            const uint32_t patch_bytes = (uint32_t)(CIN * kF2PatchRows * first2_pitch(p.in_mode) * first2_elem_bytes(p.in_mode));
             int lt = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid, ++lt) {
                 const int slot = lt % kF2Slots;
@@ -160,8 +225,8 @@ __global__ void __launch_bounds__(first2_threads(TEAMS), 1) conv_first2_kernel(c
                 const int oh0 = (r % p.tiles_h) * 8;
                 const int b = r / p.tiles_h;
                 mbar_wait(&patch_empty[slot], par ^ 1u);
-                mbar_arrive_expect_tx(&patch_full[slot], G::kPatchBytes);
-                tma_load_4d(patch_s + (size_t)slot * G::kPatchSlot, &p.x_map, &patch_full[slot], 2 * ow0 - 4, 2 * oh0 - 2, 0, b);
+                mbar_arrive_expect_tx(&patch_full[slot], patch_bytes);
+                tma_load_4d(patch_s + (size_t)slot * G::kPatchSlot, &p.x_map, &patch_full[slot], 2 * ow0 - col_off, 2 * oh0 - 2, 0, b);
             }
         }
     } else if (warp == 1) {
@@ -194,92 +259,99 @@ __global__ void __launch_bounds__(first2_threads(TEAMS), 1) conv_first2_kernel(c
         // waiter that skipped phases could not tell them apart by parity).  C_in = 3: a thread builds HALF of the K
         // range (K columns 0..39 or 40..79 = chunks 0..4 / 5..9) of two neighbouring pixels; C_in = 1: one pixel.
         const int u = tid - 64;  // 0..127
-        int lt = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid, ++lt) {
-            const int slot = lt % kF2Slots;
-            const uint32_t par = (uint32_t)(lt / kF2Slots) & 1u;
-            uint8_t* a0 = a_s + (size_t)slot * 16384;
-            const float* patch = reinterpret_cast<const float*>(patch_s + (size_t)slot * G::kPatchSlot);
-            mbar_wait(&patch_full[slot], par);
-            if constexpr (CIN == 3) {
-                const int half = u >> 6, th = (u >> 3) & 7, q = u & 7;
-                const int m0 = th * 16 + 2 * q;  // rows (pixels) m0, m0 + 1 of the tile
-                const float* pt = patch + (2 * th) * kF2PatchPitch + 4 * q;
-                uint32_t pa[20], pb[20];
-                float pend_a = 0.f, pend_b = 0.f;
-                auto rows = [&](auto first_row, auto n_rows) {
-                    constexpr int R0 = decltype(first_row)::value, NR = decltype(n_rows)::value;
+        auto build = [&](auto mode_tag) {
+            constexpr int MODE = decltype(mode_tag)::value;
+            constexpr int kPitch = first2_pitch(MODE), kShift = first2_col_off(MODE) - 4;  // element pitch, extra left margin
+            const F2Px<MODE> px{p.in_scale, p.q8_magic, p.q8_add};
+            int lt = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += grid, ++lt) {
+                const int slot = lt % kF2Slots;
+                const uint32_t par = (uint32_t)(lt / kF2Slots) & 1u;
+                uint8_t* a0 = a_s + (size_t)slot * 16384;
+                const uint8_t* patch = patch_s + (size_t)slot * G::kPatchSlot;
+                mbar_wait(&patch_full[slot], par);
+                if constexpr (CIN == 3) {
+                    const int half = u >> 6, th = (u >> 3) & 7, q = u & 7;
+                    const int m0 = th * 16 + 2 * q;  // rows (pixels) m0, m0 + 1 of the tile
+                    const int e_base = (2 * th) * kPitch + 4 * q + 2 + kShift;  // patch columns 4q+2 .. 4q+8 of row 2 th
+                    uint32_t pa[20], pb[20];
+                    float pend_a = 0.f, pend_b = 0.f;
+                    auto rows = [&](auto first_row, auto n_rows) {
+                        constexpr int R0 = decltype(first_row)::value, NR = decltype(n_rows)::value;
 #pragma unroll
-                    for (int r = R0; r < R0 + NR; ++r) {  // r = c * 5 + kh: one patch row per (channel, row tap)
-                        const int c = r / 5, kh = r % 5;
-                        const float* pr = pt + (c * kF2PatchRows + kh) * kF2PatchPitch;  // patch columns 4q+2 .. 4q+8
-                        const float2 f0 = *reinterpret_cast<const float2*>(pr + 2);
-                        const float4 f1 = *reinterpret_cast<const float4*>(pr + 4);
-                        const float f[7] = {f0.x, f0.y, f1.x, f1.y, f1.z, f1.w, pr[8]};
+                        for (int r = R0; r < R0 + NR; ++r) {  // r = c * 5 + kh: one patch row per (channel, row tap)
+                            const int c = r / 5, kh = r % 5;
+                            float f[7];
+                            px.load7(patch, e_base + (c * kF2PatchRows + kh) * kPitch, f);
 #pragma unroll
-                        for (int j = 0; j < 5; ++j) {
-                            const int k = (r - R0) * 5 + j;  // K column relative to this half (both halves start even)
-                            if (k & 1) {
-                                pa[k >> 1] = pack_bf16x2(pend_a, f[j]);
-                                pb[k >> 1] = pack_bf16x2(pend_b, f[j + 2]);
-                            } else {
-                                pend_a = f[j];
-                                pend_b = f[j + 2];
+                            for (int j = 0; j < 5; ++j) {
+                                const int k = (r - R0) * 5 + j;  // K column relative to this half (both halves start even)
+                                if (k & 1) {
+                                    pa[k >> 1] = pack_bf16x2(pend_a, f[j]);
+                                    pb[k >> 1] = pack_bf16x2(pend_b, f[j + 2]);
+                                } else {
+                                    pend_a = f[j];
+                                    pend_b = f[j + 2];
+                                }
                             }
                         }
+                    };
+                    if (half == 0) {
+                        rows(std::integral_constant<int, 0>{}, std::integral_constant<int, 8>{});  // K 0..39
+                    } else {
+                        rows(std::integral_constant<int, 8>{}, std::integral_constant<int, 7>{});  // K 40..74
+                        // K 75, 76: 1.0 against the bias hi / lo rows of W, then zeros
+                        pa[17] = pack_bf16x2(pend_a, 1.f);
+                        pb[17] = pack_bf16x2(pend_b, 1.f);
+                        pa[18] = pb[18] = pack_bf16x2(1.f, 0.f);
+                        pa[19] = pb[19] = 0u;
                     }
-                };
-                if (half == 0) {
-                    rows(std::integral_constant<int, 0>{}, std::integral_constant<int, 8>{});  // K 0..39
+                    mbar_arrive(&patch_empty[slot]);  // the patch is in registers now
+                    mbar_wait(&a_empty[slot], par ^ 1u);
+#pragma unroll
+                    for (int gg = 0; gg < 5; ++gg) {
+                        const int g = half * 5 + gg;  // 16-byte chunk of the 80-column row
+                        uint8_t* base = (g < 8) ? a0 : tail_s;
+                        const uint32_t chunk = (g < 8) ? (uint32_t)g : (uint32_t)(2 * slot + (g - 8));
+                        *reinterpret_cast<uint4*>(base + sw128_offset(m0, chunk)) =
+                            make_uint4(pa[4 * gg], pa[4 * gg + 1], pa[4 * gg + 2], pa[4 * gg + 3]);
+                        *reinterpret_cast<uint4*>(base + sw128_offset(m0 + 1, chunk)) =
+                            make_uint4(pb[4 * gg], pb[4 * gg + 1], pb[4 * gg + 2], pb[4 * gg + 3]);
+                    }
                 } else {
-                    rows(std::integral_constant<int, 8>{}, std::integral_constant<int, 7>{});  // K 40..74
-                    // K 75, 76: 1.0 against the bias hi / lo rows of W, then zeros
-                    pa[17] = pack_bf16x2(pend_a, 1.f);
-                    pb[17] = pack_bf16x2(pend_b, 1.f);
-                    pa[18] = pb[18] = pack_bf16x2(1.f, 0.f);
-                    pa[19] = pb[19] = 0u;
-                }
-                mbar_arrive(&patch_empty[slot]);  // the patch is in registers now
-                mbar_wait(&a_empty[slot], par ^ 1u);
+                    const int th = u >> 4, tw = u & 15;  // thread == pixel (row u of the tile)
+                    const int e_base = (2 * th) * kPitch + 2 * tw + 2 + kShift;  // patch columns 2tw+2 .. 2tw+6 of row 2 th
+                    uint32_t pa[16];
+                    float pend = 0.f;
 #pragma unroll
-                for (int gg = 0; gg < 5; ++gg) {
-                    const int g = half * 5 + gg;  // 16-byte chunk of the 80-column row
-                    uint8_t* base = (g < 8) ? a0 : tail_s;
-                    const uint32_t chunk = (g < 8) ? (uint32_t)g : (uint32_t)(2 * slot + (g - 8));
-                    *reinterpret_cast<uint4*>(base + sw128_offset(m0, chunk)) =
-                        make_uint4(pa[4 * gg], pa[4 * gg + 1], pa[4 * gg + 2], pa[4 * gg + 3]);
-                    *reinterpret_cast<uint4*>(base + sw128_offset(m0 + 1, chunk)) =
-                        make_uint4(pb[4 * gg], pb[4 * gg + 1], pb[4 * gg + 2], pb[4 * gg + 3]);
-                }
-            } else {
-                const int th = u >> 4, tw = u & 15;  // thread == pixel (row u of the tile)
-                const float* pt = patch + (2 * th) * kF2PatchPitch + 2 * tw;
-                uint32_t pa[16];
-                float pend = 0.f;
+                    for (int kh = 0; kh < 5; ++kh) {
+                        float f[5];
+                        px.load5(patch, e_base + kh * kPitch, f);
 #pragma unroll
-                for (int kh = 0; kh < 5; ++kh) {
-                    const float* pr = pt + kh * kF2PatchPitch;  // patch columns 2tw+2 .. 2tw+6
-                    const float2 f0 = *reinterpret_cast<const float2*>(pr + 2);
-                    const float2 f1 = *reinterpret_cast<const float2*>(pr + 4);
-                    const float f[5] = {f0.x, f0.y, f1.x, f1.y, pr[6]};
-#pragma unroll
-                    for (int j = 0; j < 5; ++j) {
-                        const int k = kh * 5 + j;
-                        if (k & 1) pa[k >> 1] = pack_bf16x2(pend, f[j]);
-                        else pend = f[j];
+                        for (int j = 0; j < 5; ++j) {
+                            const int k = kh * 5 + j;
+                            if (k & 1) pa[k >> 1] = pack_bf16x2(pend, f[j]);
+                            else pend = f[j];
+                        }
                     }
-                }
-                pa[12] = pack_bf16x2(pend, 1.f);  // K 24, then 1.0 (bias hi)
-                pa[13] = pack_bf16x2(1.f, 0.f);   // 1.0 (bias lo), zeros
-                pa[14] = pa[15] = 0u;
-                mbar_arrive(&patch_empty[slot]);
-                mbar_wait(&a_empty[slot], par ^ 1u);
+                    pa[12] = pack_bf16x2(pend, 1.f);  // K 24, then 1.0 (bias hi)
+                    pa[13] = pack_bf16x2(1.f, 0.f);   // 1.0 (bias lo), zeros
+                    pa[14] = pa[15] = 0u;
+                    mbar_arrive(&patch_empty[slot]);
+                    mbar_wait(&a_empty[slot], par ^ 1u);
 #pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    *reinterpret_cast<uint4*>(a0 + sw128_offset(u, g)) = make_uint4(pa[4 * g], pa[4 * g + 1], pa[4 * g + 2], pa[4 * g + 3]);
+                    for (int g = 0; g < 4; ++g)
+                        *reinterpret_cast<uint4*>(a0 + sw128_offset(u, g)) = make_uint4(pa[4 * g], pa[4 * g + 1], pa[4 * g + 2], pa[4 * g + 3]);
+                }
+                fence_proxy_async();
+                mbar_arrive(&a_full[slot]);
             }
-            fence_proxy_async();
-            mbar_arrive(&a_full[slot]);
+        };
+        switch (p.in_mode) {  // warp-uniform: one branch per launch, the tile loop lives inside
+            case kF2InU8: build(std::integral_constant<int, kF2InU8>{}); break;
+            case kF2InU16: build(std::integral_constant<int, kF2InU16>{}); break;
+            case kF2InU16Q8: build(std::integral_constant<int, kF2InU16Q8>{}); break;
+            default: build(std::integral_constant<int, kF2InF32>{}); break;
         }
     } else {
         // ===================== epilogue teams =====================

@@ -40,6 +40,8 @@ struct Narrow2Params {
     int strip_rows, strips, segs, total_units;
     int slots;           // A ring depth
     int relu;
+    int out_mode;        // 0 = fp32, 1 = u8, 2 = u16: rint(clamp(x_hat, 0, 1) * out_scale) (LICOS_LAYOUT_NCHW_U8 / _U16)
+    float out_scale;
 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
@@ -172,12 +174,35 @@ __global__ void __launch_bounds__(kN2Threads, 1) deconv_narrow2_kernel(const __g
                         o1[q] = up[8 + q] + mid[8 + q] + bb[q & 3];
                         if (p.relu) { o0[q] = fmaxf(o0[q], 0.f); o1[q] = fmaxf(o1[q], 0.f); }
                     }
-                    float* o = p.out + ((size_t)b * p.out_c * p.OH + 2 * i) * p.OW + 2 * j;
+                    const size_t e = ((size_t)b * p.out_c * p.OH + 2 * i) * p.OW + 2 * j;
+                    if (p.out_mode == 0) {
+                        float* o = p.out + e;
 #pragma unroll
-                    for (int c = 0; c < kN2Cpt; ++c) {
-                        if (c < p.out_c) {
-                            *reinterpret_cast<float2*>(o + c * cs) = make_float2(o0[c], o0[4 + c]);
-                            *reinterpret_cast<float2*>(o + c * cs + p.OW) = make_float2(o1[c], o1[4 + c]);
+                        for (int c = 0; c < kN2Cpt; ++c) {
+                            if (c < p.out_c) {
+                                *reinterpret_cast<float2*>(o + c * cs) = make_float2(o0[c], o0[4 + c]);
+                                *reinterpret_cast<float2*>(o + c * cs + p.OW) = make_float2(o1[c], o1[4 + c]);
+                            }
+                        }
+                    } else {
+                        // integer pixels: the clamp of decompress() (x_hat.clamp_(0, 1)) and the fp32 multiply + round
+                        // to nearest even of a host-side `round(x_hat * int_max)`, fused into the store
+                        const float sc = p.out_scale;
+                        auto q = [sc](float v) { return (uint32_t)__float2int_rn(fminf(fmaxf(v, 0.f), 1.f) * sc); };
+#pragma unroll
+                        for (int c = 0; c < kN2Cpt; ++c) {
+                            if (c < p.out_c) {
+                                const uint32_t a0 = q(o0[c]), a1 = q(o0[4 + c]), b0q = q(o1[c]), b1q = q(o1[4 + c]);
+                                if (p.out_mode == 1) {
+                                    uint8_t* o = reinterpret_cast<uint8_t*>(p.out) + e + c * cs;
+                                    *reinterpret_cast<uint16_t*>(o) = (uint16_t)(a0 | (a1 << 8));
+                                    *reinterpret_cast<uint16_t*>(o + p.OW) = (uint16_t)(b0q | (b1q << 8));
+                                } else {
+                                    uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + e + c * cs;
+                                    *reinterpret_cast<uint32_t*>(o) = a0 | (a1 << 16);
+                                    *reinterpret_cast<uint32_t*>(o + p.OW) = b0q | (b1q << 16);
+                                }
+                            }
                         }
                     }
                 }

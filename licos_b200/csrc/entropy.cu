@@ -142,8 +142,11 @@ __global__ void __launch_bounds__(256) eb_eval_tile_kernel(EbMeta m, const float
                                                            const float* __restrict__ packed, const float* __restrict__ med,
                                                            const float* __restrict__ lut, int C, int hw,
                                                            float* __restrict__ y_hat, float* __restrict__ lik,
-                                                           int32_t* __restrict__ sym, __nv_bfloat16* __restrict__ nhwc) {
+                                                           int32_t* __restrict__ sym, int16_t* __restrict__ sym16,
+                                                           __nv_bfloat16* __restrict__ nhwc, double* __restrict__ sum_ln) {
     extern __shared__ __nv_bfloat16 tile[];  // [C][kEbTilePitch]
+    __shared__ double warp_sums[8];
+    double ln_acc = 0.0;
     const int tiles_per_img = (hw + kEbTileHw - 1) / kEbTileHw;
     const int b = blockIdx.x / tiles_per_img, hw0 = (blockIdx.x % tiles_per_img) * kEbTileHw;
     const int n_hw = min(kEbTileHw, hw - hw0);  // multiple of 4
@@ -179,14 +182,35 @@ __global__ void __launch_bounds__(256) eb_eval_tile_kernel(EbMeta m, const float
                 lv[j] = (fabsf(r) <= (float)kLutR) ? __ldg(lut + (size_t)c * kLutN + ((int)r + kLutR))
                                                    : eb_likelihood_slow(packed, m, c, yv[j]);
             }
-            __stcs(reinterpret_cast<float4*>(y_hat + off), make_float4(yv[0], yv[1], yv[2], yv[3]));
-            __stcs(reinterpret_cast<float4*>(lik + off), make_float4(lv[0], lv[1], lv[2], lv[3]));
+            if (y_hat) __stcs(reinterpret_cast<float4*>(y_hat + off), make_float4(yv[0], yv[1], yv[2], yv[3]));
+            if (lik) __stcs(reinterpret_cast<float4*>(lik + off), make_float4(lv[0], lv[1], lv[2], lv[3]));
             if (sym) __stcs(reinterpret_cast<int4*>(sym + off), make_int4(sv[0], sv[1], sv[2], sv[3]));
+            if (sym16) {  // saturating: |symbol| > 32767 does not occur for a trained or conditioned model, and the coder's
+                          // escape path would spend > 8 nibbles on it anyway
+                int q[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) q[j] = min(max(sv[j], -32768), 32767) & 0xffff;
+                __stcs(reinterpret_cast<uint2*>(sym16 + off), make_uint2((uint32_t)q[0] | ((uint32_t)q[1] << 16),
+                                                                          (uint32_t)q[2] | ((uint32_t)q[3] << 16)));
+            }
+            if (sum_ln) ln_acc += (double)(logf(lv[0]) + logf(lv[1])) + (double)(logf(lv[2]) + logf(lv[3]));
             if (nhwc) {
                 __nv_bfloat162* row = reinterpret_cast<__nv_bfloat162*>(tile + c * kEbTilePitch + 4 * v);
                 row[0] = __floats2bfloat162_rn(yv[0], yv[1]);
                 row[1] = __floats2bfloat162_rn(yv[2], yv[3]);
             }
+        }
+    }
+    if (sum_ln) {  // rate term of this block: one double atomic per block
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ln_acc += __shfl_xor_sync(0xffffffffu, ln_acc, o);
+        if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = ln_acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += warp_sums[w];
+            atomicAdd(sum_ln, t);
         }
     }
     if (!nhwc) return;
@@ -957,26 +981,42 @@ int licos_eb_forward_eval(const licos_eb_params* p, const float* x, int batch, i
     return LICOS_OK;
 }
 
-int licos_eb_forward_eval_fused(const licos_eb_params* p, const float* x, int batch, int64_t hw, float* lut_ws,
-                                float* y_hat, float* lik, int32_t* symbols, void* y_hat_nhwc_bf16, void* stream) {
+int licos_eb_build_lut(const licos_eb_params* p, float* lut, void* stream) {
     EbMeta m;
     int max_w;
-    if (!make_meta(p, m, max_w) || !x || !lut_ws || !y_hat || !lik || batch < 0 || hw < 0) return LICOS_ERR_INVALID;
-    if (hw % 4 != 0 || hw > 0x7fffffff || p->channels % 2 != 0 || p->channels > 512) return LICOS_ERR_UNSUPPORTED;
-    if ((((uintptr_t)x | (uintptr_t)y_hat | (uintptr_t)lik | (uintptr_t)symbols) % 16) != 0) return LICOS_ERR_UNSUPPORTED;
-    const int64_t n = (int64_t)batch * p->channels * hw;
-    if (n == 0) return LICOS_OK;
+    if (!make_meta(p, m, max_w) || !lut) return LICOS_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t sm = (size_t)m.ppc * sizeof(float);
-    if (max_w <= 3) eb_lut_kernel<3><<<p->channels, 288, sm, s>>>(m, p->packed, p->medians, lut_ws);
-    else eb_lut_kernel<16><<<p->channels, 288, sm, s>>>(m, p->packed, p->medians, lut_ws);
+    if (max_w <= 3) eb_lut_kernel<3><<<p->channels, 288, sm, s>>>(m, p->packed, p->medians, lut);
+    else eb_lut_kernel<16><<<p->channels, 288, sm, s>>>(m, p->packed, p->medians, lut);
     LICOS_CUDA_OK(cudaGetLastError());
-    const int64_t blocks = (int64_t)batch * ((hw + kEbTileHw - 1) / kEbTileHw);
+    return LICOS_OK;
+}
+
+int licos_eb_eval_fused(const licos_eb_params* p, const licos_eb_fused_args* a, void* stream) {
+    EbMeta m;
+    int max_w;
+    if (!a || !make_meta(p, m, max_w) || !a->x || !a->lut || a->batch < 0 || a->hw < 0) return LICOS_ERR_INVALID;
+    if (!a->y_hat && !a->lik && !a->symbols && !a->symbols_i16 && !a->y_hat_nhwc_bf16 && !a->sum_ln) return LICOS_ERR_INVALID;
+    const int64_t hw = a->hw;
+    if (hw % 4 != 0 || hw > 0x7fffffff || p->channels % 2 != 0 || p->channels > 512) return LICOS_ERR_UNSUPPORTED;
+    if ((((uintptr_t)a->x | (uintptr_t)a->y_hat | (uintptr_t)a->lik | (uintptr_t)a->symbols) % 16) != 0 ||
+        ((uintptr_t)a->symbols_i16 % 8) != 0)
+        return LICOS_ERR_UNSUPPORTED;
+    const int64_t n = (int64_t)a->batch * p->channels * hw;
+    if (n == 0) return LICOS_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!a->lut_ready) {
+        const int rc = licos_eb_build_lut(p, a->lut, stream);
+        if (rc != LICOS_OK) return rc;
+    }
+    const int64_t blocks = (int64_t)a->batch * ((hw + kEbTileHw - 1) / kEbTileHw);
     if (blocks > 0x7fffffff) return LICOS_ERR_UNSUPPORTED;
-    const size_t tile_bytes = y_hat_nhwc_bf16 ? (size_t)p->channels * kEbTilePitch * sizeof(__nv_bfloat16) : 0;
+    const size_t tile_bytes = a->y_hat_nhwc_bf16 ? (size_t)p->channels * kEbTilePitch * sizeof(__nv_bfloat16) : 0;
     LICOS_CUDA_OK(ensure_max_dynamic_smem((const void*)eb_eval_tile_kernel, 96 * 1024));
-    eb_eval_tile_kernel<<<(int)blocks, 256, tile_bytes, s>>>(m, x, p->packed, p->medians, lut_ws, p->channels, (int)hw, y_hat,
-                                                            lik, symbols, (__nv_bfloat16*)y_hat_nhwc_bf16);
+    eb_eval_tile_kernel<<<(int)blocks, 256, tile_bytes, s>>>(m, a->x, p->packed, p->medians, a->lut, p->channels, (int)hw,
+                                                            a->y_hat, a->lik, a->symbols, a->symbols_i16,
+                                                            (__nv_bfloat16*)a->y_hat_nhwc_bf16, a->sum_ln);
     LICOS_CUDA_OK(cudaGetLastError());
     return LICOS_OK;
 }

@@ -445,15 +445,18 @@ class EntropyBottleneck(EntropyModel):
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if noise is None else 0
         return ops.eb_forward_noise(ebp, x, None if noise is None else noise.contiguous(), seed)
 
-    def forward_fused(self, x: Tensor, want_symbols: bool = False, want_nhwc: bool = True):
-        """Eval-mode forward in ONE pass over x: ``(y_hat, likelihoods, symbols | None, y_hat as bf16 NHWC | None)``.
-        ``symbols`` is what ``quantize(x, "symbols", medians)`` returns; the NHWC copy is the layout the fused
-        synthesis transform reads (``FusedSequential.forward(y_hat, nhwc=...)``).  Autograd-free path only."""
+    def forward_fused(self, x: Tensor, want_symbols: bool = False, want_nhwc: bool = True, want_symbols_i16: bool = False,
+                      sum_ln: Optional[Tensor] = None, want_float: bool = True):
+        """Eval-mode forward in ONE pass over x: ``(y_hat, likelihoods, symbols | None, y_hat as bf16 NHWC | None
+        [, int16 symbols])``.  ``symbols`` is what ``quantize(x, "symbols", medians)`` returns; the NHWC copy is the
+        layout the fused synthesis transform reads (``FusedSequential.forward(y_hat, nhwc=...)``); ``sum_ln`` (float64
+        device scalar) accumulates sum(ln(likelihoods)), the rate term of compute_bpp.  Autograd-free path only."""
         _require_cuda(x, "EntropyBottleneck.forward_fused")
         if _wants_grad(self, x):
             raise RuntimeError("forward_fused is an inference path: call it under torch.no_grad()")
         return ops.eb_forward_eval_fused(self.packed_params(), x.contiguous(), want_symbols=want_symbols,
-                                         want_nhwc=want_nhwc)
+                                         want_nhwc=want_nhwc, want_symbols_i16=want_symbols_i16, sum_ln=sum_ln,
+                                         want_float=want_float)
 
     # ------------------------------------------------------------------ integer path
     @staticmethod

@@ -3,10 +3,12 @@
 The reference merges through a checkpoint file guarded by a lock file: one rank at a time does
 ``theta <- w * theta_local + (1 - w) * theta_central`` with ``w = best / (best + loss)`` over every state_dict
 key (federation_utils.py:47-53) and adopts the result.  Here every rank is one GPU of one NVSwitch box, so the
-merge is synchronous: all floating-point state lives in ONE flat fp32 buffer per rank and a single
-``all_reduce`` moves it over NVLink; each rank pre-multiplies its buffer by its normalised weight (kernel
-``licos_scale_inplace``), which makes the sum the weighted average.  With two ranks and weights
-(w, 1 - w) this is exactly the reference formula, which is what the parity test checks.
+merge is synchronous: all floating-point state lives in ONE flat fp32 buffer per rank (plus one spare element) and ONE
+``ncclAllReduce`` with a PreMulSum operator moves it over NVLink (``licos_nccl_weighted_allreduce``): every rank's
+buffer is multiplied by its un-normalised weight u_r = 1 / loss_r INSIDE the collective (device scalar, no host sync),
+the spare element carries sum_r u_r, and one small kernel divides by it.  With two ranks and weights (w, 1 - w) this is
+exactly the reference formula, which is what the parity tests check (tests/test_reference_glue.py runs the reference's
+own federation_utils.py; tests/test_federated_gloo.py the 2-rank protocol on CPU).
 """
 from __future__ import annotations
 
@@ -16,7 +18,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from . import ops
+from . import _lib, ops
 
 
 def merge_pair(local_sd: Dict[str, torch.Tensor], central_sd: Dict[str, torch.Tensor], loss: float,
@@ -38,7 +40,12 @@ def merge_pair(local_sd: Dict[str, torch.Tensor], central_sd: Dict[str, torch.Te
 
 class FlatState:
     """All floating-point parameters and buffers of a model re-homed into one contiguous fp32 buffer (the
-    module's tensors become views), so a merge is one collective instead of ~150."""
+    module's tensors become views), so a merge is one collective instead of ~150.
+
+    Build it BEFORE anything captures addresses of the parameters (``GraphedTrainStep``, optimizers with fused state are
+    fine: they hold the Parameter objects, whose ``.data`` is re-pointed here, but a CUDA graph replays raw addresses) and do
+    not ``.to()`` / ``.float()`` the module afterwards: both would leave the graph or the module training storage the merge
+    never touches.  ``verify()`` (called by every merge) checks that the views are still in place."""
 
     def __init__(self, net: nn.Module):
         self.net = net
@@ -50,7 +57,9 @@ class FlatState:
                 tensors.append(t)
         total = sum(t.numel() for t in tensors)
         device = tensors[0].device
-        self.flat = torch.empty(total, dtype=torch.float32, device=device)
+        # + the spare element that carries the sum of the weights through the collective (padded to a 16-byte multiple)
+        self.buf = torch.zeros((total + 1 + 3) // 4 * 4, dtype=torch.float32, device=device)
+        self.flat = self.buf[:total]
         off = 0
         with torch.no_grad():
             for t in tensors:
@@ -60,6 +69,16 @@ class FlatState:
                 t.data = view
                 off += n
         self.numel = total
+        self._tensors = tensors
+        self._scalar = torch.zeros(1, dtype=torch.float32, device=device)
+
+    def verify(self) -> None:
+        lo = self.flat.data_ptr()
+        hi = lo + 4 * self.numel
+        for t in self._tensors:
+            if not (lo <= t.data_ptr() < hi):
+                raise RuntimeError("licos_b200.FlatState: a parameter no longer lives in the flat buffer (the module was moved "
+                                   "or re-typed after FlatState was built); rebuild FlatState -- and any CUDA graph -- first")
 
     def touch(self) -> None:
         """Bump parameter versions so kernel-layout weight caches are rebuilt after an in-place merge."""
@@ -67,24 +86,77 @@ class FlatState:
             torch.autograd.graph.increment_version(p)  # no kernel launch (p.add_(0) cost ~150 launches per merge)
 
 
-def federated_average(state: FlatState, loss: float, group: Optional[dist.ProcessGroup] = None,
+class NcclMerger:
+    """This package's own NCCL communicator over the ranks of a torch.distributed group (the 128-byte unique id travels
+    through that group once), used by ``licos_nccl_weighted_allreduce``.  One per process."""
+
+    def __init__(self, device: torch.device, group: Optional[dist.ProcessGroup] = None):
+        import ctypes
+
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            _lib.check(_lib.lib.licos_nccl_unique_id(ident.data_ptr()), "nccl_unique_id")
+        box = [ident.numpy().tobytes()]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self._id = (ctypes.c_char * 128).from_buffer_copy(box[0])
+        comm = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib.licos_nccl_comm_create(ctypes.addressof(self._id), self.world, self.rank, ctypes.byref(comm)),
+                       "nccl_comm_create")
+        self.comm, self.device = comm, device
+
+    def merge(self, state: FlatState, loss: Optional[torch.Tensor] = None, weight: Optional[torch.Tensor] = None) -> None:
+        """``loss`` / ``weight``: one-element fp32 DEVICE tensors (this rank's validation loss, or its explicit weight)."""
+        t = weight if weight is not None else loss
+        if t is None or not t.is_cuda or t.dtype != torch.float32:
+            raise ValueError("NcclMerger.merge needs a float32 CUDA scalar")
+        _lib.check(_lib.lib.licos_nccl_weighted_allreduce(
+            self.comm, state.buf.data_ptr(), state.numel, None if weight is not None else t.data_ptr(),
+            t.data_ptr() if weight is not None else None, state._scalar.data_ptr(), ops._stream()), "nccl_weighted_allreduce")
+
+    def close(self) -> None:
+        if self.comm:
+            _lib.lib.licos_nccl_comm_destroy(self.comm)
+            self.comm = None
+
+
+_MERGERS = {}
+
+
+def _device_scalar(v, device) -> torch.Tensor:
+    if isinstance(v, torch.Tensor):
+        return v.detach().reshape(1).to(device=device, dtype=torch.float32)
+    return torch.tensor([float(v)], dtype=torch.float32).to(device, non_blocking=True)
+
+
+def federated_average(state: FlatState, loss, group: Optional[dist.ProcessGroup] = None,
                       weights: Optional[Sequence[float]] = None) -> torch.Tensor:
-    """Synchronous N-way merge.  ``weights`` (one per rank, summing to 1) default to the reference's rule
-    generalised to N ranks: w_i proportional to 1 / loss_i."""
-    world = dist.get_world_size(group)
+    """Synchronous N-way merge.  ``loss``: this rank's loss (float or tensor; a device tensor avoids any host traffic).
+    ``weights`` (one per rank) default to the reference's rule generalised to N ranks: w_i proportional to 1 / loss_i,
+    normalised by their sum; a rank whose loss is not a positive finite number gets a vanishing weight."""
+    state.verify()
     rank = dist.get_rank(group)
-    flat = state.flat
-    if weights is None:
-        inv = torch.zeros(world, dtype=torch.float64, device=flat.device)
-        inv[rank] = 1.0 / max(float(loss), 1e-12)
-        dist.all_reduce(inv, group=group)
-        w = float(inv[rank] / inv.sum())
+    flat, n = state.flat, state.numel
+    if flat.is_cuda and dist.get_backend(group) == "nccl":
+        key = id(group)
+        if key not in _MERGERS:
+            _MERGERS[key] = NcclMerger(flat.device, group)
+        if weights is None:
+            _MERGERS[key].merge(state, loss=_device_scalar(loss, flat.device))
+        else:
+            _MERGERS[key].merge(state, weight=_device_scalar(weights[rank], flat.device))
     else:
-        w = float(weights[rank])
-    if flat.is_cuda:
-        ops.scale_inplace(flat, w)
-    else:  # gloo tests of the protocol on CPU ranks
-        flat.mul_(w)
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        # the same protocol in torch ops: gloo tests of the host logic on CPU ranks
+        if weights is None:
+            l = float(loss)
+            u = 1.0 / max(l, 1e-12) if (l == l and l > 0 and l != float("inf")) else 1e-20
+        else:
+            u = float(weights[rank])
+        with torch.no_grad():
+            flat.mul_(u)
+            state.buf[n] = u
+            dist.all_reduce(state.buf[:n + 1], op=dist.ReduceOp.SUM, group=group)
+            flat.div_(state.buf[n])
     state.touch()
     return flat

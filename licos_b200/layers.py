@@ -149,12 +149,20 @@ class FusedSequential(nn.Sequential):
         super().__init__(*args)
         self._packed_cache = weakref.WeakKeyDictionary()
 
-    def forward(self, x: Tensor, take_abs: bool = False, nhwc: Optional[Tensor] = None) -> Tensor:
+    def forward(self, x: Tensor, take_abs: bool = False, nhwc: Optional[Tensor] = None, *, int_max: int = 0,
+                requant8: bool = False, out_dtype: Optional[torch.dtype] = None, out_max: int = 0) -> Tensor:
         """``nhwc``: optional bf16 (B, H, W, C) copy of ``x`` that a fused producer already wrote
-        (``EntropyBottleneck.forward_fused``); saves the layout-conversion launch on the fused path."""
+        (``EntropyBottleneck.forward_fused``); saves the layout-conversion launch on the fused path.
+
+        Integer tiles (inference only): ``x`` may be uint8, or 12-bit digital numbers in uint16 / int16 storage; the first
+        layer scales them by ``1 / int_max`` (default 255 / 4095; ``requant8`` adds the reference's 8-bit step,
+        raw_image_folder.py:192-196) while it builds its patches -- bit-identical to feeding the fp32 tensor.
+        ``out_dtype`` = torch.uint8 / torch.uint16 makes the last layer write ``round(clamp(x_hat, 0, 1) * out_max)``."""
         if not x.is_cuda:
             raise RuntimeError("licos_b200: g_a / g_s / h_a / h_s need CUDA tensors on a B200 (no CPU path exists)")
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            if x.dtype != torch.float32 or out_dtype not in (None, torch.float32):
+                raise NotImplementedError("licos_b200: integer tiles are an inference path; train on float32 tensors")
             xin = torch.abs(x) if take_abs else x
             if not self._native_backward_ok(xin):
                 # no second backend: a shape the backward kernels do not take is an error, not a detour through cuDNN
@@ -163,7 +171,8 @@ class FusedSequential(nn.Sequential):
                     "every stride-2 layer needs even sizes (the reference trains on 256x256 patches, "
                     "cfg/default_cfg.toml:29) and hidden channel counts that are multiples of 64")
             return self.train_forward(xin)
-        return self.fused_forward(x, take_abs=take_abs, nhwc=nhwc)
+        return self.fused_forward(x, take_abs=take_abs, nhwc=nhwc, int_max=int_max, requant8=requant8,
+                                  out_dtype=out_dtype, out_max=out_max)
 
     # -- caches of kernel-layout parameters, rebuilt when a parameter's version or storage changes --
     def train(self, mode: bool = True):
@@ -267,8 +276,10 @@ class FusedSequential(nn.Sequential):
                 params += [gdn.beta, gdn.gamma]
         return _ChainFn.apply(self, steps, x, *params)
 
-    def fused_forward(self, x: Tensor, take_abs: bool = False, nhwc: Optional[Tensor] = None) -> Tensor:
-        """x: fp32 (B, C, H, W) on a B200.  Returns fp32 NCHW like the module chain would."""
+    def fused_forward(self, x: Tensor, take_abs: bool = False, nhwc: Optional[Tensor] = None, int_max: int = 0,
+                      requant8: bool = False, out_dtype: Optional[torch.dtype] = None, out_max: int = 0) -> Tensor:
+        """x: fp32 (or integer pixel) (B, C, H, W) on a B200.  Returns fp32 NCHW like the module chain would (or integer
+        pixels when ``out_dtype`` asks for them)."""
         if not x.is_cuda:
             raise RuntimeError("licos_b200: the fused path needs CUDA tensors (no CPU fallback exists)")
         steps = self._steps()
@@ -276,9 +287,25 @@ class FusedSequential(nn.Sequential):
             return x
 
         cur = x.contiguous()
-        layout = _lib.LAYOUT_NCHW_F32
+        layout = ops.pixel_layout_of(cur, requant8)
         first = steps[0][0]
         direct_first = (steps[0][1] == _lib.CONV_5X5_S2 and first.in_channels <= 16 and not take_abs)
+        if layout != _lib.LAYOUT_NCHW_F32 and not (direct_first and first.in_channels in (1, 3) and (
+                cur.shape[3] * cur.element_size()) % 16 == 0 and cur.data_ptr() % 16 == 0):
+            # shapes the pipelined first layer does not take (13 bands, rows that are not 16-byte multiples): scale to fp32
+            # with the standalone kernel (licos_raw_dn_to_unit, same values) and continue on the fp32 path
+            cur = ops.pixels_to_unit(cur, int_max, requant8)
+            layout = _lib.LAYOUT_NCHW_F32
+        last_layout = {None: _lib.LAYOUT_NCHW_F32, torch.float32: _lib.LAYOUT_NCHW_F32, torch.uint8: _lib.LAYOUT_NCHW_U8,
+                       torch.uint16: _lib.LAYOUT_NCHW_U16}.get(out_dtype)
+        if last_layout is None:
+            raise TypeError(f"out_dtype must be float32, uint8 or uint16, got {out_dtype}")
+        if last_layout != _lib.LAYOUT_NCHW_F32:
+            lm, lk = steps[-1][0], steps[-1][1]
+            if not (lk == _lib.DECONV_5X5_S2 and lm.out_channels <= 4 and lm.in_channels % 64 == 0 and lm.in_channels <= 256
+                    and steps[-1][2] == _lib.EPI_NONE):
+                raise NotImplementedError("licos_b200: integer pixel output needs a synthesis transform that ends in a "
+                                          "5x5 stride-2 transposed conv to <= 4 bands")
         if not direct_first:
             if nhwc is not None and not take_abs:
                 if nhwc.dtype != torch.bfloat16 or tuple(nhwc.shape) != (x.shape[0], x.shape[2], x.shape[3], x.shape[1]):
@@ -289,8 +316,10 @@ class FusedSequential(nn.Sequential):
             layout = _lib.LAYOUT_NHWC_BF16
         for n, (m, kind, epi, gdn) in enumerate(steps):
             last = n == len(steps) - 1
-            out_layout = _lib.LAYOUT_NCHW_F32 if last else _lib.LAYOUT_NHWC_BF16
-            packed, bias = self._packed_weight(m, kind, layout)
+            out_layout = last_layout if last else _lib.LAYOUT_NHWC_BF16
+            # integer pixel layouts share the fp32 first-layer weight packing
+            w_layout = _lib.LAYOUT_NCHW_F32 if layout != _lib.LAYOUT_NHWC_BF16 else layout
+            packed, bias = self._packed_weight(m, kind, w_layout)
             beta = gamma = None
             if gdn is not None:
                 if gdn.beta.numel() != m.out_channels:
@@ -298,9 +327,11 @@ class FusedSequential(nn.Sequential):
                 beta, gamma = self._packed_gdn(gdn)
                 if bias is None:
                     bias = torch.zeros(m.out_channels, dtype=torch.float32, device=cur.device)
+            lim = int_max if (n == 0 and layout not in (_lib.LAYOUT_NCHW_F32, _lib.LAYOUT_NHWC_BF16)) else (
+                out_max if (last and out_layout != _lib.LAYOUT_NCHW_F32) else 0)
             cur = ops.conv_forward(cur, kind=kind, epilogue=epi, in_layout=layout, out_layout=out_layout,
                                    in_c=m.in_channels, out_c=m.out_channels, weight=packed, bias=bias,
-                                   beta=beta, gamma=gamma)
+                                   beta=beta, gamma=gamma, int_max=lim)
             layout = out_layout
         return cur
 

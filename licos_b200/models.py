@@ -93,6 +93,23 @@ class FactorizedPrior(CompressionModel):
             x_hat = self.g_s(y_hat)
         return {"x_hat": x_hat, "likelihoods": {"y": y_likelihoods}}
 
+    @torch.no_grad()
+    def forward_tiles(self, x: Tensor, *, int_max: int = 0, requant8: bool = False, out_dtype=None, out_max: int = 0,
+                      sum_ln=None, want_float: bool = True) -> Dict:
+        """The codec loop over a batch of tiles in one call (inference): encode = g_a + quantise + likelihoods + symbols,
+        decode = g_s.  ``x`` is fp32 in [0, 1] or INTEGER tiles (uint8; 12-bit DNs in uint16 / int16 storage, scaled by
+        1 / ``int_max`` inside the first layer -- what raw_image_folder.py:192-196 does on the host -- ``requant8`` = its
+        8-bit step).  Returns ``x_hat`` (fp32, or ``round(clamp(x_hat, 0, 1) * out_max)`` as ``out_dtype`` uint8 / uint16),
+        ``likelihoods``, ``y_hat`` and the int16 ``symbols`` the range coder consumes; ``sum_ln`` (float64 device scalar)
+        accumulates sum(ln(likelihoods)) so that bpp needs no second pass (eval_utils.py:172-186)."""
+        y = self.g_a(x, int_max=int_max, requant8=requant8)
+        y_hat, lik, _, y_nhwc, sym16 = self.entropy_bottleneck.forward_fused(
+            y, want_symbols=False, want_nhwc=True, want_symbols_i16=True, sum_ln=sum_ln, want_float=want_float)
+        if out_dtype is not None and out_max == 0:
+            out_max = int_max or (255 if out_dtype == torch.uint8 else 4095)
+        x_hat = self.g_s(y_hat if y_hat is not None else y, nhwc=y_nhwc, out_dtype=out_dtype, out_max=out_max)
+        return {"x_hat": x_hat, "likelihoods": {"y": lik}, "y_hat": y_hat, "symbols": sym16}
+
     @classmethod
     def from_state_dict(cls, state_dict):
         net = cls(state_dict["g_a.0.weight"].size(0), state_dict["g_a.6.weight"].size(0))

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ConvArgs, EbParams, EbRawPtrs, WgradArgs, check, lib
+from ._lib import ConvArgs, EbFusedArgs, EbParams, EbRawPtrs, WgradArgs, check, lib
 
 
 def _stream() -> int:
@@ -93,14 +93,34 @@ def gdn_pack(beta: torch.Tensor, gamma: torch.Tensor, beta_bound: float, gamma_b
     return beta_hat, gamma_hat
 
 
+_PIXEL_LAYOUT_DTYPES = {
+    _lib.LAYOUT_NCHW_F32: (torch.float32,), _lib.LAYOUT_NCHW_U8: (torch.uint8,),
+    _lib.LAYOUT_NCHW_U16: (torch.uint16, torch.int16), _lib.LAYOUT_NCHW_U16_Q8: (torch.uint16, torch.int16),
+}
+
+
+def pixel_layout_of(x: torch.Tensor, requant8: bool = False) -> int:
+    """The LICOS_LAYOUT_* of an image tensor (B, C, H, W): fp32 in [0, 1], or integer tiles (uint8; 12-bit DNs in
+    uint16 / int16 storage, optionally with the reference's 8-bit re-quantisation, raw_image_folder.py:193-196)."""
+    if x.dtype == torch.float32:
+        return _lib.LAYOUT_NCHW_F32
+    if x.dtype == torch.uint8:
+        return _lib.LAYOUT_NCHW_U8
+    if x.dtype in (torch.uint16, torch.int16):
+        return _lib.LAYOUT_NCHW_U16_Q8 if requant8 else _lib.LAYOUT_NCHW_U16
+    raise TypeError(f"image tensors are float32, uint8 or 16-bit integers, got {x.dtype}")
+
+
 def conv_forward(x: torch.Tensor, *, kind: int, epilogue: int, in_layout: int, out_layout: int, in_c: int,
                  out_c: int, weight: torch.Tensor, bias: Optional[torch.Tensor], beta: Optional[torch.Tensor] = None,
-                 gamma: Optional[torch.Tensor] = None, sm_count: int = 0) -> torch.Tensor:
-    """One conv / deconv layer with its fused epilogue.  x is fp32 NCHW or bf16 NHWC (see in_layout)."""
+                 gamma: Optional[torch.Tensor] = None, sm_count: int = 0, int_max: int = 0) -> torch.Tensor:
+    """One conv / deconv layer with its fused epilogue.  x is fp32 / integer NCHW or bf16 NHWC (see in_layout);
+    out_layout may be an integer pixel layout for the model's last layer (int_max = full-scale value, 0 = default)."""
     _need_cuda(x, weight, bias, beta, gamma)
-    if in_layout == _lib.LAYOUT_NCHW_F32:
+    if in_layout in _PIXEL_LAYOUT_DTYPES:
         B, C, H, W = x.shape
-        _f32(x)
+        if x.dtype not in _PIXEL_LAYOUT_DTYPES[in_layout]:
+            raise TypeError(f"layout {in_layout} expects {_PIXEL_LAYOUT_DTYPES[in_layout]}, got {x.dtype}")
     else:
         B, H, W, C = x.shape
         if x.dtype != torch.bfloat16:
@@ -115,6 +135,10 @@ def conv_forward(x: torch.Tensor, *, kind: int, epilogue: int, in_layout: int, o
         OH, OW = H, W
     if out_layout == _lib.LAYOUT_NCHW_F32:
         out = torch.empty((B, out_c, OH, OW), dtype=torch.float32, device=x.device)
+    elif out_layout == _lib.LAYOUT_NCHW_U8:
+        out = torch.empty((B, out_c, OH, OW), dtype=torch.uint8, device=x.device)
+    elif out_layout == _lib.LAYOUT_NCHW_U16:
+        out = torch.empty((B, out_c, OH, OW), dtype=torch.uint16, device=x.device)
     else:
         out = torch.empty((B, OH, OW, out_c), dtype=torch.bfloat16, device=x.device)
     a = ConvArgs()
@@ -123,6 +147,7 @@ def conv_forward(x: torch.Tensor, *, kind: int, epilogue: int, in_layout: int, o
     a.in_, a.out, a.weight = x.data_ptr(), out.data_ptr(), weight.data_ptr()
     a.bias, a.beta, a.gamma = _ptr(bias), _ptr(beta), _ptr(gamma)
     a.sm_count = sm_count
+    a.int_max = int(int_max)
     ws = None
     nws = 0
     if in_layout == _lib.LAYOUT_NCHW_F32:  # only the explicit-im2col first-layer fallback needs scratch
@@ -264,6 +289,14 @@ class EbPacked:
         self.p.packed, self.p.medians = packed.data_ptr(), medians.data_ptr()
         self.p.form = form
         self.p.likelihood_bound = float(likelihood_bound)
+        self.lut = None  # [C][257] eval-mode likelihood table, built on first use (a function of the parameters only)
+
+    def eval_lut(self) -> torch.Tensor:
+        if self.lut is None or (torch.cuda.is_current_stream_capturing()):
+            lut = torch.empty(int(lib.licos_eb_lut_floats(self.p.channels)), dtype=torch.float32, device=self.packed.device)
+            check(lib.licos_eb_build_lut(ctypes.byref(self.p), lut.data_ptr(), _stream()), "eb_build_lut")
+            self.lut = lut
+        return self.lut
 
 
 def eb_forward_eval(ebp: EbPacked, x: torch.Tensor):
@@ -281,26 +314,40 @@ def eb_forward_eval(ebp: EbPacked, x: torch.Tensor):
     return y_hat, lik
 
 
-def eb_forward_eval_fused(ebp: EbPacked, x: torch.Tensor, want_symbols: bool = False, want_nhwc: bool = False):
-    """One pass: (y_hat, likelihoods, symbols | None, bf16 NHWC y_hat | None).  Falls back to the separate kernels
-    for shapes the tiled kernel does not take (hw % 4 != 0, odd channel counts)."""
-    _need_cuda(_f32(x))
+def eb_forward_eval_fused(ebp: EbPacked, x: torch.Tensor, want_symbols: bool = False, want_nhwc: bool = False,
+                          want_symbols_i16: bool = False, sum_ln: Optional[torch.Tensor] = None, want_float: bool = True):
+    """One pass: (y_hat, likelihoods, symbols | None, bf16 NHWC y_hat | None[, int16 symbols | None]).  ``sum_ln`` (a
+    one-element float64 device tensor) accumulates sum(ln(likelihoods)).  ``want_float=False`` skips y_hat / likelihoods
+    (codec loop: symbols, the NHWC copy and the rate term are all it needs).  Shapes the tiled kernel does not take
+    (hw % 4 != 0, odd channel counts) go through the separate kernels."""
+    _need_cuda(_f32(x), sum_ln)
     B, C = x.shape[0], x.shape[1]
     if C != ebp.p.channels:
         raise ValueError("channel mismatch")
     hw = x.numel() // max(B * C, 1)
     if x.numel() == 0 or hw % 4 != 0 or C % 2 != 0 or C > 512 or x.dim() != 4:
         y_hat, lik = eb_forward_eval(ebp, x)
-        sym = eb_symbols(x, ebp.medians) if want_symbols else None
-        return y_hat, lik, sym, (nchw_to_nhwc_bf16(y_hat) if want_nhwc and x.dim() == 4 and x.numel() else None)
+        sym = eb_symbols(x, ebp.medians) if (want_symbols or want_symbols_i16) else None
+        if sum_ln is not None and x.numel():
+            sum_log(lik, sum_ln)
+        res = (y_hat, lik, sym if want_symbols else None,
+               (nchw_to_nhwc_bf16(y_hat) if want_nhwc and x.dim() == 4 and x.numel() else None))
+        if want_symbols_i16:
+            res += (sym.clamp(-32768, 32767).to(torch.int16),)
+        return res
     x = x.contiguous()
-    y_hat, lik = torch.empty_like(x), torch.empty_like(x)
+    y_hat, lik = (torch.empty_like(x), torch.empty_like(x)) if want_float else (None, None)
     sym = torch.empty(x.shape, dtype=torch.int32, device=x.device) if want_symbols else None
+    sym16 = torch.empty(x.shape, dtype=torch.int16, device=x.device) if want_symbols_i16 else None
     nhwc = torch.empty((B, x.shape[2], x.shape[3], C), dtype=torch.bfloat16, device=x.device) if want_nhwc else None
-    lut = torch.empty(int(lib.licos_eb_lut_floats(C)), dtype=torch.float32, device=x.device)
-    check(lib.licos_eb_forward_eval_fused(ctypes.byref(ebp.p), x.data_ptr(), B, hw, lut.data_ptr(), y_hat.data_ptr(),
-                                          lik.data_ptr(), _ptr(sym), _ptr(nhwc), _stream()), "eb_forward_eval_fused")
-    return y_hat, lik, sym, nhwc
+    a = EbFusedArgs()
+    a.x, a.batch, a.hw = x.data_ptr(), B, hw
+    a.lut, a.lut_ready = ebp.eval_lut().data_ptr(), 1
+    a.y_hat, a.lik, a.symbols, a.symbols_i16 = _ptr(y_hat), _ptr(lik), _ptr(sym), _ptr(sym16)
+    a.y_hat_nhwc_bf16, a.sum_ln = _ptr(nhwc), _ptr(sum_ln)
+    check(lib.licos_eb_eval_fused(ctypes.byref(ebp.p), ctypes.byref(a), _stream()), "eb_eval_fused")
+    res = (y_hat, lik, sym, nhwc)
+    return res + (sym16,) if want_symbols_i16 else res
 
 
 def eb_forward_noise(ebp: EbPacked, x: torch.Tensor, noise: Optional[torch.Tensor], seed: int = 0):
@@ -499,6 +546,13 @@ def raw_dn_to_unit(dn: torch.Tensor, dn_max: int = 4095, use_full_range: bool = 
     check(lib.licos_raw_dn_to_unit(dn.data_ptr(), dn.numel(), int(dn_max), 0 if use_full_range else 1, out.data_ptr(),
                                    _stream()), "raw_dn_to_unit")
     return out
+
+
+def pixels_to_unit(x: torch.Tensor, int_max: int = 0, requant8: bool = False) -> torch.Tensor:
+    """Integer tiles -> fp32 in [0, 1] with the standalone kernel: the values the fused first layer derives on the fly."""
+    if x.dtype == torch.uint8:
+        return raw_dn_to_unit(x.to(torch.int16), int_max or 255, use_full_range=True)
+    return raw_dn_to_unit(x, int_max or 4095, use_full_range=not requant8)
 
 
 _MSSSIM_WEIGHTS = (0.0448, 0.2856, 0.3001, 0.2363, 0.1333)

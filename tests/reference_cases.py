@@ -87,13 +87,14 @@ def state_fingerprint(sd) -> np.ndarray:
 def run_eval_case(ref, name: str) -> dict:
     """ref: the namespace tests/ref_shim.reference() yields.  Returns plain numpy values."""
     net = build_weights(ref.model_utils.get_model, name)
+    fingerprint = state_fingerprint(net.state_dict())  # before update(): parameters only, no coder tables
     net.eval()
     net.update()
     img = eval_image(name)
     out_net, reconstructed, diff, nbytes = ref.eval_utils.process_img(img, net)
     x_hat = out_net["x_hat"]
     res = {
-        "fingerprint": state_fingerprint(net.state_dict()),
+        "fingerprint": fingerprint,
         "bytes": np.int64(nbytes),
         "bpp": np.float64(ref.eval_utils.compute_bpp(out_net)),
         "psnr": np.float64(ref.eval_utils.compute_psnr(img.unsqueeze(0), x_hat.cpu())),

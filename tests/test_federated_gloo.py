@@ -33,8 +33,26 @@ def _worker(rank, world, port, q):
     assert all(torch.equal(before[k], v) for k, v in net.state_dict().items())
     loss = [3.0, 1.0][rank]
     w = [0.25, 0.75]
-    federated_average(state, loss, weights=w)
+    # a rank that reports a non-finite loss must not poison the others (it keeps a vanishing weight): on a copy
+    torch.manual_seed(100 + rank)
+    probe = L.get_model("bmshj2018-factorized", False, 1, 1)
+    pstate = FlatState(probe)
+    federated_average(pstate, [3.0, float("nan")][rank])
+    nan_after = {k: v.clone() for k, v in probe.state_dict().items()}
+    # explicit weights on one copy, the default inverse-loss rule (1/3 : 1 -> 0.25 : 0.75) on the model itself
+    torch.manual_seed(100 + rank)
+    explicit = L.get_model("bmshj2018-factorized", False, 1, 1)
+    estate = FlatState(explicit)
+    federated_average(estate, loss, weights=w)
+    federated_average(state, torch.tensor(loss))
     after = {k: v.clone() for k, v in net.state_dict().items()}
+    same = all(torch.allclose(v, explicit.state_dict()[k], rtol=1e-6, atol=1e-7) for k, v in after.items())
+    moved = False
+    try:  # the ordering guard: a module moved after FlatState was built is refused
+        net.double()
+        federated_average(state, loss)
+    except RuntimeError:
+        moved = True
     gathered = [None] * world
     dist.all_gather_object(gathered, before)
     # inverse-loss default weights: 1/3 : 1 -> 0.25 : 0.75
@@ -46,7 +64,7 @@ def _worker(rank, world, port, q):
     dist.barrier()
     dist.destroy_process_group()
     npy = lambda d: {k: v.numpy() for k, v in d.items()}  # plain arrays: no fd sharing after exit
-    q.put((rank, npy(after), [npy(g) for g in gathered], ok_w, (lo, hi)))
+    q.put((rank, npy(after), [npy(g) for g in gathered], ok_w and same and moved, (lo, hi), npy(nan_after)))
 
 
 def test_two_rank_merge_equals_reference_formula():
@@ -60,9 +78,12 @@ def test_two_rank_merge_equals_reference_formula():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (_, after0, gathered, okw0, r0), (_, after1, _, okw1, r1) = res
+    (_, after0, gathered, okw0, r0, nan0), (_, after1, _, okw1, r1, nan1) = res
     tt = lambda d: {k: torch.from_numpy(v) for k, v in d.items()}
-    after0, after1, gathered = tt(after0), tt(after1), [tt(g) for g in gathered]
+    after0, after1, gathered, nan0, nan1 = tt(after0), tt(after1), [tt(g) for g in gathered], tt(nan0), tt(nan1)
+    for k, v in gathered[0].items():  # NaN-loss rank 1 contributed (almost) nothing: everyone holds rank 0's model
+        if v.dtype == torch.float32 and v.numel() > 0:
+            assert torch.allclose(nan0[k], v, rtol=1e-5, atol=1e-7) and torch.equal(nan0[k], nan1[k]), k
     assert okw0 and okw1
     # reference rule with rank 0 as "local" (loss 3, best 1 -> weight 0.25) and rank 1 as "central"
     fp = {k: v for k, v in gathered[0].items() if v.dtype == torch.float32 and v.numel() > 0}
