@@ -45,12 +45,21 @@ struct F2Px {
     float scale;        // fl(1 / int_max) (integer modes), or fl(1 / 255) after the 8-bit re-quantisation
     uint32_t q8_magic;  // ceil(2^43 / (2 int_max)): exact (v * 510 + int_max) / (2 int_max) for v < 65536 (host-verified)
     uint32_t q8_add;    // int_max
-    __device__ __forceinline__ float cvt(uint32_t v) const {
+    // Integer -> scaled float without the quarter-rate I2F: PRMT builds the float 2^23 + v (bits 0x4B000000 | v, exact for
+    // v < 2^23) and ONE FFMA computes rn((2^23 + v) * scale - 2^23 * scale) = rn(v * scale): 2^23 * scale is exactly
+    // representable, so this is bit-identical to float(v) * scale.
+    __device__ __forceinline__ float scaled(uint32_t biased_bits) const {
+        return fmaf(__uint_as_float(biased_bits), scale, -8388608.f * scale);
+    }
+    template <uint32_t SEL>  // PRMT selector picking the integer's byte(s) out of `word`
+    __device__ __forceinline__ float pick(uint32_t word) const {
+        const uint32_t biased = __byte_perm(word, 0x4B000000u, SEL);
         if (MODE == kF2InU16Q8) {  // img_as_ubyte(v / int_max) / 255: rint(v / int_max * 255) by exact integer arithmetic
+            const uint32_t v = biased & 0xffffu;
             const uint64_t n = (uint64_t)(v * 510u + q8_add) * q8_magic;
-            v = (uint32_t)(n >> 43);
+            return scaled(0x4B000000u | (uint32_t)(n >> 43));
         }
-        return (float)v * scale;  // host-verified per int_max: bf16(this) == bf16(float32(float64(v) / int_max)) for all v
+        return scaled(biased);  // host-verified per int_max: bf16(this) == bf16(float32(float64(v) / int_max)) for all v
     }
     __device__ __forceinline__ void load7(const uint8_t* patch, int e0, float (&f)[7]) const {
         if (MODE == kF2InF32) {
@@ -60,17 +69,17 @@ struct F2Px {
             f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = b.z; f[5] = b.w; f[6] = pr[6];
         } else if (MODE == kF2InU8) {
             const uint8_t* pr = patch + e0;
-            const uint32_t a = *reinterpret_cast<const uint16_t*>(pr), b = *reinterpret_cast<const uint32_t*>(pr + 2);
-            f[0] = cvt(a & 0xffu); f[1] = cvt(a >> 8);
-            f[2] = cvt(b & 0xffu); f[3] = cvt((b >> 8) & 0xffu); f[4] = cvt((b >> 16) & 0xffu); f[5] = cvt(b >> 24);
-            f[6] = cvt(pr[6]);
+            const uint32_t a = *reinterpret_cast<const uint16_t*>(pr), b = *reinterpret_cast<const uint32_t*>(pr + 2), c = pr[6];
+            f[0] = pick<0x7540>(a); f[1] = pick<0x7541>(a);
+            f[2] = pick<0x7540>(b); f[3] = pick<0x7541>(b); f[4] = pick<0x7542>(b); f[5] = pick<0x7543>(b);
+            f[6] = pick<0x7540>(c);
         } else {
             const uint16_t* pr = reinterpret_cast<const uint16_t*>(patch) + e0;
-            const uint32_t a = *reinterpret_cast<const uint32_t*>(pr);
+            const uint32_t a = *reinterpret_cast<const uint32_t*>(pr), c = pr[6];
             const uint2 b = *reinterpret_cast<const uint2*>(pr + 2);
-            f[0] = cvt(a & 0xffffu); f[1] = cvt(a >> 16);
-            f[2] = cvt(b.x & 0xffffu); f[3] = cvt(b.x >> 16); f[4] = cvt(b.y & 0xffffu); f[5] = cvt(b.y >> 16);
-            f[6] = cvt(pr[6]);
+            f[0] = pick<0x7510>(a); f[1] = pick<0x7532>(a);
+            f[2] = pick<0x7510>(b.x); f[3] = pick<0x7532>(b.x); f[4] = pick<0x7510>(b.y); f[5] = pick<0x7532>(b.y);
+            f[6] = pick<0x7510>(c);
         }
     }
     __device__ __forceinline__ void load5(const uint8_t* patch, int e0, float (&f)[5]) const {
@@ -80,12 +89,12 @@ struct F2Px {
             f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = pr[4];
         } else if (MODE == kF2InU8) {
             const uint8_t* pr = patch + e0;
-            const uint32_t a = *reinterpret_cast<const uint16_t*>(pr), b = *reinterpret_cast<const uint16_t*>(pr + 2);
-            f[0] = cvt(a & 0xffu); f[1] = cvt(a >> 8); f[2] = cvt(b & 0xffu); f[3] = cvt(b >> 8); f[4] = cvt(pr[4]);
+            const uint32_t a = *reinterpret_cast<const uint16_t*>(pr), b = *reinterpret_cast<const uint16_t*>(pr + 2), c = pr[4];
+            f[0] = pick<0x7540>(a); f[1] = pick<0x7541>(a); f[2] = pick<0x7540>(b); f[3] = pick<0x7541>(b); f[4] = pick<0x7540>(c);
         } else {
             const uint16_t* pr = reinterpret_cast<const uint16_t*>(patch) + e0;
-            const uint32_t a = *reinterpret_cast<const uint32_t*>(pr), b = *reinterpret_cast<const uint32_t*>(pr + 2);
-            f[0] = cvt(a & 0xffffu); f[1] = cvt(a >> 16); f[2] = cvt(b & 0xffffu); f[3] = cvt(b >> 16); f[4] = cvt(pr[4]);
+            const uint32_t a = *reinterpret_cast<const uint32_t*>(pr), b = *reinterpret_cast<const uint32_t*>(pr + 2), c = pr[4];
+            f[0] = pick<0x7510>(a); f[1] = pick<0x7532>(a); f[2] = pick<0x7510>(b); f[3] = pick<0x7532>(b); f[4] = pick<0x7510>(c);
         }
     }
 };

@@ -26,6 +26,7 @@ import torch.nn.functional as F
 from torch import Tensor
 
 from . import _lib, ops
+from . import torch_ops as T
 from .layers import LowerBound
 
 
@@ -78,12 +79,12 @@ class _EbTrainFn(torch.autograd.Function):
         if not training:
             # eval mode under autograd (e.g. a validation loss that is differentiated): rounding has zero gradient with
             # respect to x, the density parameters get theirs from the same backward kernel evaluated at y_hat
-            y_hat, lik = ops.eb_forward_eval(ebp, x.detach().contiguous())
+            y_hat, lik = T.eb_forward_eval(ebp, x.detach().contiguous())
         else:
             if noise is None and seed is None:
                 # device-side draw from torch's generator: no host sync in the training step, legal under graph capture
                 noise = torch.empty_like(x).uniform_(-0.5, 0.5)
-            y_hat, lik = ops.eb_forward_noise(ebp, x.detach().contiguous(), None if noise is None else noise.contiguous(),
+            y_hat, lik = T.eb_forward_noise(ebp, x.detach().contiguous(), None if noise is None else noise.contiguous(),
                                               0 if seed is None else seed)
         ctx.eb, ctx.ebp, ctx.training = eb, ebp, bool(training)
         ctx.save_for_backward(y_hat, *raw)
@@ -95,7 +96,7 @@ class _EbTrainFn(torch.autograd.Function):
         y_hat, *raw = ctx.saved_tensors
         g_yhat = None if g_yhat is None else g_yhat.contiguous()
         g_lik = None if g_lik is None else g_lik.contiguous()
-        d_x, d_packed = ops.eb_backward(ctx.ebp, y_hat, g_lik, g_yhat)
+        d_x, d_packed = T.eb_backward(ctx.ebp, y_hat, g_lik, g_yhat)
         if not ctx.training:
             d_x = torch.zeros_like(d_x)  # y_hat = round(x - median) + median
         ms, bs, fs = _split_raw(eb, [t.detach().contiguous() for t in raw])
@@ -136,7 +137,7 @@ class _GcTrainFn(torch.autograd.Function):
         y, scales = y.detach().contiguous(), scales.detach().contiguous()
         means = None if means is None else means.detach().contiguous()
         bound = gc.likelihood_bound if gc.use_likelihood_bound else 0.0
-        y_hat, lik = ops.gc_forward(y, scales, means, noise.contiguous() if training else None, training=bool(training),
+        y_hat, lik = T.gc_forward(y, scales, means, noise.contiguous() if training else None, training=bool(training),
                                     scale_bound=gc._scale_bound_f, likelihood_bound=bound)
         ctx.gc, ctx.bound, ctx.has_means, ctx.training = gc, bound, means is not None, bool(training)
         ctx.save_for_backward(y_hat, scales, *([means] if means is not None else []))
@@ -146,7 +147,7 @@ class _GcTrainFn(torch.autograd.Function):
     def backward(ctx, g_yhat, g_lik):
         y_hat, scales, *rest = ctx.saved_tensors
         means = rest[0] if ctx.has_means else None
-        d_y, d_s, d_m = ops.gc_backward(y_hat, scales, means, None if g_lik is None else g_lik.contiguous(),
+        d_y, d_s, d_m = T.gc_backward(y_hat, scales, means, None if g_lik is None else g_lik.contiguous(),
                                         None if g_yhat is None else g_yhat.contiguous(), ctx.gc._scale_bound_f, ctx.bound,
                                         want_means=ctx.has_means and ctx.needs_input_grad[3])
         if not ctx.training:
@@ -187,7 +188,7 @@ class EntropyModel(nn.Module):
         if mode == "symbols":
             _require_cuda(inputs, "quantize('symbols')")
             m = None if means is None else means.expand_as(inputs).contiguous()
-            return ops.gc_symbols(inputs.detach().contiguous(), m)
+            return T.gc_symbols(inputs.detach().contiguous(), m)
         outputs = inputs.clone()
         if means is not None:
             outputs -= means
@@ -440,10 +441,10 @@ class EntropyBottleneck(EntropyModel):
         x = x.contiguous()
         ebp = self.packed_params()
         if not training:
-            return ops.eb_forward_eval(ebp, x)
+            return T.eb_forward_eval(ebp, x)
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if noise is None else 0
-        return ops.eb_forward_noise(ebp, x, None if noise is None else noise.contiguous(), seed)
+        return T.eb_forward_noise(ebp, x, None if noise is None else noise.contiguous(), seed)
 
     def forward_fused(self, x: Tensor, want_symbols: bool = False, want_nhwc: bool = True, want_symbols_i16: bool = False,
                       sum_ln: Optional[Tensor] = None, want_float: bool = True):
@@ -454,7 +455,7 @@ class EntropyBottleneck(EntropyModel):
         _require_cuda(x, "EntropyBottleneck.forward_fused")
         if _wants_grad(self, x):
             raise RuntimeError("forward_fused is an inference path: call it under torch.no_grad()")
-        return ops.eb_forward_eval_fused(self.packed_params(), x.contiguous(), want_symbols=want_symbols,
+        return T.eb_forward_eval_fused(self.packed_params(), x.contiguous(), want_symbols=want_symbols,
                                          want_nhwc=want_nhwc, want_symbols_i16=want_symbols_i16, sum_ln=sum_ln,
                                          want_float=want_float)
 
@@ -472,7 +473,7 @@ class EntropyBottleneck(EntropyModel):
 
     def symbols(self, x: Tensor) -> Tensor:
         """round(x - medians) as int32, on the device (the quantiser the range coder consumes)."""
-        return ops.eb_symbols(x.contiguous(), self.packed_params().medians)
+        return T.eb_symbols(x.contiguous(), self.packed_params().medians)
 
     def compress(self, x: Tensor):
         if x.dim() < 2:
@@ -510,7 +511,7 @@ class EntropyBottleneck(EntropyModel):
             sym = ops.rans_decode_batch(list(strings), idx, C * n_spatial, cdf, lengths, offsets,
                                         threads=self.coder_threads)
             symbols = torch.from_numpy(sym).reshape(len(strings), C, *size).to(self.quantiles.device)
-        return ops.eb_dequantize(symbols.contiguous(), self.packed_params().medians)
+        return T.eb_dequantize(symbols.contiguous(), self.packed_params().medians)
 
 
 def _cpu_twin(eb: EntropyBottleneck) -> EntropyBottleneck:
@@ -607,7 +608,7 @@ class GaussianConditional(EntropyModel):
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (training and noise is None) else 0
         m = None if means is None else means.expand_as(inputs).contiguous()
-        return ops.gc_forward(inputs.contiguous(), scales.contiguous(), m,
+        return T.gc_forward(inputs.contiguous(), scales.contiguous(), m,
                               None if noise is None else noise.contiguous(), training=bool(training),
                               scale_bound=self._scale_bound_f,
                               likelihood_bound=self.likelihood_bound if self.use_likelihood_bound else 0.0,
@@ -615,4 +616,4 @@ class GaussianConditional(EntropyModel):
 
     def build_indexes(self, scales: Tensor) -> Tensor:
         _require_cuda(scales, "GaussianConditional.build_indexes")
-        return ops.gc_build_indexes(scales.detach().contiguous(), self.scale_table.contiguous(), self._scale_bound_f)
+        return T.gc_build_indexes(scales.detach().contiguous(), self.scale_table.contiguous(), self._scale_bound_f)

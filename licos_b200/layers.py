@@ -17,6 +17,7 @@ import torch.nn.functional as F
 from torch import Tensor
 
 from . import _lib, ops
+from . import torch_ops as T
 
 
 class _LowerBoundFn(torch.autograd.Function):
@@ -312,7 +313,7 @@ class FusedSequential(nn.Sequential):
                     raise ValueError("nhwc must be the bf16 (B, H, W, C) copy of x")
                 cur = nhwc.contiguous()
             else:
-                cur = ops.nchw_to_nhwc_bf16(cur, take_abs=take_abs)
+                cur = T.nchw_to_nhwc_bf16(cur, take_abs=take_abs)
             layout = _lib.LAYOUT_NHWC_BF16
         for n, (m, kind, epi, gdn) in enumerate(steps):
             last = n == len(steps) - 1
@@ -329,7 +330,7 @@ class FusedSequential(nn.Sequential):
                     bias = torch.zeros(m.out_channels, dtype=torch.float32, device=cur.device)
             lim = int_max if (n == 0 and layout not in (_lib.LAYOUT_NCHW_F32, _lib.LAYOUT_NHWC_BF16)) else (
                 out_max if (last and out_layout != _lib.LAYOUT_NCHW_F32) else 0)
-            cur = ops.conv_forward(cur, kind=kind, epilogue=epi, in_layout=layout, out_layout=out_layout,
+            cur = T.conv_forward(cur, kind=kind, epilogue=epi, in_layout=layout, out_layout=out_layout,
                                    in_c=m.in_channels, out_c=m.out_channels, weight=packed, bias=bias,
                                    beta=beta, gamma=gamma, int_max=lim)
             layout = out_layout
@@ -355,7 +356,7 @@ class _ChainFn(torch.autograd.Function):
         layout = L.LAYOUT_NCHW_F32
         first = steps[0][0]
         if not (steps[0][1] == L.CONV_5X5_S2 and first.in_channels <= 16):
-            cur = ops.nchw_to_nhwc_bf16(cur)
+            cur = T.nchw_to_nhwc_bf16(cur)
             layout = L.LAYOUT_NHWC_BF16
         saved = []
         for n, (m, kind, epi, gdn) in enumerate(steps):
@@ -368,16 +369,16 @@ class _ChainFn(torch.autograd.Function):
                 C = m.out_channels
                 if bias is None:
                     bias = torch.zeros(C, dtype=torch.float32, device=dev)
-                v = ops.conv_forward(cur, kind=kind, epilogue=L.EPI_NONE, in_layout=layout, out_layout=L.LAYOUT_NHWC_BF16,
+                v = T.conv_forward(cur, kind=kind, epilogue=L.EPI_NONE, in_layout=layout, out_layout=L.LAYOUT_NHWC_BF16,
                                      in_c=m.in_channels, out_c=C, weight=packed, bias=bias)
                 beta_hat, gamma_hat = seq._packed_gdn(gdn, force=True)
                 rec["gdn_packed"] = (beta_hat, gamma_hat)
                 eye = _identity_1x1(C, dev)
-                cur = ops.conv_forward(v, kind=L.CONV_1X1, epilogue=epi, in_layout=L.LAYOUT_NHWC_BF16, out_layout=out_layout,
+                cur = T.conv_forward(v, kind=L.CONV_1X1, epilogue=epi, in_layout=L.LAYOUT_NHWC_BF16, out_layout=out_layout,
                                        in_c=C, out_c=C, weight=eye, bias=_zeros(C, dev), beta=beta_hat, gamma=gamma_hat)
                 rec["v"] = v
             else:
-                cur = ops.conv_forward(cur, kind=kind, epilogue=epi, in_layout=layout, out_layout=out_layout,
+                cur = T.conv_forward(cur, kind=kind, epilogue=epi, in_layout=layout, out_layout=out_layout,
                                        in_c=m.in_channels, out_c=m.out_channels, weight=packed, bias=bias)
                 if epi == L.EPI_RELU:
                     rec["y"] = cur
@@ -430,19 +431,19 @@ class _ChainFn(torch.autograd.Function):
                 # g_s[6]: C -> C_img transposed conv, gradient arrives as fp32 NCHW
                 patches = ops.im2col5x5s2(g)
                 kp = patches.shape[-1]
-                dw = ops.conv_wgrad(a_in, patches, L.CONV_1X1, out=take(Ci * kp))[0][:, :Co * 25].reshape(Ci, Co, 5, 5)
+                dw = T.conv_wgrad(a_in, patches, L.CONV_1X1, out=take(Ci * kp))[0][:, :Co * 25].reshape(Ci, Co, 5, 5)
                 db = g.sum(dim=(0, 2, 3)) if m.bias is not None else None
                 grads.append([dw, db])
                 if need_dgrad:
                     wd = ops.pack_conv_weight(m.weight.detach().contiguous(), L.CONV_5X5_S2, Ci, Co, L.LAYOUT_NCHW_F32)
-                    g = ops.conv_forward(g, kind=L.CONV_5X5_S2, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NCHW_F32,
+                    g = T.conv_forward(g, kind=L.CONV_5X5_S2, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NCHW_F32,
                                          out_layout=L.LAYOUT_NHWC_BF16, in_c=Co, out_c=Ci, weight=wd, bias=None)
                     g_layout = L.LAYOUT_NHWC_BF16
                 continue
             if g_layout == L.LAYOUT_NCHW_F32:
                 if epi == L.EPI_RELU:
                     g = g * (rec["y"] > 0).to(g.dtype)  # last layer of h_s: fp32 NCHW output
-                g = ops.nchw_to_nhwc_bf16(g)
+                g = T.nchw_to_nhwc_bf16(g)
                 g_layout = L.LAYOUT_NHWC_BF16
             elif epi == L.EPI_RELU:
                 g = ops.relu_bwd(rec["y"], g)
@@ -454,17 +455,17 @@ class _ChainFn(torch.autograd.Function):
                 d_beta_hat, d_gamma_hat = take(C), take(C * C)
                 db = take(C) if m.bias is not None else None
                 if C == 128 and not _UNFUSED_GDN_BWD:
-                    g = ops.gdn_backward(v, g, gamma_hat, beta_hat, gdn.inverse, d_gamma_hat, d_beta_hat, db)
+                    g = T.gdn_backward(v, g, gamma_hat, beta_hat, gdn.inverse, d_gamma_hat, d_beta_hat, db)
                 else:
                     gamma_hat_t = gamma_hat.t().contiguous()
                     x2 = ops.square_bf16(v)
-                    norm = ops.conv_forward(x2, kind=L.CONV_1X1, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NHWC_BF16,
+                    norm = T.conv_forward(x2, kind=L.CONV_1X1, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NHWC_BF16,
                                             out_layout=L.LAYOUT_NHWC_BF16, in_c=C, out_c=C, weight=gamma_hat, bias=beta_hat)
                     d_norm, d_direct = ops.gdn_bwd_mid(v, g, norm, gdn.inverse, sum_out=d_beta_hat)
-                    t = ops.conv_forward(d_norm, kind=L.CONV_1X1, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NHWC_BF16,
+                    t = T.conv_forward(d_norm, kind=L.CONV_1X1, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NHWC_BF16,
                                          out_layout=L.LAYOUT_NHWC_BF16, in_c=C, out_c=C, weight=gamma_hat_t, bias=None)
                     g = ops.gdn_bwd_out(v, t, d_direct, sum_out=db)
-                    ops.conv_wgrad(d_norm, x2, L.CONV_1X1, out=d_gamma_hat)
+                    T.conv_wgrad(d_norm, x2, L.CONV_1X1, out=d_gamma_hat)
                 d_beta, d_gamma = ops.gdn_param_grad(
                     gdn.beta.detach(), gdn.gamma.detach(), d_beta_hat, d_gamma_hat.view(C, C),
                     gdn.beta_reparam.bound_f, gdn.gamma_reparam.bound_f)
@@ -474,12 +475,12 @@ class _ChainFn(torch.autograd.Function):
             if in_layout == L.LAYOUT_NCHW_F32:  # g_a[0]: image in, K = 25 C_in
                 patches = ops.im2col5x5s2(a_in)
                 kp = patches.shape[-1]
-                dw = ops.conv_wgrad(g, patches, L.CONV_1X1, out=take(Co * kp))[0][:, :Ci * 25].reshape(Co, Ci, 5, 5)
+                dw = T.conv_wgrad(g, patches, L.CONV_1X1, out=take(Co * kp))[0][:, :Ci * 25].reshape(Co, Ci, 5, 5)
             elif kind == L.DECONV_5X5_S2:
-                dw = ops.conv_wgrad(a_in, g, kind, out=take(25 * Ci * Co)).permute(1, 2, 0).reshape(Ci, Co, 5, 5)
+                dw = T.conv_wgrad(a_in, g, kind, out=take(25 * Ci * Co)).permute(1, 2, 0).reshape(Ci, Co, 5, 5)
             else:
                 k = 3 if kind == L.CONV_3X3_S1 else 5
-                dw = ops.conv_wgrad(g, a_in, kind, out=take(k * k * Co * Ci)).permute(1, 2, 0).reshape(Co, Ci, k, k)
+                dw = T.conv_wgrad(g, a_in, kind, out=take(k * k * Co * Ci)).permute(1, 2, 0).reshape(Co, Ci, k, k)
             grads.append([dw, db] + ([d_beta, d_gamma] if gdn is not None else []))
             if need_dgrad:
                 out_layout = L.LAYOUT_NHWC_BF16 if n > 0 else L.LAYOUT_NCHW_F32
@@ -492,7 +493,7 @@ class _ChainFn(torch.autograd.Function):
                     dk, build = L.CONV_3X3_S1, (lambda: ops.pack_conv_weight(w.flip(2, 3).transpose(0, 1).contiguous(), L.CONV_3X3_S1, Ci, Co,
                                                                               L.LAYOUT_NHWC_BF16))
                 wd = build()
-                g = ops.conv_forward(g, kind=dk, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NHWC_BF16, out_layout=out_layout,
+                g = T.conv_forward(g, kind=dk, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NHWC_BF16, out_layout=out_layout,
                                      in_c=Co, out_c=Ci, weight=wd, bias=None)
                 g_layout = out_layout
         grads.reverse()

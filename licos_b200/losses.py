@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from . import torch_ops as T
 
 
 class _RDTermsFn(torch.autograd.Function):
@@ -19,9 +20,9 @@ class _RDTermsFn(torch.autograd.Function):
         acc = torch.zeros(2, dtype=torch.float64, device=target.device)
         liks = [lk.contiguous() for lk in liks]
         for lk in liks:
-            ops.sum_log(lk, acc[0:1])
+            T.sum_log(lk, acc[0:1])
         x_hat, target = x_hat.contiguous(), target.contiguous()
-        ops.sum_sq_err(x_hat, target, acc[1:2])
+        T.sum_sq_err(x_hat, target, acc[1:2])
         ctx.save_for_backward(x_hat, target, *liks)
         ctx.num_pixels = num_pixels
         return (acc[0] / (-math.log(2) * num_pixels)).float(), (acc[1] / target.numel()).float()
@@ -57,8 +58,8 @@ class RateDistortionLoss(nn.Module):
         else:
             acc = torch.zeros(2, dtype=torch.float64, device=target.device)
             for lk in output["likelihoods"].values():
-                ops.sum_log(lk.contiguous(), acc[0:1])
-            ops.sum_sq_err(output["x_hat"].contiguous(), target.contiguous(), acc[1:2])
+                T.sum_log(lk.contiguous(), acc[0:1])
+            T.sum_sq_err(output["x_hat"].contiguous(), target.contiguous(), acc[1:2])
             out["bpp_loss"] = (acc[0] / (-math.log(2) * num_pixels)).float()
             out["mse_loss"] = (acc[1] / target.numel()).float()
         distortion = 255 ** 2 * out["mse_loss"]
@@ -73,14 +74,14 @@ def compute_bpp(out_net) -> float:
     num_pixels = size[0] * size[2] * size[3]
     acc = torch.zeros(1, dtype=torch.float64, device=out_net["x_hat"].device)
     for lk in out_net["likelihoods"].values():
-        ops.sum_log(lk.contiguous(), acc)
+        T.sum_log(lk.contiguous(), acc)
     return float(acc.item() / (-math.log(2) * num_pixels))
 
 
 @torch.no_grad()
 def compute_psnr(a, b) -> float:
     """eval_utils.py:145-156"""
-    acc = ops.sum_sq_err(a.contiguous(), b.contiguous())
+    acc = T.sum_sq_err(a.contiguous(), b.contiguous())
     return -10 * math.log10(acc.item() / a.numel())
 
 
