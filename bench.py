@@ -62,7 +62,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=256, help="tiles per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=16, help="tiles per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-chunk", type=int, default=32)
+    ap.add_argument("--e2e-chunk", type=int, default=128)
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (BASELINE.json configs[4])")
     ap.add_argument("--no-legs", action="store_true", help="skip the cfg3 / cfg4 / library-baseline legs (profiling runs)")

@@ -118,7 +118,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Whole-warp wait for warp-uniform issue loops: the vote makes the loop condition provably uniform, so the compiler
 // keeps the loop state of the caller in uniform registers (a per-thread spin makes everything after it "divergent").
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
+    const long long t0 = clock64();  // (only read once a wait has already failed: nothing on the fast path)
     while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+        if (clock64() - t0 > 8000000000LL) __trap();  // a pipeline bug becomes a CUDA error, not a hung GPU
     }
 }
 
@@ -270,6 +273,105 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
+// CTA pairs (cta_group::2): two CTAs of a cluster on the two SMs of a TPC run ONE tcgen05.mma with M = 256 -- each SM
+// computes its own 128 rows from its own A tile, the N x K weight tile is split (N / 2 rows in each SM's shared memory) and
+// exchanged by the hardware.  Measured (tools/mma_bench7.cu, all 148 SMs): M128 N128 K16 in cta_group::1 reads 8 KB of
+// operands per 64-cycle MMA = the whole 128 B/clk shared-memory port -> 74.5 cycles per MMA, 91 with one barrier wait per 8
+// MMAs; the pair reads 6 KB per SM -> 64.0 cycles, waits hidden.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+// arrive on a barrier of another (or this) CTA of the cluster; releases this thread's prior writes at cluster scope
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a local barrier whose arrivals come from both CTAs (acquire at cluster scope)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > 8000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_wait_warp_cluster(uint64_t* bar, uint32_t parity) {
+    if (__all_sync(0xffffffffu, mbar_try_wait_cluster(bar, parity))) return;
+    const long long t0 = clock64();
+    while (!__all_sync(0xffffffffu, mbar_try_wait_cluster(bar, parity))) {
+        if (clock64() - t0 > 8000000000LL) __trap();
+    }
+}
+// TMA loads of a CTA pair: the data lands in THIS CTA's shared memory, the transaction bytes are counted on a barrier of
+// the pair's leader (`leader_bar` = mapa_shared(barrier, 0))
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1, int c2,
+                                                 int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B^T over the pair: issued by ONE thread of the leader CTA, M = 256 in the descriptor
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs once the pair's previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -551,6 +551,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     }
 }
 
+}  // namespace licos
+
+#include "conv_pair.cuh"
+
+namespace licos {
+
 // ----------------------------------------------------------------------------------------------
 // small helper kernels: weight / GDN packing, first-layer im2col
 // ----------------------------------------------------------------------------------------------
@@ -706,10 +712,11 @@ static unsigned long long* g_conv_probe = nullptr;
 //   LICOS_PREFER_NACC2=1   two single-buffered accumulators instead of one double-buffered one when both do not fit
 //   LICOS_NO_SMALL_TILES=1 keep 16-row tiles even when there are fewer of them than SMs
 //   LICOS_FORCE_NACC1=1    8-row tiles everywhere (tile-quantisation experiments at small batches)
+//   LICOS_NO_PAIR=1        single-CTA engine (cta_group::1) everywhere: the A/B switch for the CTA-pair kernel
 //   LICOS_SA / LICOS_SB    force the slab / weight ring depths
 //   LICOS_DBG_FLAGS        bit 0 / 1: load every slab / weight ring slot only once (isolates the mainloop from data movement)
 struct DevKnobs {
-    bool first_v1, prefer_nacc2, no_small_tiles, force_nacc1;
+    bool first_v1, prefer_nacc2, no_small_tiles, force_nacc1, no_pair;
     int sa, sb, dbg_flags;
 };
 static const DevKnobs& knobs() {
@@ -719,6 +726,7 @@ static const DevKnobs& knobs() {
         v.prefer_nacc2 = getenv("LICOS_PREFER_NACC2") != nullptr;
         v.no_small_tiles = getenv("LICOS_NO_SMALL_TILES") != nullptr;
         v.force_nacc1 = getenv("LICOS_FORCE_NACC1") != nullptr;
+        v.no_pair = getenv("LICOS_NO_PAIR") != nullptr;
         if (const char* e = getenv("LICOS_SA")) v.sa = atoi(e);
         if (const char* e = getenv("LICOS_SB")) v.sb = atoi(e);
         if (const char* e = getenv("LICOS_DBG_FLAGS")) v.dbg_flags = atoi(e);
@@ -1319,6 +1327,16 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
         p.pass_info[pi] = info;
     }
 
+    // ---- CTA pairs (conv_pair.cuh): every lean shape; the weight and gamma tiles are split between the two CTAs ----
+    int sms = a->sm_count;
+    if (sms <= 0) {
+        int dev = 0;
+        LICOS_CUDA_OK(cudaGetDevice(&dev));
+        LICOS_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const bool use_pair = p.lean && !knobs().no_pair && sms >= 2 && pl.N % 16 == 0 && g_conv_probe == nullptr;
+    const uint32_t w_box_rows = use_pair ? (uint32_t)pl.N / 2 : (uint32_t)pl.N;
+
     // ---- tensor maps ---------------------------------------------------------------------------
     const uint64_t C = (uint64_t)cin_pad, H = (uint64_t)in_h, W = (uint64_t)in_w, B = (uint64_t)a->batch;
     const uint32_t in_box[4] = {(uint32_t)kKChunk, (uint32_t)kTileW, (uint32_t)R, 1};
@@ -1340,13 +1358,13 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
         const uint64_t w_taps = pointwise ? 1 : (uint64_t)taps_of(kind);
         const uint64_t dims[2] = {C, w_taps * (uint64_t)pl.rows};
         const uint64_t strides[1] = {C};
-        const uint32_t box[2] = {(uint32_t)kKChunk, (uint32_t)pl.N};
+        const uint32_t box[2] = {(uint32_t)kKChunk, w_box_rows};
         if (!make_map(&p.w_map, a->weight, 2, dims, strides, box)) return LICOS_ERR_CUDA;
     }
     if (gdn) {
         const uint64_t dims[2] = {(uint64_t)a->out_c, (uint64_t)a->out_c};
         const uint64_t strides[1] = {(uint64_t)a->out_c};
-        const uint32_t box[2] = {(uint32_t)kKChunk, (uint32_t)pl.N};
+        const uint32_t box[2] = {(uint32_t)kKChunk, w_box_rows};
         if (!make_map(&p.g_map, a->gamma, 2, dims, strides, box)) return LICOS_ERR_CUDA;
     } else {
         p.g_map = p.w_map;
@@ -1374,9 +1392,9 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
 
     // ---- shared memory plan --------------------------------------------------------------------
     p.a_slot_bytes = (uint32_t)R * kRowBytes;
-    p.b_slot_bytes = (uint32_t)pl.N * 128u;
+    p.b_slot_bytes = w_box_rows * 128u;
     p.staging_bytes = (gdn || a->out_layout == LICOS_LAYOUT_NHWC_BF16) ? (uint32_t)(pl.N / kKChunk) * 128u * 128u : 0u;
-    p.gamma_bytes = gdn ? (uint32_t)(pl.N / kKChunk) * (uint32_t)pl.N * 128u : 0u;
+    p.gamma_bytes = gdn ? (uint32_t)(pl.N / kKChunk) * w_box_rows * 128u : 0u;
     const int64_t b_slot_al = p.b_slot_bytes;  // N is a multiple of 16, so N*128 is a multiple of 2 KB
     int sa = 0, sb = 0;
     for (p.n_teams = 2; p.n_teams >= 1; --p.n_teams) {
@@ -1410,17 +1428,35 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     p.dbg = g_conv_probe;
     p.dbg_flags = knobs().dbg_flags;
 
-    int sms = a->sm_count;
-    if (sms <= 0) {
-        int dev = 0;
-        LICOS_CUDA_OK(cudaGetDevice(&dev));
-        LICOS_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int grid = (int)(tiles < sms ? tiles : sms);
+    if (use_pair) {
+        // pair work items: two spatial tiles (one per CTA) that share a channel split
+        const int64_t spatial = (int64_t)a->batch * p.tiles_h * p.tiles_w;
+        const int64_t items = (spatial + 1) / 2 * p.n_split;
+        p.total_tiles = (int)items;
+        const int64_t pairs = items < sms / 2 ? items : sms / 2;
+        grid = (int)(2 * pairs);
     }
-    const int grid = (int)(tiles < sms ? tiles : sms);
     const bool nhwc = a->out_layout == LICOS_LAYOUT_NHWC_BF16;
     cudaError_t err = cudaErrorInvalidValue;
 #define LICOS_LAUNCH_X(E, O, X)                                                                         \
     do {                                                                                                \
+        if (use_pair) {                                                                                 \
+            const cudaError_t attr = ensure_max_dynamic_smem((const void*)conv_igemm_pair_kernel<E, O, X>, kMaxDynSmem); \
+            if (attr != cudaSuccess) { err = attr; break; }                                             \
+            cudaLaunchConfig_t cfg = {};                                                                \
+            cfg.gridDim = dim3((unsigned)grid);                                                         \
+            cfg.blockDim = dim3(kThreads);                                                              \
+            cfg.dynamicSmemBytes = smem_bytes;                                                          \
+            cfg.stream = s;                                                                             \
+            cudaLaunchAttribute at[1];                                                                  \
+            at[0].id = cudaLaunchAttributeClusterDimension;                                             \
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;         \
+            cfg.attrs = at;                                                                             \
+            cfg.numAttrs = 1;                                                                           \
+            err = cudaLaunchKernelEx(&cfg, conv_igemm_pair_kernel<E, O, X>, p);                         \
+            break;                                                                                      \
+        }                                                                                               \
         const cudaError_t attr = ensure_max_dynamic_smem((const void*)conv_igemm_kernel<E, O, X>,      \
                                                          kMaxDynSmem);                                  \
         if (attr != cudaSuccess) { err = attr; break; }                                                 \

@@ -1,0 +1,392 @@
+// The conv engine on CTA PAIRS (tcgen05 cta_group::2): the same slab / tap / pass walk, tiles, rings, TMEM double
+// buffering and in-place GDN epilogue as conv_igemm_kernel (conv_engine.cu), but two CTAs on the two SMs of a TPC run every
+// MMA together with M = 256: each CTA brings its OWN 16 x 16-position tile (its own activation slabs, its own two 128-row
+// accumulators in its own TMEM, its own epilogue), the pair shares every weight tile -- each CTA loads and holds only
+// HALF of it (N / 2 rows), the tensor cores exchange the halves.
+//
+// Why (tools/mma_bench7.cu, all 148 SMs busy): a cta_group::1 MMA of M128 N128 K16 reads 4 KB of A + 4 KB of B per 64-cycle
+// instruction -- the entire 128 B/clk shared-memory read port -- and runs at 74.5 cycles, 91 with one barrier wait per tap;
+// the engine measured 104-110 cycles per MMA with or without its TMA traffic (tools/probe_sweep.sh), i.e. it was never
+// bandwidth-bound from L2, it was starved at the operand port.  The pair reads 4 + 2 KB per SM and instruction: 64.0
+// cycles per MMA, barrier waits hidden behind the queue.  The fused gamma GEMM runs pair-wide for the same reason (and
+// because a kernel must not mix cta_group::1 and ::2 tcgen05 instructions).
+//
+// Protocol (L = the barrier of the pair's leader, CTA rank 0, is the one that is used; B = each CTA uses its own copy):
+//   a_full / b_full [L]   count 1: the leader's producer arrives with expect_tx of BOTH CTAs' bytes; each CTA's TMA load
+//                         (cp.async.bulk.tensor ... cta_group::2) lands in its own shared memory and completes its bytes on
+//                         the leader's barrier
+//   a_empty / b_empty [B] tcgen05.commit ... multicast to both CTAs: each producer refills its own ring
+//   acc_full [B]          multicast commit: both epilogues start
+//   acc_empty [L]         count 2 x 128 x jobs: every epilogue thread of both CTAs arrives (the peer's remotely)
+//   stg_full [L]          count 2 per team: "this CTA's x^2 tile is in shared memory"; then the leader's team warp issues the
+//                         pair-wide gamma GEMM and commits (multicast) to norm_full [B]
+// Only lean passes (every slab's taps walk consecutive slab rows, one group) take this kernel; the merged narrow deconv
+// and other table-walk shapes stay on conv_igemm_kernel.
+#pragma once
+
+namespace licos {
+
+struct PairTile {
+    int b, gh0, gw0, ns;
+    bool live;
+};
+// work item w of the pair -> this CTA's tile: spatial tile 2 q + rank, channel split ns (the pair shares ns: same weights)
+__device__ __forceinline__ PairTile decode_pair_tile(const ConvParams& p, int w, uint32_t rank) {
+    PairTile t;
+    t.ns = w % p.n_split;
+    int sp = (w / p.n_split) * 2 + (int)rank;
+    const int spatial = p.batch * p.tiles_h * p.tiles_w;
+    t.live = sp < spatial;
+    if (!t.live) sp = spatial;  // -> b == batch: every TMA load is zero fill, every TMA store is clipped away
+    t.gw0 = (sp % p.tiles_w) * kTileW;
+    sp /= p.tiles_w;
+    t.gh0 = (sp % p.tiles_h) * (kAccRows * p.n_acc);
+    t.b = sp / p.tiles_h;
+    return t;
+}
+
+template <int EPI, bool OUT_NHWC, int XC>
+__global__ void __launch_bounds__(kThreads, 1) conv_igemm_pair_kernel(const __grid_constant__ ConvParams p) {
+    constexpr bool kGdn = (EPI == LICOS_EPI_GDN || EPI == LICOS_EPI_IGDN);
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], b_full[kMaxSB], b_empty[kMaxSB];
+    __shared__ uint64_t acc_full[2], acc_empty[2], norm_full[2], stg_full[2], g_full;
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ __align__(16) float bias_s[512];
+    __shared__ __align__(16) float beta_s[256];
+    __shared__ int16_t w_taps_s[kMaxPasses][kMaxSlabs * kMaxTaps];
+    __shared__ int n_taps_s[kMaxPasses];
+
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = a_ring + (size_t)p.sa * p.a_slot_bytes;
+    uint8_t* staging_all = b_ring + (size_t)p.sb * p.b_slot_bytes;          // one tile per epilogue team
+    uint8_t* gamma_s = staging_all + (size_t)p.n_teams * p.staging_bytes;   // this CTA's HALF of gamma: (N / 64) atoms of [N / 2][64]
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader_cta = rank == 0;
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int half_n = p.N / 2;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.sa; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < p.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 2u * 128u * (uint32_t)p.jobs_per_pass);
+            mbar_init(&norm_full[i], 1);
+            mbar_init(&stg_full[i], 2);
+        }
+        mbar_init(&g_full, 1);
+        mbar_fence_init();
+    }
+    for (int i = threadIdx.x; i < p.N * p.n_split; i += kThreads) bias_s[i] = (p.bias && i < p.out_c) ? p.bias[i] : 0.f;
+    if (kGdn)
+        for (int i = threadIdx.x; i < p.N; i += kThreads) beta_s[i] = p.beta[i];
+    if (threadIdx.x < p.n_passes) {
+        const Pass& ps = p.passes[threadIdx.x];
+        int n = 0;
+        for (int sl = 0; sl < ps.n_slabs; ++sl)
+            for (int k = 0; k < ps.slabs[sl].n_taps; ++k) w_taps_s[threadIdx.x][n++] = ps.slabs[sl].taps[k].w_tap;
+        n_taps_s[threadIdx.x] = n;
+    }
+    if (warp == 2) {
+        tmem_alloc_pair(&tmem_base_smem, kTmemCols);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();  // both CTAs' barriers are initialised before anyone signals across the pair
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+    const int n_items = p.total_tiles;  // pair work items (spatial tile pairs x channel splits)
+
+    if (warp == 0 && lane == 0) {
+        // ===================== A producer (each CTA loads the slabs of its own tile) =====================
+        for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.in_maps[i]);
+        Ring ra;
+        for (int w = pair; w < n_items; w += n_pairs) {
+            const PairTile t = decode_pair_tile(p, w, rank);
+            for (int pi = 0; pi < p.n_passes; ++pi) {
+                const Pass& ps = p.passes[pi];
+                for (int c = 0; c < p.cin_chunks; ++c) {
+                    for (int s = 0; s < ps.n_slabs; ++s) {
+                        const Slab& sl = ps.slabs[s];
+                        mbar_wait(&a_empty[ra.slot], ra.phase ^ 1u);
+                        if (leader_cta) mbar_arrive_expect_tx(&a_full[ra.slot], 2u * p.a_slot_bytes);
+                        tma_load_4d_pair(a_ring + (size_t)ra.slot * p.a_slot_bytes, &p.in_maps[sl.in_map],
+                                         mapa_shared(smem_u32(&a_full[ra.slot]), 0), c * kKChunk, t.gw0 + sl.dw, t.gh0 - 1, t.b);
+                        ra.advance(p.sa);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== B producer: this CTA's half (N / 2 rows) of every weight tile =====================
+        if (lane == 0) {
+            tma_prefetch_desc(&p.w_map);
+            if (kGdn) {  // this CTA's half of gamma stays resident for the whole kernel
+                tma_prefetch_desc(&p.g_map);
+                if (leader_cta) mbar_arrive_expect_tx(&g_full, 2u * p.gamma_bytes);
+                const uint32_t gbar = mapa_shared(smem_u32(&g_full), 0);
+                for (int gc = 0; gc < p.N / kKChunk; ++gc)
+                    tma_load_2d_pair(gamma_s + (size_t)gc * half_n * 128, &p.g_map, gbar, gc * kKChunk, (int)rank * half_n);
+            }
+        }
+        __syncwarp();
+        uint32_t slot = 0, phase = 0;
+        for (int w = pair; w < n_items; w += n_pairs) {
+            const int ns_row = (w % p.n_split) * p.N + (int)rank * half_n;
+            for (int pi = 0; pi < p.n_passes; ++pi) {
+                const int nt = n_taps_s[pi];
+                for (int c = 0; c < p.cin_chunks; ++c) {
+                    for (int i = 0; i < nt; ++i) {
+                        const int row = (int)w_taps_s[pi][i] * p.w_rows_per_tap + ns_row;
+                        mbar_wait_warp(&b_empty[slot], phase ^ 1u);
+                        if (elect_one()) {
+                            if (leader_cta) mbar_arrive_expect_tx(&b_full[slot], 2u * p.b_slot_bytes);
+                            tma_load_2d_pair(b_ring + (size_t)slot * p.b_slot_bytes, &p.w_map, mapa_shared(smem_u32(&b_full[slot]), 0),
+                                             c * kKChunk, row);
+                        }
+                        __syncwarp();
+                        slot = (slot + 1 == (uint32_t)p.sb) ? 0u : slot + 1;
+                        phase ^= (slot == 0u) ? 1u : 0u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== MMA issuer: the leader CTA issues for the pair =====================
+        if (leader_cta) {
+            const uint32_t idesc = umma_idesc_bf16(256, p.N);
+            const uint64_t desc_hi = umma_desc_sw128(0);
+            const uint32_t a_ring_addr = smem_u32(a_ring) >> 4, b_ring_addr = smem_u32(b_ring) >> 4;
+            const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_slot16 = p.b_slot_bytes >> 4;
+            const uint32_t n_acc = p.n_acc, N = p.N, sa = p.sa, sb = p.sb;
+            constexpr uint32_t kAccStep16 = (kAccRows * kRowBytes) >> 4;
+            uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0, pit = 0;
+            for (int w = pair; w < n_items; w += n_pairs) {
+                for (int pi = 0; pi < p.n_passes; ++pi, ++pit) {
+                    const Pass& ps = p.passes[pi];
+                    const uint32_t buf = pit % (uint32_t)p.n_buf;
+                    mbar_wait_warp_cluster(&acc_empty[buf], ((pit / (uint32_t)p.n_buf) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t tmem_set = tmem_base + buf * (uint32_t)(ps.n_groups * (int)n_acc) * N;
+                    const int n_slabs = ps.n_slabs;
+                    uint32_t accumulate = 0;
+                    for (int c = 0; c < p.cin_chunks; ++c) {
+                        unsigned long long info = p.pass_info[pi];
+                        for (int s = 0; s < n_slabs; ++s) {
+                            const int nt = (int)(info & 3u) + 1;
+                            uint32_t a_lo = a_ring_addr + a_slot * a_slot16 + ((uint32_t)(info >> 2) & 3u) * (kRowBytes >> 4);
+                            const uint32_t a_step = (info & 16u) ? 0u - (kRowBytes >> 4) : (kRowBytes >> 4);
+                            info >>= 5;
+                            mbar_wait_warp(&a_full[a_slot], a_phase);
+                            for (int k = 0; k < nt; ++k) {
+                                mbar_wait_warp(&b_full[b_slot], b_phase);
+                                tc_fence_after();
+                                const uint64_t bd = desc_hi | (uint64_t)(b_ring_addr + b_slot * b_slot16);
+                                const uint64_t ad = desc_hi | (uint64_t)a_lo;
+                                if (elect_one()) {
+                                    if (n_acc == 2) {
+                                        umma_bf16_pair(tmem_set, ad, bd, idesc, accumulate);
+                                        umma_bf16_pair(tmem_set + N, ad + kAccStep16, bd, idesc, accumulate);
+#pragma unroll
+                                        for (uint32_t ks = 1; ks < 4; ++ks) {
+                                            umma_bf16_pair(tmem_set, ad + 2 * ks, bd + 2 * ks, idesc, 1u);
+                                            umma_bf16_pair(tmem_set + N, ad + kAccStep16 + 2 * ks, bd + 2 * ks, idesc, 1u);
+                                        }
+                                    } else {
+                                        umma_bf16_pair(tmem_set, ad, bd, idesc, accumulate);
+#pragma unroll
+                                        for (uint32_t ks = 1; ks < 4; ++ks) umma_bf16_pair(tmem_set, ad + 2 * ks, bd + 2 * ks, idesc, 1u);
+                                    }
+                                    umma_commit_pair(&b_empty[b_slot]);
+                                }
+                                __syncwarp();
+                                accumulate = 1;
+                                a_lo += a_step;
+                                b_slot = (b_slot + 1 == sb) ? 0u : b_slot + 1;
+                                b_phase ^= (b_slot == 0u) ? 1u : 0u;
+                            }
+                            if (elect_one()) umma_commit_pair(&a_empty[a_slot]);
+                            __syncwarp();
+                            a_slot = (a_slot + 1 == sa) ? 0u : a_slot + 1;
+                            a_phase ^= (a_slot == 0u) ? 1u : 0u;
+                        }
+                    }
+                    if (elect_one()) umma_commit_pair(&acc_full[buf]);
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: two teams of 4 warps per CTA, alternate accumulators =====================
+        const int team = (warp - 4) >> 2;
+        const int et = (warp & 3) * 32 + lane;  // == TMEM lane == row of the 128-row sub-tile
+        const uint32_t lane_sel = ((uint32_t)(warp & 3) * 32u) << 16;
+        const bool leader = et == 0;
+        const int th = et / kTileW, tw = et % kTileW;
+        uint8_t* staging = staging_all + (size_t)team * p.staging_bytes;
+        uint32_t pit = 0, nit = 0, job = 0;
+        const int n32 = p.N / 32;
+        const uint32_t idesc = umma_idesc_bf16(256, p.N);
+        const uint32_t staging16 = smem_u32(staging) >> 4, gamma16 = smem_u32(gamma_s) >> 4;
+        const uint32_t acc_empty_leader[2] = {mapa_shared(smem_u32(&acc_empty[0]), 0), mapa_shared(smem_u32(&acc_empty[1]), 0)};
+        const uint32_t stg_full_leader = mapa_shared(smem_u32(&stg_full[team]), 0);
+        bool gamma_ready = false;
+        for (int w = pair; w < n_items; w += n_pairs) {
+            const PairTile t = decode_pair_tile(p, w, rank);
+            const float* bias_t = bias_s + t.ns * p.N;
+            for (int pi = 0; pi < p.n_passes; ++pi, ++pit) {
+                const Pass& ps = p.passes[pi];
+                const uint32_t buf = pit % (uint32_t)p.n_buf;
+                const uint32_t tmem_set = tmem_base + lane_sel + buf * (uint32_t)(ps.n_groups * p.n_acc) * p.N;
+                bool waited = false;
+                for (int a = 0; a < p.n_acc; ++a) {
+                    if (((job++) & (uint32_t)(p.n_teams - 1)) != (uint32_t)team) continue;
+                    if (!waited) {
+                        mbar_wait(&acc_full[buf], (pit / (uint32_t)p.n_buf) & 1u);
+                        tc_fence_after();
+                        waited = true;
+                    }
+                    const uint32_t acc = (uint32_t)a;
+                    const uint32_t t_acc = tmem_set + acc * p.N;
+
+                    if (OUT_NHWC || kGdn) {
+                        // this team's previous TMA store must have finished reading `staging` before it is rewritten
+                        if (OUT_NHWC && leader) tma_store_wait_read();
+                        named_bar_sync(1 + team, 128);
+                    }
+                    uint32_t xs[kGdn ? XC * 16 : 1];  // v = acc + bias kept as packed bf16 pairs
+                    if (kGdn) {
+                        // stage 1: v^2 (bf16) -> staging = this CTA's 128 rows of the gamma GEMM's A operand; the pair-wide
+                        // GEMM then overwrites both CTAs' accumulators IN PLACE with the norm
+#pragma unroll
+                        for (int cc = 0; cc < XC; ++cc) {
+                            if (cc < n32) {
+                                float v[32];
+                                tmem_ld32(t_acc + cc * 32, v);
+                                tmem_ld_wait();
+                                uint32_t sq[16];
+                                gdn_stage1_32<true>(v, bias_t + cc * 32, xs + cc * 16, sq);
+                                store_row32(staging, et, cc, sq);
+                            }
+                        }
+                        fence_proxy_async();
+                        tc_fence_before();
+                        named_bar_sync(1 + team, 128);
+                        if ((warp & 3) == 0) {  // the team's first warp, converged after the barrier
+                            if (elect_one()) mbar_arrive_cluster(stg_full_leader);
+                            __syncwarp();
+                            if (leader_cta) {
+                                if (!gamma_ready) { mbar_wait(&g_full, 0); gamma_ready = true; }
+                                mbar_wait_warp_cluster(&stg_full[team], nit & 1u);
+                                tc_fence_after();
+                                if (elect_one()) {
+                                    issue_gamma_gemm_pair_n(tmem_set - lane_sel + acc * p.N, staging16, gamma16, (uint32_t)p.N, idesc);
+                                    umma_commit_pair(&norm_full[team]);
+                                }
+                                __syncwarp();
+                            }
+                        }
+                        mbar_wait(&norm_full[team], nit & 1u);
+                        tc_fence_after();
+                        ++nit;
+                    }
+
+                    // stage 2: activation, then write out
+                    const int gh = t.gh0 + a * kAccRows + th, gw = t.gw0 + tw;
+                    const int oh = gh * p.out_s + ps.dy[0], ow = gw * p.out_s + ps.dx[0];
+                    const bool in_range = t.live && gh < p.grid_h && gw < p.grid_w && oh < p.out_h && ow < p.out_w;
+                    const size_t cs = (size_t)p.out_h * p.out_w;
+                    float* o = OUT_NHWC ? nullptr
+                                        : p.out_f32 + ((size_t)t.b * p.out_c * p.out_h + oh) * p.out_w + ow +
+                                              (size_t)(t.ns * p.N) * cs;
+                    const int c_left = p.out_c - t.ns * p.N;  // valid channels from this split's base
+#pragma unroll
+                    for (int cc = 0; cc < XC; ++cc) {
+                        if (cc < n32) {
+                            float v[32];
+                            tmem_ld32(t_acc + cc * 32, v);  // GDN: the norm; otherwise the accumulator
+                            tmem_ld_wait();
+                            if (kGdn) {
+                                uint32_t out[16];
+                                gdn_stage2_32<EPI == LICOS_EPI_IGDN>(v, beta_s + cc * 32, xs + cc * 16, out);
+                                if (OUT_NHWC) {
+                                    store_row32(staging, et, cc, out);
+                                } else if (in_range) {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) {
+                                        if (cc * 32 + 2 * j < c_left) o[(size_t)(cc * 32 + 2 * j) * cs] = __uint_as_float(out[j] << 16);
+                                        if (cc * 32 + 2 * j + 1 < c_left) o[(size_t)(cc * 32 + 2 * j + 1) * cs] = __uint_as_float(out[j] & 0xffff0000u);
+                                    }
+                                }
+                            } else {
+                                const float4* b4 = reinterpret_cast<const float4*>(bias_t + cc * 32);
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    const float4 b = b4[q];
+                                    v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+                                    if (EPI == LICOS_EPI_RELU) {
+#pragma unroll
+                                        for (int i = 0; i < 4; ++i) v[4 * q + i] = fmaxf(v[4 * q + i], 0.f);
+                                    }
+                                }
+                                if (OUT_NHWC) {
+                                    uint32_t out[16];
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) out[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+                                    store_row32(staging, et, cc, out);
+                                } else if (in_range) {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j)
+                                        if (cc * 32 + j < c_left) o[(size_t)(cc * 32 + j) * cs] = v[j];
+                                }
+                            }
+                        }
+                    }
+                    if (!OUT_NHWC && !kGdn && (p.N & 16)) {  // trailing 16 columns (N % 32 == 16)
+                        float h[16];
+                        tmem_ld16(t_acc + n32 * 32, h);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float x = h[j] + bias_t[n32 * 32 + j];
+                            if (EPI == LICOS_EPI_RELU) x = fmaxf(x, 0.f);
+                            if (in_range && n32 * 32 + j < c_left) o[(size_t)(n32 * 32 + j) * cs] = x;
+                        }
+                    }
+                    // this accumulator has been read: hand it back to the pair's MMA issuer
+                    tc_fence_before();
+                    mbar_arrive_cluster(acc_empty_leader[buf]);
+                    if (OUT_NHWC) {
+                        fence_proxy_async();
+                        named_bar_sync(1 + team, 128);
+                        if (leader) {
+                            for (int at = 0; at < p.N / kKChunk; ++at) {
+                                tma_store_4d(&p.out_maps[ps.out_map[0]], staging + (size_t)at * (128 * 128),
+                                             at * kKChunk, t.gw0, t.gh0 + a * kAccRows, t.b);
+                            }
+                            tma_store_commit();
+                        }
+                    }
+                }
+            }
+        }
+        if (leader) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();  // neither CTA leaves (or frees TMEM) while the other may still reach into it
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, kTmemCols);
+    }
+}
+
+}  // namespace licos

@@ -122,4 +122,27 @@ __device__ __forceinline__ void issue_gamma_gemm_n(uint32_t d_tmem, uint32_t stg
     }
 }
 
+// The same GEMM on a CTA pair (cta_group::2, M = 256): each CTA's staging tile is its 128 rows of A, each CTA holds
+// N / 2 rows of gamma (atoms of [N / 2][64]).  Issued by one elected lane of the LEADER CTA.
+template <int KS>
+__device__ __forceinline__ void issue_gamma_gemm_pair(uint32_t d_tmem, uint32_t stg16, uint32_t gamma16, uint32_t half_rows,
+                                                      uint32_t idesc) {
+    const uint64_t desc_hi = umma_desc_sw128(0);
+#pragma unroll
+    for (uint32_t ks = 0; ks < (uint32_t)KS; ++ks) {
+        const uint32_t atom = ks >> 2, off = (ks & 3) * 2;
+        umma_bf16_pair(d_tmem, desc_hi | (uint64_t)(stg16 + atom * 1024 + off),
+                       desc_hi | (uint64_t)(gamma16 + atom * (half_rows * 8) + off), idesc, (uint32_t)(ks > 0));
+    }
+}
+__device__ __forceinline__ void issue_gamma_gemm_pair_n(uint32_t d_tmem, uint32_t stg16, uint32_t gamma16, uint32_t N,
+                                                        uint32_t idesc) {
+    switch (N) {
+        case 64: issue_gamma_gemm_pair<4>(d_tmem, stg16, gamma16, N / 2, idesc); break;
+        case 128: issue_gamma_gemm_pair<8>(d_tmem, stg16, gamma16, N / 2, idesc); break;
+        case 192: issue_gamma_gemm_pair<12>(d_tmem, stg16, gamma16, N / 2, idesc); break;
+        default: issue_gamma_gemm_pair<16>(d_tmem, stg16, gamma16, N / 2, idesc); break;  // 256
+    }
+}
+
 }  // namespace licos

@@ -64,12 +64,12 @@ def _conv_out_shape(x, kind, in_layout, out_layout, out_c):
     return (B, out_c, OH, OW), {_lib.LAYOUT_NCHW_U8: torch.uint8, _lib.LAYOUT_NCHW_U16: torch.uint16}.get(out_layout, torch.float32)
 
 
-def _conv_forward_cuda(x, kind, epilogue, in_layout, out_layout, in_c, out_c, weight, bias, beta, gamma, int_max):
+def _conv_forward_cuda(x, kind, epilogue, in_layout, out_layout, in_c, out_c, weight, bias, beta, gamma, int_max=0):
     return ops.conv_forward(x, kind=kind, epilogue=epilogue, in_layout=in_layout, out_layout=out_layout, in_c=in_c, out_c=out_c,
                             weight=weight, bias=bias, beta=beta, gamma=gamma, int_max=int_max)
 
 
-def _conv_forward_meta(x, kind, epilogue, in_layout, out_layout, in_c, out_c, weight, bias, beta, gamma, int_max):
+def _conv_forward_meta(x, kind, epilogue, in_layout, out_layout, in_c, out_c, weight, bias, beta, gamma, int_max=0):
     shape, dtype = _conv_out_shape(x, kind, in_layout, out_layout, out_c)
     return torch.empty(shape, dtype=dtype, device=x.device)
 
@@ -92,8 +92,8 @@ _register("gdn_backward(Tensor x, Tensor g, Tensor gamma_hat, Tensor beta_hat, b
           lambda x, g, gh, bh, inv, dgh, dbh, db: torch.empty_like(x))
 
 _register("nchw_to_nhwc_bf16(Tensor x, bool take_abs=False) -> Tensor",
-          lambda x, take_abs: ops.nchw_to_nhwc_bf16(x, take_abs=take_abs),
-          lambda x, take_abs: torch.empty((x.shape[0], x.shape[2], x.shape[3], x.shape[1]), dtype=torch.bfloat16, device=x.device))
+          lambda x, take_abs=False: ops.nchw_to_nhwc_bf16(x, take_abs=take_abs),
+          lambda x, take_abs=False: torch.empty((x.shape[0], x.shape[2], x.shape[3], x.shape[1]), dtype=torch.bfloat16, device=x.device))
 
 # ---------------------------------------------------------------------------------------------------------------------
 # entropy bottleneck
