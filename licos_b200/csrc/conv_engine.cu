@@ -1334,7 +1334,7 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
         LICOS_CUDA_OK(cudaGetDevice(&dev));
         LICOS_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    const bool use_pair = p.lean && !knobs().no_pair && sms >= 2 && pl.N % 16 == 0 && g_conv_probe == nullptr;
+    const bool use_pair = p.lean && !knobs().no_pair && sms >= 2 && pl.N % 16 == 0;
     const uint32_t w_box_rows = use_pair ? (uint32_t)pl.N / 2 : (uint32_t)pl.N;
 
     // ---- tensor maps ---------------------------------------------------------------------------
@@ -1439,22 +1439,26 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     }
     const bool nhwc = a->out_layout == LICOS_LAYOUT_NHWC_BF16;
     cudaError_t err = cudaErrorInvalidValue;
+#define LICOS_LAUNCH_PAIR(E, O, XP, TWP)                                                                \
+    do {                                                                                                \
+        const cudaError_t attr = ensure_max_dynamic_smem((const void*)conv_igemm_pair_kernel<E, O, XP, TWP>, kMaxDynSmem); \
+        if (attr != cudaSuccess) { err = attr; break; }                                                 \
+        cudaLaunchConfig_t cfg = {};                                                                    \
+        cfg.gridDim = dim3((unsigned)grid);                                                             \
+        cfg.blockDim = dim3(pair_threads(TWP));                                                         \
+        cfg.dynamicSmemBytes = smem_bytes;                                                              \
+        cfg.stream = s;                                                                                 \
+        cudaLaunchAttribute at[1];                                                                      \
+        at[0].id = cudaLaunchAttributeClusterDimension;                                                 \
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;             \
+        cfg.attrs = at;                                                                                 \
+        cfg.numAttrs = 1;                                                                               \
+        err = cudaLaunchKernelEx(&cfg, conv_igemm_pair_kernel<E, O, XP, TWP>, p);                       \
+    } while (0)
 #define LICOS_LAUNCH_X(E, O, X)                                                                         \
     do {                                                                                                \
         if (use_pair) {                                                                                 \
-            const cudaError_t attr = ensure_max_dynamic_smem((const void*)conv_igemm_pair_kernel<E, O, X>, kMaxDynSmem); \
-            if (attr != cudaSuccess) { err = attr; break; }                                             \
-            cudaLaunchConfig_t cfg = {};                                                                \
-            cfg.gridDim = dim3((unsigned)grid);                                                         \
-            cfg.blockDim = dim3(kThreads);                                                              \
-            cfg.dynamicSmemBytes = smem_bytes;                                                          \
-            cfg.stream = s;                                                                             \
-            cudaLaunchAttribute at[1];                                                                  \
-            at[0].id = cudaLaunchAttributeClusterDimension;                                             \
-            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;         \
-            cfg.attrs = at;                                                                             \
-            cfg.numAttrs = 1;                                                                           \
-            err = cudaLaunchKernelEx(&cfg, conv_igemm_pair_kernel<E, O, X>, p);                         \
+            LICOS_LAUNCH_PAIR(E, O, X, 4);                                                              \
             break;                                                                                      \
         }                                                                                               \
         const cudaError_t attr = ensure_max_dynamic_smem((const void*)conv_igemm_kernel<E, O, X>,      \
@@ -1482,6 +1486,7 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     }
 #undef LICOS_LAUNCH
 #undef LICOS_LAUNCH_X
+#undef LICOS_LAUNCH_PAIR
     LICOS_CUDA_OK(err);
     return LICOS_OK;
 }

@@ -45,9 +45,28 @@ __device__ __forceinline__ PairTile decode_pair_tile(const ConvParams& p, int w,
     return t;
 }
 
-template <int EPI, bool OUT_NHWC, int XC>
-__global__ void __launch_bounds__(kThreads, 1) conv_igemm_pair_kernel(const __grid_constant__ ConvParams p) {
+// Epilogue teams of TW warps.  TW = 4 is what is instantiated.  TW = 8 (two warps per TMEM lane quadrant taking alternate
+// 32-channel chunks, 256 threads per job) halves the time of the per-row loops but leaves only 96 registers per thread
+// (640 threads) and did not shorten a job: measured on the transposed-conv + IGDN layers (8 epilogue jobs per tile), the
+// kernel as a whole is bound by the 128 B/clk shared-memory port once the MMAs run on CTA pairs -- operand reads 6 KB per
+// MMA, slab / weight TMA writes, the x^2 and output staging tiles and the TMA store's reads add up to 4.6 MB per tile
+// against 3.8 MB of port capacity in the ideal MMA time.
+__host__ __device__ constexpr int pair_threads(int tw) { return (4 + 2 * tw) * 32; }
+
+#ifdef LICOS_PAIR_PROBES  // development: per-role cycle counters (tools/probe_conv.py); build with LICOS_NVCC_EXTRA=-DLICOS_PAIR_PROBES
+#define PP_T0(v) const long long v = clock64()
+#define PP_ADD(acc, v) (acc) += clock64() - (v)
+#else
+#define PP_T0(v) (void)0
+#define PP_ADD(acc, v) (void)0
+#endif
+
+// XC = 32-channel chunks PER THREAD the epilogue is unrolled for (TW = 4: 4 / 6 / 8 for N <= 128 / 192 / 256; TW = 8: half)
+template <int EPI, bool OUT_NHWC, int XC, int TW>
+__global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(const __grid_constant__ ConvParams p) {
     constexpr bool kGdn = (EPI == LICOS_EPI_GDN || EPI == LICOS_EPI_IGDN);
+    constexpr int kNT = pair_threads(TW);
+    constexpr uint32_t kTeamThreads = TW * 32;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], b_full[kMaxSB], b_empty[kMaxSB];
     __shared__ uint64_t acc_full[2], acc_empty[2], norm_full[2], stg_full[2], g_full;
@@ -76,16 +95,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_pair_kernel(const __gr
         for (int i = 0; i < p.sb; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 2u * 128u * (uint32_t)p.jobs_per_pass);
+            mbar_init(&acc_empty[i], 2u * kTeamThreads * (uint32_t)p.jobs_per_pass);
             mbar_init(&norm_full[i], 1);
             mbar_init(&stg_full[i], 2);
         }
         mbar_init(&g_full, 1);
         mbar_fence_init();
     }
-    for (int i = threadIdx.x; i < p.N * p.n_split; i += kThreads) bias_s[i] = (p.bias && i < p.out_c) ? p.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < p.N * p.n_split; i += kNT) bias_s[i] = (p.bias && i < p.out_c) ? p.bias[i] : 0.f;
     if (kGdn)
-        for (int i = threadIdx.x; i < p.N; i += kThreads) beta_s[i] = p.beta[i];
+        for (int i = threadIdx.x; i < p.N; i += kNT) beta_s[i] = p.beta[i];
     if (threadIdx.x < p.n_passes) {
         const Pass& ps = p.passes[threadIdx.x];
         int n = 0;
@@ -108,6 +127,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_pair_kernel(const __gr
         // ===================== A producer (each CTA loads the slabs of its own tile) =====================
         for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.in_maps[i]);
         Ring ra;
+        int n_loaded = 0;
         for (int w = pair; w < n_items; w += n_pairs) {
             const PairTile t = decode_pair_tile(p, w, rank);
             for (int pi = 0; pi < p.n_passes; ++pi) {
@@ -116,6 +136,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_pair_kernel(const __gr
                     for (int s = 0; s < ps.n_slabs; ++s) {
                         const Slab& sl = ps.slabs[s];
                         mbar_wait(&a_empty[ra.slot], ra.phase ^ 1u);
+                        if ((p.dbg_flags & 1) && n_loaded >= p.sa) {  // development: every ring slot loaded only once
+                            if (leader_cta) mbar_arrive(&a_full[ra.slot]);
+                            ra.advance(p.sa);
+                            continue;
+                        }
+                        ++n_loaded;
                         if (leader_cta) mbar_arrive_expect_tx(&a_full[ra.slot], 2u * p.a_slot_bytes);
                         tma_load_4d_pair(a_ring + (size_t)ra.slot * p.a_slot_bytes, &p.in_maps[sl.in_map],
                                          mapa_shared(smem_u32(&a_full[ra.slot]), 0), c * kKChunk, t.gw0 + sl.dw, t.gh0 - 1, t.b);
@@ -138,6 +164,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_pair_kernel(const __gr
         }
         __syncwarp();
         uint32_t slot = 0, phase = 0;
+        int n_loaded = 0;
         for (int w = pair; w < n_items; w += n_pairs) {
             const int ns_row = (w % p.n_split) * p.N + (int)rank * half_n;
             for (int pi = 0; pi < p.n_passes; ++pi) {
@@ -147,11 +174,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_pair_kernel(const __gr
                         const int row = (int)w_taps_s[pi][i] * p.w_rows_per_tap + ns_row;
                         mbar_wait_warp(&b_empty[slot], phase ^ 1u);
                         if (elect_one()) {
-                            if (leader_cta) mbar_arrive_expect_tx(&b_full[slot], 2u * p.b_slot_bytes);
-                            tma_load_2d_pair(b_ring + (size_t)slot * p.b_slot_bytes, &p.w_map, mapa_shared(smem_u32(&b_full[slot]), 0),
-                                             c * kKChunk, row);
+                            if ((p.dbg_flags & 2) && n_loaded >= p.sb) {
+                                if (leader_cta) mbar_arrive(&b_full[slot]);
+                            } else {
+                                if (leader_cta) mbar_arrive_expect_tx(&b_full[slot], 2u * p.b_slot_bytes);
+                                tma_load_2d_pair(b_ring + (size_t)slot * p.b_slot_bytes, &p.w_map,
+                                                 mapa_shared(smem_u32(&b_full[slot]), 0), c * kKChunk, row);
+                            }
                         }
                         __syncwarp();
+                        ++n_loaded;
                         slot = (slot + 1 == (uint32_t)p.sb) ? 0u : slot + 1;
                         phase ^= (slot == 0u) ? 1u : 0u;
                     }
@@ -168,11 +200,40 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_pair_kernel(const __gr
             const uint32_t n_acc = p.n_acc, N = p.N, sa = p.sa, sb = p.sb;
             constexpr uint32_t kAccStep16 = (kAccRows * kRowBytes) >> 4;
             uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0, pit = 0;
+#ifdef LICOS_PAIR_PROBES
+            long long w_a = 0, w_b = 0, w_acc = 0, n_tiles = 0;
+            const long long t_begin = clock64();
+#endif
+            // Look-ahead barrier checks.  A completed mbarrier wait costs this thread ~150 cycles, and tcgen05.mma issue does
+            // not run far enough ahead of the pipe to hide them: one wait per tap and one per slab idled the tensor pipe 40 %
+            // of the time (tools/probe_sweep.sh: the same with every load switched off).  So the NEXT barrier is probed with a
+            // non-blocking, RELAXED test_wait BEFORE the current tap's MMAs are issued (an acquire there would serialise the
+            // MMAs behind its latency) and its predicate is only read AFTER them: the latency runs under the 8 MMAs.  The
+            // acquire is a fence on the consuming side; the blocking wait remains as the (rare) slow path.
+            asm volatile(".reg .pred licos_nb, licos_na;");
+            const uint32_t a_full0 = smem_u32(&a_full[0]), b_full0 = smem_u32(&b_full[0]);
+            uint32_t have_a = 0, have_b = 0;  // 1 = the look-ahead probe of the current slot already saw its phase complete
+
+            auto wait_slow = [&](uint32_t bar, uint32_t parity) {  // the look-ahead probe missed: a blocking (bounded) wait
+                if (__all_sync(0xffffffffu, mbar_try_wait_addr(bar, parity) ? 1u : 0u)) return;
+                const long long t0 = clock64();
+                while (!__all_sync(0xffffffffu, mbar_try_wait_addr(bar, parity) ? 1u : 0u)) {
+                    if (clock64() - t0 > 8000000000LL) __trap();  // a pipeline bug becomes a CUDA error, not a hung GPU
+                }
+            };
+
             for (int w = pair; w < n_items; w += n_pairs) {
+#ifdef LICOS_PAIR_PROBES
+                ++n_tiles;
+#endif
                 for (int pi = 0; pi < p.n_passes; ++pi, ++pit) {
                     const Pass& ps = p.passes[pi];
                     const uint32_t buf = pit % (uint32_t)p.n_buf;
-                    mbar_wait_warp_cluster(&acc_empty[buf], ((pit / (uint32_t)p.n_buf) & 1u) ^ 1u);
+                    {
+                        PP_T0(_t);
+                        mbar_wait_warp_cluster(&acc_empty[buf], ((pit / (uint32_t)p.n_buf) & 1u) ^ 1u);
+                        PP_ADD(w_acc, _t);
+                    }
                     tc_fence_after();
                     const uint32_t tmem_set = tmem_base + buf * (uint32_t)(ps.n_groups * (int)n_acc) * N;
                     const int n_slabs = ps.n_slabs;
@@ -184,12 +245,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_pair_kernel(const __gr
                             uint32_t a_lo = a_ring_addr + a_slot * a_slot16 + ((uint32_t)(info >> 2) & 3u) * (kRowBytes >> 4);
                             const uint32_t a_step = (info & 16u) ? 0u - (kRowBytes >> 4) : (kRowBytes >> 4);
                             info >>= 5;
-                            mbar_wait_warp(&a_full[a_slot], a_phase);
+                            if (!__all_sync(0xffffffffu, have_a)) {
+                                PP_T0(_t);
+                                wait_slow(a_full0 + a_slot * 8u, a_phase);
+                                PP_ADD(w_a, _t);
+                            }
+                            const uint32_t na_slot = (a_slot + 1 == sa) ? 0u : a_slot + 1;
+                            const uint32_t na_phase = a_phase ^ ((na_slot == 0u) ? 1u : 0u);
                             for (int k = 0; k < nt; ++k) {
-                                mbar_wait_warp(&b_full[b_slot], b_phase);
+                                if (!__all_sync(0xffffffffu, have_b)) {
+                                    PP_T0(_t);
+                                    wait_slow(b_full0 + b_slot * 8u, b_phase);
+                                    PP_ADD(w_b, _t);
+                                }
+                                asm volatile("fence.acq_rel.cta;" ::: "memory");  // pairs with the relaxed look-ahead probes
                                 tc_fence_after();
                                 const uint64_t bd = desc_hi | (uint64_t)(b_ring_addr + b_slot * b_slot16);
                                 const uint64_t ad = desc_hi | (uint64_t)a_lo;
+                                const uint32_t nb_slot = (b_slot + 1 == sb) ? 0u : b_slot + 1;
+                                const uint32_t nb_phase = b_phase ^ ((nb_slot == 0u) ? 1u : 0u);
+                                // probe the next tap's weights and, on a slab's last tap, the next slab -- the predicates are read
+                                // after the MMAs below
+                                asm volatile("mbarrier.test_wait.parity.relaxed.cta.shared::cta.b64 licos_nb, [%0], %1;" ::"r"(b_full0 + nb_slot * 8u),
+                                             "r"(nb_phase)
+                                             : "memory");
+                                if (k == nt - 1)
+                                    asm volatile("mbarrier.test_wait.parity.relaxed.cta.shared::cta.b64 licos_na, [%0], %1;" ::"r"(a_full0 + na_slot * 8u),
+                                                 "r"(na_phase)
+                                                 : "memory");
                                 if (elect_one()) {
                                     if (n_acc == 2) {
                                         umma_bf16_pair(tmem_set, ad, bd, idesc, accumulate);
@@ -207,37 +290,54 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_pair_kernel(const __gr
                                     umma_commit_pair(&b_empty[b_slot]);
                                 }
                                 __syncwarp();
+                                asm volatile("selp.b32 %0, 1, 0, licos_nb;" : "=r"(have_b));
                                 accumulate = 1;
                                 a_lo += a_step;
-                                b_slot = (b_slot + 1 == sb) ? 0u : b_slot + 1;
-                                b_phase ^= (b_slot == 0u) ? 1u : 0u;
+                                b_slot = nb_slot;
+                                b_phase = nb_phase;
                             }
                             if (elect_one()) umma_commit_pair(&a_empty[a_slot]);
                             __syncwarp();
-                            a_slot = (a_slot + 1 == sa) ? 0u : a_slot + 1;
-                            a_phase ^= (a_slot == 0u) ? 1u : 0u;
+                            asm volatile("selp.b32 %0, 1, 0, licos_na;" : "=r"(have_a));
+                            a_slot = na_slot;
+                            a_phase = na_phase;
                         }
                     }
                     if (elect_one()) umma_commit_pair(&acc_full[buf]);
                     __syncwarp();
                 }
             }
+#ifdef LICOS_PAIR_PROBES
+            if (p.dbg && lane == 0) {
+                unsigned long long* d = p.dbg + blockIdx.x * 16;
+                d[DBG_MMA_A] = w_a; d[DBG_MMA_B] = w_b; d[DBG_MMA_ACC] = w_acc; d[DBG_MMA_X2] = 0;
+                d[DBG_MMA_TOTAL] = clock64() - t_begin; d[DBG_TILES] = n_tiles;
+            }
+#endif
         }
     } else if (warp >= 4) {
-        // ===================== epilogue: two teams of 4 warps per CTA, alternate accumulators =====================
-        const int team = (warp - 4) >> 2;
-        const int et = (warp & 3) * 32 + lane;  // == TMEM lane == row of the 128-row sub-tile
+        // ===================== epilogue: two teams of TW warps per CTA, alternate accumulators =====================
+        const int team = (warp - 4) / TW;
+        const int half = TW == 8 ? (((warp - 4) >> 2) & 1) : 0;  // TW = 8: this warp takes chunks cc with (cc & 1) == half
+        constexpr int kStride = TW == 8 ? 2 : 1;
+        const int et = (warp & 3) * 32 + lane;   // == TMEM lane == row of the 128-row sub-tile
         const uint32_t lane_sel = ((uint32_t)(warp & 3) * 32u) << 16;
-        const bool leader = et == 0;
+        const bool leader = et == 0 && half == 0;
+        const bool first_warp = ((warp - 4) % TW) == 0;
         const int th = et / kTileW, tw = et % kTileW;
         uint8_t* staging = staging_all + (size_t)team * p.staging_bytes;
         uint32_t pit = 0, nit = 0, job = 0;
         const int n32 = p.N / 32;
-        const uint32_t idesc = umma_idesc_bf16(256, p.N);
-        const uint32_t staging16 = smem_u32(staging) >> 4, gamma16 = smem_u32(gamma_s) >> 4;
         const uint32_t acc_empty_leader[2] = {mapa_shared(smem_u32(&acc_empty[0]), 0), mapa_shared(smem_u32(&acc_empty[1]), 0)};
         const uint32_t stg_full_leader = mapa_shared(smem_u32(&stg_full[team]), 0);
+        const uint32_t idesc = umma_idesc_bf16(256, p.N);
+        const uint32_t staging16 = smem_u32(staging) >> 4, gamma16 = smem_u32(gamma_s) >> 4;
         bool gamma_ready = false;
+#ifdef LICOS_PAIR_PROBES
+        const bool eprobe = p.dbg && leader && team == 0 && leader_cta;
+        long long e_acc = 0, e_s1 = 0, e_norm = 0, e_s2 = 0, e_store = 0;
+        const long long e_begin = clock64();
+#endif
         for (int w = pair; w < n_items; w += n_pairs) {
             const PairTile t = decode_pair_tile(p, w, rank);
             const float* bias_t = bias_s + t.ns * p.N;
@@ -249,7 +349,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_pair_kernel(const __gr
                 for (int a = 0; a < p.n_acc; ++a) {
                     if (((job++) & (uint32_t)(p.n_teams - 1)) != (uint32_t)team) continue;
                     if (!waited) {
+                        PP_T0(_t);
                         mbar_wait(&acc_full[buf], (pit / (uint32_t)p.n_buf) & 1u);
+                        PP_ADD(e_acc, _t);
                         tc_fence_after();
                         waited = true;
                     }
@@ -258,28 +360,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_pair_kernel(const __gr
 
                     if (OUT_NHWC || kGdn) {
                         // this team's previous TMA store must have finished reading `staging` before it is rewritten
+                        PP_T0(_t);
                         if (OUT_NHWC && leader) tma_store_wait_read();
-                        named_bar_sync(1 + team, 128);
+                        named_bar_sync(1 + team, kTeamThreads);
+                        PP_ADD(e_store, _t);
                     }
                     uint32_t xs[kGdn ? XC * 16 : 1];  // v = acc + bias kept as packed bf16 pairs
                     if (kGdn) {
                         // stage 1: v^2 (bf16) -> staging = this CTA's 128 rows of the gamma GEMM's A operand; the pair-wide
                         // GEMM then overwrites both CTAs' accumulators IN PLACE with the norm
+                        PP_T0(_s1);
 #pragma unroll
-                        for (int cc = 0; cc < XC; ++cc) {
+                        for (int i = 0; i < XC; ++i) {
+                            const int cc = kStride * i + half;
                             if (cc < n32) {
                                 float v[32];
                                 tmem_ld32(t_acc + cc * 32, v);
                                 tmem_ld_wait();
                                 uint32_t sq[16];
-                                gdn_stage1_32<true>(v, bias_t + cc * 32, xs + cc * 16, sq);
+                                gdn_stage1_32<true>(v, bias_t + cc * 32, xs + i * 16, sq);
                                 store_row32(staging, et, cc, sq);
                             }
                         }
                         fence_proxy_async();
                         tc_fence_before();
-                        named_bar_sync(1 + team, 128);
-                        if ((warp & 3) == 0) {  // the team's first warp, converged after the barrier
+                        named_bar_sync(1 + team, kTeamThreads);
+                        if (first_warp) {
+                            // "staged" across the pair; once both CTAs are, the leader's warp issues the pair-wide gamma GEMM.
+                            // (Issuing it from the main MMA thread instead -- it owns the pipe's queue -- was measured and was
+                            // no faster: in pair mode the kernel is bound by the 128 B/clk shared-memory port, not by issue.)
                             if (elect_one()) mbar_arrive_cluster(stg_full_leader);
                             __syncwarp();
                             if (leader_cta) {
@@ -293,12 +402,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_pair_kernel(const __gr
                                 __syncwarp();
                             }
                         }
+                        PP_ADD(e_s1, _s1);
+                        PP_T0(_n);
                         mbar_wait(&norm_full[team], nit & 1u);
+                        PP_ADD(e_norm, _n);
                         tc_fence_after();
                         ++nit;
                     }
 
                     // stage 2: activation, then write out
+                    PP_T0(_s2);
                     const int gh = t.gh0 + a * kAccRows + th, gw = t.gw0 + tw;
                     const int oh = gh * p.out_s + ps.dy[0], ow = gw * p.out_s + ps.dx[0];
                     const bool in_range = t.live && gh < p.grid_h && gw < p.grid_w && oh < p.out_h && ow < p.out_w;
@@ -308,14 +421,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_pair_kernel(const __gr
                                               (size_t)(t.ns * p.N) * cs;
                     const int c_left = p.out_c - t.ns * p.N;  // valid channels from this split's base
 #pragma unroll
-                    for (int cc = 0; cc < XC; ++cc) {
+                    for (int i = 0; i < XC; ++i) {
+                        const int cc = kStride * i + half;
                         if (cc < n32) {
                             float v[32];
                             tmem_ld32(t_acc + cc * 32, v);  // GDN: the norm; otherwise the accumulator
                             tmem_ld_wait();
                             if (kGdn) {
                                 uint32_t out[16];
-                                gdn_stage2_32<EPI == LICOS_EPI_IGDN>(v, beta_s + cc * 32, xs + cc * 16, out);
+                                gdn_stage2_32<EPI == LICOS_EPI_IGDN>(v, beta_s + cc * 32, xs + i * 16, out);
                                 if (OUT_NHWC) {
                                     store_row32(staging, et, cc, out);
                                 } else if (in_range) {
@@ -333,13 +447,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_pair_kernel(const __gr
                                     v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
                                     if (EPI == LICOS_EPI_RELU) {
 #pragma unroll
-                                        for (int i = 0; i < 4; ++i) v[4 * q + i] = fmaxf(v[4 * q + i], 0.f);
+                                        for (int ii = 0; ii < 4; ++ii) v[4 * q + ii] = fmaxf(v[4 * q + ii], 0.f);
                                     }
                                 }
                                 if (OUT_NHWC) {
                                     uint32_t out[16];
 #pragma unroll
-                                    for (int i = 0; i < 16; ++i) out[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+                                    for (int ii = 0; ii < 16; ++ii) out[ii] = pack_bf16x2(v[2 * ii], v[2 * ii + 1]);
                                     store_row32(staging, et, cc, out);
                                 } else if (in_range) {
 #pragma unroll
@@ -349,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_pair_kernel(const __gr
                             }
                         }
                     }
-                    if (!OUT_NHWC && !kGdn && (p.N & 16)) {  // trailing 16 columns (N % 32 == 16)
+                    if (!OUT_NHWC && !kGdn && (p.N & 16) && half == (TW == 8 ? (n32 & 1) : 0)) {  // trailing 16 columns (N % 32 == 16)
                         float h[16];
                         tmem_ld16(t_acc + n32 * 32, h);
                         tmem_ld_wait();
@@ -362,10 +476,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_pair_kernel(const __gr
                     }
                     // this accumulator has been read: hand it back to the pair's MMA issuer
                     tc_fence_before();
-                    mbar_arrive_cluster(acc_empty_leader[buf]);
+                    mbar_arrive_cluster_relaxed(acc_empty_leader[buf]);  // orders TMEM reads (the tcgen05 fence), no memory
+                    PP_ADD(e_s2, _s2);
+                    PP_T0(_st);
                     if (OUT_NHWC) {
                         fence_proxy_async();
-                        named_bar_sync(1 + team, 128);
+                        named_bar_sync(1 + team, kTeamThreads);
                         if (leader) {
                             for (int at = 0; at < p.N / kKChunk; ++at) {
                                 tma_store_4d(&p.out_maps[ps.out_map[0]], staging + (size_t)at * (128 * 128),
@@ -374,10 +490,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_pair_kernel(const __gr
                             tma_store_commit();
                         }
                     }
+                    PP_ADD(e_store, _st);
                 }
             }
         }
         if (leader) tma_store_wait_all();
+#ifdef LICOS_PAIR_PROBES
+        if (eprobe) {
+            unsigned long long* d = p.dbg + blockIdx.x * 16;
+            d[DBG_EPI_ACC] = e_acc; d[DBG_EPI_S1] = e_s1; d[DBG_EPI_NORM] = e_norm; d[DBG_EPI_S2] = e_s2;
+            d[DBG_EPI_STORE] = e_store; d[DBG_EPI_TOTAL] = clock64() - e_begin;
+        }
+#endif
     }
 
     tc_fence_before();

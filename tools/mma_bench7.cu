@@ -15,11 +15,6 @@
 extern "C" void licos_set_last_cuda_error(int) {}
 using namespace licos;
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
 }
@@ -132,16 +127,24 @@ __global__ void __launch_bounds__(192, 1) bench(int taps, int flags, const uint8
             const uint32_t lane_sel = ((uint32_t)(warp & 3) * 32u) << 16;
             uint8_t* stg = smem + 114688 + (warp - 2) * 4096;
             float acc = 0.f;
+            long long iters = 0;
+            const long long e0 = clock64();
             while (!stop) {
                 float v[32];
                 tmem_ld32(tmem + lane_sel + 256 + ((warp & 1) * 32), v);
                 tmem_ld_wait();
+                if (!(flags & 64)) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    *reinterpret_cast<float4*>(stg + ((lane * 8 + q) & 255) * 16) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                    acc += v[4 * q];
+                    for (int q = 0; q < 8; ++q) {
+                        *reinterpret_cast<float4*>(stg + ((lane * 8 + q) & 255) * 16) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        acc += v[4 * q];
+                    }
+                } else {
+                    acc += v[0] + v[31];
                 }
+                ++iters;
             }
+            if (warp == 2 && lane == 0) out[2 * blockIdx.x + 1] = (clock64() - e0) / (iters ? iters : 1);  // cycles per tcgen05.ld.x32 round trip
             if (acc == 12345.f) out[1] = 1;
         }
     }
@@ -184,14 +187,16 @@ static void run(int flags, int taps, int grid, const uint8_t* src, long long* d)
     cudaEventElapsedTime(&ms, e0, e1);
     long long h[2 * 160];
     cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-    double sum = 0; int n = 0;
+    double sum = 0, ldsum = 0; int n = 0, nld = 0;
     for (int i = 0; i < grid; ++i) if (h[2 * i] > 0) { sum += (double)h[2 * i]; ++n; }
+    for (int i = 0; i < grid; ++i) if (h[2 * i + 1] > 1) { ldsum += (double)h[2 * i + 1]; ++nld; }
     const double cyc = n ? sum / n / taps / 8.0 : 0;
     const int sms = pair ? (grid & ~1) : grid;
     const int Nn = (flags & 32) ? 256 : 128;
     const double tflops = 2.0 * 128 * Nn * 16 * 8.0 * taps * sms / (ms * 1e-3) / 1e12;
-    printf("flags %2d grid %3d: %.1f cycles/MMA (ideal %d)  %.3f ms  %.0f TFLOP/s  eff clock %.2f GHz [%s %s]\n", flags, grid, cyc,
-           Nn / 2, ms, tflops, n ? (sum / n) / (ms * 1e-3) / 1e9 : 0.0, cudaGetErrorString(err), cudaGetErrorString(e));
+    printf("flags %3d grid %3d: %.1f cycles/MMA (ideal %d)  %.3f ms  %.0f TFLOP/s  eff clock %.2f GHz  tmem_ld32 loop %.0f cycles [%s %s]\n",
+           flags, grid, cyc, Nn / 2, ms, tflops, n ? (sum / n) / (ms * 1e-3) / 1e9 : 0.0, nld ? ldsum / nld : 0.0, cudaGetErrorString(err),
+           cudaGetErrorString(e));
 }
 
 int main(int argc, char** argv) {
@@ -200,7 +205,7 @@ int main(int argc, char** argv) {
     uint8_t* src; cudaMalloc(&src, (size_t)2048 * 18432 + 65536); cudaMemset(src, 0, (size_t)2048 * 18432);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    const int sets[] = {0, 1, 2, 3, 4, 8, 12, 15, 16, 19, 31, 32, 35, 48, 51, 63};
+    const int sets[] = {0, 3, 4, 4 + 64, 15, 16, 19, 16 + 4, 16 + 4 + 64, 31, 31 + 64, 32, 48, 63};
     printf("== one CTA\n");
     run(0, taps, 1, src, d); run(3, taps, 1, src, d); run(15, taps, 1, src, d);
     printf("== all %d SMs\n", sms);
