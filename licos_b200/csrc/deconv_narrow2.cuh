@@ -11,7 +11,9 @@
 //   rows     in the epilogue, for free.  The accumulators of consecutive input rows sit in a ring of 8 TMEM slots; the
 //            thread that owns pixel j (TMEM lane j) sums the <= 3 row taps from the slots of rows i'-1, i', i'+1 --
 //            all in its own lane -- adds the bias and stores the 2 x 2 x C_out outputs of its pixel as float2 pairs
-//            (a warp store = 256 contiguous bytes of one NCHW output row).
+//            (a warp store = 256 contiguous bytes of one NCHW output row).  TWO epilogue teams take alternate rows: one
+//            team working the rows serially (wait, three TMEM loads, 16 outputs, 8 stores, ~2 700 cycles per row) was what
+//            bounded the kernel at half its HBM roofline; a slot is handed back when its three readers have all read it.
 //
 // No im2col, no shared-memory staging of partial sums, no atomics; every input byte is fetched from L2 once per strip.
 #pragma once
@@ -20,7 +22,7 @@
 
 namespace licos {
 
-constexpr int kN2Threads = 6 * 32;       // warp 0 loader, warp 1 MMA issuer, warps 2-5 epilogue
+constexpr int kN2Threads = 10 * 32;      // warp 0 loader, warp 1 MMA issuer, warps 2-5 / 6-9 the two epilogue teams
 constexpr int kN2N = 48;                 // MMA N: 5 row taps x 2 column parities x 4 channel slots = 40, padded
 constexpr int kN2Cpt = 4;                // channel slots
 constexpr int kN2SegPx = 128;            // pixels per row segment (= MMA M)
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) deconv_narrow2_kernel(const __g
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int i = 0; i < kN2MaxSlots; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < kN2AccSlots; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < kN2AccSlots; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 3 * 128); }
         mbar_init(&w_bar, 1);
         mbar_fence_init();
     }
@@ -140,7 +142,11 @@ __global__ void __launch_bounds__(kN2Threads, 1) deconv_narrow2_kernel(const __g
             }
         }
     } else {
-        // ===================== epilogue: row taps + bias, straight to NCHW =====================
+        // ===================== epilogue: row taps + bias, straight to NCHW; two teams, alternate rows =====================
+        // The GEMM of input row t is read by three output-row iterations (k = t - 2 as the upper row, t - 1 as the middle one,
+        // t as the lower one), now by different teams at different times: each reader arrives on the slot's barrier (count
+        // 3 x 128) and the first / last iteration of a strip arrive for the readers that do not exist at the strip's edges.
+        const int team = (warp - 2) >> 2;
         const int m = (warp & 3) * 32 + lane;  // pixel of the segment == TMEM lane
         const uint32_t lane_sel = ((uint32_t)(warp & 3) * 32u) << 16;
         const float b0 = bias_s[0], b1 = bias_s[1], b2 = bias_s[2], b3 = bias_s[3];
@@ -152,7 +158,7 @@ __global__ void __launch_bounds__(kN2Threads, 1) deconv_narrow2_kernel(const __g
             r /= p.segs;
             const int r0 = (r % p.strips) * S;
             const int b = r / p.strips;
-            for (int k = 0; k < S; ++k) {
+            for (int k = team; k < S; k += 2) {
                 const uint32_t g_lo = n0 + k, g_mid = g_lo + 1, g_up = g_lo + 2;  // GEMMs of rows i-1, i, i+1
                 mbar_wait(&acc_full[g_up % kN2AccSlots], (g_up / kN2AccSlots) & 1u);
                 tc_fence_after();
@@ -162,7 +168,9 @@ __global__ void __launch_bounds__(kN2Threads, 1) deconv_narrow2_kernel(const __g
                 tmem_ld8(tmem_base + lane_sel + (g_lo % kN2AccSlots) * kN2AccStride + 32, lo);     // kh = 4
                 tmem_ld_wait();
                 tc_fence_before();
-                mbar_arrive(&acc_empty[g_lo % kN2AccSlots]);
+                mbar_arrive_n(&acc_empty[g_lo % kN2AccSlots], k == 0 ? 3u : 1u);
+                mbar_arrive_n(&acc_empty[g_mid % kN2AccSlots], 1u + (k == 0 ? 1u : 0u) + (k == S - 1 ? 1u : 0u));
+                mbar_arrive_n(&acc_empty[g_up % kN2AccSlots], k == S - 1 ? 3u : 1u);
                 const int i = r0 + k;
                 if (i < p.H && j < p.W) {
                     // columns are [kh][b][c]: a = 0 <- kh 0 (up), 2 (mid), 4 (lo);  a = 1 <- kh 1 (up), 3 (mid)
@@ -207,10 +215,6 @@ __global__ void __launch_bounds__(kN2Threads, 1) deconv_narrow2_kernel(const __g
                     }
                 }
             }
-            // the two trailing rows of the strip are not the "row i-1" of any iteration: release them here
-            tc_fence_before();
-            mbar_arrive(&acc_empty[(n0 + S) % kN2AccSlots]);
-            mbar_arrive(&acc_empty[(n0 + S + 1) % kN2AccSlots]);
             n0 += S + 2;
         }
     }
