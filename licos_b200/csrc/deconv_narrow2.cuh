@@ -110,35 +110,75 @@ __global__ void __launch_bounds__(kN2Threads, 1) deconv_narrow2_kernel(const __g
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            mbar_wait(&w_bar, 0);
-            const uint32_t idesc = umma_idesc_bf16(128, kN2N);
-            const uint64_t desc_hi = umma_desc_sw128(0);
-            const uint32_t a16 = smem_u32(a_s) >> 4, w16 = smem_u32(w_s) >> 4;
-            uint32_t n = 0;
-            for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
-                for (int t = 0; t < S + 2; ++t, ++n) {
-                    const uint32_t slot = n % (uint32_t)p.slots, acc = n % kN2AccSlots;
-                    mbar_wait(&a_full[slot], (n / (uint32_t)p.slots) & 1u);
-                    mbar_wait(&acc_empty[acc], ((n / kN2AccSlots) & 1u) ^ 1u);
-                    tc_fence_after();
-                    const uint32_t d = tmem_base + acc * kN2AccStride;
-                    uint32_t accumulate = 0;
-                    for (int s = 0; s < 3; ++s) {        // column shift dw = s - 1: the operand starts s pixels in
-                        for (int c = 0; c < p.chunks; ++c) {
-                            const uint32_t ab = a16 + ((slot * slot_bytes + (uint32_t)c * kN2ChunkStride + (uint32_t)s * 128u) >> 4);
-                            const uint32_t wb = w16 + (((uint32_t)(s * p.chunks + c) * kN2WTile) >> 4);
+        // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+        // One wait for the row's operands and one for a free accumulator slot per 24 short MMAs (N = 48: 24 cycles each)
+        // left the tensor pipe idle three quarters of the time: a completed wait costs the issuing thread ~150 cycles.  The
+        // NEXT row's two barriers are therefore probed (non-blocking, relaxed) before this row's MMAs are issued and read
+        // after them -- the same look-ahead as conv_pair.cuh -- and the MMAs of the usual C = 128 are fully unrolled.
+        mbar_wait_warp(&w_bar, 0);
+        const uint32_t idesc = umma_idesc_bf16(128, kN2N);
+        const uint64_t desc_hi = umma_desc_sw128(0);
+        const uint32_t a16 = smem_u32(a_s) >> 4, w16 = smem_u32(w_s) >> 4;
+        const uint32_t a_full0 = smem_u32(&a_full[0]), acc_empty0 = smem_u32(&acc_empty[0]);
+        const uint32_t slots = (uint32_t)p.slots, slot16 = slot_bytes >> 4;
+        asm volatile(".reg .pred licos_n2a, licos_n2c;");
+        uint32_t slot = 0, a_par = 0, acc = 0, c_par = 1, have_a = 0, have_c = 0;
+        auto wait_slow = [&](uint32_t bar, uint32_t parity) {
+            if (__all_sync(0xffffffffu, mbar_try_wait_addr(bar, parity) ? 1u : 0u)) return;
+            const long long t0 = clock64();
+            while (!__all_sync(0xffffffffu, mbar_try_wait_addr(bar, parity) ? 1u : 0u)) {
+                if (clock64() - t0 > 8000000000LL) __trap();
+            }
+        };
+        for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
+            for (int t = 0; t < S + 2; ++t) {
+                if (!__all_sync(0xffffffffu, have_a)) wait_slow(a_full0 + slot * 8u, a_par);
+                if (!__all_sync(0xffffffffu, have_c)) wait_slow(acc_empty0 + acc * 8u, c_par);
+                asm volatile("fence.acq_rel.cta;" ::: "memory");  // pairs with the relaxed probes
+                tc_fence_after();
+                const uint32_t n_slot = (slot + 1 == slots) ? 0u : slot + 1, n_apar = a_par ^ (n_slot == 0u ? 1u : 0u);
+                const uint32_t n_acc = (acc + 1) & (kN2AccSlots - 1), n_cpar = c_par ^ (n_acc == 0u ? 1u : 0u);
+                asm volatile("mbarrier.test_wait.parity.relaxed.cta.shared::cta.b64 licos_n2a, [%0], %1;" ::"r"(a_full0 + n_slot * 8u),
+                             "r"(n_apar)
+                             : "memory");
+                asm volatile("mbarrier.test_wait.parity.relaxed.cta.shared::cta.b64 licos_n2c, [%0], %1;" ::"r"(acc_empty0 + n_acc * 8u),
+                             "r"(n_cpar)
+                             : "memory");
+                const uint32_t d = tmem_base + acc * kN2AccStride;
+                const uint32_t a_row = a16 + slot * slot16;
+                if (elect_one()) {
+                    if (p.chunks == 2) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                umma_bf16(d, desc_hi | (uint64_t)(ab + 2 * k), desc_hi | (uint64_t)(wb + 2 * k), idesc, accumulate);
-                                accumulate = 1;
+                        for (int s = 0; s < 3; ++s)  // column shift dw = s - 1: the operand starts s pixels in
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) {
+                                const uint32_t ab = a_row + (((uint32_t)c * kN2ChunkStride + (uint32_t)s * 128u) >> 4);
+                                const uint32_t wb = w16 + (((uint32_t)(s * 2 + c) * kN2WTile) >> 4);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    umma_bf16(d, desc_hi | (uint64_t)(ab + 2 * k), desc_hi | (uint64_t)(wb + 2 * k), idesc,
+                                              (uint32_t)((s | c | k) != 0));
                             }
-                        }
+                    } else {
+                        uint32_t accumulate = 0;
+                        for (int s = 0; s < 3; ++s)
+                            for (int c = 0; c < p.chunks; ++c) {
+                                const uint32_t ab = a_row + (((uint32_t)c * kN2ChunkStride + (uint32_t)s * 128u) >> 4);
+                                const uint32_t wb = w16 + (((uint32_t)(s * p.chunks + c) * kN2WTile) >> 4);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    umma_bf16(d, desc_hi | (uint64_t)(ab + 2 * k), desc_hi | (uint64_t)(wb + 2 * k), idesc, accumulate);
+                                    accumulate = 1;
+                                }
+                            }
                     }
                     umma_commit(&a_empty[slot]);
                     umma_commit(&acc_full[acc]);
                 }
+                __syncwarp();
+                asm volatile("selp.b32 %0, 1, 0, licos_n2a;" : "=r"(have_a));
+                asm volatile("selp.b32 %0, 1, 0, licos_n2c;" : "=r"(have_c));
+                slot = n_slot; a_par = n_apar; acc = n_acc; c_par = n_cpar;
             }
         }
     } else {
