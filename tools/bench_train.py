@@ -1,7 +1,7 @@
 """cfg 5 training step on one GPU (licos/train.py:148-212 train_one_batch): forward in train mode + rate-distortion
 loss + backward + clip + Adam + aux step, 32 tiles of 3x256x256.  Times the whole step with CUDA events and, with
---profile, prints the per-kernel share from torch.profiler.  LICOS_EAGER_AUTOGRAD=1 selects the cuDNN autograd path
-(the library baseline this replaces).  One JSON line."""
+--profile, prints the per-kernel share from torch.profiler.  (The cuDNN-autograd baseline of the same step is timed by
+bench.py's gpu_library_baseline leg, with the oracle's modules on the GPU.)  One JSON line."""
 import argparse
 import json
 import os
@@ -74,8 +74,7 @@ if args.graph:
 step_ms = timed(train_step, args.steps, args.warmup)
 loss = float(train_step().detach())
 tr_ms = timed(fwd_bwd_transforms, args.steps, 2)
-res = {"config": f"cfg5 training step, {args.model} q1, {args.batch} x 3x256x256", "path": "cuDNN autograd" if os.environ.get(
-    "LICOS_EAGER_AUTOGRAD", "0") == "1" else "native sm_100a forward + dgrad + wgrad", "step_ms": step_ms,
+res = {"config": f"cfg5 training step, {args.model} q1, {args.batch} x 3x256x256", "path": "native sm_100a forward + dgrad + wgrad", "step_ms": step_ms,
     "graph": bool(args.graph), "train_mpix_s": args.batch * 65536 / step_ms / 1e3, "transforms_fwd_bwd_ms": tr_ms, "loss": loss}
 if args.profile:
     from torch.profiler import ProfilerActivity, profile
