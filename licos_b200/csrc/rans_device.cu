@@ -255,6 +255,226 @@ __global__ void __launch_bounds__(32) rans_decode_kernel(const uint32_t* __restr
     status[b] = bad ? -1 : 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-per-image coders (round 2).  The one-thread-per-image kernels above spend ~640 cycles per symbol: every lane
+// walks its own image, so every load is a scattered gather whose latency nothing hides (32 images per warp, 8 warps for
+// a 256-tile batch).  Here ONE WARP owns an image: the 32 lanes fetch and look up a chunk of 32 symbols in parallel
+// (coalesced, two chunks ahead of the coder), and the sequential state update runs from shared memory / registers only.
+// Same bitstream: the arithmetic of rans_put_symbol / rans_put_escape / RansReader is unchanged.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kRansMaxTables = 1024;  // offsets / sizes staged in shared memory
+
+__global__ void __launch_bounds__(32) rans_encode_warp_kernel(const int32_t* __restrict__ symbols, const int32_t* __restrict__ indexes,
+                                                              int64_t idx_stride, int batch, int n, int n_spatial,
+                                                              const int32_t* __restrict__ cdfs, int n_cdfs, int stride,
+                                                              const int32_t* __restrict__ sizes, const int32_t* __restrict__ offsets,
+                                                              const uint64_t* __restrict__ rcp, uint32_t* __restrict__ work,
+                                                              int64_t cap_words, int32_t* __restrict__ lengths) {
+    __shared__ int32_t s_size[kRansMaxTables], s_off[kRansMaxTables];
+    __shared__ uint32_t s_start[2][32], s_range[2][32], s_raw[2][32];
+    __shared__ uint64_t s_rcp[2][32];
+    const int b = blockIdx.x, lane = threadIdx.x;
+    for (int i = lane; i < n_cdfs; i += 32) { s_size[i] = sizes[i]; s_off[i] = offsets[i]; }
+    __syncwarp();
+    const int32_t* sym = symbols + (size_t)b * n;
+    const int32_t* idx = indexes ? indexes + (size_t)b * idx_stride : nullptr;
+    uint32_t* const row = work + (size_t)b * cap_words;
+    RansState st{(uint32_t)kRansLow, 0u, row + cap_words};
+    bool bad = false;
+    const int n_chunks = (n + 31) / 32;
+    // chunk t, lane j holds the (32 t + j)-th symbol in CODING order = position n - 1 - 32 t - j (the coder runs backwards)
+    auto pos_of = [&](int t) { return n - 1 - 32 * t - lane; };
+    // level 1: the symbol and its table index (independent loads)
+    auto load_l1 = [&](int t, int32_t& sv, int32_t& c) {
+        const int p = pos_of(t);
+        sv = 0; c = -1;
+        if (t < n_chunks && p >= 0) {
+            sv = __ldg(sym + p);
+            c = idx ? __ldg(idx + p) : p / n_spatial;
+        }
+    };
+    // level 2: (start, range | escape flag, reciprocal, raw bypass value) of a level-1 pair
+    auto load_l2 = [&](int32_t sv, int32_t c, uint32_t& start, uint32_t& range, uint64_t& rc, uint32_t& raw) {
+        start = 0; range = 0; rc = 0; raw = 0;
+        if (c >= 0 && c < n_cdfs) {
+            const int32_t escape = s_size[c] - 2;
+            int32_t v = sv - s_off[c];
+            bool esc = false;
+            if (v < 0) { raw = (uint32_t)(-2 * v - 1); v = escape; esc = true; }
+            else if (v >= escape) { raw = (uint32_t)(2 * (v - escape)); v = escape; esc = true; }
+            if (escape >= 0) {
+                const uint32_t e = (uint32_t)c * (uint32_t)stride + (uint32_t)v;
+                const uint32_t s0 = (uint32_t)__ldg(cdfs + e), s1 = (uint32_t)__ldg(cdfs + e + 1);
+                start = s0;
+                range = (s1 > s0 ? s1 - s0 : 0u) | (esc ? 0x80000000u : 0u);
+                rc = __ldg(rcp + e);
+            }
+        }
+    };
+    auto publish = [&](int buf, uint32_t start, uint32_t range, uint64_t rc, uint32_t raw) {
+        s_start[buf][lane] = start; s_range[buf][lane] = range; s_rcp[buf][lane] = rc; s_raw[buf][lane] = raw;
+    };
+    int32_t sv1, c1, sv2, c2;
+    {
+        int32_t sv0, c0;
+        load_l1(0, sv0, c0);
+        load_l1(1, sv1, c1);
+        uint32_t a, r, w; uint64_t q;
+        load_l2(sv0, c0, a, r, q, w);
+        publish(0, a, r, q, w);
+    }
+    __syncwarp();
+    for (int t = 0; t < n_chunks; ++t) {
+        // in flight while lane 0 codes chunk t: the symbols of chunk t + 2, the table entries of chunk t + 1
+        load_l1(t + 2, sv2, c2);
+        uint32_t a1, r1, w1; uint64_t q1;
+        load_l2(sv1, c1, a1, r1, q1, w1);
+        if (lane == 0) {
+            const int buf = t & 1;
+            const int cnt = min(32, n - 32 * t);
+            if (st.wp - row < 32 * 12) {
+                bad = true;  // scratch row nearly full: the host coder takes over
+            } else {
+                // groups of 8: the group's entries are read from shared memory up front (24 independent loads), so that
+                // the state chain below runs on registers only
+                for (int j0 = 0; j0 < cnt; j0 += 8) {
+                    uint32_t rg[8], sta[8];
+                    uint64_t rc[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int j = min(j0 + k, 31);
+                        rg[k] = s_range[buf][j]; sta[k] = s_start[buf][j]; rc[k] = s_rcp[buf][j];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (j0 + k < cnt) {
+                            const uint32_t range = rg[k] & 0x7fffffffu;
+                            if (range == 0) { bad = true; continue; }
+                            if (rg[k] & 0x80000000u) rans_put_escape(st, s_raw[buf][j0 + k]);  // rare: kept out of line
+                            rans_put_symbol(st, sta[k], range, rc[k]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        publish((t + 1) & 1, a1, r1, q1, w1);
+        sv1 = sv2; c1 = c2;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        *--st.wp = st.hi;
+        *--st.wp = st.lo;
+        lengths[b] = bad ? -1 : (int32_t)(row + cap_words - st.wp);
+    }
+}
+
+// Decoder, index == position / n_spatial (the EntropyBottleneck layout), rows of <= 96 entries: the CDF row of the current
+// channel lives in three registers per lane, the search is three compares + ballots, the word stream is prefetched 32
+// words at a time and handed out by shuffles, and the coder state is replicated in every lane (uniform control flow).
+__global__ void __launch_bounds__(32) rans_decode_warp_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ word_offsets,
+                                                              const int32_t* __restrict__ n_words_all, int batch, int n, int n_spatial,
+                                                              const int32_t* __restrict__ cdfs, int n_cdfs, int stride,
+                                                              const int32_t* __restrict__ sizes, const int32_t* __restrict__ offsets,
+                                                              int32_t* __restrict__ out, int32_t* __restrict__ status) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const uint32_t* words = packed + word_offsets[b];
+    const int n_words = n_words_all[b];
+    if (n_words < 2) { if (lane == 0) status[b] = -1; return; }
+    // word window: lane j holds words[win0 + j]
+    int win0 = 0;
+    uint32_t wreg = lane < n_words ? __ldg(words + lane) : 0u;
+    int pos = 0;
+    auto next_word = [&]() -> uint32_t {
+        if (pos - win0 >= 32) {
+            win0 += 32;
+            wreg = (win0 + lane) < n_words ? __ldg(words + win0 + lane) : 0u;
+        }
+        const uint32_t w = __shfl_sync(0xffffffffu, wreg, (pos - win0) & 31);
+        const uint32_t r = pos < n_words ? w : 0u;
+        ++pos;
+        return r;
+    };
+    uint32_t lo = next_word(), hi = next_word();
+    auto refill = [&]() { if (hi == 0 && lo < (uint32_t)kRansLow) { hi = lo; lo = next_word(); } };
+    auto nibble = [&]() -> uint32_t {
+        const uint32_t v = lo & kRansBypassMax;
+        lo = (lo >> kRansBypassBits) | (hi << (32 - kRansBypassBits));
+        hi >>= kRansBypassBits;
+        refill();
+        return v;
+    };
+    int32_t* o = out + (size_t)b * n;
+    bool bad = false;
+    int32_t outv = 0;
+    int ci = -1;
+    uint32_t r0 = 0xffffffffu, r1 = 0xffffffffu, r2 = 0xffffffffu;  // this lane's three entries of the current row
+    int32_t escape = 0, offset = 0;
+    int rem = n_spatial;  // symbols left in the current channel (0 = load the next row)
+    rem = 0;
+    for (int i = 0; i < n; ++i) {
+        if (rem == 0) {  // uniform: a new channel every n_spatial symbols
+            rem = n_spatial;
+            const int c = ++ci;
+            if (c < n_cdfs) {
+                const int32_t len = __ldg(sizes + c);
+                const int32_t* cdf = cdfs + (size_t)c * stride;
+                r0 = lane < len ? (uint32_t)__ldg(cdf + lane) : 0xffffffffu;
+                r1 = lane + 32 < len ? (uint32_t)__ldg(cdf + lane + 32) : 0xffffffffu;
+                r2 = lane + 64 < len ? (uint32_t)__ldg(cdf + lane + 64) : 0xffffffffu;
+                escape = len - 2;
+                offset = __ldg(offsets + c);
+            } else {
+                r0 = r1 = r2 = 0xffffffffu;
+                escape = -2;
+            }
+        }
+        int32_t v = 0;
+        if (escape < 0) {
+            bad = true;
+        } else {
+            const uint32_t target = lo & 0xffffu;
+            // entries <= target form a prefix of the (strictly increasing) row: their count - 1 is the symbol
+            const int below = __popc(__ballot_sync(0xffffffffu, r0 <= target)) + __popc(__ballot_sync(0xffffffffu, r1 <= target)) +
+                              __popc(__ballot_sync(0xffffffffu, r2 <= target));
+            const int sidx = below - 1, s1 = below;  // below >= 1 (cdf[0] == 0); s1 <= len - 1 for a valid stream
+            const uint32_t cand_a = sidx < 32 ? r0 : (sidx < 64 ? r1 : r2), cand_b = s1 < 32 ? r0 : (s1 < 64 ? r1 : r2);
+            const uint32_t start = __shfl_sync(0xffffffffu, cand_a, sidx & 31);
+            const uint32_t freq = __shfl_sync(0xffffffffu, cand_b, s1 & 31) - start;
+            if (sidx < 0 || s1 >= 96 || freq == 0 || freq > 65536u) { bad = true; }
+            const uint64_t x = ((uint64_t)hi << 32) | lo;
+            const uint64_t nx = (uint64_t)freq * (x >> kRansPrecision) + target - start;
+            lo = (uint32_t)nx;
+            hi = (uint32_t)(nx >> 32);
+            refill();
+            v = sidx;
+            if (v == escape) {
+                uint32_t d = nibble();
+                uint32_t nibbles = d;
+                while (d == kRansBypassMax) {
+                    d = nibble();
+                    nibbles += d;
+                    if (nibbles > 64) { bad = true; break; }
+                }
+                uint32_t raw = 0;
+                for (uint32_t j = 0; j < nibbles; ++j) {
+                    const uint32_t nb = nibble();
+                    if (j < 8) raw |= nb << (j * kRansBypassBits);
+                }
+                v = (int32_t)(raw >> 1);
+                v = (raw & 1u) ? -v - 1 : v + escape;
+            }
+            v += offset;
+        }
+        --rem;
+        if ((i & 31) == lane) outv = v;
+        if ((i & 31) == 31) o[i - 31 + lane] = outv;  // one coalesced store per 32 symbols
+    }
+    if ((n & 31) != 0 && lane < (n & 31)) o[(n & ~31) + lane] = outv;
+    if (lane == 0) status[b] = bad ? -1 : 0;
+}
+
 }  // namespace licos
 
 using namespace licos;
@@ -274,10 +494,17 @@ int licos_rans_encode_device(const int32_t* symbols, const int32_t* indexes, int
     rans_rcp_kernel<<<(int)((entries + 255) / 256 < 1184 ? (entries + 255) / 256 : 1184), 256, 0, (cudaStream_t)stream>>>(
         cdfs, n_cdfs, cdf_stride, cdf_sizes, rcp_ws);
     LICOS_CUDA_OK(cudaGetLastError());
-    rans_encode_kernel<<<(batch + 31) / 32, 32, 0, (cudaStream_t)stream>>>(symbols, indexes, index_stride, batch, n,
-                                                                            n_spatial > 0 ? n_spatial : 1, cdfs, n_cdfs,
-                                                                            cdf_stride, cdf_sizes, offsets, rcp_ws, work,
-                                                                            cap_words, lengths);
+    if (n_cdfs <= kRansMaxTables && n < 0x7fffffff && n_spatial < 0x7fffffff) {
+        // one warp per image: coalesced look-ups two chunks ahead of the sequential coder
+        rans_encode_warp_kernel<<<batch, 32, 0, (cudaStream_t)stream>>>(symbols, indexes, index_stride, batch, (int)n,
+                                                                        (int)(n_spatial > 0 ? n_spatial : 1), cdfs, n_cdfs, cdf_stride,
+                                                                        cdf_sizes, offsets, rcp_ws, work, cap_words, lengths);
+    } else {
+        rans_encode_kernel<<<(batch + 31) / 32, 32, 0, (cudaStream_t)stream>>>(symbols, indexes, index_stride, batch, n,
+                                                                                n_spatial > 0 ? n_spatial : 1, cdfs, n_cdfs,
+                                                                                cdf_stride, cdf_sizes, offsets, rcp_ws, work,
+                                                                                cap_words, lengths);
+    }
     LICOS_CUDA_OK(cudaGetLastError());
     return LICOS_OK;
 }
@@ -300,9 +527,15 @@ int licos_rans_decode_device(const uint32_t* packed, const int64_t* word_offsets
         return LICOS_ERR_INVALID;
     if (!indexes && n_spatial < 1) return LICOS_ERR_INVALID;
     if (batch == 0 || n == 0) return LICOS_OK;
-    rans_decode_kernel<<<(batch + 31) / 32, 32, 0, (cudaStream_t)stream>>>(packed, word_offsets, n_words, indexes, index_stride,
-                                                                            batch, n, n_spatial > 0 ? n_spatial : 1, cdfs, n_cdfs,
-                                                                            cdf_stride, cdf_sizes, offsets, symbols, status);
+    if (!indexes && cdf_stride <= 96 && n < 0x7fffffff && n_spatial < 0x7fffffff) {
+        // the EntropyBottleneck layout: one warp per image, the channel's CDF row in registers
+        rans_decode_warp_kernel<<<batch, 32, 0, (cudaStream_t)stream>>>(packed, word_offsets, n_words, batch, (int)n, (int)n_spatial,
+                                                                        cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets, symbols, status);
+    } else {
+        rans_decode_kernel<<<(batch + 31) / 32, 32, 0, (cudaStream_t)stream>>>(packed, word_offsets, n_words, indexes, index_stride,
+                                                                                batch, n, n_spatial > 0 ? n_spatial : 1, cdfs,
+                                                                                n_cdfs, cdf_stride, cdf_sizes, offsets, symbols, status);
+    }
     LICOS_CUDA_OK(cudaGetLastError());
     return LICOS_OK;
 }

@@ -706,8 +706,23 @@ def rans_encode_device(symbols: torch.Tensor, indexes: Optional[torch.Tensor], n
     packed = torch.empty(total, dtype=torch.int32, device=dev)
     check(lib.licos_rans_pack_device(work.data_ptr(), cap, lengths.data_ptr(), word_offsets.data_ptr(), B,
                                      packed.data_ptr(), _stream()), "rans_pack_device")
-    raw = packed.cpu().numpy().tobytes()
-    return [raw[4 * s: 4 * (s + l)] for s, l in zip(starts, lens)]
+    stage = _pinned_words(total)
+    stage[:total].copy_(packed, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    view = memoryview(stage.numpy()).cast("B")
+    return [view[4 * s: 4 * (s + l)].tobytes() for s, l in zip(starts, lens)]
+
+
+_PINNED = {}
+
+
+def _pinned_words(n: int) -> torch.Tensor:
+    """A cached pinned int32 staging buffer of at least n words (the byte strings leave the device through it)."""
+    buf = _PINNED.get("w")
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n, 1 << 20), dtype=torch.int32).pin_memory()
+        _PINNED["w"] = buf
+    return buf
 
 
 def rans_decode_device(strings, indexes: Optional[torch.Tensor], n: int, n_spatial: int, cdfs: torch.Tensor,
@@ -722,11 +737,17 @@ def rans_decode_device(strings, indexes: Optional[torch.Tensor], n: int, n_spati
     sizes = [len(s) for s in strings]
     if any(sz % 4 or sz < 8 for sz in sizes):
         return None
-    words = np.frombuffer(b"".join(strings), dtype=np.uint32)
     n_words = np.asarray([sz // 4 for sz in sizes], dtype=np.int32)
     offs = np.zeros(B, dtype=np.int64)
     np.cumsum(n_words[:-1], out=offs[1:])
-    packed = torch.from_numpy(words.view(np.int32).copy()).to(dev)
+    total = int(n_words.sum())
+    stage = _pinned_words(total)
+    dst = memoryview(stage.numpy()).cast("B")
+    at = 0
+    for st in strings:  # straight into pinned memory: one host copy, then one async H2D
+        dst[at: at + len(st)] = st
+        at += len(st)
+    packed = stage[:total].to(dev, non_blocking=True)
     offs_d, nw_d = torch.from_numpy(offs).to(dev), torch.from_numpy(n_words).to(dev)
     idx, stride = None, 0
     if indexes is not None:

@@ -60,3 +60,48 @@ for _ in range(3):
     e1.record()
     torch.cuda.synchronize()
     print(f"rans kernels only: {e0.elapsed_time(e1):.2f} ms")
+
+# decompress(): device decoder + dequantise + g_s
+comp = net.compress(x)
+for _ in range(2):
+    dec = net.decompress(comp["strings"], comp["shape"])
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(5):
+    dec = net.decompress(comp["strings"], comp["shape"])
+torch.cuda.synchronize()
+dt = (time.perf_counter() - t0) / 5
+print(f"decompress: {dt * 1e3:.2f} ms per {B} tiles = {B * 65536 / dt / 1e6:.0f} MPix/s")
+strings = list(comp["strings"][0])
+for _ in range(3):
+    e0, e1 = ev(), ev()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record()
+    symd = ops.rans_decode_device(strings, None, sym[0].numel(), 256, eb._quantized_cdf, eb._cdf_length, eb._offset)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"rans_decode_device: wall {1e3 * (time.perf_counter() - t0):.2f} ms, device span {e0.elapsed_time(e1):.2f} ms, "
+          f"equal to the encoder's input: {bool(torch.equal(symd.reshape(sym.shape), sym))}")
+
+# decoder kernel alone (strings already packed on the device)
+import numpy as np
+sizes = [len(s) for s in strings]
+words = np.frombuffer(b"".join(strings), dtype=np.uint32)
+n_words = np.asarray([sz // 4 for sz in sizes], dtype=np.int32)
+offs = np.zeros(B, dtype=np.int64)
+np.cumsum(n_words[:-1], out=offs[1:])
+packed_d = torch.from_numpy(words.view(np.int32).copy()).to(dev)
+offs_d, nw_d = torch.from_numpy(offs).to(dev), torch.from_numpy(n_words).to(dev)
+outd = torch.empty((B, sym[0].numel()), dtype=torch.int32, device=dev)
+status = torch.empty(B, dtype=torch.int32, device=dev)
+for _ in range(3):
+    e0, e1 = ev(), ev()
+    e0.record()
+    lib.licos_rans_decode_device(packed_d.data_ptr(), offs_d.data_ptr(), nw_d.data_ptr(), None, 0, B, outd.shape[1], 256,
+                                 eb._quantized_cdf.data_ptr(), eb._quantized_cdf.shape[0], eb._quantized_cdf.shape[1],
+                                 eb._cdf_length.data_ptr(), eb._offset.data_ptr(), outd.data_ptr(), status.data_ptr(),
+                                 torch.cuda.current_stream().cuda_stream)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"rans decode kernel only: {e0.elapsed_time(e1):.2f} ms (cdf stride {eb._quantized_cdf.shape[1]}, ok {int(status.min()) == 0})")
