@@ -150,6 +150,27 @@ class FusedSequential(nn.Sequential):
         super().__init__(*args)
         self._packed_cache = weakref.WeakKeyDictionary()
 
+    def __getstate__(self):
+        # kernel-layout weight copies are a cache keyed on live modules: never part of a pickle (torch.save(net))
+        state = self.__dict__.copy()
+        state.pop("_packed_cache", None)
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._packed_cache = weakref.WeakKeyDictionary()
+
+    def __deepcopy__(self, memo):
+        import copy
+
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k != "_packed_cache":
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        new._packed_cache = weakref.WeakKeyDictionary()
+        return new
+
     def forward(self, x: Tensor, take_abs: bool = False, nhwc: Optional[Tensor] = None, *, int_max: int = 0,
                 requant8: bool = False, out_dtype: Optional[torch.dtype] = None, out_max: int = 0) -> Tensor:
         """``nhwc``: optional bf16 (B, H, W, C) copy of ``x`` that a fused producer already wrote

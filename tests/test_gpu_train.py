@@ -468,3 +468,17 @@ def test_g_a_input_gradient_vs_oracle(cuda, in_ch):
     g = torch.Generator().manual_seed(17)
     x = torch.rand(2, in_ch, 64, 64, generator=g)
     _check_chain(cuda, net.g_a, ref.g_a, x, f"g_a c{in_ch} with input gradient", x_grad=True)
+
+
+def test_wide_bottlenecks_and_odd_sizes_are_refused_at_forward_time(cuda):
+    """No detour through torch autograd: shapes the backward kernels do not take raise NotImplementedError when the forward
+    is called (not from inside autograd's backward in the middle of a step)."""
+    net = L.get_model("bmshj2018-factorized", False, 16, 1).to(cuda).train()   # filters (16, 16, 3, 3): 409 parameters / channel
+    x = torch.rand(1, 16, 64, 64, device=cuda)
+    with pytest.raises(NotImplementedError, match="density parameters"):
+        net(x)
+    with torch.no_grad():                                                        # inference on the same model is fine
+        assert net.eval()(x)["x_hat"].shape == x.shape
+    net3 = L.image_models["bmshj2018-factorized"](quality=1, pretrained=False).to(cuda).train()
+    with pytest.raises(NotImplementedError, match="even sizes"):
+        net3(torch.rand(1, 3, 66, 70, device=cuda))                              # 66 -> 33: odd under a stride-2 layer

@@ -138,3 +138,49 @@ def test_gdn_reparam_and_lower_bound_gradient():
     xb = torch.tensor([0.5, 2.0, 0.5], requires_grad=True)
     L.LowerBound(1.0)(xb).backward(torch.tensor([1.0, 1.0, -1.0]))
     assert xb.grad.tolist() == [0.0, 1.0, -1.0]
+
+
+def test_update_follows_the_forward_likelihood_form():
+    """One switch drives forward() and update(), as in every upstream release: the tables update() writes describe the
+    density forward() evaluates.  The two forms round differently on some rows, so the switch must actually reach update()."""
+    import torch
+    from oracle import compressai_ref as R
+
+    torch.manual_seed(7)
+    net = L.image_models["bmshj2018-factorized"](quality=1, pretrained=False)
+    from licos_b200 import synth
+    synth.condition_weights(net)
+    ref = R.image_models["bmshj2018-factorized"](quality=1)
+    ref.load_state_dict(net.state_dict())
+    tables = {}
+    for form in ("plain", "stable"):
+        net.entropy_bottleneck.likelihood_form = ref.entropy_bottleneck.likelihood_form = form
+        net.update(force=True)
+        ref.update(force=True)
+        assert torch.equal(net.entropy_bottleneck._quantized_cdf, ref.entropy_bottleneck._quantized_cdf), form
+        tables[form] = net.entropy_bottleneck._quantized_cdf.clone()
+    assert tables["plain"].shape == tables["stable"].shape
+    assert not torch.equal(tables["plain"], tables["stable"])  # the forms are not interchangeable: hence one switch
+
+
+def test_kernel_parameter_cache_is_not_part_of_a_copy_or_pickle():
+    """EntropyBottleneck caches a ctypes parameter block after the first kernel call; deepcopy (EMA / best-model
+    snapshots) and pickling must drop it, not choke on it."""
+    import copy
+    import io
+    import torch
+    from licos_b200 import ops
+
+    net = L.image_models["bmshj2018-factorized"](quality=1, pretrained=False)
+    eb = net.entropy_bottleneck
+    eb._packed = ops.EbPacked.__new__(ops.EbPacked)           # what packed_params() leaves behind (no GPU here)
+    eb._packed.p = __import__("licos_b200")._lib.EbParams()   # a ctypes Structure with pointers: not picklable
+    eb._packed_key = ("stale",)
+    clone = copy.deepcopy(net)
+    assert clone.entropy_bottleneck._packed is None and clone.entropy_bottleneck._packed_key is None
+    buf = io.BytesIO()
+    torch.save(net, buf)
+    buf.seek(0)
+    back = torch.load(buf, weights_only=False)
+    assert back.entropy_bottleneck._packed is None
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), back.state_dict().values()))
