@@ -491,7 +491,7 @@ def run_b200(args):
                     "rank0_numa_node": numa_node, "bpp": e2e.get("bpp")},
             "gpu_launches": n_launch,
             "roofline": {"bound": "tensor",
-                         "kernel": "conv_igemm_kernel (6 launches per step: g_a[2,4,6], g_s[0,2,4], GDN/IGDN fused)",
+                         "kernel": "conv_igemm_pair_kernel (6 launches per step: g_a[2,4,6], g_s[0,2,4], GDN/IGDN fused; CTA pairs, wide slabs)",
                          "achieved": achieved_tflops, "peak": pk["tflops"], "unit": "TFLOP/s",
                          "frac": achieved_tflops / pk["tflops"],
                          "frac_sustained": achieved_tflops / pk["tflops_sustained"], "traffic": traffic,

@@ -92,6 +92,14 @@ struct ConvParams {
     int sa, sb;
     uint32_t a_slot_bytes, b_slot_bytes, staging_bytes, gamma_bytes;
     unsigned long long pass_info[kMaxPasses];  // lean issue loop: per slab 5 bits {n_taps-1 : 2, first row_off : 2, descending : 1}
+    // CTA-pair kernel (conv_pair.cuh): the geometry of a tile and the taps of every slab.  wide = 1: an accumulator is a
+    // block of 16 rows x 8 columns and a slab is one (16 + 2) x (8 n_acc + 2)-pixel window of a parity view that serves
+    // EVERY tap of that view through row- and column-shifted operand starts (the stride between 8-row groups is the slab's
+    // row pitch); wide = 0: the 8-row x 16-column blocks and 16-pixel-wide, per-column-tap slabs of conv_igemm_kernel.
+    unsigned long long tap_list[kMaxPasses][kMaxSlabs];  // [0:4) taps of the slab, then (row_off : 2, col_off : 2) per tap
+    int wide, tile_h, tile_w;
+    uint32_t a_tx_bytes;                      // bytes one slab load delivers (the ring slot is that rounded up to 1 KB)
+    uint32_t a_pitch16, a_sbo16, acc_step16;  // slab row pitch, 8-row-group stride, operand offset of accumulator 1 (16-byte units)
     int lean;           // 1 = every slab's taps walk consecutive slab rows (pass_info valid), 0 = generic per-tap table walk
     int n_teams;        // epilogue teams that take jobs (2, or 1 when two staging tiles do not fit in shared memory)
     int jobs_per_pass;  // accumulators per pass (n_groups * n_acc): each is one epilogue job
@@ -713,10 +721,11 @@ static unsigned long long* g_conv_probe = nullptr;
 //   LICOS_NO_SMALL_TILES=1 keep 16-row tiles even when there are fewer of them than SMs
 //   LICOS_FORCE_NACC1=1    8-row tiles everywhere (tile-quantisation experiments at small batches)
 //   LICOS_NO_PAIR=1        single-CTA engine (cta_group::1) everywhere: the A/B switch for the CTA-pair kernel
+//   LICOS_NO_WIDE=1        CTA pairs on the per-column-tap slabs (no wide slabs): the A/B switch for the wide-slab geometry
 //   LICOS_SA / LICOS_SB    force the slab / weight ring depths
 //   LICOS_DBG_FLAGS        bit 0 / 1: load every slab / weight ring slot only once (isolates the mainloop from data movement)
 struct DevKnobs {
-    bool first_v1, prefer_nacc2, no_small_tiles, force_nacc1, no_pair;
+    bool first_v1, prefer_nacc2, no_small_tiles, force_nacc1, no_pair, no_wide;
     int sa, sb, dbg_flags;
 };
 static const DevKnobs& knobs() {
@@ -727,6 +736,7 @@ static const DevKnobs& knobs() {
         v.no_small_tiles = getenv("LICOS_NO_SMALL_TILES") != nullptr;
         v.force_nacc1 = getenv("LICOS_FORCE_NACC1") != nullptr;
         v.no_pair = getenv("LICOS_NO_PAIR") != nullptr;
+        v.no_wide = getenv("LICOS_NO_WIDE") != nullptr;
         if (const char* e = getenv("LICOS_SA")) v.sa = atoi(e);
         if (const char* e = getenv("LICOS_SB")) v.sb = atoi(e);
         if (const char* e = getenv("LICOS_DBG_FLAGS")) v.dbg_flags = atoi(e);
@@ -1205,12 +1215,22 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
                          pl.n_split == 1 && !gdn);
     const int groups = merged ? 4 : 1;
 
+    // CTA pairs (conv_pair.cuh) take every single-group shape; all but the 1x1 layers on wide slabs
+    int sms = a->sm_count;
+    if (sms <= 0) {
+        int dev = 0;
+        LICOS_CUDA_OK(cudaGetDevice(&dev));
+        LICOS_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const bool use_pair = groups == 1 && !knobs().no_pair && sms >= 2 && pl.N % 16 == 0;
+    const bool wide = use_pair && !pointwise && kind != LICOS_CONV_1X1 && !knobs().no_wide;
+
     // accumulators per tile
     // GDN accumulates its norm in place, so TMEM holds only accumulators; two sets when they fit so that the
     // epilogue of one pass overlaps the mainloop of the next
     int n_acc = 2;
     if (groups * 2 * pl.N > (int)kTmemCols) n_acc = 1;
-    if (p.grid_h <= kAccRows) n_acc = 1;
+    if (wide ? p.grid_w <= 8 : p.grid_h <= kAccRows) n_acc = 1;
     if (n_acc == 2 && 2 * groups * 2 * pl.N > (int)kTmemCols && 2 * groups * pl.N <= (int)kTmemCols &&
         !knobs().prefer_nacc2)
         n_acc = 1;  // one double-buffered accumulator beats two single-buffered ones that share weight tiles
@@ -1229,11 +1249,66 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     p.n_acc = n_acc;
     p.n_buf = (2 * groups * n_acc * pl.N <= (int)kTmemCols) ? 2 : 1;
     p.jobs_per_pass = groups * n_acc;
-    const int TH = kAccRows * n_acc;
-    const int R = TH + 2;
+    const int TH = wide ? 16 : kAccRows * n_acc;       // tile rows
+    const int TW = wide ? 8 * n_acc : kTileW;          // tile columns
+    const int R = TH + 2;                              // slab rows
+    const int SW = wide ? TW + 2 : kTileW;             // slab columns
+    p.wide = wide ? 1 : 0;
+    p.tile_h = TH;
+    p.tile_w = TW;
+    p.a_pitch16 = (uint32_t)SW * 8u;
+    p.a_sbo16 = wide ? p.a_pitch16 : 64u;
+    p.acc_step16 = wide ? 64u : (uint32_t)(kAccRows * kRowBytes) >> 4;
 
     // ---- passes ------------------------------------------------------------------------------
-    if (pointwise || kind == LICOS_CONV_1X1) {
+    int8_t col_offs[kMaxPasses][kMaxSlabs][kMaxTaps];
+    memset(col_offs, 0, sizeof(col_offs));
+    if (wide) {
+        // one slab per parity view / pass, origin one pixel up-left of the tile, every tap a (row, column) offset into it
+        auto add_tap = [&](int pi, int si, Slab& sl, int row_off, int col_off, int w_tap) {
+            col_offs[pi][si][sl.n_taps] = (int8_t)col_off;
+            set_tap(sl, sl.n_taps, row_off, 0, w_tap);
+            ++sl.n_taps;
+        };
+        if (kind == LICOS_CONV_5X5_S2) {
+            p.n_passes = 1;
+            Pass& ps = p.passes[0];
+            ps.n_groups = 1;
+            ps.n_slabs = 4;
+            for (int ph = 0; ph < 2; ++ph)
+                for (int pw = 0; pw < 2; ++pw) {
+                    const int si = ph * 2 + pw;
+                    Slab& sl = ps.slabs[si];
+                    sl.in_map = (int8_t)si; sl.dw = -1; sl.n_taps = 0;
+                    for (int kh = ph; kh < 5; kh += 2)
+                        for (int kw = pw; kw < 5; kw += 2)
+                            add_tap(0, si, sl, (kh - 2 - ph) / 2 + 1, (kw - 2 - pw) / 2 + 1, kh * 5 + kw);
+                }
+        } else if (kind == LICOS_CONV_3X3_S1) {
+            p.n_passes = 1;
+            Pass& ps = p.passes[0];
+            ps.n_groups = 1;
+            ps.n_slabs = 1;
+            Slab& sl = ps.slabs[0];
+            sl.in_map = 0; sl.dw = -1; sl.n_taps = 0;
+            for (int kh = 0; kh < 3; ++kh)
+                for (int kw = 0; kw < 3; ++kw) add_tap(0, 0, sl, kh, kw, kh * 3 + kw);
+        } else {  // transposed conv: one pass per output parity, the same input window each time
+            p.n_passes = 4;
+            for (int pi = 0; pi < 4; ++pi) {
+                const int aa = pi >> 1, b = pi & 1;
+                Pass& ps = p.passes[pi];
+                ps.n_groups = 1;
+                ps.dy[0] = (int8_t)aa; ps.dx[0] = (int8_t)b; ps.out_map[0] = (int8_t)pi;
+                ps.n_slabs = 1;
+                Slab& sl = ps.slabs[0];
+                sl.in_map = 0; sl.dw = -1; sl.n_taps = 0;
+                for (int kh = aa; kh < 5; kh += 2)
+                    for (int kw = b; kw < 5; kw += 2)
+                        add_tap(pi, 0, sl, (aa + 2 - kh) / 2 + 1, (b + 2 - kw) / 2 + 1, kh * 5 + kw);
+            }
+        }
+    } else if (pointwise || kind == LICOS_CONV_1X1) {
         p.n_passes = 1;
         Pass& ps = p.passes[0];
         ps.n_slabs = 1; ps.n_groups = 1;
@@ -1327,19 +1402,22 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
         p.pass_info[pi] = info;
     }
 
-    // ---- CTA pairs (conv_pair.cuh): every lean shape; the weight and gamma tiles are split between the two CTAs ----
-    int sms = a->sm_count;
-    if (sms <= 0) {
-        int dev = 0;
-        LICOS_CUDA_OK(cudaGetDevice(&dev));
-        LICOS_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // ---- CTA pairs (conv_pair.cuh): the taps of every slab; the weight and gamma tiles are split between the two CTAs ----
+    if (use_pair) {
+        for (int pi = 0; pi < p.n_passes; ++pi)
+            for (int si = 0; si < p.passes[pi].n_slabs; ++si) {
+                const Slab& sl = p.passes[pi].slabs[si];
+                unsigned long long v = (unsigned long long)sl.n_taps;
+                for (int k = 0; k < sl.n_taps; ++k)
+                    v |= (unsigned long long)((sl.taps[k].row_off & 3) | ((col_offs[pi][si][k] & 3) << 2)) << (4 + 4 * k);
+                p.tap_list[pi][si] = v;
+            }
     }
-    const bool use_pair = p.lean && !knobs().no_pair && sms >= 2 && pl.N % 16 == 0;
     const uint32_t w_box_rows = use_pair ? (uint32_t)pl.N / 2 : (uint32_t)pl.N;
 
     // ---- tensor maps ---------------------------------------------------------------------------
     const uint64_t C = (uint64_t)cin_pad, H = (uint64_t)in_h, W = (uint64_t)in_w, B = (uint64_t)a->batch;
-    const uint32_t in_box[4] = {(uint32_t)kKChunk, (uint32_t)kTileW, (uint32_t)R, 1};
+    const uint32_t in_box[4] = {(uint32_t)kKChunk, (uint32_t)SW, (uint32_t)R, 1};
     if (!pointwise && kind == LICOS_CONV_5X5_S2) {
         for (int ph = 0; ph < 2; ++ph)
             for (int pw = 0; pw < 2; ++pw) {
@@ -1371,7 +1449,7 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     }
     if (a->out_layout == LICOS_LAYOUT_NHWC_BF16) {
         const uint64_t OC = (uint64_t)a->out_c, OH = (uint64_t)out_h, OW = (uint64_t)out_w;
-        const uint32_t box[4] = {(uint32_t)kKChunk, (uint32_t)kTileW, (uint32_t)kAccRows, 1};
+        const uint32_t box[4] = {(uint32_t)kKChunk, wide ? 8u : (uint32_t)kTileW, wide ? 16u : (uint32_t)kAccRows, 1};
         if (kind == LICOS_DECONV_5X5_S2 && !pointwise) {
             for (int pi = 0; pi < 4; ++pi) {
                 const int aa = pi >> 1, b = pi & 1;
@@ -1391,7 +1469,8 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     }
 
     // ---- shared memory plan --------------------------------------------------------------------
-    p.a_slot_bytes = (uint32_t)R * kRowBytes;
+    p.a_tx_bytes = (uint32_t)R * (uint32_t)SW * 128u;
+    p.a_slot_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
     p.b_slot_bytes = w_box_rows * 128u;
     p.staging_bytes = (gdn || a->out_layout == LICOS_LAYOUT_NHWC_BF16) ? (uint32_t)(pl.N / kKChunk) * 128u * 128u : 0u;
     p.gamma_bytes = gdn ? (uint32_t)(pl.N / kKChunk) * w_box_rows * 128u : 0u;
@@ -1421,7 +1500,7 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;  // one CTA per SM: each CTA owns all 512 TMEM columns
 
     p.tiles_h = (p.grid_h + TH - 1) / TH;
-    p.tiles_w = (p.grid_w + kTileW - 1) / kTileW;
+    p.tiles_w = (p.grid_w + TW - 1) / TW;
     const int64_t tiles = (int64_t)a->batch * p.tiles_h * p.tiles_w * p.n_split;
     if (tiles > 0x7fffffff) return LICOS_ERR_UNSUPPORTED;
     p.total_tiles = (int)tiles;

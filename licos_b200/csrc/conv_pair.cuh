@@ -38,9 +38,9 @@ __device__ __forceinline__ PairTile decode_pair_tile(const ConvParams& p, int w,
     const int spatial = p.batch * p.tiles_h * p.tiles_w;
     t.live = sp < spatial;
     if (!t.live) sp = spatial;  // -> b == batch: every TMA load is zero fill, every TMA store is clipped away
-    t.gw0 = (sp % p.tiles_w) * kTileW;
+    t.gw0 = (sp % p.tiles_w) * p.tile_w;
     sp /= p.tiles_w;
-    t.gh0 = (sp % p.tiles_h) * (kAccRows * p.n_acc);
+    t.gh0 = (sp % p.tiles_h) * p.tile_h;
     t.b = sp / p.tiles_h;
     return t;
 }
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
                             continue;
                         }
                         ++n_loaded;
-                        if (leader_cta) mbar_arrive_expect_tx(&a_full[ra.slot], 2u * p.a_slot_bytes);
+                        if (leader_cta) mbar_arrive_expect_tx(&a_full[ra.slot], 2u * p.a_tx_bytes);
                         tma_load_4d_pair(a_ring + (size_t)ra.slot * p.a_slot_bytes, &p.in_maps[sl.in_map],
                                          mapa_shared(smem_u32(&a_full[ra.slot]), 0), c * kKChunk, t.gw0 + sl.dw, t.gh0 - 1, t.b);
                         ra.advance(p.sa);
@@ -198,7 +198,10 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
             const uint32_t a_ring_addr = smem_u32(a_ring) >> 4, b_ring_addr = smem_u32(b_ring) >> 4;
             const uint32_t a_slot16 = p.a_slot_bytes >> 4, b_slot16 = p.b_slot_bytes >> 4;
             const uint32_t n_acc = p.n_acc, N = p.N, sa = p.sa, sb = p.sb;
-            constexpr uint32_t kAccStep16 = (kAccRows * kRowBytes) >> 4;
+            const uint32_t acc_step16 = p.acc_step16, pitch16 = p.a_pitch16;
+            // the A operand's stride between 8-row groups is the geometry's (1 KB inside a 16-pixel slab row, or the whole row
+            // pitch of a wide slab); weights keep the standard K-major tile
+            const uint64_t desc_hi_a = ((uint64_t)1 << 16) | ((uint64_t)p.a_sbo16 << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
             uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0, pit = 0;
 #ifdef LICOS_PAIR_PROBES
             long long w_a = 0, w_b = 0, w_acc = 0, n_tiles = 0;
@@ -239,12 +242,11 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
                     const int n_slabs = ps.n_slabs;
                     uint32_t accumulate = 0;
                     for (int c = 0; c < p.cin_chunks; ++c) {
-                        unsigned long long info = p.pass_info[pi];
                         for (int s = 0; s < n_slabs; ++s) {
-                            const int nt = (int)(info & 3u) + 1;
-                            uint32_t a_lo = a_ring_addr + a_slot * a_slot16 + ((uint32_t)(info >> 2) & 3u) * (kRowBytes >> 4);
-                            const uint32_t a_step = (info & 16u) ? 0u - (kRowBytes >> 4) : (kRowBytes >> 4);
-                            info >>= 5;
+                            unsigned long long taps = p.tap_list[pi][s];  // [0:4) count, then (row_off : 2, col_off : 2) per tap
+                            const int nt = (int)(taps & 15u);
+                            taps >>= 4;
+                            const uint32_t a_slab = a_ring_addr + a_slot * a_slot16;
                             if (!__all_sync(0xffffffffu, have_a)) {
                                 PP_T0(_t);
                                 wait_slow(a_full0 + a_slot * 8u, a_phase);
@@ -261,7 +263,8 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
                                 asm volatile("fence.acq_rel.cta;" ::: "memory");  // pairs with the relaxed look-ahead probes
                                 tc_fence_after();
                                 const uint64_t bd = desc_hi | (uint64_t)(b_ring_addr + b_slot * b_slot16);
-                                const uint64_t ad = desc_hi | (uint64_t)a_lo;
+                                const uint64_t ad = desc_hi_a | (uint64_t)(a_slab + ((uint32_t)taps & 3u) * pitch16 + (((uint32_t)taps >> 2) & 3u) * 8u);
+                                taps >>= 4;
                                 const uint32_t nb_slot = (b_slot + 1 == sb) ? 0u : b_slot + 1;
                                 const uint32_t nb_phase = b_phase ^ ((nb_slot == 0u) ? 1u : 0u);
                                 // probe the next tap's weights and, on a slab's last tap, the next slab -- the predicates are read
@@ -276,11 +279,11 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
                                 if (elect_one()) {
                                     if (n_acc == 2) {
                                         umma_bf16_pair(tmem_set, ad, bd, idesc, accumulate);
-                                        umma_bf16_pair(tmem_set + N, ad + kAccStep16, bd, idesc, accumulate);
+                                        umma_bf16_pair(tmem_set + N, ad + acc_step16, bd, idesc, accumulate);
 #pragma unroll
                                         for (uint32_t ks = 1; ks < 4; ++ks) {
                                             umma_bf16_pair(tmem_set, ad + 2 * ks, bd + 2 * ks, idesc, 1u);
-                                            umma_bf16_pair(tmem_set + N, ad + kAccStep16 + 2 * ks, bd + 2 * ks, idesc, 1u);
+                                            umma_bf16_pair(tmem_set + N, ad + acc_step16 + 2 * ks, bd + 2 * ks, idesc, 1u);
                                         }
                                     } else {
                                         umma_bf16_pair(tmem_set, ad, bd, idesc, accumulate);
@@ -292,7 +295,6 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
                                 __syncwarp();
                                 asm volatile("selp.b32 %0, 1, 0, licos_nb;" : "=r"(have_b));
                                 accumulate = 1;
-                                a_lo += a_step;
                                 b_slot = nb_slot;
                                 b_phase = nb_phase;
                             }
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
         const uint32_t lane_sel = ((uint32_t)(warp & 3) * 32u) << 16;
         const bool leader = et == 0 && half == 0;
         const bool first_warp = ((warp - 4) % TW) == 0;
-        const int th = et / kTileW, tw = et % kTileW;
+        const int th = p.wide ? et >> 3 : et >> 4, tw = p.wide ? (et & 7) : (et & 15);  // position of this TMEM lane in its accumulator block
         uint8_t* staging = staging_all + (size_t)team * p.staging_bytes;
         uint32_t pit = 0, nit = 0, job = 0;
         const int n32 = p.N / 32;
@@ -412,7 +414,8 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
 
                     // stage 2: activation, then write out
                     PP_T0(_s2);
-                    const int gh = t.gh0 + a * kAccRows + th, gw = t.gw0 + tw;
+                    const int bh0 = t.gh0 + (p.wide ? 0 : a * kAccRows), bw0 = t.gw0 + (p.wide ? 8 * a : 0);  // the block's origin
+                    const int gh = bh0 + th, gw = bw0 + tw;
                     const int oh = gh * p.out_s + ps.dy[0], ow = gw * p.out_s + ps.dx[0];
                     const bool in_range = t.live && gh < p.grid_h && gw < p.grid_w && oh < p.out_h && ow < p.out_w;
                     const size_t cs = (size_t)p.out_h * p.out_w;
@@ -485,7 +488,7 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
                         if (leader) {
                             for (int at = 0; at < p.N / kKChunk; ++at) {
                                 tma_store_4d(&p.out_maps[ps.out_map[0]], staging + (size_t)at * (128 * 128),
-                                             at * kKChunk, t.gw0, t.gh0 + a * kAccRows, t.b);
+                                             at * kKChunk, bw0, bh0, t.b);
                             }
                             tma_store_commit();
                         }
