@@ -114,6 +114,9 @@ typedef struct licos_conv_args {
     int64_t workspace_bytes;
     int sm_count;       /* 0 = query the device                                                */
     int int_max;        /* integer pixel layouts: full-scale value (0 = the layout's default)   */
+    void* pre_act;      /* optional, EPI_GDN / EPI_IGDN only: also write v = conv + bias (the GDN's input,
+                           bf16 NHWC [batch][out_h][out_w][out_c]) -- what the backward pass keeps
+                           (train.py:193); NULL in inference                                   */
 } licos_conv_args;
 
 /* Scratch bytes licos_conv_forward needs for these args (0 unless in_layout == NCHW_F32). */

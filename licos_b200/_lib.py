@@ -38,7 +38,7 @@ class ConvArgs(ctypes.Structure):
         ("kind", c_int), ("epilogue", c_int), ("batch", c_int), ("in_h", c_int), ("in_w", c_int),
         ("in_c", c_int), ("out_c", c_int), ("in_layout", c_int), ("out_layout", c_int),
         ("in_", c_vp), ("out", c_vp), ("weight", c_vp), ("bias", c_vp), ("beta", c_vp), ("gamma", c_vp),
-        ("workspace", c_vp), ("workspace_bytes", c_i64), ("sm_count", c_int), ("int_max", c_int),
+        ("workspace", c_vp), ("workspace_bytes", c_i64), ("sm_count", c_int), ("int_max", c_int), ("pre_act", c_vp),
     ]
 
 

@@ -87,6 +87,7 @@ struct ConvParams {
     int out_layout;
     int out_c, out_h, out_w, out_s;
     float* out_f32;
+    __nv_bfloat16* pre_out;  // optional (GDN epilogues): v = conv + bias, bf16 NHWC -- the backward pass's saved input
     const float* bias;
     const float* beta;
     int sa, sb;
@@ -469,6 +470,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                                             : p.out_f32 + ((size_t)t.b * p.out_c * p.out_h + oh) * p.out_w + ow +
                                                   (size_t)(t.ns * p.N) * cs;
                         const int c_left = p.out_c - t.ns * p.N;  // valid channels from this split's base
+                        __nv_bfloat16* pre_px = (kGdn && p.pre_out && in_range)
+                                                    ? p.pre_out + (((size_t)t.b * p.out_h + oh) * p.out_w + ow) * p.out_c + t.ns * p.N
+                                                    : nullptr;
 #pragma unroll
                         for (int cc = 0; cc < XC; ++cc) {
                             if (cc < n32) {
@@ -476,6 +480,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                                 tmem_ld32(t_acc + cc * 32, v);  // GDN: the norm; otherwise the accumulator
                                 tmem_ld_wait();
                                 if (kGdn) {
+                                    if (pre_px && cc * 32 < c_left) {
+#pragma unroll
+                                        for (int q = 0; q < 4; ++q)
+                                            reinterpret_cast<uint4*>(pre_px + cc * 32)[q] =
+                                                make_uint4(xs[cc * 16 + 4 * q], xs[cc * 16 + 4 * q + 1], xs[cc * 16 + 4 * q + 2], xs[cc * 16 + 4 * q + 3]);
+                                    }
                                     uint32_t out[16];
                                     gdn_stage2_32<EPI == LICOS_EPI_IGDN>(v, beta_s + cc * 32, xs + cc * 16, out);
                                     if (OUT_NHWC) {
@@ -916,6 +926,8 @@ static int launch_first2(const licos_conv_args* a, cudaStream_t s) {
     p.N = a->out_c;
     p.k_pad = first_kpad(a->in_c);
     const int OH = (a->in_h + 1) / 2, OW = (a->in_w + 1) / 2;
+    p.pre_out = (__nv_bfloat16*)a->pre_act;
+    p.out_h = OH; p.out_w = OW;
     p.tiles_h = (OH + 7) / 8; p.tiles_w = (OW + 15) / 16;
     const int64_t tiles = (int64_t)a->batch * p.tiles_h * p.tiles_w;
     if (tiles > 0x7fffffff) return LICOS_ERR_UNSUPPORTED;
@@ -1132,6 +1144,7 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     const bool gdn = (a->epilogue == LICOS_EPI_GDN || a->epilogue == LICOS_EPI_IGDN);
     if (a->epilogue < LICOS_EPI_NONE || a->epilogue > LICOS_EPI_RELU) return LICOS_ERR_INVALID;
     if (gdn && (!a->beta || !a->gamma || !a->bias)) return LICOS_ERR_INVALID;
+    if (a->pre_act && (!gdn || a->out_c % 32 != 0 || ((uintptr_t)a->pre_act & 15) != 0)) return LICOS_ERR_INVALID;
     const bool int_out = a->out_layout == LICOS_LAYOUT_NCHW_U8 || a->out_layout == LICOS_LAYOUT_NCHW_U16;
     if (a->out_layout != LICOS_LAYOUT_NCHW_F32 && a->out_layout != LICOS_LAYOUT_NHWC_BF16 && !int_out) return LICOS_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
@@ -1142,7 +1155,10 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
         return launch_first2(a, s);
     }
     if (a->in_layout == LICOS_LAYOUT_NCHW_F32 && use_first_direct(a->kind, a->in_c, a->out_c, a->out_layout))
+    {
+        if (!use_first2(a) && a->pre_act) return LICOS_ERR_UNSUPPORTED;  // only the pipelined kernel writes the pre-activation
         return use_first2(a) ? launch_first2(a, s) : launch_first(a, s);
+    }
     if (a->in_layout == LICOS_LAYOUT_NHWC_BF16 && use_narrow(a->kind, a->out_c, a->in_c)) {
         if ((a->out_layout != LICOS_LAYOUT_NCHW_F32 && !int_out) || gdn) return LICOS_ERR_UNSUPPORTED;
         return launch_narrow(a, s);
@@ -1164,6 +1180,7 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     p.bias = a->bias;
     p.beta = a->beta;
     p.out_f32 = (a->out_layout == LICOS_LAYOUT_NCHW_F32) ? (float*)a->out : nullptr;
+    p.pre_out = (__nv_bfloat16*)a->pre_act;
 
     if (a->out_layout == LICOS_LAYOUT_NHWC_BF16 && (a->out_c % 64 != 0 || a->out_c > 256)) return LICOS_ERR_UNSUPPORTED;
     if (gdn && (a->out_c % 64 != 0 || a->out_c > 256)) return LICOS_ERR_UNSUPPORTED;

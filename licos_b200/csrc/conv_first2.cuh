@@ -107,6 +107,8 @@ struct First2Params {
     const __nv_bfloat16* w;  // packed weight [N][k_pad] (K columns 64.. are copied by hand)
     const float* bias;
     const float* beta;
+    __nv_bfloat16* pre_out;  // optional (GDN): v = conv + bias, bf16 NHWC [B][out_h][out_w][N]
+    int out_h, out_w;
     int k_pad;
     int N;
     int tiles_h, tiles_w, total_tiles;
@@ -417,6 +419,10 @@ __global__ void __launch_bounds__(first2_threads(TEAMS), 1) conv_first2_kernel(c
                 tc_fence_after();
                 ++nit;
             }
+            const int oh = oh0 + (row >> 4), ow = ow0 + (row & 15);  // staging rows run w-fastest over the 8 x 16 tile
+            __nv_bfloat16* pre_px = (kGdn && p.pre_out && oh < p.out_h && ow < p.out_w)
+                                        ? p.pre_out + (((size_t)b * p.out_h + oh) * p.out_w + ow) * N
+                                        : nullptr;
 #pragma unroll
             for (int cc = 0; cc < kXC; ++cc) {
                 if (cc < n32) {
@@ -425,6 +431,12 @@ __global__ void __launch_bounds__(first2_threads(TEAMS), 1) conv_first2_kernel(c
                     tmem_ld_wait();
                     uint32_t out[16];
                     if (kGdn) {
+                        if (pre_px) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                reinterpret_cast<uint4*>(pre_px + cc * 32)[q] =
+                                    make_uint4(xs[cc * 16 + 4 * q], xs[cc * 16 + 4 * q + 1], xs[cc * 16 + 4 * q + 2], xs[cc * 16 + 4 * q + 3]);
+                        }
                         gdn_stage2_32<EPI == LICOS_EPI_IGDN>(v, beta_s + cc * 32, xs + cc * 16, out);
                     } else {
 #pragma unroll

@@ -423,6 +423,9 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
                                         : p.out_f32 + ((size_t)t.b * p.out_c * p.out_h + oh) * p.out_w + ow +
                                               (size_t)(t.ns * p.N) * cs;
                     const int c_left = p.out_c - t.ns * p.N;  // valid channels from this split's base
+                    __nv_bfloat16* pre_px = (kGdn && p.pre_out && in_range)
+                                                ? p.pre_out + (((size_t)t.b * p.out_h + oh) * p.out_w + ow) * p.out_c + t.ns * p.N
+                                                : nullptr;
 #pragma unroll
                     for (int i = 0; i < XC; ++i) {
                         const int cc = kStride * i + half;
@@ -431,6 +434,12 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
                             tmem_ld32(t_acc + cc * 32, v);  // GDN: the norm; otherwise the accumulator
                             tmem_ld_wait();
                             if (kGdn) {
+                                if (pre_px && cc * 32 < c_left) {
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q)
+                                        reinterpret_cast<uint4*>(pre_px + cc * 32)[q] =
+                                            make_uint4(xs[i * 16 + 4 * q], xs[i * 16 + 4 * q + 1], xs[i * 16 + 4 * q + 2], xs[i * 16 + 4 * q + 3]);
+                                }
                                 uint32_t out[16];
                                 gdn_stage2_32<EPI == LICOS_EPI_IGDN>(v, beta_s + cc * 32, xs + i * 16, out);
                                 if (OUT_NHWC) {

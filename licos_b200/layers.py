@@ -363,7 +363,7 @@ class FusedSequential(nn.Sequential):
 # ---------------------------------------------------------------------------------------------
 
 class _ChainFn(torch.autograd.Function):
-    """forward: conv (+ bias) on the engine with the pre-activation kept, GDN / IGDN as its own 1x1 layer;
+    """forward: conv + bias + GDN / IGDN in one launch on the engine, which also writes the pre-activation for backward;
     backward: data gradients on the engine (conv <-> transposed conv with the same weight), weight / gamma gradients on
     ``licos_conv_wgrad``, bias / beta gradients by column sums.  Activations and their gradients are bf16 NHWC."""
 
@@ -390,13 +390,22 @@ class _ChainFn(torch.autograd.Function):
                 C = m.out_channels
                 if bias is None:
                     bias = torch.zeros(C, dtype=torch.float32, device=dev)
-                v = T.conv_forward(cur, kind=kind, epilogue=L.EPI_NONE, in_layout=layout, out_layout=L.LAYOUT_NHWC_BF16,
-                                     in_c=m.in_channels, out_c=C, weight=packed, bias=bias)
                 beta_hat, gamma_hat = seq._packed_gdn(gdn, force=True)
                 rec["gdn_packed"] = (beta_hat, gamma_hat)
-                eye = _identity_1x1(C, dev)
-                cur = T.conv_forward(v, kind=L.CONV_1X1, epilogue=epi, in_layout=L.LAYOUT_NHWC_BF16, out_layout=out_layout,
-                                       in_c=C, out_c=C, weight=eye, bias=_zeros(C, dev), beta=beta_hat, gamma=gamma_hat)
+                B, _, OH, OW = _out_shape(kind, cur, layout)
+                v = torch.empty((B, OH, OW, C), dtype=torch.bfloat16, device=dev)
+                try:
+                    # one launch: the fused conv + GDN epilogue also writes its input v = conv + bias for the backward pass
+                    cur = T.conv_forward(cur, kind=kind, epilogue=epi, in_layout=layout, out_layout=out_layout,
+                                         in_c=m.in_channels, out_c=C, weight=packed, bias=bias, beta=beta_hat, gamma=gamma_hat,
+                                         pre_act=v)
+                except NotImplementedError:
+                    # shapes the fused kernels refuse (LICOS_ERR_UNSUPPORTED): conv with v kept, then the GDN as a 1x1 layer
+                    v = T.conv_forward(cur, kind=kind, epilogue=L.EPI_NONE, in_layout=layout, out_layout=L.LAYOUT_NHWC_BF16,
+                                       in_c=m.in_channels, out_c=C, weight=packed, bias=bias)
+                    cur = T.conv_forward(v, kind=L.CONV_1X1, epilogue=epi, in_layout=L.LAYOUT_NHWC_BF16, out_layout=out_layout,
+                                         in_c=C, out_c=C, weight=_identity_1x1(C, dev), bias=_zeros(C, dev), beta=beta_hat,
+                                         gamma=gamma_hat)
                 rec["v"] = v
             else:
                 cur = T.conv_forward(cur, kind=kind, epilogue=epi, in_layout=layout, out_layout=out_layout,
@@ -525,6 +534,19 @@ class _ChainFn(torch.autograd.Function):
 
 
 _CONST_CACHE = {}
+
+
+def _out_shape(kind: int, x: Tensor, layout: int):
+    """(B, -, OH, OW) of a conv_forward launch of this kind (ops.conv_forward's own rule)."""
+    if layout == _lib.LAYOUT_NHWC_BF16:
+        B, H, W = x.shape[0], x.shape[1], x.shape[2]
+    else:
+        B, H, W = x.shape[0], x.shape[2], x.shape[3]
+    if kind == _lib.CONV_5X5_S2:
+        return B, None, (H + 1) // 2, (W + 1) // 2
+    if kind == _lib.DECONV_5X5_S2:
+        return B, None, 2 * H, 2 * W
+    return B, None, H, W
 
 
 def _identity_1x1(C: int, dev) -> Tensor:

@@ -113,7 +113,8 @@ def pixel_layout_of(x: torch.Tensor, requant8: bool = False) -> int:
 
 def conv_forward(x: torch.Tensor, *, kind: int, epilogue: int, in_layout: int, out_layout: int, in_c: int,
                  out_c: int, weight: torch.Tensor, bias: Optional[torch.Tensor], beta: Optional[torch.Tensor] = None,
-                 gamma: Optional[torch.Tensor] = None, sm_count: int = 0, int_max: int = 0) -> torch.Tensor:
+                 gamma: Optional[torch.Tensor] = None, sm_count: int = 0, int_max: int = 0,
+                 pre_act: Optional[torch.Tensor] = None) -> torch.Tensor:
     """One conv / deconv layer with its fused epilogue.  x is fp32 / integer NCHW or bf16 NHWC (see in_layout);
     out_layout may be an integer pixel layout for the model's last layer (int_max = full-scale value, 0 = default)."""
     _need_cuda(x, weight, bias, beta, gamma)
@@ -148,6 +149,11 @@ def conv_forward(x: torch.Tensor, *, kind: int, epilogue: int, in_layout: int, o
     a.bias, a.beta, a.gamma = _ptr(bias), _ptr(beta), _ptr(gamma)
     a.sm_count = sm_count
     a.int_max = int(int_max)
+    if pre_act is not None:
+        _need_cuda(pre_act)
+        if pre_act.dtype != torch.bfloat16 or tuple(pre_act.shape) != (B, OH, OW, out_c):
+            raise ValueError("pre_act must be a bf16 (B, out_h, out_w, out_c) tensor")
+        a.pre_act = pre_act.data_ptr()
     ws = None
     nws = 0
     if in_layout == _lib.LAYOUT_NCHW_F32:  # only the explicit-im2col first-layer fallback needs scratch

@@ -64,18 +64,18 @@ def _conv_out_shape(x, kind, in_layout, out_layout, out_c):
     return (B, out_c, OH, OW), {_lib.LAYOUT_NCHW_U8: torch.uint8, _lib.LAYOUT_NCHW_U16: torch.uint16}.get(out_layout, torch.float32)
 
 
-def _conv_forward_cuda(x, kind, epilogue, in_layout, out_layout, in_c, out_c, weight, bias, beta, gamma, int_max=0):
+def _conv_forward_cuda(x, kind, epilogue, in_layout, out_layout, in_c, out_c, weight, bias, beta, gamma, int_max=0, pre_act=None):
     return ops.conv_forward(x, kind=kind, epilogue=epilogue, in_layout=in_layout, out_layout=out_layout, in_c=in_c, out_c=out_c,
-                            weight=weight, bias=bias, beta=beta, gamma=gamma, int_max=int_max)
+                            weight=weight, bias=bias, beta=beta, gamma=gamma, int_max=int_max, pre_act=pre_act)
 
 
-def _conv_forward_meta(x, kind, epilogue, in_layout, out_layout, in_c, out_c, weight, bias, beta, gamma, int_max=0):
+def _conv_forward_meta(x, kind, epilogue, in_layout, out_layout, in_c, out_c, weight, bias, beta, gamma, int_max=0, pre_act=None):
     shape, dtype = _conv_out_shape(x, kind, in_layout, out_layout, out_c)
     return torch.empty(shape, dtype=dtype, device=x.device)
 
 
 _register("conv_forward(Tensor x, int kind, int epilogue, int in_layout, int out_layout, int in_c, int out_c, Tensor weight, "
-          "Tensor? bias, Tensor? beta, Tensor? gamma, int int_max=0) -> Tensor", _conv_forward_cuda, _conv_forward_meta)
+          "Tensor? bias, Tensor? beta, Tensor? gamma, int int_max=0, Tensor(a!)? pre_act=None) -> Tensor", _conv_forward_cuda, _conv_forward_meta)
 
 def _wgrad(small, big, kind, out):
     ops.conv_wgrad(small, big, kind, out=out)
@@ -188,8 +188,9 @@ T = torch.ops.licos_b200
 # ops.py-compatible entry points for the module code
 # ---------------------------------------------------------------------------------------------------------------------
 def conv_forward(x: Tensor, *, kind: int, epilogue: int, in_layout: int, out_layout: int, in_c: int, out_c: int, weight: Tensor,
-                 bias: Optional[Tensor], beta: Optional[Tensor] = None, gamma: Optional[Tensor] = None, int_max: int = 0) -> Tensor:
-    return T.conv_forward(x, kind, epilogue, in_layout, out_layout, in_c, out_c, weight, bias, beta, gamma, int_max)
+                 bias: Optional[Tensor], beta: Optional[Tensor] = None, gamma: Optional[Tensor] = None, int_max: int = 0,
+                 pre_act: Optional[Tensor] = None) -> Tensor:
+    return T.conv_forward(x, kind, epilogue, in_layout, out_layout, in_c, out_c, weight, bias, beta, gamma, int_max, pre_act)
 
 
 def conv_wgrad(small: Tensor, big: Tensor, kind: int, out: Tensor) -> Tensor:

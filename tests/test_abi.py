@@ -33,7 +33,7 @@ def test_header_symbols_exported_and_bound():
 
 def test_struct_layouts_match_header():
     # licos_conv_args: 9 ints, 6 pointers, pointer + int64, 2 ints
-    assert ctypes.sizeof(_lib.ConvArgs) == 9 * 4 + 4 + 7 * 8 + 8 + 2 * 4
+    assert ctypes.sizeof(_lib.ConvArgs) == 9 * 4 + 4 + 7 * 8 + 8 + 2 * 4 + 8  # ..., sm_count, int_max, pre_act
     assert _lib.ConvArgs.in_.offset == 40 and _lib.ConvArgs.workspace_bytes.offset == 96
     assert _lib.EbParams.packed.offset == 48 and ctypes.sizeof(_lib.EbParams) == 72
 

@@ -73,6 +73,23 @@ def _run(cuda, kind, B, cin, cout, H, W, epi=_lib.EPI_NONE, out_nchw=False, firs
     got = out.cpu() if out_nchw else out.float().cpu().permute(0, 3, 1, 2)
     assert got.shape == ref.shape
     _check(got, ref, f"kind={kind} {cin}->{cout} {H}x{W} epi={epi} nchw_out={out_nchw} first={first}", not out_nchw)
+    if beta is not None:
+        # training's variant: same launch also writes v = conv + bias (bf16 NHWC).  The output must not change, every
+        # element of v must be written, and v must be what the EPI_NONE launch of the same conv stores.
+        Bo, Co, OH, OW = ref.shape
+        v = torch.full((Bo, OH, OW, Co), float("nan"), dtype=torch.bfloat16, device=cuda)
+        try:
+            out2 = ops.conv_forward(xd, kind=kind, epilogue=epi, in_layout=in_layout, out_layout=out_layout, in_c=cin,
+                                    out_c=cout, weight=packed, bias=bias.to(cuda), beta=bh, gamma=gh, pre_act=v)
+        except NotImplementedError:
+            # only the generic first-layer kernel (conv_edge.cuh) refuses; FusedSequential then runs conv and GDN apart
+            assert first and (cin not in (1, 3) or (W * 4) % 16 != 0)
+            return
+        plain = ops.conv_forward(xd, kind=kind, epilogue=_lib.EPI_NONE, in_layout=in_layout,
+                                 out_layout=_lib.LAYOUT_NHWC_BF16, in_c=cin, out_c=cout, weight=packed, bias=bias.to(cuda))
+        torch.cuda.synchronize()
+        assert torch.equal(out2, out), "pre_act changed the layer's output"
+        assert torch.equal(v.view(torch.int16), plain.view(torch.int16)), "pre_act differs from the conv's own output"
 
 
 def test_conv3x3_s1_nhwc(cuda):
