@@ -184,6 +184,15 @@ int licos_colsum_bf16(const void* x, int64_t rows, int channels, float* acc, voi
  * licos_im2col5x5s2_kpad(channels) bf16 columns (the next multiple of 16). */
 int64_t licos_im2col5x5s2_kpad(int channels);
 int licos_im2col5x5s2(const float* x, int batch, int channels, int h, int w, void* rows, void* stream);
+/* The same weight gradient WITHOUT the patch matrix in HBM (the im2col tile is built in shared memory):
+ *   out[cs][k] += sum_{b,oh,ow} small[b][oh][ow][cs] * image[b][c][2 oh + kh - 2][2 ow + kw - 2],  k = (c*5 + kh)*5 + kw
+ * small_t bf16 NHWC [batch][ceil(h/2)][ceil(w/2)][small_c] (g_a[0]: the conv output's gradient -> Conv2d.weight.grad[cs][c][kh][kw];
+ * g_s[6]: the layer input -> ConvTranspose2d.weight.grad[cs][c][kh][kw]), image fp32 NCHW [batch][channels][h][w],
+ * out fp32 [small_c][licos_im2col5x5s2_kpad(channels)], 16-byte aligned, accumulated (the caller zeroes it).
+ * Built for channels in {1, 3}, small_c a multiple of 64 <= 256, w % 4 == 0, 16-byte aligned tensors; anything else
+ * returns LICOS_ERR_UNSUPPORTED (take licos_im2col5x5s2 + licos_conv_wgrad(CONV_1X1)). */
+int licos_conv_wgrad_image(const void* small_t, const float* image, int batch, int channels, int h, int w, int small_c,
+                           float* out, int sm_count, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* EntropyBottleneck (compressai.entropy_models.EntropyBottleneck)   */

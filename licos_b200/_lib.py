@@ -94,6 +94,7 @@ SIGNATURES = {
     "licos_colsum_bf16": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
     "licos_im2col5x5s2_kpad": (c_i64, [c_int]),
     "licos_im2col5x5s2": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "licos_conv_wgrad_image": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]),
     "licos_eb_lut_floats": (c_i64, [c_int]),
     "licos_eb_forward_eval": (c_int, [ctypes.POINTER(EbParams), c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "licos_eb_build_lut": (c_int, [ctypes.POINTER(EbParams), c_vp, c_vp]),

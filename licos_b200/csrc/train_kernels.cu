@@ -18,6 +18,7 @@
 #include "gdn_bwd.cuh"
 
 #include <stdlib.h>
+#include <type_traits>
 #include <string.h>
 #include <mutex>
 
@@ -218,6 +219,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
         tmem_dealloc(tmem_base, 512);
     }
 }
+
+}  // namespace licos
+#include "wgrad_image.cuh"
+namespace licos {
 
 // ----------------------------------------------------------------------------------------------
 // elementwise / reduction kernels of the GDN, ReLU and bias backward passes (bf16 NHWC, 8 channels per thread)
@@ -627,6 +632,67 @@ int licos_conv_wgrad(const licos_wgrad_args* a, void* stream) {
     LICOS_CUDA_OK(ensure_max_dynamic_smem((const void*)wgrad_kernel, (int)smem));
     const int grid = p.n_units < sms ? p.n_units : sms;
     wgrad_kernel<<<grid, kWgThreads, smem, (cudaStream_t)stream>>>(p);
+    LICOS_CUDA_OK(cudaGetLastError());
+    return LICOS_OK;
+}
+
+int licos_conv_wgrad_image(const void* small_t, const float* image, int batch, int channels, int h, int w, int small_c,
+                           float* out, int sm_count, void* stream) {
+    if (!small_t || !image || !out || batch < 0 || channels < 1 || h < 1 || w < 1 || small_c < 1) return LICOS_ERR_INVALID;
+    if (((uintptr_t)out & 15) != 0) return LICOS_ERR_INVALID;
+    if (batch == 0) return LICOS_OK;
+    // the fused kernel is built for the reference's band counts with TMA-loadable rows; anything else takes
+    // licos_im2col5x5s2 + licos_conv_wgrad(CONV_1X1)
+    if ((channels != 1 && channels != 3) || small_c % 64 != 0 || small_c > 256 || (w % 4) != 0 || ((uintptr_t)image & 15) != 0 ||
+        ((uintptr_t)small_t & 15) != 0)
+        return LICOS_ERR_UNSUPPORTED;
+    const int OH = (h + 1) / 2, OW = (w + 1) / 2;
+    WgImageParams p;
+    memset(&p, 0, sizeof(p));
+    p.Cs = small_c;
+    p.m_blocks = (small_c + 127) / 128;
+    p.k_pad = (int)licos_im2col5x5s2_kpad(channels);
+    p.tiles_h = (OH + 7) / 8;
+    p.tiles_w = (OW + 15) / 16;
+    const int64_t tiles = (int64_t)batch * p.tiles_h * p.tiles_w;
+    if (tiles > 0x7fffffff) return LICOS_ERR_UNSUPPORTED;
+    p.total_tiles = (int)tiles;
+    p.slots = p.m_blocks == 1 ? 3 : 2;
+    p.out = out;
+    {
+        EncodeTiledFn fn = wg_encode_fn();
+        if (!fn) return LICOS_ERR_CUDA;
+        const cuuint64_t gdims[4] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)channels, (cuuint64_t)batch};
+        const cuuint64_t gstrides[3] = {(cuuint64_t)w * 4, (cuuint64_t)h * w * 4, (cuuint64_t)channels * h * w * 4};
+        const cuuint32_t gbox[4] = {(cuuint32_t)kWiPatchPitch, (cuuint32_t)kWiPatchRows, (cuuint32_t)channels, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (fn(&p.x_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(image), gdims, gstrides, gbox, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return LICOS_ERR_CUDA;
+    }
+    {
+        const uint64_t C = (uint64_t)small_c, H = (uint64_t)OH, W = (uint64_t)OW, B = (uint64_t)batch;
+        const uint64_t dims[4] = {C, W, H, B};
+        const uint64_t strides[3] = {C, W * C, H * W * C};
+        const uint32_t box[4] = {64, 16, 8, 1};
+        if (!wg_make_map(&p.s_map, small_t, dims, strides, box)) return LICOS_ERR_CUDA;
+    }
+    int sms = sm_count;
+    if (sms <= 0) {
+        int dev = 0;
+        LICOS_CUDA_OK(cudaGetDevice(&dev));
+        LICOS_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    const size_t smem = wg_image_smem_bytes(channels, p.m_blocks, p.slots);
+    if (channels == 3) {
+        LICOS_CUDA_OK(ensure_max_dynamic_smem((const void*)wgrad_image_kernel<3>, 228000));
+        wgrad_image_kernel<3><<<grid, kWiThreads, smem, (cudaStream_t)stream>>>(p);
+    } else {
+        LICOS_CUDA_OK(ensure_max_dynamic_smem((const void*)wgrad_image_kernel<1>, 228000));
+        wgrad_image_kernel<1><<<grid, kWiThreads, smem, (cudaStream_t)stream>>>(p);
+    }
     LICOS_CUDA_OK(cudaGetLastError());
     return LICOS_OK;
 }

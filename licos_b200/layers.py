@@ -459,9 +459,7 @@ class _ChainFn(torch.autograd.Function):
             Co, Ci = m.out_channels, m.in_channels
             if narrow:
                 # g_s[6]: C -> C_img transposed conv, gradient arrives as fp32 NCHW
-                patches = ops.im2col5x5s2(g)
-                kp = patches.shape[-1]
-                dw = T.conv_wgrad(a_in, patches, L.CONV_1X1, out=take(Ci * kp))[0][:, :Co * 25].reshape(Ci, Co, 5, 5)
+                dw = _edge_wgrad(a_in, g, take)[:, :Co * 25].reshape(Ci, Co, 5, 5)
                 db = g.sum(dim=(0, 2, 3)) if m.bias is not None else None
                 grads.append([dw, db])
                 if need_dgrad:
@@ -503,9 +501,7 @@ class _ChainFn(torch.autograd.Function):
                 db = ops.colsum_bf16(g, acc=take(Co))
             # g is now the gradient with respect to conv + bias
             if in_layout == L.LAYOUT_NCHW_F32:  # g_a[0]: image in, K = 25 C_in
-                patches = ops.im2col5x5s2(a_in)
-                kp = patches.shape[-1]
-                dw = T.conv_wgrad(g, patches, L.CONV_1X1, out=take(Co * kp))[0][:, :Ci * 25].reshape(Co, Ci, 5, 5)
+                dw = _edge_wgrad(g, a_in, take)[:, :Ci * 25].reshape(Co, Ci, 5, 5)
             elif kind == L.DECONV_5X5_S2:
                 dw = T.conv_wgrad(a_in, g, kind, out=take(25 * Ci * Co)).permute(1, 2, 0).reshape(Ci, Co, 5, 5)
             else:
@@ -534,6 +530,18 @@ class _ChainFn(torch.autograd.Function):
 
 
 _CONST_CACHE = {}
+
+
+def _edge_wgrad(small: Tensor, image: Tensor, take) -> Tensor:
+    """fp32 [Cs][k_pad] weight gradient of a 5x5 stride-2 edge layer (g_a[0], g_s[6]): ``small`` is the bf16 NHWC tensor on
+    the many-channel side, ``image`` the fp32 NCHW one on the band side.  One fused launch where the kernel is built for
+    the shape (1 / 3 bands); otherwise the patch matrix goes through HBM (im2col + a 1x1 weight gradient)."""
+    cs, kp = small.shape[-1], ops.im2col_kpad(image.shape[1])
+    out = take(cs * kp)
+    try:
+        return T.conv_wgrad_image(small, image, out)
+    except NotImplementedError:
+        return T.conv_wgrad(small, ops.im2col5x5s2(image), _lib.CONV_1X1, out=out)[0]
 
 
 def _out_shape(kind: int, x: Tensor, layout: int):

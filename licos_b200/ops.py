@@ -200,6 +200,27 @@ def conv_wgrad(small: torch.Tensor, big: torch.Tensor, kind: int, sm_count: int 
     return out
 
 
+def im2col_kpad(channels: int) -> int:
+    return int(lib.licos_im2col5x5s2_kpad(channels))
+
+
+def conv_wgrad_image(small: torch.Tensor, image: torch.Tensor, out: torch.Tensor, sm_count: int = 0) -> torch.Tensor:
+    """Weight gradient of the 5x5 stride-2 edge layers with the im2col tile built in shared memory:
+    out[cs][k] += sum_pixels small[b][oh][ow][cs] * image[b][c][2 oh + kh - 2][2 ow + kw - 2], k = (c*5 + kh)*5 + kw.
+    small bf16 (B, ceil(H/2), ceil(W/2), Cs), image fp32 (B, C, H, W), out ZEROED fp32 with Cs * k_pad elements.
+    Raises NotImplementedError for shapes the fused kernel is not built for (use im2col5x5s2 + conv_wgrad)."""
+    _need_cuda(_bf16(small), _f32(image), _f32(out))
+    B, C, H, W = image.shape
+    if tuple(small.shape[:3]) != (B, (H + 1) // 2, (W + 1) // 2):
+        raise ValueError("small must be (B, ceil(H/2), ceil(W/2), Cs)")
+    cs, kp = small.shape[-1], im2col_kpad(C)
+    if out.numel() != cs * kp:
+        raise ValueError("out must hold small_c * k_pad float32 values")
+    check(lib.licos_conv_wgrad_image(small.data_ptr(), image.data_ptr(), B, C, H, W, cs, out.data_ptr(), sm_count, _stream()),
+          "conv_wgrad_image")
+    return out.view(cs, kp)
+
+
 def gdn_backward(x: torch.Tensor, g: torch.Tensor, gamma_hat: torch.Tensor, beta_hat: torch.Tensor, inverse: bool,
                  d_gamma_hat: torch.Tensor, d_beta_hat: torch.Tensor, d_bias: Optional[torch.Tensor], sm_count: int = 0):
     """Fused GDN / IGDN backward (128 channels): returns dx, accumulates into the zeroed fp32 d_gamma_hat [C][C],

@@ -86,6 +86,15 @@ _register("conv_wgrad(Tensor small, Tensor big, int kind, Tensor(a!) out) -> Ten
           lambda small, big, kind, out: out)
 
 
+def _wgrad_image(small, image, out):
+    ops.conv_wgrad_image(small, image, out)
+    return out
+
+
+_register("conv_wgrad_image(Tensor small, Tensor image, Tensor(a!) out) -> Tensor(a!)", _wgrad_image,
+          lambda small, image, out: out)
+
+
 _register("gdn_backward(Tensor x, Tensor g, Tensor gamma_hat, Tensor beta_hat, bool inverse, Tensor(a!) d_gamma_hat, "
           "Tensor(b!) d_beta_hat, Tensor(c!)? d_bias) -> Tensor",
           lambda x, g, gh, bh, inv, dgh, dbh, db: ops.gdn_backward(x, g, gh, bh, inv, dgh, dbh, db),
@@ -193,6 +202,11 @@ def conv_forward(x: Tensor, *, kind: int, epilogue: int, in_layout: int, out_lay
     return T.conv_forward(x, kind, epilogue, in_layout, out_layout, in_c, out_c, weight, bias, beta, gamma, int_max, pre_act)
 
 
+def conv_wgrad_image(small: Tensor, image: Tensor, out: Tensor) -> Tensor:
+    T.conv_wgrad_image(small, image, out)
+    return out.view(small.shape[-1], -1)
+
+
 def conv_wgrad(small: Tensor, big: Tensor, kind: int, out: Tensor) -> Tensor:
     taps = {_lib.CONV_5X5_S2: 25, _lib.DECONV_5X5_S2: 25, _lib.CONV_3X3_S1: 9, _lib.CONV_1X1: 1}[kind]
     T.conv_wgrad(small, big, kind, out)
@@ -276,6 +290,6 @@ def sum_sq_err(a: Tensor, b: Tensor, acc: Optional[Tensor] = None) -> Tensor:
     return T.sum_sq_err(a, b, acc)
 
 
-OPS: List[str] = ["conv_forward", "conv_wgrad", "gdn_backward", "nchw_to_nhwc_bf16", "eb_forward_eval", "eb_eval_fused", "eb_build_lut",
+OPS: List[str] = ["conv_forward", "conv_wgrad", "conv_wgrad_image", "gdn_backward", "nchw_to_nhwc_bf16", "eb_forward_eval", "eb_eval_fused", "eb_build_lut",
                   "eb_forward_noise", "eb_backward", "eb_symbols", "eb_dequantize", "gc_forward", "gc_backward", "gc_build_indexes",
                   "gc_symbols", "sum_log", "sum_sq_err"]

@@ -145,6 +145,36 @@ def test_conv1x1_engine_and_im2col(cuda):
     assert float(rows[..., 75:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("bands,cs,batch,h,w", [(3, 128, 2, 64, 64), (1, 128, 1, 48, 40), (3, 192, 2, 34, 52), (3, 64, 1, 19, 28),
+                                               (1, 256, 1, 16, 96), (3, 128, 40, 128, 128)])
+def test_edge_wgrad_fused_equals_patch_matrix_path(cuda, bands, cs, batch, h, w):
+    """licos_conv_wgrad_image (im2col tile built in shared memory) against the float64 product of the SAME bf16 operands
+    (the patch matrix of licos_im2col5x5s2, which the test above pins to F.unfold), ragged tiles, 1 / 3 bands, 1 / 2
+    accumulator blocks, more tiles than SMs."""
+    g = torch.Generator().manual_seed(bands * 1000 + cs + h)
+    oh, ow = (h + 1) // 2, (w + 1) // 2
+    img = torch.rand(batch, bands, h, w, generator=g).to(cuda)
+    small = torch.randn(batch, oh, ow, cs, generator=g).bfloat16().to(cuda)
+    kp = ops.im2col_kpad(bands)
+    out = torch.zeros(cs * kp, dtype=torch.float32, device=cuda)
+    got = ops.conv_wgrad_image(small, img, out)
+    rows = ops.im2col5x5s2(img)
+    ref = (small.reshape(-1, cs).double().t() @ rows.reshape(-1, kp).double()).cpu()
+    assert got.shape == (cs, kp)
+    assert _rel(got, ref) <= 2e-5
+    assert float(got[:, bands * 25:].abs().max()) == 0.0
+    ops.conv_wgrad_image(small, img, out)  # accumulates
+    assert _rel(out.view(cs, kp), 2 * ref) <= 2e-5
+
+
+def test_edge_wgrad_fused_refuses_what_it_is_not_built_for(cuda):
+    small = torch.zeros(1, 8, 8, 128, dtype=torch.bfloat16, device=cuda)
+    with pytest.raises(NotImplementedError):  # 13 bands: the patch-matrix path
+        ops.conv_wgrad_image(small, torch.zeros(1, 13, 16, 16, device=cuda), torch.zeros(128 * ops.im2col_kpad(13), device=cuda))
+    with pytest.raises(NotImplementedError):  # rows TMA cannot load (width not a multiple of 4)
+        ops.conv_wgrad_image(small, torch.zeros(1, 3, 16, 15, device=cuda), torch.zeros(128 * 80, device=cuda))
+
+
 # ---------------------------------------------------------------------------------------------
 # chain level
 # ---------------------------------------------------------------------------------------------
