@@ -380,17 +380,39 @@ class _ChainFn(torch.autograd.Function):
             cur = T.nchw_to_nhwc_bf16(cur)
             layout = L.LAYOUT_NHWC_BF16
         saved = []
+        # Every operand re-pack of the chain (forward layouts, GDN parameters, the data-gradient layouts backward needs)
+        # is issued up front on a side stream: a dozen ~5 us launches that now run beside the first layers instead of
+        # between them (under graph capture: a parallel branch of the graph).  Layer n waits for its own event only.
+        main = torch.cuda.current_stream(dev)
+        side = _pack_stream(dev)
+        side.wait_stream(main)
+        pre, lay = [], layout
+        with torch.cuda.stream(side):
+            for n, (m, kind, epi, gdn) in enumerate(steps):
+                # the training path never trusts the version-keyed caches (see FusedSequential.train)
+                ent = {"w": seq._packed_weight(m, kind, lay, force=True),
+                       "gdn": None if gdn is None else seq._packed_gdn(gdn, force=True)}
+                ent["ready"] = side.record_event()
+                pre.append(ent)
+                lay = L.LAYOUT_NHWC_BF16
+            for n, (m, kind, epi, gdn) in enumerate(steps):
+                pre[n]["wd"] = _dgrad_weight(m, kind, n == len(steps) - 1) if (n > 0 or x.requires_grad) else None
+            packs_done = side.record_event()
+        for ent in pre:
+            for t in (*ent["w"], *(ent["gdn"] or ()), ent["wd"]):
+                if t is not None and t.is_cuda:
+                    t.record_stream(main)
         for n, (m, kind, epi, gdn) in enumerate(steps):
             last = n == len(steps) - 1
             out_layout = L.LAYOUT_NCHW_F32 if last else L.LAYOUT_NHWC_BF16
-            # the training path never trusts the version-keyed caches (see FusedSequential.train)
-            packed, bias = seq._packed_weight(m, kind, layout, force=True)
-            rec = {"in": cur, "in_layout": layout}
+            main.wait_event(pre[n]["ready"])
+            packed, bias = pre[n]["w"]
+            rec = {"in": cur, "in_layout": layout, "wd": pre[n]["wd"]}
             if gdn is not None:
                 C = m.out_channels
                 if bias is None:
                     bias = torch.zeros(C, dtype=torch.float32, device=dev)
-                beta_hat, gamma_hat = seq._packed_gdn(gdn, force=True)
+                beta_hat, gamma_hat = pre[n]["gdn"]
                 rec["gdn_packed"] = (beta_hat, gamma_hat)
                 B, _, OH, OW = _out_shape(kind, cur, layout)
                 v = torch.empty((B, OH, OW, C), dtype=torch.bfloat16, device=dev)
@@ -414,6 +436,7 @@ class _ChainFn(torch.autograd.Function):
                     rec["y"] = cur
             layout = out_layout
             saved.append(rec)
+        main.wait_event(packs_done)  # join: backward (and the end of a graph capture) finds every pack finished
         ctx.seq, ctx.steps, ctx.saved = seq, steps, saved
         # The chain's OUTPUT doubles as the ReLU mask of its last layer (h_s): keep it through save_for_backward so that an
         # in-place edit by the caller (clamp_, mul_) trips autograd's version check instead of silently corrupting the mask.
@@ -463,7 +486,7 @@ class _ChainFn(torch.autograd.Function):
                 db = g.sum(dim=(0, 2, 3)) if m.bias is not None else None
                 grads.append([dw, db])
                 if need_dgrad:
-                    wd = ops.pack_conv_weight(m.weight.detach().contiguous(), L.CONV_5X5_S2, Ci, Co, L.LAYOUT_NCHW_F32)
+                    wd = rec["wd"]
                     g = T.conv_forward(g, kind=L.CONV_5X5_S2, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NCHW_F32,
                                          out_layout=L.LAYOUT_NHWC_BF16, in_c=Co, out_c=Ci, weight=wd, bias=None)
                     g_layout = L.LAYOUT_NHWC_BF16
@@ -510,15 +533,8 @@ class _ChainFn(torch.autograd.Function):
             grads.append([dw, db] + ([d_beta, d_gamma] if gdn is not None else []))
             if need_dgrad:
                 out_layout = L.LAYOUT_NHWC_BF16 if n > 0 else L.LAYOUT_NCHW_F32
-                w = m.weight.detach()
-                if kind == L.CONV_5X5_S2:
-                    dk, build = L.DECONV_5X5_S2, (lambda: ops.pack_conv_weight(w.contiguous(), L.DECONV_5X5_S2, Ci, Co, L.LAYOUT_NHWC_BF16))
-                elif kind == L.DECONV_5X5_S2:
-                    dk, build = L.CONV_5X5_S2, (lambda: ops.pack_conv_weight(w.contiguous(), L.CONV_5X5_S2, Ci, Co, L.LAYOUT_NHWC_BF16))
-                else:
-                    dk, build = L.CONV_3X3_S1, (lambda: ops.pack_conv_weight(w.flip(2, 3).transpose(0, 1).contiguous(), L.CONV_3X3_S1, Ci, Co,
-                                                                              L.LAYOUT_NHWC_BF16))
-                wd = build()
+                dk = {L.CONV_5X5_S2: L.DECONV_5X5_S2, L.DECONV_5X5_S2: L.CONV_5X5_S2}.get(kind, L.CONV_3X3_S1)
+                wd = rec["wd"]
                 g = T.conv_forward(g, kind=dk, epilogue=L.EPI_NONE, in_layout=L.LAYOUT_NHWC_BF16, out_layout=out_layout,
                                      in_c=Co, out_c=Ci, weight=wd, bias=None)
                 g_layout = out_layout
@@ -530,6 +546,30 @@ class _ChainFn(torch.autograd.Function):
 
 
 _CONST_CACHE = {}
+
+
+_PACK_STREAMS = {}
+
+
+def _pack_stream(dev) -> "torch.cuda.Stream":
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _PACK_STREAMS:
+        _PACK_STREAMS[key] = torch.cuda.Stream(device=key)
+    return _PACK_STREAMS[key]
+
+
+def _dgrad_weight(m: nn.Module, kind: int, last: bool) -> Tensor:
+    """The layer's weight packed for its DATA gradient: conv 5x5 s2 <-> transposed conv with the same (O, I, 5, 5) tensor,
+    conv 3x3 with the flipped, transposed one; g_s's narrow last layer (``last``) takes the fp32-NCHW-input layout."""
+    L = _lib
+    w, Co, Ci = m.weight.detach(), m.out_channels, m.in_channels
+    if kind == L.DECONV_5X5_S2 and last and Co <= 4:
+        return ops.pack_conv_weight(w.contiguous(), L.CONV_5X5_S2, Ci, Co, L.LAYOUT_NCHW_F32)
+    if kind == L.CONV_5X5_S2:
+        return ops.pack_conv_weight(w.contiguous(), L.DECONV_5X5_S2, Ci, Co, L.LAYOUT_NHWC_BF16)
+    if kind == L.DECONV_5X5_S2:
+        return ops.pack_conv_weight(w.contiguous(), L.CONV_5X5_S2, Ci, Co, L.LAYOUT_NHWC_BF16)
+    return ops.pack_conv_weight(w.flip(2, 3).transpose(0, 1).contiguous(), L.CONV_3X3_S1, Ci, Co, L.LAYOUT_NHWC_BF16)
 
 
 def _edge_wgrad(small: Tensor, image: Tensor, take) -> Tensor:
