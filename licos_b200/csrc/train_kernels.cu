@@ -724,6 +724,18 @@ int licos_gdn_backward(const void* x, const void* g, const void* gamma_hat_bf16,
     }
     const int grid = (int)(tiles < sms ? tiles : sms);
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool one_team = getenv("LICOS_GDN_BWD_ONE_TEAM") != nullptr;  // A/B knob: the round-1 kernel
+    if (!one_team) {
+        if (inverse) {
+            LICOS_CUDA_OK(ensure_max_dynamic_smem((const void*)gdn_bwd_fused2_kernel<true>, (int)kGb2Smem));
+            gdn_bwd_fused2_kernel<true><<<grid, kGb2Threads, kGb2Smem, st>>>(p);
+        } else {
+            LICOS_CUDA_OK(ensure_max_dynamic_smem((const void*)gdn_bwd_fused2_kernel<false>, (int)kGb2Smem));
+            gdn_bwd_fused2_kernel<false><<<grid, kGb2Threads, kGb2Smem, st>>>(p);
+        }
+        LICOS_CUDA_OK(cudaGetLastError());
+        return LICOS_OK;
+    }
     if (inverse) {
         LICOS_CUDA_OK(ensure_max_dynamic_smem((const void*)gdn_bwd_fused_kernel<true>, (int)kGbSmem));
         gdn_bwd_fused_kernel<true><<<grid, kGbThreads, kGbSmem, st>>>(p);
