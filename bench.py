@@ -410,7 +410,7 @@ def run_b200(args):
 
         # ---- end to end through the public model API with HOST buffers ----
         if args.no_e2e:
-            e2e = {"ms_per_step": float("nan"), "h2d": 0, "d2h": 0}
+            e2e = {"ms_per_step": float("nan"), "h2d": 0, "d2h": 0, "copy_ms_per_step": float("nan")}
         else:
             e2e = run_e2e(net, tiles_host, args, torch, device, world)
         del tiles
@@ -434,11 +434,11 @@ def run_b200(args):
 
     # max over ranks
     t = torch.tensor([total_ms, enc_ms, dec_ms, conv_ms_per_step, e2e["ms_per_step"], engine_ms_per_step, first_ms,
-                      last_ms, eb_ms_step, fp32_ms], dtype=torch.float64, device=device)
+                      last_ms, eb_ms_step, fp32_ms, e2e["copy_ms_per_step"]], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     (total_ms, enc_ms, dec_ms, conv_ms_per_step, e2e_ms, engine_ms_per_step, first_ms, last_ms, eb_ms_step,
-     fp32_ms) = t.tolist()
+     fp32_ms, copy_ms) = t.tolist()
 
     pix_per_step = B * TILE[1] * TILE[2] * world
     ms_per_step = total_ms / args.steps
@@ -488,7 +488,11 @@ def run_b200(args):
                     "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                     "path": "pinned host uint8 tiles -> model.forward_tiles (g_a / entropy_bottleneck / g_s) -> uint8 x_hat, "
                             "int16 symbols, bpp on host",
-                    "rank0_numa_node": numa_node, "bpp": e2e.get("bpp")},
+                    "rank0_numa_node": numa_node, "bpp": e2e.get("bpp"),
+                    "copy_floor": {"ms_per_step": copy_ms, "mpix_s": pix_per_step / (copy_ms * 1e-3) / 1e6,
+                                   "host_gb_s_all_ranks": world * (e2e["h2d"] + e2e["d2h"]) / (copy_ms * 1e-3) / 1e9,
+                                   "what": "the same host<->device copies (same streams, same chunks, all ranks at once) with no "
+                                           "kernel in between: the rate the box's host memory / PCIe path allows"}},
             "gpu_launches": n_launch,
             "roofline": {"bound": "tensor",
                          "kernel": "conv_igemm_pair_kernel (6 launches per step: g_a[2,4,6], g_s[0,2,4], GDN/IGDN fused; CTA pairs, wide slabs)",
@@ -737,8 +741,41 @@ def run_e2e(net, tiles_host, args, torch, device, world):
     run(steps)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / steps
+
+    # The same bytes over the same streams and chunks WITHOUT any kernel: what this box's host memory / PCIe path delivers to
+    # all ranks at once.  When e2e sits on this floor (it does at 8 ranks), the bound is the host side, not the GPU.
+    x_dev = torch.empty((chunk,) + tuple(x_host.shape[1:]), dtype=torch.uint8, device=device)
+    sym_dev = torch.empty((chunk,) + ysz[1:], dtype=torch.int16, device=device)
+
+    def run_copies(n_steps):
+        main = torch.cuda.current_stream()
+        for s in streams:
+            s.wait_stream(main)
+        k = 0
+        for it in range(n_steps):
+            for lo in range(0, B, chunk):
+                hi = min(B, lo + chunk)
+                si = k % len(streams)
+                k += 1
+                with torch.cuda.stream(streams[si]):
+                    vb = x_host[lo:hi].to(device, non_blocking=True)
+                    xhat_host[lo:hi].copy_(vb, non_blocking=True)
+                    sym_host[lo:hi].copy_(sym_dev[:hi - lo], non_blocking=True)
+        for s in streams:
+            main.wait_stream(s)
+
+    bpp0 = float(bpp_host[0].item())
+    run_copies(2)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run_copies(steps)
+    torch.cuda.synchronize()
+    dt_copy = (time.perf_counter() - t0) / steps
+    del x_dev
     return {"ms_per_step": dt * 1e3, "h2d": x_host.numel(), "d2h": xhat_host.numel() + sym_host.numel() * 2 + 8,
-            "bpp": float(bpp_host[0].item())}
+            "bpp": bpp0, "copy_ms_per_step": dt_copy * 1e3}
 
 
 if __name__ == "__main__":
