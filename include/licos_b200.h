@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define LICOS_ABI_VERSION 2
+#define LICOS_ABI_VERSION 3 /* 3: licos_conv_args.pre_act, licos_conv_wgrad_image */
 
 enum {
     LICOS_OK = 0,

@@ -12,7 +12,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "liblicos_b200.so")
 
 LICOS_OK = 0
-ABI_VERSION = 2
+ABI_VERSION = 3
 ERR_NAMES = {
     -1: "LICOS_ERR_INVALID", -2: "LICOS_ERR_CUDA", -3: "LICOS_ERR_UNSUPPORTED", -4: "LICOS_ERR_NO_DEVICE",
     -5: "LICOS_ERR_DOMAIN", -6: "LICOS_ERR_NOMEM", -7: "LICOS_ERR_BUFFER",

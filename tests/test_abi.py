@@ -28,7 +28,7 @@ def test_header_symbols_exported_and_bound():
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in licos_b200/_lib.py"
     assert set(_lib.SIGNATURES) <= set(names) | {"licos_set_last_cuda_error"}
-    assert lib.licos_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.licos_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header():
