@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(32) rans_decode_kernel(const uint32_t* __restr
 // a 256-tile batch).  Here ONE WARP owns an image: the 32 lanes fetch and look up a chunk of 32 symbols in parallel
 // (coalesced, two chunks ahead of the coder); the coder state is replicated in every lane, a symbol's table entry reaches
 // the chain by shuffles that do not depend on the state, and renormalisation is predicated (no divergent lane-0 section,
-// no shared-memory hand-off: 6.0 -> 3.2 ms per 256 tiles).  Same bitstream: the arithmetic of rans_put_symbol /
+// no shared-memory hand-off: 6.0 -> 3.0 ms per 256 tiles).  Same bitstream: the arithmetic of rans_put_symbol /
 // rans_put_escape / RansReader is unchanged.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kRansMaxTables = 1024;  // offsets / sizes staged in shared memory
@@ -318,13 +318,19 @@ __global__ void __launch_bounds__(32) rans_encode_warp_kernel(const int32_t* __r
     // from the lane that looked it up by four shuffles that do not depend on the state, so they issue ahead of the chain; no
     // shared-memory hand-off, no divergent lane-0 section, and the renormalisation is a predicated store + two selects.
     auto put = [&](uint32_t start, uint32_t range, uint32_t rc_lo, uint32_t rc_hi) {
+        // Both outcomes of the renormalisation test are divided speculatively (the renormalised state is the 32-bit st.hi
+        // alone), so the test itself is off the dependent chain and only selects at the end.
         const bool ren = st.hi >= (range << 15);  // x >= ((L >> 16) << 32) * range
         if (ren) *--st.wp = st.lo;                 // (every lane writes the same word to the same address)
-        const uint32_t xl = ren ? st.hi : st.lo, xh = ren ? 0u : st.hi;
-        const uint64_t x = ((uint64_t)xh << 32) | xl;
-        uint64_t q = __umul64hi(x, ((uint64_t)rc_hi << 32) | rc_lo);
-        uint32_t r = xl - (uint32_t)q * range;
-        if (r >= range) { r -= range; ++q; }
+        const uint64_t rcp = ((uint64_t)rc_hi << 32) | rc_lo;
+        uint64_t qn = __umul64hi(((uint64_t)st.hi << 32) | st.lo, rcp);
+        uint32_t rn = st.lo - (uint32_t)qn * range;
+        if (rn >= range) { rn -= range; ++qn; }
+        uint32_t qr = (uint32_t)__umul64hi((uint64_t)st.hi, rcp);  // st.hi < 2^32: the quotient fits 32 bits
+        uint32_t rr = st.hi - qr * range;
+        if (rr >= range) { rr -= range; ++qr; }
+        const uint64_t q = ren ? (uint64_t)qr : qn;
+        const uint32_t r = ren ? rr : rn;
         st.hi = (uint32_t)(q >> 16);
         st.lo = ((uint32_t)q << 16) | (r + start);
     };
