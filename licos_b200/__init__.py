@@ -8,7 +8,7 @@ from .losses import RateDistortionLoss, compute_bpp, compute_msssim, compute_psn
 from .models import (CompressionModel, FactorizedPrior, FactorizedPriorReLU, ScaleHyperprior, image_models,
                      model_architectures)
 from .optimizers import net_aux_optimizer
-from .graphs import GraphedTrainStep
+from .graphs import GraphedForward, GraphedTrainStep
 
 __version__ = "0.1.0"
 

@@ -405,7 +405,7 @@ class EntropyBottleneck(EntropyModel):
 
     def packed_params(self, force: bool = False) -> ops.EbPacked:
         key = tuple((p.data_ptr(), p._version) for p in self._params()) + (self.likelihood_form,)
-        if key != self._packed_key or force or (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()):
+        if key != self._packed_key or force or ops.capture_rebuild():
             with torch.no_grad():
                 C = self.channels
                 parts = []

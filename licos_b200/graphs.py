@@ -69,3 +69,69 @@ class GraphedTrainStep:
         for p in self._params:
             torch.autograd.graph.increment_version(p)
         return self.out
+
+
+def _cached_tensors(net: nn.Module):
+    """Every tensor the modules' kernel-layout caches hold right now (packed weights, GDN tables, bottleneck tables)."""
+    keep = []
+
+    def walk(v):
+        if isinstance(v, torch.Tensor):
+            keep.append(v)
+        elif isinstance(v, (tuple, list)):
+            for t in v:
+                walk(t)
+        elif isinstance(v, dict):
+            for t in v.values():
+                walk(t)
+        elif hasattr(v, "tensors"):  # layers._Packed
+            walk(v.tensors)
+
+    for m in net.modules():
+        cache = getattr(m, "_packed_cache", None)
+        if cache is not None:
+            for ent in list(cache.values()):
+                walk(ent)
+        ebp = getattr(m, "_packed", None)
+        if ebp is not None:
+            walk([getattr(ebp, n, None) for n in ("packed", "medians", "lut")])
+    return keep
+
+
+class GraphedForward:
+    """``fwd = GraphedForward(net, example)``; then ``out = fwd(x)`` replays ``net(x)`` (eval mode, no autograd) as ONE CUDA
+    graph launch.  For small inputs -- one crop per call, e.g. eval_utils.process_img -- the ~30 launches of a forward pass
+    cost more on the host than on the GPU.  The parameters are constants of the graph (the packed weights and tables are
+    the cached ones, kept alive here): after changing them (``load_state_dict``, a training step) build a new one.  Inputs
+    must have the shape and dtype of ``example``; the returned tensors are overwritten by the next call."""
+
+    def __init__(self, net: nn.Module, example: torch.Tensor, warmup: int = 3, fn=None):
+        if not example.is_cuda:
+            raise RuntimeError("licos_b200: GraphedForward needs CUDA tensors on a B200 (no CPU path exists)")
+        from . import ops
+
+        self.net = net.eval()
+        self.x = example.detach().clone()
+        self._fn = fn if fn is not None else (lambda t: net(t))
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(max(warmup, 1)):  # fills the layout caches, the allocator, per-device kernel attributes
+                self._fn(self.x)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        ops._FROZEN_CAPTURE = True
+        try:
+            with torch.no_grad(), torch.cuda.graph(self.graph):
+                self.out = self._fn(self.x)
+        finally:
+            ops._FROZEN_CAPTURE = False
+        self._keep = _cached_tensors(net)  # the graph holds raw addresses of these: they must outlive it
+
+    def __call__(self, x: torch.Tensor):
+        if x.shape != self.x.shape or x.dtype != self.x.dtype:
+            raise ValueError(f"input {tuple(x.shape)} {x.dtype} differs from the captured {tuple(self.x.shape)} {self.x.dtype}")
+        self.x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.out

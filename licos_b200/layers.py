@@ -137,7 +137,7 @@ def _version_key(*params: Optional[Tensor]):
 def _capturing() -> bool:
     """Under CUDA-graph capture every tensor derived from a parameter is rebuilt inside the graph (the optimizer step
     of a replay changes the parameters without touching their version counters)."""
-    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+    return ops.capture_rebuild()
 
 
 class FusedSequential(nn.Sequential):

@@ -29,6 +29,16 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+_FROZEN_CAPTURE = False  # set by graphs.GraphedForward: parameters are constants of the graph being captured
+
+
+def capture_rebuild() -> bool:
+    """True while a CUDA graph is being captured whose replays may see CHANGED parameters (a training step: the optimizer
+    updates them in place without touching version counters), so everything derived from a parameter -- packed weights,
+    GDN tables, the bottleneck's tables -- must be rebuilt inside the graph instead of being taken from a cache."""
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing() and not _FROZEN_CAPTURE
+
+
 def _need_cuda(*tensors: Optional[torch.Tensor]) -> None:
     for t in tensors:
         if t is None:
@@ -319,7 +329,7 @@ class EbPacked:
         self.lut = None  # [C][257] eval-mode likelihood table, built on first use (a function of the parameters only)
 
     def eval_lut(self) -> torch.Tensor:
-        if self.lut is None or (torch.cuda.is_current_stream_capturing()):
+        if self.lut is None or capture_rebuild():
             lut = torch.empty(int(lib.licos_eb_lut_floats(self.p.channels)), dtype=torch.float32, device=self.packed.device)
             check(lib.licos_eb_build_lut(ctypes.byref(self.p), lut.data_ptr(), _stream()), "eb_build_lut")
             self.lut = lut

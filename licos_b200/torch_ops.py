@@ -233,7 +233,7 @@ def eb_forward_eval(ebp: ops.EbPacked, x: Tensor):
 
 def eb_forward_eval_fused(ebp: ops.EbPacked, x: Tensor, want_symbols=False, want_nhwc=False, want_symbols_i16=False,
                           sum_ln: Optional[Tensor] = None, want_float=True):
-    if ebp.lut is None or torch.cuda.is_current_stream_capturing():
+    if ebp.lut is None or ops.capture_rebuild():
         ebp.lut = T.eb_build_lut(*_eb_args(ebp))
     y_hat, lik, sym, nhwc, sym16 = T.eb_eval_fused(x, *_eb_args(ebp), ebp.lut, want_float, want_symbols, want_symbols_i16,
                                                    want_nhwc, sum_ln)

@@ -225,3 +225,31 @@ def test_full_size_other_baseline_configs(cuda):
         # the coded size tracks the model's rate (rANS overhead above it; below it where the 1e-9 likelihood floor charges
         # 30 bits for out-of-support symbols that the bypass nibbles code in fewer)
         assert 0.7 * bpp_model <= bpp_coded <= 1.1 * bpp_model + 0.05, (bpp_coded, bpp_model)
+
+
+@pytest.mark.parametrize("name,shape", [("bmshj2018-factorized", (2, 3, 128, 192)), ("bmshj2018-hyperprior", (1, 3, 128, 128))])
+def test_graphed_forward_equals_eager(cuda, name, shape):
+    """licos_b200.GraphedForward: the eval forward replayed as one CUDA graph gives the eager tensors bit for bit, for new
+    inputs too, and keeps doing so after the module's caches have been dropped (the graph owns what it captured)."""
+    import licos_b200 as L
+    from licos_b200 import synth
+
+    torch.manual_seed(3)
+    net = L.image_models[name](quality=1, pretrained=False)
+    synth.condition_weights(net)
+    net = net.to(cuda).eval()
+    g = torch.Generator().manual_seed(5)
+    x0, x1 = torch.rand(shape, generator=g).to(cuda), torch.rand(shape, generator=g).to(cuda)
+    with torch.no_grad():
+        ref0, ref1 = net(x0), net(x1)
+    fwd = L.GraphedForward(net, x0)
+    for x, ref in ((x0, ref0), (x1, ref1), (x0, ref0)):
+        out = fwd(x)
+        assert torch.equal(out["x_hat"], ref["x_hat"])
+        for k in ref["likelihoods"]:
+            assert torch.equal(out["likelihoods"][k], ref["likelihoods"][k])
+    net.train(); net.eval()  # clears the layout caches
+    out = fwd(x1)
+    assert torch.equal(out["x_hat"], ref1["x_hat"])
+    with pytest.raises(ValueError):
+        fwd(x1[:, :, :64])
