@@ -1137,6 +1137,20 @@ int64_t licos_conv_workspace_bytes(const licos_conv_args* a) {
     return (int64_t)a->batch * oh * ow * first_kpad(a->in_c) * 2;
 }
 
+// `setmaxnreg.inc` draws on the registers the CTA's own warps released and was launched with: a kernel built with fewer
+// registers per thread than the budget assumes would wait for ever, so refuse to launch it instead.
+static bool pair_regs_ok(const void* kernel, bool pipelined, int threads) {
+#ifdef LICOS_NO_EPI_PIPE
+    (void)kernel; (void)pipelined; (void)threads;
+    return true;
+#else
+    if (!pipelined) return true;
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) return false;
+    return (int64_t)fa.numRegs * threads >= 128 * kPairCtrlRegs + (int64_t)(threads - 128) * kPairTeamRegs;
+#endif
+}
+
 int licos_conv_forward(const licos_conv_args* a, void* stream) {
     if (!a || !a->in || !a->out || !a->weight) return LICOS_ERR_INVALID;
     if (a->batch < 0 || a->in_h < 1 || a->in_w < 1 || a->in_c < 1 || a->out_c < 1) return LICOS_ERR_INVALID;
@@ -1539,6 +1553,11 @@ int licos_conv_forward(const licos_conv_args* a, void* stream) {
     do {                                                                                                \
         const cudaError_t attr = ensure_max_dynamic_smem((const void*)conv_igemm_pair_kernel<E, O, XP, TWP>, kMaxDynSmem); \
         if (attr != cudaSuccess) { err = attr; break; }                                                 \
+        if (!pair_regs_ok((const void*)conv_igemm_pair_kernel<E, O, XP, TWP>,                           \
+                          (E == LICOS_EPI_GDN || E == LICOS_EPI_IGDN) && TWP == 4 && XP <= 4, pair_threads(TWP))) { \
+            err = cudaErrorLaunchOutOfResources;                                                        \
+            break;                                                                                      \
+        }                                                                                               \
         cudaLaunchConfig_t cfg = {};                                                                    \
         cfg.gridDim = dim3((unsigned)grid);                                                             \
         cfg.blockDim = dim3(pair_threads(TWP));                                                         \

@@ -52,6 +52,7 @@ __device__ __forceinline__ PairTile decode_pair_tile(const ConvParams& p, int w,
 // MMA, slab / weight TMA writes, the x^2 and output staging tiles and the TMA store's reads add up to 4.6 MB per tile
 // against 3.8 MB of port capacity in the ideal MMA time.
 __host__ __device__ constexpr int pair_threads(int tw) { return (4 + 2 * tw) * 32; }
+constexpr int kPairCtrlRegs = 96, kPairTeamRegs = 200;  // must fit what the CTA was launched with: 128 x 96 + 256 x 200 <= 384 x 168 (the pool is the CTA's own registers)
 
 #ifdef LICOS_PAIR_PROBES  // development: per-role cycle counters (tools/probe_conv.py); build with LICOS_NVCC_EXTRA=-DLICOS_PAIR_PROBES
 #define PP_T0(v) const long long v = clock64()
@@ -123,6 +124,17 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
     const uint32_t tmem_base = tmem_base_smem;
     const int n_items = p.total_tiles;  // pair work items (spatial tile pairs x channel splits)
 
+    // GDN epilogues, TW = 4: the four control warps are exactly warpgroup 0 and need few registers; handing theirs to the two
+    // epilogue teams (warpgroups 1 and 2) lets a team keep x AND two 32-column TMEM pieces in registers, so the next piece is
+    // in flight while this one is worked on (at the 168 registers of a 384-thread CTA there was room for one).
+#ifdef LICOS_NO_EPI_PIPE  // A/B knob (compile time)
+    constexpr bool kPipe = false;
+#else
+    constexpr bool kPipe = kGdn && TW == 4 && XC <= 4;  // (N = 192 keeps 96 words of x: no room for a second piece)
+#endif
+    // (each setmaxnreg sits at the top of its role's branch: ptxas budgets the code that FOLLOWS it in that branch)
+    if (warp < 4) {
+    if (kPipe) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(kPairCtrlRegs));
     if (warp == 0 && lane == 0) {
         // ===================== A producer (each CTA loads the slabs of its own tile) =====================
         for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.in_maps[i]);
@@ -317,7 +329,9 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
             }
 #endif
         }
-    } else if (warp >= 4) {
+    }
+    } else {
+        if (kPipe) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(kPairTeamRegs));
         // ===================== epilogue: two teams of TW warps per CTA, alternate accumulators =====================
         const int team = (warp - 4) / TW;
         const int half = TW == 8 ? (((warp - 4) >> 2) & 1) : 0;  // TW = 8: this warp takes chunks cc with (cc & 1) == half
@@ -368,19 +382,21 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
                         PP_ADD(e_store, _t);
                     }
                     uint32_t xs[kGdn ? XC * 16 : 1];  // v = acc + bias kept as packed bf16 pairs
+                    float vp[kPipe ? 2 : 1][32];
                     if (kGdn) {
                         // stage 1: v^2 (bf16) -> staging = this CTA's 128 rows of the gamma GEMM's A operand; the pair-wide
                         // GEMM then overwrites both CTAs' accumulators IN PLACE with the norm
                         PP_T0(_s1);
+                        if (kPipe) tmem_ld32(t_acc + half * 32, vp[0]);
 #pragma unroll
                         for (int i = 0; i < XC; ++i) {
                             const int cc = kStride * i + half;
                             if (cc < n32) {
-                                float v[32];
-                                tmem_ld32(t_acc + cc * 32, v);
+                                if (!kPipe) tmem_ld32(t_acc + cc * 32, vp[0]);
                                 tmem_ld_wait();
+                                if (kPipe && cc + kStride < n32) tmem_ld32(t_acc + (cc + kStride) * 32, vp[kPipe ? ((i + 1) & 1) : 0]);
                                 uint32_t sq[16];
-                                gdn_stage1_32<true>(v, bias_t + cc * 32, xs + i * 16, sq);
+                                gdn_stage1_32<true>(vp[kPipe ? (i & 1) : 0], bias_t + cc * 32, xs + i * 16, sq);
                                 store_row32(staging, et, cc, sq);
                             }
                         }
@@ -410,6 +426,7 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
                         PP_ADD(e_norm, _n);
                         tc_fence_after();
                         ++nit;
+                        if (kPipe) tmem_ld32(t_acc + half * 32, vp[0]);
                     }
 
                     // stage 2: activation, then write out
@@ -430,9 +447,15 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
                     for (int i = 0; i < XC; ++i) {
                         const int cc = kStride * i + half;
                         if (cc < n32) {
-                            float v[32];
-                            tmem_ld32(t_acc + cc * 32, v);  // GDN: the norm; otherwise the accumulator
-                            tmem_ld_wait();
+                            float vs[kPipe ? 1 : 32];
+                            if constexpr (kPipe) {
+                                tmem_ld_wait();
+                                if (cc + kStride < n32) tmem_ld32(t_acc + (cc + kStride) * 32, vp[(i + 1) & 1]);
+                            } else {
+                                tmem_ld32(t_acc + cc * 32, vs);  // GDN: the norm; otherwise the accumulator
+                                tmem_ld_wait();
+                            }
+                            float (&v)[32] = *reinterpret_cast<float (*)[32]>(kPipe ? &vp[kPipe ? (i & 1) : 0][0] : &vs[0]);
                             if (kGdn) {
                                 if (pre_px && cc * 32 < c_left) {
 #pragma unroll

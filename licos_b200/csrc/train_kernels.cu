@@ -726,6 +726,11 @@ int licos_gdn_backward(const void* x, const void* g, const void* gamma_hat_bf16,
     cudaStream_t st = (cudaStream_t)stream;
     static const bool one_team = getenv("LICOS_GDN_BWD_ONE_TEAM") != nullptr;  // A/B knob: the round-1 kernel
     if (!one_team) {
+        // the kernel's setmaxnreg budget (2 x 128 x 224 + 128 x 56) must fit the registers the CTA is launched with
+        cudaFuncAttributes fa;
+        const void* fn = inverse ? (const void*)gdn_bwd_fused2_kernel<true> : (const void*)gdn_bwd_fused2_kernel<false>;
+        LICOS_CUDA_OK(cudaFuncGetAttributes(&fa, fn));
+        if ((int64_t)fa.numRegs * kGb2Threads < 256 * kGb2TeamRegs + 128 * kGb2IssuerRegs) return LICOS_ERR_UNSUPPORTED;
         if (inverse) {
             LICOS_CUDA_OK(ensure_max_dynamic_smem((const void*)gdn_bwd_fused2_kernel<true>, (int)kGb2Smem));
             gdn_bwd_fused2_kernel<true><<<grid, kGb2Threads, kGb2Smem, st>>>(p);
