@@ -407,7 +407,14 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
                             // "staged" across the pair; once both CTAs are, the leader's warp issues the pair-wide gamma GEMM.
                             // (Issuing it from the main MMA thread instead -- it owns the pipe's queue -- was measured and was
                             // no faster: in pair mode the kernel is bound by the 128 B/clk shared-memory port, not by issue.)
+#ifdef LICOS_STG_RELEASE  // A/B knob (compile time): the cluster-scope release arrive of the first version
                             if (elect_one()) mbar_arrive_cluster(stg_full_leader);
+#else
+                            // The staged tile never leaves this SM: cta_group::2 makes THIS SM's tensor core read it, and the
+                            // stores were fenced for the async proxy and ordered by the team barrier above.  What crosses to
+                            // the leader CTA is only the signal, so it needs no cluster-scope release (~1.5 k cycles).
+                            if (elect_one()) mbar_arrive_cluster_relaxed(stg_full_leader);
+#endif
                             __syncwarp();
                             if (leader_cta) {
                                 if (!gamma_ready) { mbar_wait(&g_full, 0); gamma_ready = true; }

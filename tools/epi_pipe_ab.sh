@@ -3,7 +3,7 @@
 L=licos_b200/lib
 cp $L/liblicos_b200.so $L/pipe.so.bin
 run() {
-  timeout 120 python bench.py --steps 60 --warmup 10 --no-legs --no-train --no-cpu-baseline --no-e2e 2>/dev/null | tail -1 | python -c "
+  timeout 120 python bench.py --steps 40 --warmup 8 --no-legs --no-train --no-cpu-baseline --no-e2e 2>/dev/null | tail -1 | python -c "
 import sys, json
 d = json.loads(sys.stdin.read()); r=d['roofline']; print('$1', round(d['ms_per_step'],4), round(r['achieved']), r['per_launch_ms'])"
 }
