@@ -1,5 +1,10 @@
 #!/bin/bash
-# same box: pipelined GDN epilogue (A) vs not (B), three runs each, interleaved
+# Same-box A/B of two BUILDS of the library (compile-time knobs of the CTA-pair engine's GDN epilogue), three runs each,
+# interleaved.  Prepare both here before the gpurun call:
+#   (cd licos_b200/csrc && LICOS_NVCC_EXTRA=-DLICOS_NO_EPI_PIPE python -c "import build; build.build(force=True)")   # or -DLICOS_STG_RELEASE
+#   cp licos_b200/lib/liblicos_b200.so licos_b200/lib/nopipe.so.bin                                                   # variant B
+#   (cd licos_b200/csrc && python -c "import build; build.build(force=True)")                                        # variant A = default
+# then: gpurun -- bash tools/epi_pipe_ab.sh      (the script restores variant A at the end)
 L=licos_b200/lib
 cp $L/liblicos_b200.so $L/pipe.so.bin
 run() {
