@@ -374,10 +374,10 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
                     const uint32_t acc = (uint32_t)a;
                     const uint32_t t_acc = tmem_set + acc * p.N;
 
-                    if (OUT_NHWC || kGdn) {
+                    if (OUT_NHWC && !kGdn) {
                         // this team's previous TMA store must have finished reading `staging` before it is rewritten
                         PP_T0(_t);
-                        if (OUT_NHWC && leader) tma_store_wait_read();
+                        if (leader) tma_store_wait_read();
                         named_bar_sync(1 + team, kTeamThreads);
                         PP_ADD(e_store, _t);
                     }
@@ -397,6 +397,12 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
                                 if (kPipe && cc + kStride < n32) tmem_ld32(t_acc + (cc + kStride) * 32, vp[kPipe ? ((i + 1) & 1) : 0]);
                                 uint32_t sq[16];
                                 gdn_stage1_32<true>(vp[kPipe ? (i & 1) : 0], bias_t + cc * 32, xs + i * 16, sq);
+                                if (i == 0) {
+                                    // (GDN: the wait for the previous TMA store's read of `staging` comes only here, after
+                                    // the first piece has been loaded and squared: it overlaps that work)
+                                    if (OUT_NHWC && leader) tma_store_wait_read();
+                                    named_bar_sync(1 + team, kTeamThreads);
+                                }
                                 store_row32(staging, et, cc, sq);
                             }
                         }
