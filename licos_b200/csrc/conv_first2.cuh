@@ -386,8 +386,12 @@ __global__ void __launch_bounds__(first2_threads(TEAMS), 1) conv_first2_kernel(c
             const int buf = lt % kBufs;
             const uint32_t t_acc = tmem_base + lane_sel + (uint32_t)buf * (uint32_t)N;
 
-            if (leader) tma_store_wait_read();  // this team's previous store has read the staging tile
-            named_bar_sync(1 + team, 128);
+            // (the wait for this team's previous TMA store to have read the staging tile comes after the first accumulator piece
+            // has been loaded and worked on, right before the first write to the tile: it overlaps that work)
+            auto staging_free = [&]() {
+                if (leader) tma_store_wait_read();
+                named_bar_sync(1 + team, 128);
+            };
             mbar_wait(&acc_full[buf], (uint32_t)(lt / kBufs) & 1u);
             tc_fence_after();
 
@@ -401,6 +405,7 @@ __global__ void __launch_bounds__(first2_threads(TEAMS), 1) conv_first2_kernel(c
                         tmem_ld_wait();
                         uint32_t sq[16];
                         gdn_stage1_32<false>(v, nullptr, xs + cc * 16, sq);
+                        if (cc == 0) staging_free();
                         store_row32(stg, row, cc, sq);
                     }
                 }
@@ -446,6 +451,7 @@ __global__ void __launch_bounds__(first2_threads(TEAMS), 1) conv_first2_kernel(c
                             out[i] = pack_bf16x2(x0, x1);
                         }
                     }
+                    if (!kGdn && cc == 0) staging_free();
                     store_row32(stg, row, cc, out);
                 }
             }
