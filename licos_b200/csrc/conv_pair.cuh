@@ -463,7 +463,16 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
                             float vs[kPipe ? 1 : 32];
                             if constexpr (kPipe) {
                                 tmem_ld_wait();
-                                if (cc + kStride < n32) tmem_ld32(t_acc + (cc + kStride) * 32, vp[(i + 1) & 1]);
+                                if (cc + kStride < n32) {
+                                    tmem_ld32(t_acc + (cc + kStride) * 32, vp[(i + 1) & 1]);
+                                } else {
+#ifndef LICOS_LATE_ACC_RELEASE  // (A/B knob, compile time)
+                                    // the last piece is in registers: this thread is done with the accumulator -- hand it back
+                                    // to the pair's MMA issuer now, one piece of arithmetic and stores earlier
+                                    tc_fence_before();
+                                    mbar_arrive_cluster_relaxed(acc_empty_leader[buf]);
+#endif
+                                }
                             } else {
                                 tmem_ld32(t_acc + cc * 32, vs);  // GDN: the norm; otherwise the accumulator
                                 tmem_ld_wait();
@@ -523,8 +532,13 @@ __global__ void __launch_bounds__(pair_threads(TW), 1) conv_igemm_pair_kernel(co
                         }
                     }
                     // this accumulator has been read: hand it back to the pair's MMA issuer
-                    tc_fence_before();
-                    mbar_arrive_cluster_relaxed(acc_empty_leader[buf]);  // orders TMEM reads (the tcgen05 fence), no memory
+#ifndef LICOS_LATE_ACC_RELEASE
+                    if (!kPipe)
+#endif
+                    {
+                        tc_fence_before();
+                        mbar_arrive_cluster_relaxed(acc_empty_leader[buf]);  // orders TMEM reads (the tcgen05 fence), no memory
+                    }
                     PP_ADD(e_s2, _s2);
                     PP_T0(_st);
                     if (OUT_NHWC) {
